@@ -1,0 +1,419 @@
+/*
+ * pmm_oracle.c — CPU restatement of polars-matmul's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this.  The product (libpmm_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * What it restates (reference = NivekNey/polars-matmul v0.1.4, paths relative to the reference root):
+ *   metric parsing ............ src/metrics.rs:19-36
+ *   C = A * B^T ............... src/metrics.rs:40-97 (f64), :204-255 (f32)   [contraction = faer 0.19]
+ *   row norms ................. src/metrics.rs:367-393                        [ndarray 0.16 `dot`]
+ *   cosine / euclidean pass ... src/metrics.rs:258-365
+ *   per-row top-k ............. src/topk.rs:6-75
+ *   k clamp, f32->f64 widen ... src/matmul.rs:443, :447, :506
+ *   List -> dense marshalling . src/matmul.rs:231-286 (null -> 0, short row zero padded)
+ *
+ * PARITY PIN STATUS.  The contraction lives in faer 0.19 (Cargo.toml:22, semver range, no Cargo.lock)
+ * and the norm reduction in ndarray 0.16; neither crate is vendored under the reference and no Rust
+ * toolchain exists in this image, so the reference itself cannot be run here.  The oracle is pinned
+ * against every known-answer vector the reference's own tests hold for this path
+ * (tests/golden/reference_known_answers.json, checked by tests/test_oracle_golden.py).  What those
+ * vectors do NOT pin, and what is therefore "parity unpinned": (1) the f32/f64 summation order inside
+ * the contraction (reference tests use rtol=1e-5 vs NumPy), (2) tie order in top-k (never asserted).
+ * Choices made here for the unpinned parts:
+ *   - contraction: one fused multiply-add per element, sequential in the vector dimension
+ *     (published algorithm of the `gemm` crate microkernels: FMA accumulate over k);
+ *   - norms: ndarray's `unrolled_dot` order — 8 partial sums, separate multiply and add,
+ *     combined as (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then a sequential tail;
+ *   - ties: score best-first, then LOWER corpus index first (BASELINE.json north_star rule);
+ *     NaN scores rank last; -0.0 == +0.0.
+ *
+ * Build: see oracle/Makefile (gcc -O3 -mavx2 -mfma -fopenmp -ffp-contract=off).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define PMM_COSINE 0
+#define PMM_DOT 1
+#define PMM_EUCLIDEAN 2
+
+#define JB 16 /* corpus rows per transposed block (vector lanes = independent outputs) */
+#define IB 8  /* query rows per block */
+
+/* ---------------------------------------------------------------- metric parsing */
+/* src/metrics.rs:19-27: lower-case, "l2" alias, error text. Returns 0 ok / 1 unknown (msg filled). */
+int pmm_oracle_metric_from_str(const char *s, int *metric, char *msg, int msg_len) {
+    char low[64];
+    size_t n = strlen(s);
+    if (n < sizeof(low)) {
+        for (size_t i = 0; i <= n; ++i) low[i] = (char)tolower((unsigned char)s[i]);
+        if (!strcmp(low, "cosine")) { *metric = PMM_COSINE; return 0; }
+        if (!strcmp(low, "dot")) { *metric = PMM_DOT; return 0; }
+        if (!strcmp(low, "euclidean") || !strcmp(low, "l2")) { *metric = PMM_EUCLIDEAN; return 0; }
+    }
+    if (msg && msg_len > 0)
+        snprintf(msg, (size_t)msg_len, "Unknown metric: '%s'. Supported: cosine, dot, euclidean", s);
+    return 1;
+}
+
+/* src/metrics.rs:30-35 */
+int pmm_oracle_higher_is_better(int metric) { return metric != PMM_EUCLIDEAN; }
+
+int pmm_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---------------------------------------------------------------- norms (src/metrics.rs:367-393) */
+#define DEF_UNROLLED_DOT(NAME, T)                                                         \
+    static T NAME(const T *x, const T *y, int64_t n) {                                    \
+        T p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, sum = 0;        \
+        int64_t i = 0;                                                                    \
+        for (; i + 8 <= n; i += 8) {                                                      \
+            p0 = p0 + x[i + 0] * y[i + 0];                                                \
+            p1 = p1 + x[i + 1] * y[i + 1];                                                \
+            p2 = p2 + x[i + 2] * y[i + 2];                                                \
+            p3 = p3 + x[i + 3] * y[i + 3];                                                \
+            p4 = p4 + x[i + 4] * y[i + 4];                                                \
+            p5 = p5 + x[i + 5] * y[i + 5];                                                \
+            p6 = p6 + x[i + 6] * y[i + 6];                                                \
+            p7 = p7 + x[i + 7] * y[i + 7];                                                \
+        }                                                                                 \
+        sum = sum + (p0 + p4);                                                            \
+        sum = sum + (p1 + p5);                                                            \
+        sum = sum + (p2 + p6);                                                            \
+        sum = sum + (p3 + p7);                                                            \
+        for (; i < n; ++i) sum = sum + x[i] * y[i];                                       \
+        return sum;                                                                       \
+    }
+DEF_UNROLLED_DOT(unrolled_dot_f32, float)
+DEF_UNROLLED_DOT(unrolled_dot_f64, double)
+
+void pmm_oracle_sqnorms_f32(const float *x, int64_t n, int64_t d, float *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = unrolled_dot_f32(x + i * d, x + i * d, d);
+}
+void pmm_oracle_norms_f32(const float *x, int64_t n, int64_t d, float *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = sqrtf(unrolled_dot_f32(x + i * d, x + i * d, d));
+}
+void pmm_oracle_sqnorms_f64(const double *x, int64_t n, int64_t d, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = unrolled_dot_f64(x + i * d, x + i * d, d);
+}
+void pmm_oracle_norms_f64(const double *x, int64_t n, int64_t d, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = sqrt(unrolled_dot_f64(x + i * d, x + i * d, d));
+}
+
+/* ---------------------------------------------------------------- similarity post-pass */
+/* src/metrics.rs:323-344 (f32, eps 1e-6) and :346-362 */
+static inline float finish_f32(float dot, int metric, float qa, float ca) {
+    if (metric == PMM_COSINE) {
+        if (qa > 1e-6f) {
+            if (ca > 1e-6f) return dot / (qa * ca);
+            return 0.0f;
+        }
+        return 0.0f;
+    }
+    if (metric == PMM_EUCLIDEAN) {
+        float sq = (qa + ca) - 2.0f * dot;
+        return sqrtf(fmaxf(sq, 0.0f)); /* f32::max ignores NaN, as fmaxf does */
+    }
+    return dot;
+}
+/* src/metrics.rs:267-290 (f64, eps 1e-10) and :292-308 */
+static inline double finish_f64(double dot, int metric, double qa, double ca) {
+    if (metric == PMM_COSINE) {
+        if (qa > 1e-10) {
+            if (ca > 1e-10) return dot / (qa * ca);
+            return 0.0;
+        }
+        return 0.0;
+    }
+    if (metric == PMM_EUCLIDEAN) {
+        double sq = (qa + ca) - 2.0 * dot;
+        return sqrt(fmax(sq, 0.0));
+    }
+    return dot;
+}
+
+/* ---------------------------------------------------------------- blocked contraction
+ * dot[i][j] = sum_d q[i][d]*c[j][d], one FMA per element, sequential in d (src/metrics.rs:204-255).
+ * A block of JB corpus rows is transposed so the JB independent outputs vectorise; every output
+ * still sees exactly the sequential order. */
+#define DEF_BLOCK_DOTS(NAME, T, FMA)                                                      \
+    static void NAME(const T *qrow, const T *ct /* [d][JB] */, int64_t d, T *acc) {       \
+        T a[JB];                                                                          \
+        for (int j = 0; j < JB; ++j) a[j] = 0;                                            \
+        for (int64_t t = 0; t < d; ++t) {                                                 \
+            const T qv = qrow[t];                                                         \
+            const T *cr = ct + t * JB;                                                    \
+            for (int j = 0; j < JB; ++j) a[j] = FMA(qv, cr[j], a[j]);                     \
+        }                                                                                 \
+        for (int j = 0; j < JB; ++j) acc[j] = a[j];                                       \
+    }
+DEF_BLOCK_DOTS(block_dots_f32, float, fmaf)
+DEF_BLOCK_DOTS(block_dots_f64, double, fma)
+
+#define DEF_TRANSPOSE(NAME, T)                                                            \
+    static void NAME(const T *c, int64_t j0, int64_t n, int64_t d, T *ct) {               \
+        for (int j = 0; j < JB; ++j) {                                                    \
+            if (j0 + j < n) {                                                             \
+                const T *src = c + (j0 + j) * d;                                          \
+                for (int64_t t = 0; t < d; ++t) ct[t * JB + j] = src[t];                  \
+            } else {                                                                      \
+                for (int64_t t = 0; t < d; ++t) ct[t * JB + j] = 0;                       \
+            }                                                                             \
+        }                                                                                 \
+    }
+DEF_TRANSPOSE(transpose_block_f32, float)
+DEF_TRANSPOSE(transpose_block_f64, double)
+
+/* Full similarity matrix (src/metrics.rs:258-365). metric < 0 => raw dot (matmul path). */
+#define DEF_SCORES(NAME, T, BLOCK, TRANSP, FINISH, NORMS, SQNORMS)                        \
+    void NAME(const T *q, const T *c, int64_t nq, int64_t n, int64_t d, int metric,       \
+              T *out) {                                                                   \
+        T *qa = NULL, *ca = NULL;                                                         \
+        if (metric == PMM_COSINE || metric == PMM_EUCLIDEAN) {                            \
+            qa = (T *)malloc(sizeof(T) * (size_t)(nq > 0 ? nq : 1));                      \
+            ca = (T *)malloc(sizeof(T) * (size_t)(n > 0 ? n : 1));                        \
+            if (metric == PMM_COSINE) { NORMS(q, nq, d, qa); NORMS(c, n, d, ca); }        \
+            else { SQNORMS(q, nq, d, qa); SQNORMS(c, n, d, ca); }                         \
+        }                                                                                 \
+        int64_t nblk = (n + JB - 1) / JB;                                                 \
+        _Pragma("omp parallel")                                                           \
+        {                                                                                 \
+            T *ct = (T *)malloc(sizeof(T) * (size_t)d * JB + 64);                         \
+            T acc[JB];                                                                    \
+            _Pragma("omp for schedule(dynamic, 4)")                                       \
+            for (int64_t b = 0; b < nblk; ++b) {                                          \
+                int64_t j0 = b * JB;                                                      \
+                TRANSP(c, j0, n, d, ct);                                                  \
+                for (int64_t i = 0; i < nq; ++i) {                                        \
+                    BLOCK(q + i * d, ct, d, acc);                                         \
+                    for (int j = 0; j < JB && j0 + j < n; ++j) {                          \
+                        T v = acc[j];                                                     \
+                        if (qa) v = FINISH(v, metric, qa[i], ca[j0 + j]);                 \
+                        out[i * n + j0 + j] = v;                                          \
+                    }                                                                     \
+                }                                                                         \
+            }                                                                             \
+            free(ct);                                                                     \
+        }                                                                                 \
+        free(qa);                                                                         \
+        free(ca);                                                                         \
+    }
+DEF_SCORES(pmm_oracle_scores_f32, float, block_dots_f32, transpose_block_f32, finish_f32,
+           pmm_oracle_norms_f32, pmm_oracle_sqnorms_f32)
+DEF_SCORES(pmm_oracle_scores_f64, double, block_dots_f64, transpose_block_f64, finish_f64,
+           pmm_oracle_norms_f64, pmm_oracle_sqnorms_f64)
+
+/* raw matmul, src/matmul.rs:295-417 -> src/metrics.rs:160-202 / :111-157 */
+void pmm_oracle_matmul_f32(const float *q, const float *c, int64_t nq, int64_t n, int64_t d, float *out) {
+    pmm_oracle_scores_f32(q, c, nq, n, d, PMM_DOT, out);
+}
+void pmm_oracle_matmul_f64(const double *q, const double *c, int64_t nq, int64_t n, int64_t d, double *out) {
+    pmm_oracle_scores_f64(q, c, nq, n, d, PMM_DOT, out);
+}
+
+/* ---------------------------------------------------------------- top-k (src/topk.rs:6-75)
+ * Total order: better score first (descending for cosine/dot, ascending for euclidean); NaN last;
+ * -0.0 == +0.0; equal scores -> lower index first.  better(a,b) != 0 iff a ranks strictly before b. */
+#define DEF_BETTER(NAME, T, ISNAN)                                                        \
+    static inline int NAME(T sa, int64_t ia, T sb, int64_t ib, int higher) {              \
+        int na = ISNAN(sa), nb = ISNAN(sb);                                               \
+        if (na || nb) {                                                                   \
+            if (na && nb) return ia < ib;                                                 \
+            return nb; /* a is a number, b is NaN -> a first */                           \
+        }                                                                                 \
+        if (sa == sb) return ia < ib;                                                     \
+        return higher ? (sa > sb) : (sa < sb);                                            \
+    }
+DEF_BETTER(better_f32, float, isnan)
+DEF_BETTER(better_f64, double, isnan)
+
+/* Bounded heap holding the k best seen so far; root = worst of them. */
+#define DEF_HEAP(SUFFIX, T, BETTER)                                                       \
+    typedef struct { T s; int64_t i; } ent_##SUFFIX;                                      \
+    static inline void sift_down_##SUFFIX(ent_##SUFFIX *h, int64_t n, int64_t p, int hi) {\
+        for (;;) {                                                                        \
+            int64_t l = 2 * p + 1, r = l + 1, w = p;                                      \
+            /* w = the WORST among p,l,r (worst = every other is better) */               \
+            if (l < n && BETTER(h[w].s, h[w].i, h[l].s, h[l].i, hi)) w = l;               \
+            if (r < n && BETTER(h[w].s, h[w].i, h[r].s, h[r].i, hi)) w = r;               \
+            if (w == p) return;                                                           \
+            ent_##SUFFIX t = h[p]; h[p] = h[w]; h[w] = t;                                 \
+            p = w;                                                                        \
+        }                                                                                 \
+    }                                                                                     \
+    static inline void heap_offer_##SUFFIX(ent_##SUFFIX *h, int64_t *cnt, int64_t k,      \
+                                           T s, int64_t idx, int hi) {                    \
+        if (*cnt < k) {                                                                   \
+            int64_t p = (*cnt)++;                                                         \
+            h[p].s = s; h[p].i = idx;                                                     \
+            while (p > 0) { /* sift up: parent must be worse-or-equal than child */       \
+                int64_t par = (p - 1) / 2;                                                \
+                if (BETTER(h[par].s, h[par].i, h[p].s, h[p].i, hi)) {                     \
+                    ent_##SUFFIX t = h[p]; h[p] = h[par]; h[par] = t; p = par;            \
+                } else break;                                                             \
+            }                                                                             \
+        } else if (k > 0 && BETTER(s, idx, h[0].s, h[0].i, hi)) {                         \
+            h[0].s = s; h[0].i = idx;                                                     \
+            sift_down_##SUFFIX(h, k, 0, hi);                                              \
+        }                                                                                 \
+    }                                                                                     \
+    /* heap -> sorted best-first, in place */                                             \
+    static void heap_finish_##SUFFIX(ent_##SUFFIX *h, int64_t cnt, int hi) {              \
+        for (int64_t n = cnt; n > 1; --n) {                                               \
+            ent_##SUFFIX t = h[0]; h[0] = h[n - 1]; h[n - 1] = t;                         \
+            sift_down_##SUFFIX(h, n - 1, 0, hi);                                          \
+        }                                                                                 \
+    }
+DEF_HEAP(f32, float, better_f32)
+DEF_HEAP(f64, double, better_f64)
+
+/* O1/O2: src/matmul.rs:420-469 (k clamp :443, f32 scores widened exactly :447) + src/topk.rs.
+ * out_index [nq*k_eff] u32 (`idx as u32`, src/matmul.rs:506), out_score [nq*k_eff] f64,
+ * out_gap [nq] (optional) = |score_k - score_{k+1}| in working precision widened to f64
+ * (+inf when k_eff == n): the parity checker uses it for the north_star near-tie exemption.
+ * Returns k_eff = min(k, n). */
+#define DEF_TOPK(NAME, T, SUFFIX, BLOCK, TRANSP, FINISH, NORMS, SQNORMS)                  \
+    int64_t NAME(const T *q, const T *c, int64_t nq, int64_t n, int64_t d, int64_t k,     \
+                 int metric, uint32_t *out_index, double *out_score, double *out_gap) {   \
+        int64_t keff = k < n ? k : n;                                                     \
+        if (keff < 0) keff = 0;                                                           \
+        int hi = pmm_oracle_higher_is_better(metric);                                     \
+        int64_t kh = keff < n ? keff + 1 : keff; /* keep one extra to report the gap */   \
+        T *qa = NULL, *ca = NULL;                                                         \
+        if (metric == PMM_COSINE || metric == PMM_EUCLIDEAN) {                            \
+            qa = (T *)malloc(sizeof(T) * (size_t)(nq > 0 ? nq : 1));                      \
+            ca = (T *)malloc(sizeof(T) * (size_t)(n > 0 ? n : 1));                        \
+            if (metric == PMM_COSINE) { NORMS(q, nq, d, qa); NORMS(c, n, d, ca); }        \
+            else { SQNORMS(q, nq, d, qa); SQNORMS(c, n, d, ca); }                         \
+        }                                                                                 \
+        int64_t nblk = (n + JB - 1) / JB;                                                 \
+        int64_t nqb = (nq + IB - 1) / IB;                                                 \
+        _Pragma("omp parallel")                                                           \
+        {                                                                                 \
+            T *ct = (T *)malloc(sizeof(T) * (size_t)d * JB + 64);                         \
+            ent_##SUFFIX *heaps = (ent_##SUFFIX *)malloc(sizeof(ent_##SUFFIX) *           \
+                                                         (size_t)(IB * (kh > 0 ? kh : 1)));\
+            int64_t cnt[IB];                                                              \
+            T acc[JB];                                                                    \
+            _Pragma("omp for schedule(dynamic, 1)")                                       \
+            for (int64_t qb = 0; qb < nqb; ++qb) {                                        \
+                int64_t i0 = qb * IB, i1 = i0 + IB < nq ? i0 + IB : nq;                   \
+                for (int r = 0; r < IB; ++r) cnt[r] = 0;                                  \
+                for (int64_t b = 0; b < nblk; ++b) {                                      \
+                    int64_t j0 = b * JB;                                                  \
+                    TRANSP(c, j0, n, d, ct);                                              \
+                    for (int64_t i = i0; i < i1; ++i) {                                   \
+                        BLOCK(q + i * d, ct, d, acc);                                     \
+                        for (int j = 0; j < JB && j0 + j < n; ++j) {                      \
+                            T v = acc[j];                                                 \
+                            if (qa) v = FINISH(v, metric, qa[i], ca[j0 + j]);             \
+                            heap_offer_##SUFFIX(heaps + (i - i0) * kh, &cnt[i - i0], kh,  \
+                                                v, j0 + j, hi);                           \
+                        }                                                                 \
+                    }                                                                     \
+                }                                                                         \
+                for (int64_t i = i0; i < i1; ++i) {                                       \
+                    ent_##SUFFIX *h = heaps + (i - i0) * kh;                              \
+                    heap_finish_##SUFFIX(h, cnt[i - i0], hi);                             \
+                    for (int64_t t = 0; t < keff; ++t) {                                  \
+                        out_index[i * keff + t] = (uint32_t)h[t].i;                       \
+                        out_score[i * keff + t] = (double)h[t].s;                         \
+                    }                                                                     \
+                    if (out_gap) {                                                        \
+                        if (kh > keff && keff > 0)                                        \
+                            out_gap[i] = fabs((double)h[keff - 1].s - (double)h[keff].s); \
+                        else out_gap[i] = INFINITY;                                       \
+                    }                                                                     \
+                }                                                                         \
+            }                                                                             \
+            free(ct);                                                                     \
+            free(heaps);                                                                  \
+        }                                                                                 \
+        free(qa);                                                                         \
+        free(ca);                                                                         \
+        return keff;                                                                      \
+    }
+DEF_TOPK(pmm_oracle_topk_f32, float, f32, block_dots_f32, transpose_block_f32, finish_f32,
+         pmm_oracle_norms_f32, pmm_oracle_sqnorms_f32)
+DEF_TOPK(pmm_oracle_topk_f64, double, f64, block_dots_f64, transpose_block_f64, finish_f64,
+         pmm_oracle_norms_f64, pmm_oracle_sqnorms_f64)
+
+/* Selection alone on a given score matrix (src/topk.rs unit tests :82-125). */
+void pmm_oracle_select_f64(const double *m, int64_t nq, int64_t n, int64_t k, int higher,
+                           int64_t *out_index, double *out_score) {
+    int64_t keff = k < n ? k : n;
+    ent_f64 *h = (ent_f64 *)malloc(sizeof(ent_f64) * (size_t)(keff > 0 ? keff : 1));
+    for (int64_t i = 0; i < nq; ++i) {
+        int64_t cnt = 0;
+        for (int64_t j = 0; j < n; ++j) heap_offer_f64(h, &cnt, keff, m[i * n + j], j, higher);
+        heap_finish_f64(h, cnt, higher);
+        for (int64_t t = 0; t < keff; ++t) { out_index[i * keff + t] = h[t].i; out_score[i * keff + t] = h[t].s; }
+    }
+    free(h);
+}
+void pmm_oracle_select_f32(const float *m, int64_t nq, int64_t n, int64_t k, int higher,
+                           int64_t *out_index, float *out_score) {
+    int64_t keff = k < n ? k : n;
+    ent_f32 *h = (ent_f32 *)malloc(sizeof(ent_f32) * (size_t)(keff > 0 ? keff : 1));
+    for (int64_t i = 0; i < nq; ++i) {
+        int64_t cnt = 0;
+        for (int64_t j = 0; j < n; ++j) heap_offer_f32(h, &cnt, keff, m[i * n + j], j, higher);
+        heap_finish_f32(h, cnt, higher);
+        for (int64_t t = 0; t < keff; ++t) { out_index[i * keff + t] = h[t].i; out_score[i * keff + t] = h[t].s; }
+    }
+    free(h);
+}
+
+/* ---------------------------------------------------------------- List -> dense (src/matmul.rs:231-286)
+ * dim = length of row 0 (caller passes it); null element -> 0; null row -> zeros; short row zero
+ * padded.  A row LONGER than dim is an out-of-bounds panic in the reference (ndarray index);
+ * here: return 2.  validity / row_validity are Arrow LSB bitmaps or NULL. Returns 0 ok. */
+#define DEF_LIST_TO_DENSE(NAME, T)                                                        \
+    int NAME(const T *values, const int64_t *offsets, const uint8_t *validity,            \
+             const uint8_t *row_validity, int64_t n_rows, int64_t dim, T *out) {          \
+        for (int64_t i = 0; i < n_rows; ++i) {                                            \
+            T *dst = out + i * dim;                                                       \
+            for (int64_t t = 0; t < dim; ++t) dst[t] = 0;                                 \
+            if (row_validity && !((row_validity[i >> 3] >> (i & 7)) & 1)) continue;       \
+            int64_t b = offsets[i], e = offsets[i + 1];                                   \
+            if (e - b > dim) return 2;                                                    \
+            for (int64_t p = b; p < e; ++p) {                                             \
+                if (validity && !((validity[p >> 3] >> (p & 7)) & 1)) continue;           \
+                dst[p - b] = values[p];                                                   \
+            }                                                                             \
+        }                                                                                 \
+        return 0;                                                                         \
+    }
+DEF_LIST_TO_DENSE(pmm_oracle_list_to_dense_f32, float)
+DEF_LIST_TO_DENSE(pmm_oracle_list_to_dense_f64, double)
+
+/* f16 storage: the reference has no f16 code; README.md:154-156 tells users to cast to f32 first,
+ * so the reference result for f16-stored input is "exact upcast, then the f32 path". */
+void pmm_oracle_f16_to_f32(const uint16_t *h, int64_t n, float *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t x = h[i], sign = (x & 0x8000u) << 16, e = (x >> 10) & 0x1f, m = x & 0x3ffu, bits;
+        if (e == 0) {
+            if (m == 0) bits = sign;
+            else {
+                int sh = 0;
+                while (!(m & 0x400u)) { m <<= 1; ++sh; }
+                m &= 0x3ffu;
+                bits = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | (m << 13);
+            }
+        } else if (e == 31) bits = sign | 0x7f800000u | (m << 13);
+        else bits = sign | ((e + 112u) << 23) | (m << 13);
+        memcpy(out + i, &bits, 4);
+    }
+}
