@@ -1,0 +1,189 @@
+/*
+ * pmm.h — C ABI of libpmm_b200.so: the B200-native replacement for polars-matmul's native layer.
+ *
+ * This is the drop-in boundary for the one hot path of NivekNey/polars-matmul v0.1.4:
+ *     pl.col(..).pmm.topk(corpus, k, metric)   and   pl.col(..).pmm.matmul(corpus, flatten)
+ * The reference crosses Python -> Rust at src/lib.rs:15-55 (`_matmul`, `_topk`, PyO3) and does all
+ * numeric work in src/matmul.rs, src/metrics.rs, src/topk.rs on the CPU (faer GEMM + serial
+ * quickselect).  A maintainer of the reference keeps src/lib.rs and python/polars_matmul/__init__.py
+ * and replaces the bodies of `topk_impl` (src/matmul.rs:473) and `matmul_impl` (src/matmul.rs:295)
+ * with calls to `pmm_topk` / `pmm_matmul` below (binding stubs: INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C, pointers and sizes only; no CUDA, torch or Arrow types in signatures
+ *     (a `void* stream` is a cudaStream_t passed opaquely; NULL = the library's own stream);
+ *   - every function returns PMM_OK (0) or a PMM_ERR_* code; the message is in pmm_last_error()
+ *     (thread-local) and contains the same substrings the reference's errors carry
+ *     ("Unknown metric", "Empty series", "Dimension mismatch", "Zero-dimensional vectors",
+ *     "First element is null"), so the Python shim can raise RuntimeError(msg) exactly as
+ *     src/lib.rs:28,53 does;
+ *   - the caller owns every input and output buffer; the library owns all device memory;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PMM_ERR_CUDA.
+ */
+#ifndef PMM_H_
+#define PMM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PMM_API __attribute__((visibility("default")))
+#else
+#define PMM_API
+#endif
+
+#define PMM_OK 0
+#define PMM_ERR_INVALID 1     /* bad argument / reference-visible compute error (message matters) */
+#define PMM_ERR_CUDA 2        /* CUDA runtime / driver failure, or no device */
+#define PMM_ERR_UNSUPPORTED 3 /* valid request this build does not cover (says which) */
+
+/* Storage dtype of a values buffer.  Working precision follows src/matmul.rs:308,427:
+ * f32 iff BOTH sides are f32 (f16 storage is upcast exactly and counts as f32, README.md:154-156). */
+#define PMM_DTYPE_F16 0
+#define PMM_DTYPE_F32 1
+#define PMM_DTYPE_F64 2
+
+/* src/metrics.rs:10-17 */
+#define PMM_METRIC_COSINE 0
+#define PMM_METRIC_DOT 1
+#define PMM_METRIC_EUCLIDEAN 2
+
+/*
+ * One embedding column in Arrow layout — what `series_to_matrix[_f32]` (src/matmul.rs:131-164) and
+ * `try_extract_contiguous_*` (src/matmul.rs:39-95) read from a Polars Series.
+ *   offsets == NULL : fixed-size rows (pl.Array / FixedSizeList): row i = values[i*dim .. (i+1)*dim)
+ *   offsets != NULL : pl.List as 64-bit offsets (LargeList): row i = values[offsets[i] .. offsets[i+1]);
+ *                     `dim` = length of row 0 (src/matmul.rs:237-239); shorter rows are zero padded;
+ *                     a longer row is an error here (the reference panics, ndarray out-of-bounds).
+ *   validity        : Arrow LSB validity bitmap over the child values (bit p for values[p]) or NULL;
+ *                     a null element reads as 0.0 (src/matmul.rs:192,224,251,280).
+ *   row_validity    : validity bitmap over rows or NULL; a null row reads as zeros (src/matmul.rs:248).
+ * For the host entry points all pointers are host pointers; for the pmm_dev_* entry points all
+ * pointers are device pointers.
+ */
+typedef struct pmm_matrix {
+    const void *values;
+    const int64_t *offsets;
+    const uint8_t *validity;
+    const uint8_t *row_validity;
+    int64_t n_rows;
+    int64_t dim;
+    int32_t dtype; /* PMM_DTYPE_* */
+    int32_t reserved;
+} pmm_matrix_t;
+
+/* ------------------------------------------------------------------ small helpers */
+
+/* Metric::from_str, src/metrics.rs:19-27: case-insensitive, "l2" == euclidean.
+ * Error text: "Unknown metric: '<name>'. Supported: cosine, dot, euclidean". */
+PMM_API int pmm_metric_from_str(const char *name, int32_t *metric);
+
+/* Metric::higher_is_better, src/metrics.rs:30-35. Returns 1/0. */
+PMM_API int pmm_higher_is_better(int32_t metric);
+
+/* is_f32_series x2, src/matmul.rs:13-19,308,427. Returns PMM_DTYPE_F32 or PMM_DTYPE_F64. */
+PMM_API int pmm_working_dtype(int32_t left_dtype, int32_t right_dtype);
+
+/* ------------------------------------------------------------------ host entry points (the boundary) */
+
+/*
+ * Replaces `_topk` (src/lib.rs:33-55) -> `topk_impl` (src/matmul.rs:473-519) ->
+ * `compute_topk_indices_scores` (src/matmul.rs:420-469) -> `compute_similarity_matrix[_f32]`
+ * (src/metrics.rs:258,314) -> `select_topk_with_scores[_f32]` (src/topk.rs:6,42).
+ *
+ *   k_eff = min(k, corpus->n_rows)  (src/matmul.rs:443), written to *k_actual.
+ *   out_index [queries->n_rows * k_eff]  u32 corpus row numbers (`idx as u32`, src/matmul.rs:506)
+ *   out_score [queries->n_rows * k_eff]  f64 (f32 working scores widened exactly, src/matmul.rs:447)
+ *   Row i of both = the i-th query's matches, best first; ties: lower corpus index first; NaN last.
+ * These are exactly the two child buffers of the List[Struct{index:u32, score:f64}] the reference
+ * builds row by row (src/matmul.rs:497-518); list offsets are i*k_eff.
+ *
+ * Order of checks follows the reference: zero queries -> PMM_OK with *k_actual = min(k, N) and nothing
+ * written, BEFORE the metric is parsed (src/matmul.rs:480-490); then metric; then "Empty series";
+ * then "Dimension mismatch: left has {} dimensional vectors, right has {} dimensional vectors".
+ * k < 0 -> PMM_ERR_INVALID (PyO3 rejects negative usize with OverflowError before the call).
+ */
+PMM_API int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k, const char *metric,
+             uint32_t *out_index, double *out_score, int64_t *k_actual);
+
+/*
+ * Replaces `_matmul` (src/lib.rs:15-30) -> `matmul_impl` (src/matmul.rs:295-417) ->
+ * `matmul_slice_f32/_f64` (src/metrics.rs:160,111) / `matmul_f32/_f64` (src/metrics.rs:204,40).
+ * out [left->n_rows * right->n_rows], row-major, element type = pmm_working_dtype(left, right):
+ * the flat buffer the reference reshapes to Array[T, N] (src/matmul.rs:100-125); `flatten=True`
+ * is the same buffer read as 1-D (python/polars_matmul/__init__.py:173-187).
+ * Zero left rows -> PMM_OK, nothing written (src/matmul.rs:297-305).
+ */
+PMM_API int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out);
+
+/* ------------------------------------------------------------------ resident corpus
+ * The reference re-marshals the corpus on every map_batches call (src/matmul.rs:430-431).  A handle
+ * keeps the prepared corpus (tensor-core operand planes + norms) in HBM across calls. */
+typedef struct pmm_corpus pmm_corpus_t;
+
+/* `corpus` holds host pointers. `query_dtype` fixes the working precision (pmm_working_dtype). */
+PMM_API int pmm_corpus_create(const pmm_matrix_t *corpus, int32_t query_dtype, pmm_corpus_t **out);
+PMM_API int pmm_corpus_destroy(pmm_corpus_t *corpus);
+PMM_API int64_t pmm_corpus_rows(const pmm_corpus_t *corpus);
+/* Same contract as pmm_topk, corpus taken from the handle (host query buffers, host outputs). */
+PMM_API int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *corpus, int64_t k,
+                    const char *metric, uint32_t *out_index, double *out_score, int64_t *k_actual);
+
+/* ------------------------------------------------------------------ device entry points
+ * Same computations with every pointer in device memory (HBM-resident inputs and outputs), enqueued
+ * on `stream`.  Used by the multi-GPU driver (one process per GPU) and for kernel-only measurement. */
+
+/*
+ * Local top-k of `queries` against `corpus` (a shard). Corpus row j is reported as index
+ * index_base + j (global index of a sharded corpus).
+ *   d_index / d_score : [Q * k_eff] final outputs, or both NULL
+ *   d_candidates      : [Q * k_eff] packed candidates or NULL.  A candidate is one u64:
+ *                       (ordered score key << 32) | ~index ; larger = better under the total order
+ *                       (score best-first, lower index first), so shards merge by plain u64 max.
+ *                       f32 working precision only.
+ */
+PMM_API int pmm_dev_topk(const pmm_matrix_t *d_queries, const pmm_matrix_t *d_corpus, int64_t k, int32_t metric,
+                 int64_t index_base, uint32_t *d_index, double *d_score, uint64_t *d_candidates,
+                 void *stream);
+
+/* K-way merge of `n_lists` candidate lists laid out [n_lists][n_queries][k_in] (each sorted best
+ * first, as pmm_dev_topk writes them; e.g. the all-gathered shards) into the final
+ * [n_queries * k_out] index/score buffers.  k_out <= k_in <= 128. */
+PMM_API int pmm_dev_merge_candidates(const uint64_t *d_lists, int64_t n_lists, int64_t n_queries, int64_t k_in,
+                             int64_t k_out, int32_t metric, uint32_t *d_index, double *d_score,
+                             void *stream);
+
+/* Raw left * right^T into d_out [Q*N] of the working dtype. */
+PMM_API int pmm_dev_matmul(const pmm_matrix_t *d_left, const pmm_matrix_t *d_right, void *d_out, void *stream);
+
+/* Row norms (squared != 0: squared norms) in the storage-derived working dtype (f16 -> f32),
+ * compute_norms_* / compute_squared_norms_*, src/metrics.rs:367-393. d_out [n_rows]. */
+PMM_API int pmm_dev_norms(const pmm_matrix_t *d_x, int32_t squared, void *d_out, void *stream);
+
+/* ------------------------------------------------------------------ runtime */
+PMM_API const char *pmm_last_error(void);     /* thread-local, never NULL */
+PMM_API const char *pmm_version(void);
+PMM_API int pmm_device_count(void);           /* 0 when no CUDA device is usable */
+PMM_API int pmm_set_device(int32_t device);   /* device used by the calling thread's subsequent calls */
+
+/* Number of kernels this library has launched since load / since the last reset (process-wide). */
+PMM_API int64_t pmm_kernel_launch_count(void);
+PMM_API void pmm_reset_kernel_launch_count(void);
+
+/* Tuning / diagnostics. Known keys: "force_generic" (0/1: route f32 top-k through the SIMT
+ * scores+select path), "profile" (0/1: bracket kernels with CUDA events on the launching stream
+ * and accumulate per-kernel milliseconds, read back with pmm_get_stat). */
+PMM_API int pmm_set_option(const char *key, int64_t value);
+/* Accumulated statistics since the last pmm_reset_stats(): "<kernel>_ms", "<kernel>_launches",
+ * "h2d_bytes", "d2h_bytes". Unknown name -> 0. */
+PMM_API double pmm_get_stat(const char *name);
+PMM_API void pmm_reset_stats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMM_H_ */

@@ -1,0 +1,253 @@
+"""
+ctypes binding to libpmm_b200.so (C ABI: include/pmm.h).
+
+This is the Python side of the boundary the reference crosses with PyO3 at src/lib.rs:15-55.
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+ctypes releases the GIL for the duration of every foreign call, like `py.detach` in the reference
+(src/lib.rs:25,45).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmm_b200.so")
+
+PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_UNSUPPORTED = 0, 1, 2, 3
+DTYPE_F16, DTYPE_F32, DTYPE_F64 = 0, 1, 2
+METRIC_COSINE, METRIC_DOT, METRIC_EUCLIDEAN = 0, 1, 2
+
+_NP_TO_CODE = {np.dtype(np.float16): DTYPE_F16, np.dtype(np.float32): DTYPE_F32, np.dtype(np.float64): DTYPE_F64}
+_CODE_TO_NP = {v: k for k, v in _NP_TO_CODE.items()}
+
+
+class PmmMatrix(ctypes.Structure):
+    """struct pmm_matrix (include/pmm.h)."""
+    _fields_ = [
+        ("values", ctypes.c_void_p),
+        ("offsets", ctypes.c_void_p),
+        ("validity", ctypes.c_void_p),
+        ("row_validity", ctypes.c_void_p),
+        ("n_rows", ctypes.c_int64),
+        ("dim", ctypes.c_int64),
+        ("dtype", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class PmmError(RuntimeError):
+    """Raised for every non-zero status; str(e) is pmm_last_error() — the same text the reference
+    wraps into PyRuntimeError (src/lib.rs:28,53)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libpmm_b200.so; raises ImportError (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m polars_matmul_b200.build` "
+            "(nvcc, sm_100a). polars_matmul_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    P = ctypes.POINTER(PmmMatrix)
+    i32, i64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+    sigs = {
+        "pmm_metric_from_str": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(i32)]),
+        "pmm_higher_is_better": (ctypes.c_int, [i32]),
+        "pmm_working_dtype": (ctypes.c_int, [i32, i32]),
+        "pmm_topk": (ctypes.c_int, [P, P, i64, ctypes.c_char_p, vp, vp, ctypes.POINTER(i64)]),
+        "pmm_matmul": (ctypes.c_int, [P, P, vp]),
+        "pmm_corpus_create": (ctypes.c_int, [P, i32, ctypes.POINTER(vp)]),
+        "pmm_corpus_destroy": (ctypes.c_int, [vp]),
+        "pmm_corpus_rows": (i64, [vp]),
+        "pmm_topk_corpus": (ctypes.c_int, [P, vp, i64, ctypes.c_char_p, vp, vp, ctypes.POINTER(i64)]),
+        "pmm_dev_topk": (ctypes.c_int, [P, P, i64, i32, i64, vp, vp, vp, vp]),
+        "pmm_dev_merge_candidates": (ctypes.c_int, [vp, i64, i64, i64, i64, i32, vp, vp, vp]),
+        "pmm_dev_matmul": (ctypes.c_int, [P, P, vp, vp]),
+        "pmm_dev_norms": (ctypes.c_int, [P, i32, vp, vp]),
+        "pmm_last_error": (ctypes.c_char_p, []),
+        "pmm_version": (ctypes.c_char_p, []),
+        "pmm_device_count": (ctypes.c_int, []),
+        "pmm_set_device": (ctypes.c_int, [i32]),
+        "pmm_kernel_launch_count": (i64, []),
+        "pmm_reset_kernel_launch_count": (None, []),
+        "pmm_set_option": (ctypes.c_int, [ctypes.c_char_p, i64]),
+        "pmm_get_stat": (ctypes.c_double, [ctypes.c_char_p]),
+        "pmm_reset_stats": (None, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)  # AttributeError if the .so does not export what include/pmm.h declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "pmm_metric_from_str", "pmm_higher_is_better", "pmm_working_dtype", "pmm_topk", "pmm_matmul",
+    "pmm_corpus_create", "pmm_corpus_destroy", "pmm_corpus_rows", "pmm_topk_corpus", "pmm_dev_topk",
+    "pmm_dev_merge_candidates", "pmm_dev_matmul", "pmm_dev_norms", "pmm_last_error", "pmm_version",
+    "pmm_device_count", "pmm_set_device", "pmm_kernel_launch_count", "pmm_reset_kernel_launch_count",
+    "pmm_set_option", "pmm_get_stat", "pmm_reset_stats",
+]
+
+
+def check(rc: int) -> None:
+    if rc != PMM_OK:
+        raise PmmError(rc, lib().pmm_last_error().decode("utf-8", "replace"))
+
+
+# ------------------------------------------------------------------------------------------ host matrices
+@dataclass
+class HostMatrix:
+    """An embedding column in Arrow layout held by NumPy views (see polars_matmul_b200.arrow)."""
+    values: np.ndarray                       # 1-D child values, f16/f32/f64, C-contiguous
+    n_rows: int
+    dim: int
+    offsets: Optional[np.ndarray] = None     # int64 [n_rows+1] or None (fixed-size rows)
+    validity: Optional[np.ndarray] = None    # uint8 Arrow bitmap over child values
+    row_validity: Optional[np.ndarray] = None
+
+    @property
+    def dtype_code(self) -> int:
+        return _NP_TO_CODE[self.values.dtype]
+
+    def c_struct(self) -> PmmMatrix:
+        def ptr(a):
+            return None if a is None else a.ctypes.data
+
+        return PmmMatrix(ptr(self.values) if self.values.size else None, ptr(self.offsets), ptr(self.validity),
+                         ptr(self.row_validity), self.n_rows, self.dim, self.dtype_code, 0)
+
+
+def metric_from_str(name: str) -> int:
+    m = ctypes.c_int32(-1)
+    check(lib().pmm_metric_from_str(str(name).encode(), ctypes.byref(m)))
+    return m.value
+
+
+def working_dtype(left: HostMatrix, right: HostMatrix):
+    return _CODE_TO_NP[lib().pmm_working_dtype(left.dtype_code, right.dtype_code)]
+
+
+def topk(queries: HostMatrix, corpus: HostMatrix, k: int, metric: str):
+    """pmm_topk. Returns (index uint32 [Q, k_eff], score float64 [Q, k_eff])."""
+    if k < 0:
+        raise OverflowError("can't convert negative int to unsigned")  # what PyO3 raises for usize
+    keff = min(int(k), corpus.n_rows)
+    idx = np.empty((queries.n_rows, keff), np.uint32)
+    sc = np.empty((queries.n_rows, keff), np.float64)
+    ka = ctypes.c_int64(0)
+    q, c = queries.c_struct(), corpus.c_struct()
+    check(lib().pmm_topk(ctypes.byref(q), ctypes.byref(c), int(k), str(metric).encode(),
+                         idx.ctypes.data, sc.ctypes.data, ctypes.byref(ka)))
+    assert ka.value == keff
+    return idx, sc
+
+
+def matmul(left: HostMatrix, right: HostMatrix) -> np.ndarray:
+    """pmm_matmul. Returns [Q, N] in the working dtype."""
+    out = np.empty((left.n_rows, right.n_rows), working_dtype(left, right))
+    l, r = left.c_struct(), right.c_struct()
+    check(lib().pmm_matmul(ctypes.byref(l), ctypes.byref(r), out.ctypes.data))
+    return out
+
+
+class ResidentCorpus:
+    """pmm_corpus_t: the prepared corpus kept in HBM across calls."""
+
+    def __init__(self, corpus: HostMatrix, query_dtype_code: int = DTYPE_F32):
+        self._h = ctypes.c_void_p(None)
+        c = corpus.c_struct()
+        check(lib().pmm_corpus_create(ctypes.byref(c), query_dtype_code, ctypes.byref(self._h)))
+        self.n_rows = int(lib().pmm_corpus_rows(self._h))
+
+    def topk(self, queries: HostMatrix, k: int, metric: str):
+        if k < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        keff = min(int(k), self.n_rows)
+        idx = np.empty((queries.n_rows, keff), np.uint32)
+        sc = np.empty((queries.n_rows, keff), np.float64)
+        ka = ctypes.c_int64(0)
+        q = queries.c_struct()
+        check(lib().pmm_topk_corpus(ctypes.byref(q), self._h, int(k), str(metric).encode(),
+                                    idx.ctypes.data, sc.ctypes.data, ctypes.byref(ka)))
+        return idx, sc
+
+    def close(self):
+        if self._h:
+            lib().pmm_corpus_destroy(self._h)
+            self._h = ctypes.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------ device level
+def dev_matrix(data_ptr: int, n_rows: int, dim: int, dtype_code: int, offsets_ptr: int = 0) -> PmmMatrix:
+    """Describes a device-resident matrix (e.g. a torch CUDA tensor's data_ptr())."""
+    return PmmMatrix(data_ptr or None, offsets_ptr or None, None, None, n_rows, dim, dtype_code, 0)
+
+
+def dev_topk(dq: PmmMatrix, dc: PmmMatrix, k: int, metric: int, index_base: int = 0, index_ptr: int = 0,
+             score_ptr: int = 0, cand_ptr: int = 0, stream: int = 0) -> None:
+    check(lib().pmm_dev_topk(ctypes.byref(dq), ctypes.byref(dc), k, metric, index_base, index_ptr or None,
+                             score_ptr or None, cand_ptr or None, stream or None))
+
+
+def dev_merge_candidates(lists_ptr: int, n_lists: int, n_queries: int, k_in: int, k_out: int, metric: int,
+                         index_ptr: int, score_ptr: int, stream: int = 0) -> None:
+    check(lib().pmm_dev_merge_candidates(lists_ptr, n_lists, n_queries, k_in, k_out, metric, index_ptr or None,
+                                         score_ptr or None, stream or None))
+
+
+def dev_matmul(dl: PmmMatrix, dr: PmmMatrix, out_ptr: int, stream: int = 0) -> None:
+    check(lib().pmm_dev_matmul(ctypes.byref(dl), ctypes.byref(dr), out_ptr, stream or None))
+
+
+def dev_norms(dx: PmmMatrix, squared: bool, out_ptr: int, stream: int = 0) -> None:
+    check(lib().pmm_dev_norms(ctypes.byref(dx), int(bool(squared)), out_ptr, stream or None))
+
+
+def set_option(key: str, value: int) -> None:
+    check(lib().pmm_set_option(key.encode(), int(value)))
+
+
+def get_stat(name: str) -> float:
+    return float(lib().pmm_get_stat(name.encode()))
+
+
+def reset_stats() -> None:
+    lib().pmm_reset_stats()
+
+
+def kernel_launch_count() -> int:
+    return int(lib().pmm_kernel_launch_count())
+
+
+def reset_kernel_launch_count() -> None:
+    lib().pmm_reset_kernel_launch_count()
+
+
+def device_count() -> int:
+    return int(lib().pmm_device_count())
+
+
+def set_device(device: int) -> None:
+    check(lib().pmm_set_device(device))

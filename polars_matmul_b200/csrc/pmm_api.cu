@@ -1,0 +1,740 @@
+// pmm_api.cu — the C ABI (include/pmm.h): validation in the reference's order, host<->device staging,
+// path selection and kernel orchestration.  Host-side counterpart of src/matmul.rs:288-519
+// (matmul_impl / compute_topk_indices_scores / topk_impl) and src/lib.rs:15-55.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pmm.h"
+#include "pmm_kernels.h"
+
+using namespace pmm;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ errors
+thread_local std::string g_err = "";
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail(PMM_ERR_CUDA, "CUDA error: %s (%s)", cudaGetErrorString(e__), #expr); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ options / stats
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{4};
+std::atomic<int64_t> g_generic_ws_mb{1024};
+
+std::mutex g_stat_mu;
+std::map<std::string, double> g_stats;
+struct PendingEvent {
+    std::string name;
+    cudaEvent_t a, b;
+};
+std::vector<PendingEvent> g_pending;
+
+void stat_add(const std::string &name, double v) {
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    g_stats[name] += v;
+}
+
+void resolve_pending_locked() {
+    for (auto &p : g_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_stats[p.name + "_ms"] += ms;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_pending.clear();
+}
+
+// Counts the launch and, when profiling, brackets it with CUDA events on the launching stream.
+template <typename F>
+cudaError_t launch_counted(const char *name, cudaStream_t s, F &&f) {
+    g_launches.fetch_add(1);
+    if (!g_profile.load()) return f();
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    cudaError_t e = f();
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    g_pending.push_back({name, a, b});
+    g_stats[std::string(name) + "_launches"] += 1;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------ device info
+struct DevInfo {
+    int num_sms = 0;
+    bool tc = false;
+    bool init = false;
+};
+DevInfo &dev_info() {
+    static thread_local DevInfo info[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevInfo &d = info[dev & 15];
+    if (!d.init) {
+        cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        d.tc = tc_supported();
+        d.init = true;
+        // keep freed stream-ordered allocations in the pool instead of returning them to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    return d;
+}
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(PMM_ERR_CUDA, "no CUDA device available (libpmm_b200 has no CPU fallback): %s",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return PMM_OK;
+}
+
+// Stream-ordered device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        release();
+        s = stream;
+        if (bytes == 0) bytes = 16;
+        return cudaMallocAsync(&p, bytes, stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+int esize(int dtype) { return dtype == PMM_DTYPE_F16 ? 2 : dtype == PMM_DTYPE_F32 ? 4 : 8; }
+
+// ------------------------------------------------------------------------------------------------ prepared operands
+struct Prepared {
+    int mode = PREP_DENSE;   // PREP_*
+    bool f64 = false;
+    int64_t n_rows = 0, dim = 0, rows_pad = 0, ld = 0;
+    DevBuf p0, p1, norm, sqnorm;
+};
+
+// Runs the prep kernel on a device-resident matrix. row_tile: pad rows to this multiple (planes only).
+int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool want_norm, bool want_sq, int *d_err,
+            cudaStream_t s, Prepared *out) {
+    out->mode = mode;
+    out->f64 = f64;
+    out->n_rows = m.n_rows;
+    out->dim = m.dim;
+    const int64_t wsz = f64 ? 8 : 4;
+    if (mode == PREP_DENSE) {
+        out->rows_pad = m.n_rows;
+        out->ld = m.dim;
+        CUDA_TRY(out->p0.alloc((size_t)(m.n_rows * m.dim * wsz), s));
+    } else {
+        const int64_t kq = mode == PREP_F16 ? 64 : 32;
+        const int64_t es = mode == PREP_F16 ? 2 : 4;
+        out->rows_pad = round_up(m.n_rows, row_tile);
+        out->ld = round_up(m.dim, kq);
+        CUDA_TRY(out->p0.alloc((size_t)(out->rows_pad * out->ld * es), s));
+        if (mode == PREP_TF32) CUDA_TRY(out->p1.alloc((size_t)(out->rows_pad * out->ld * es), s));
+    }
+    if (want_norm) CUDA_TRY(out->norm.alloc((size_t)(out->rows_pad * wsz), s));
+    if (want_sq) CUDA_TRY(out->sqnorm.alloc((size_t)(out->rows_pad * wsz), s));
+    PrepArgs a;
+    a.values = m.values;
+    a.offsets = m.offsets;
+    a.validity = m.validity;
+    a.row_validity = m.row_validity;
+    a.n_rows = m.n_rows;
+    a.dim = m.dim;
+    a.rows_out = out->rows_pad;
+    a.ld_out = out->ld;
+    a.out0 = out->p0.p;
+    a.out1 = out->p1.p;
+    a.norm_out = out->norm.p;
+    a.sqnorm_out = out->sqnorm.p;
+    a.error_flag = d_err;
+    CUDA_TRY(launch_counted("prep", s, [&] { return launch_prep(a, m.dtype, mode, f64 ? 1 : 0, s); }));
+    return PMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ validation
+int check_matrix(const pmm_matrix_t *m, const char *what) {
+    if (!m) return fail(PMM_ERR_INVALID, "%s: null matrix descriptor", what);
+    if (m->dtype < PMM_DTYPE_F16 || m->dtype > PMM_DTYPE_F64) return fail(PMM_ERR_INVALID, "%s: unknown dtype %d", what, m->dtype);
+    if (m->n_rows < 0 || m->dim < 0) return fail(PMM_ERR_INVALID, "%s: negative shape", what);
+    return PMM_OK;
+}
+
+// Shared shape checks in the reference's order (src/matmul.rs:131-175, :433-441).
+int check_pair(const pmm_matrix_t *l, const pmm_matrix_t *r) {
+    if (l->n_rows == 0 || r->n_rows == 0) return fail(PMM_ERR_INVALID, "Empty series");
+    if (l->dim == 0 || r->dim == 0) return fail(PMM_ERR_INVALID, "Zero-dimensional vectors");
+    if (l->dim != r->dim)
+        return fail(PMM_ERR_INVALID, "Dimension mismatch: left has %lld dimensional vectors, right has %lld dimensional vectors",
+                    (long long)l->dim, (long long)r->dim);
+    if (r->n_rows >= 0xffffffffll) return fail(PMM_ERR_UNSUPPORTED, "corpus of 2^32-1 or more rows per call is not supported");
+    return PMM_OK;
+}
+
+int finish_error_flag(int *d_err, cudaStream_t s) {
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h)
+        return fail(PMM_ERR_INVALID,
+                    "ragged list column: a row is longer than row 0 (the reference panics here: ndarray index out of bounds)");
+    return PMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ top-k on device
+struct TopkOut {
+    uint32_t *index;
+    double *score;
+    uint64_t *cand;
+};
+
+// Generic SIMT path on prepared DENSE operands.
+int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric, int64_t index_base, TopkOut o,
+                 cudaStream_t s) {
+    const bool f64 = q.f64;
+    if (f64 && o.cand) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
+    const int64_t Q = q.n_rows, N = c.n_rows, D = q.dim;
+    const int64_t wsz = f64 ? 8 : 4;
+    int64_t chunk = (g_generic_ws_mb.load() << 20) / (N * wsz);
+    chunk = chunk / 64 * 64;
+    if (chunk < 64) chunk = 64;
+    if (chunk > 1 << 20) chunk = 1 << 20;
+    if (chunk > Q) chunk = Q;
+    DevBuf slab, scratch;
+    CUDA_TRY(slab.alloc((size_t)(chunk * N * wsz), s));
+    const int kpad = select_kpad(keff);
+    if (kpad > select_smem_kpad_limit(f64)) CUDA_TRY(scratch.alloc((size_t)chunk * kpad * 12, s));
+    const bool higher = metric != PMM_METRIC_EUCLIDEAN;
+    const void *qa = metric == PMM_METRIC_COSINE ? q.norm.p : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.p : nullptr;
+    const void *ca = metric == PMM_METRIC_COSINE ? c.norm.p : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.p : nullptr;
+    for (int64_t q0 = 0; q0 < Q; q0 += chunk) {
+        const int64_t nq = (Q - q0 < chunk) ? Q - q0 : chunk;
+        uint32_t *oi = o.index ? o.index + q0 * keff : nullptr;
+        double *os = o.score ? o.score + q0 * keff : nullptr;
+        uint64_t *oc = o.cand ? o.cand + q0 * keff : nullptr;
+        if (f64) {
+            CUDA_TRY(launch_counted("scores_f64", s, [&] {
+                return launch_scores_f64(q.p0.as<double>() + q0 * D, c.p0.as<double>(), qa ? (const double *)qa + q0 : nullptr,
+                                         (const double *)ca, nq, N, D, metric, slab.as<double>(), N, s);
+            }));
+            CUDA_TRY(launch_counted("select_f64", s, [&] {
+                return launch_select_f64(slab.as<double>(), N, nq, N, keff, higher, index_base, oi, os, scratch.p, s);
+            }));
+        } else {
+            CUDA_TRY(launch_counted("scores_f32", s, [&] {
+                return launch_scores_f32(q.p0.as<float>() + q0 * D, c.p0.as<float>(), qa ? (const float *)qa + q0 : nullptr,
+                                         (const float *)ca, nq, N, D, metric, slab.as<float>(), N, s);
+            }));
+            CUDA_TRY(launch_counted("select_f32", s, [&] {
+                return launch_select_f32(slab.as<float>(), N, nq, N, keff, higher, index_base, oi, os, oc, scratch.p, s);
+            }));
+        }
+    }
+    return PMM_OK;
+}
+
+// Tensor-core path on prepared PLANES.
+int topk_tc(const Prepared &q, const Prepared &c, int64_t keff, int metric, int64_t index_base, TopkOut o,
+            cudaStream_t s) {
+    DevInfo &di = dev_info();
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q_hi = q.p0.p;
+    a.q_lo = q.p1.p;
+    a.c_hi = c.p0.p;
+    a.c_lo = c.p1.p;
+    a.q_rows_pad = q.rows_pad;
+    a.c_rows_pad = c.rows_pad;
+    a.dim_pad = q.ld;
+    a.nq = q.n_rows;
+    a.n = c.n_rows;
+    a.f16 = q.mode == PREP_F16 ? 1 : 0;
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms, g_tc_group.load());
+    a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
+    a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
+    a.index_base = index_base;
+    a.metric = metric;
+    a.k = (int)keff;
+    a.kp = keff <= 32 ? 32 : keff <= 64 ? 64 : 128;
+    DevBuf partial;
+    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * TC_TILE_M * a.kp * 8, s));
+    a.partial = partial.as<uint64_t>();
+    cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : "tc_topk_tf32x3", s, [&] { return launch_tc_topk(a, s); });
+    if (e != cudaSuccess)
+        return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
+    CUDA_TRY(launch_counted("merge", s, [&] {
+        return launch_merge_tiles(a.partial, a.sched, a.kp, q.n_rows, (int)keff, metric != PMM_METRIC_EUCLIDEAN, o.index,
+                                  o.score, o.cand, s);
+    }));
+    return PMM_OK;
+}
+
+struct PathChoice {
+    bool tc;
+    bool f64;
+    int mode;  // prep mode for both operands
+};
+PathChoice choose_path(int q_dtype, int c_dtype, int64_t keff) {
+    PathChoice pc;
+    pc.f64 = pmm_working_dtype(q_dtype, c_dtype) == PMM_DTYPE_F64;
+    pc.tc = !pc.f64 && keff <= 128 && !g_force_generic.load() && dev_info().tc;
+    pc.mode = !pc.tc ? PREP_DENSE : (q_dtype == PMM_DTYPE_F16 && c_dtype == PMM_DTYPE_F16) ? PREP_F16 : PREP_TF32;
+    return pc;
+}
+
+// All pointers device-resident. `pc_corpus`: an already prepared corpus or NULL.
+int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared *pc_corpus, int corpus_dtype, int64_t k,
+                  int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
+    const int64_t N = pc_corpus ? pc_corpus->n_rows : dc->n_rows;
+    const int64_t keff = k < N ? k : N;
+    if (keff == 0) return PMM_OK;
+    PathChoice pc = choose_path(dq->dtype, corpus_dtype, keff);
+    if (pc_corpus && (pc_corpus->mode != pc.mode || pc_corpus->f64 != pc.f64))
+        return fail(PMM_ERR_UNSUPPORTED,
+                    "resident corpus was prepared for a different path (query dtype or k > 128 changed); recreate the handle");
+    const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
+    DevBuf err;
+    CUDA_TRY(err.alloc(sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    Prepared q, c_local;
+    int rc = prepare(*dq, pc.mode, pc.f64, TC_TILE_M, want_norm, want_sq, err.as<int>(), s, &q);
+    if (rc) return rc;
+    const Prepared *c = pc_corpus;
+    if (!c) {
+        rc = prepare(*dc, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c_local);
+        if (rc) return rc;
+        c = &c_local;
+    }
+    rc = pc.tc ? topk_tc(q, *c, keff, metric, index_base, o, s) : topk_generic(q, *c, keff, metric, index_base, o, s);
+    if (rc) return rc;
+    if (dq->offsets || (dc && dc->offsets)) return finish_error_flag(err.as<int>(), s);
+    return PMM_OK;
+}
+
+int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, cudaStream_t s) {
+    PathChoice pc = choose_path(dl->dtype, dr->dtype, 1);
+    DevBuf err;
+    CUDA_TRY(err.alloc(sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    Prepared l, r;
+    int rc = prepare(*dl, pc.mode, pc.f64, TC_TILE_M, false, false, err.as<int>(), s, &l);
+    if (rc) return rc;
+    rc = prepare(*dr, pc.mode, pc.f64, TC_TILE_N, false, false, err.as<int>(), s, &r);
+    if (rc) return rc;
+    const int64_t Q = dl->n_rows, N = dr->n_rows, D = dl->dim;
+    if (pc.tc) {
+        DevInfo &di = dev_info();
+        TcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.q_hi = l.p0.p;
+        a.q_lo = l.p1.p;
+        a.c_hi = r.p0.p;
+        a.c_lo = r.p1.p;
+        a.q_rows_pad = l.rows_pad;
+        a.c_rows_pad = r.rows_pad;
+        a.dim_pad = l.ld;
+        a.nq = Q;
+        a.n = N;
+        a.f16 = pc.mode == PREP_F16 ? 1 : 0;
+        a.sched = make_tc_schedule(Q, N, di.num_sms, g_tc_group.load());
+        a.metric = PMM_METRIC_DOT;
+        a.k = 1;
+        a.kp = 32;
+        a.out = (float *)d_out;
+        cudaError_t e = launch_counted(a.f16 ? "tc_matmul_f16" : "tc_matmul_tf32x3", s, [&] { return launch_tc_matmul(a, s); });
+        if (e != cudaSuccess)
+            return fail(PMM_ERR_CUDA, "tensor-core matmul launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
+    } else if (pc.f64) {
+        for (int64_t q0 = 0; q0 < Q; q0 += (1 << 20)) {
+            int64_t nq = Q - q0 < (1 << 20) ? Q - q0 : (1 << 20);
+            CUDA_TRY(launch_counted("scores_f64", s, [&] {
+                return launch_scores_f64(l.p0.as<double>() + q0 * D, r.p0.as<double>(), nullptr, nullptr, nq, N, D, PMM_METRIC_DOT,
+                                         (double *)d_out + q0 * N, N, s);
+            }));
+        }
+    } else {
+        for (int64_t q0 = 0; q0 < Q; q0 += (1 << 20)) {
+            int64_t nq = Q - q0 < (1 << 20) ? Q - q0 : (1 << 20);
+            CUDA_TRY(launch_counted("scores_f32", s, [&] {
+                return launch_scores_f32(l.p0.as<float>() + q0 * D, r.p0.as<float>(), nullptr, nullptr, nq, N, D, PMM_METRIC_DOT,
+                                         (float *)d_out + q0 * N, N, s);
+            }));
+        }
+    }
+    if (dl->offsets || dr->offsets) return finish_error_flag(err.as<int>(), s);
+    return PMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host staging
+cudaStream_t host_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    static thread_local int dev_of_stream = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!s || dev_of_stream != dev) {
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        dev_of_stream = dev;
+    }
+    return s;
+}
+
+// A host matrix uploaded to the device. `dm` describes it with device pointers.
+struct Uploaded {
+    DevBuf values, offsets, validity, row_validity;
+    pmm_matrix_t dm;
+};
+
+int upload(const pmm_matrix_t *m, cudaStream_t s, Uploaded *u) {
+    u->dm = *m;
+    const int es = esize(m->dtype);
+    int64_t first = 0, last = m->n_rows * m->dim;
+    if (m->offsets) {
+        first = m->offsets[0];
+        last = m->offsets[m->n_rows];
+        if (last < first) return fail(PMM_ERR_INVALID, "list offsets are not monotonic");
+        CUDA_TRY(u->offsets.alloc((size_t)(m->n_rows + 1) * 8, s));
+        CUDA_TRY(cudaMemcpyAsync(u->offsets.p, m->offsets, (size_t)(m->n_rows + 1) * 8, cudaMemcpyHostToDevice, s));
+        u->dm.offsets = u->offsets.as<int64_t>();
+        stat_add("h2d_bytes", (double)(m->n_rows + 1) * 8);
+    }
+    const size_t vbytes = (size_t)(last - first) * es;
+    CUDA_TRY(u->values.alloc(vbytes, s));
+    if (vbytes)
+        CUDA_TRY(cudaMemcpyAsync(u->values.p, (const char *)m->values + (size_t)first * es, vbytes, cudaMemcpyHostToDevice, s));
+    stat_add("h2d_bytes", (double)vbytes);
+    // kernels index child values by absolute position: rebase so that position `first` is byte 0 of the buffer
+    u->dm.values = (const char *)u->values.p - (size_t)first * es;
+    if (m->validity) {
+        const size_t nb = (size_t)((last + 7) / 8);
+        CUDA_TRY(u->validity.alloc(nb, s));
+        CUDA_TRY(cudaMemcpyAsync(u->validity.p, m->validity, nb, cudaMemcpyHostToDevice, s));
+        u->dm.validity = u->validity.as<uint8_t>();
+        stat_add("h2d_bytes", (double)nb);
+    }
+    if (m->row_validity) {
+        const size_t nb = (size_t)((m->n_rows + 7) / 8);
+        CUDA_TRY(u->row_validity.alloc(nb, s));
+        CUDA_TRY(cudaMemcpyAsync(u->row_validity.p, m->row_validity, nb, cudaMemcpyHostToDevice, s));
+        u->dm.row_validity = u->row_validity.as<uint8_t>();
+        stat_add("h2d_bytes", (double)nb);
+    }
+    return PMM_OK;
+}
+
+int list_dim_check(const pmm_matrix_t *m, const char *) {
+    // src/matmul.rs:237-239: a List column takes its dimension from row 0; a null first row is an error
+    if (m->offsets && m->n_rows > 0 && m->row_validity && !(m->row_validity[0] & 1))
+        return fail(PMM_ERR_INVALID, "First element is null");
+    return PMM_OK;
+}
+
+}  // namespace
+
+struct pmm_corpus {
+    Prepared prep;
+    int device = 0;
+    int storage_dtype = PMM_DTYPE_F32;
+    int query_dtype = PMM_DTYPE_F32;
+    cudaStream_t stream = nullptr;
+};
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char *pmm_last_error(void) { return g_err.c_str(); }
+const char *pmm_version(void) { return "0.1.4+b200.r1"; }
+
+int pmm_metric_from_str(const char *name, int32_t *metric) {
+    if (!name || !metric) return fail(PMM_ERR_INVALID, "Unknown metric: ''. Supported: cosine, dot, euclidean");
+    std::string low(name);
+    for (auto &ch : low) ch = (char)tolower((unsigned char)ch);
+    if (low == "cosine") { *metric = PMM_METRIC_COSINE; return PMM_OK; }
+    if (low == "dot") { *metric = PMM_METRIC_DOT; return PMM_OK; }
+    if (low == "euclidean" || low == "l2") { *metric = PMM_METRIC_EUCLIDEAN; return PMM_OK; }
+    return fail(PMM_ERR_INVALID, "Unknown metric: '%s'. Supported: cosine, dot, euclidean", name);
+}
+
+int pmm_higher_is_better(int32_t metric) { return metric != PMM_METRIC_EUCLIDEAN; }
+
+int pmm_working_dtype(int32_t l, int32_t r) {
+    const bool lf = (l == PMM_DTYPE_F32 || l == PMM_DTYPE_F16), rf = (r == PMM_DTYPE_F32 || r == PMM_DTYPE_F16);
+    return (lf && rf) ? PMM_DTYPE_F32 : PMM_DTYPE_F64;
+}
+
+int pmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pmm_set_device(int32_t device) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    return PMM_OK;
+}
+
+int64_t pmm_kernel_launch_count(void) { return g_launches.load(); }
+void pmm_reset_kernel_launch_count(void) { g_launches.store(0); }
+
+int pmm_set_option(const char *key, int64_t value) {
+    if (!key) return fail(PMM_ERR_INVALID, "null option key");
+    std::string k(key);
+    if (k == "force_generic") g_force_generic.store((int)value);
+    else if (k == "profile") g_profile.store((int)value);
+    else if (k == "tc_group") g_tc_group.store(value < 1 ? 1 : (int)value);
+    else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
+    else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
+    return PMM_OK;
+}
+
+double pmm_get_stat(const char *name) {
+    if (!name) return 0.0;
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    resolve_pending_locked();
+    auto it = g_stats.find(name);
+    return it == g_stats.end() ? 0.0 : it->second;
+}
+
+void pmm_reset_stats(void) {
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    resolve_pending_locked();
+    g_stats.clear();
+}
+
+// ---------------------------------------------------------------------------------------------- device entry points
+int pmm_dev_topk(const pmm_matrix_t *dq, const pmm_matrix_t *dc, int64_t k, int32_t metric, int64_t index_base,
+                 uint32_t *d_index, double *d_score, uint64_t *d_candidates, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_matrix(dq, "queries")) || (rc = check_matrix(dc, "corpus"))) return rc;
+    if (dq->n_rows == 0) return PMM_OK;
+    if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
+    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative");
+    if ((rc = check_pair(dq, dc))) return rc;
+    TopkOut o{d_index, d_score, d_candidates};
+    return dev_topk_impl(dq, dc, nullptr, dc->dtype, k, metric, index_base, o, (cudaStream_t)stream);
+}
+
+int pmm_dev_merge_candidates(const uint64_t *d_lists, int64_t n_lists, int64_t n_queries, int64_t k_in, int64_t k_out,
+                             int32_t metric, uint32_t *d_index, double *d_score, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n_lists < 1 || k_in < 1 || k_in > 128 || k_out < 0 || k_out > k_in)
+        return fail(PMM_ERR_INVALID, "merge: need 1 <= k_out <= k_in <= 128 and at least one list");
+    if (n_queries == 0 || k_out == 0) return PMM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(launch_counted("merge", s, [&] {
+        return launch_merge_regular(d_lists, n_lists, n_queries * k_in, k_in, n_queries, (int)k_in, (int)k_out,
+                                    metric != PMM_METRIC_EUCLIDEAN, d_index, d_score, nullptr, s);
+    }));
+    return PMM_OK;
+}
+
+int pmm_dev_matmul(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_matrix(dl, "left")) || (rc = check_matrix(dr, "right"))) return rc;
+    if (dl->n_rows == 0) return PMM_OK;
+    if ((rc = check_pair(dl, dr))) return rc;
+    return dev_matmul_impl(dl, dr, d_out, (cudaStream_t)stream);
+}
+
+int pmm_dev_norms(const pmm_matrix_t *dx, int32_t squared, void *d_out, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_matrix(dx, "matrix"))) return rc;
+    if (dx->n_rows == 0) return PMM_OK;
+    PrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.values = dx->values;
+    a.offsets = dx->offsets;
+    a.validity = dx->validity;
+    a.row_validity = dx->row_validity;
+    a.n_rows = dx->n_rows;
+    a.dim = dx->dim;
+    a.rows_out = dx->n_rows;
+    if (squared) a.sqnorm_out = d_out;
+    else a.norm_out = d_out;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(launch_counted("norms", s, [&] { return launch_norms(a, dx->dtype, s); }));
+    return PMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host entry points
+int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k, const char *metric, uint32_t *out_index,
+             double *out_score, int64_t *k_actual) {
+    int rc;
+    if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus, "corpus"))) return rc;
+    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative (can't convert negative int to unsigned)");
+    const int64_t keff = k < corpus->n_rows ? k : corpus->n_rows;
+    if (k_actual) *k_actual = keff;
+    if (queries->n_rows == 0) return PMM_OK;  // before the metric is parsed, src/matmul.rs:480-490
+    int32_t m;
+    if ((rc = pmm_metric_from_str(metric, &m))) return rc;
+    if ((rc = check_pair(queries, corpus))) return rc;
+    if ((rc = list_dim_check(queries, "queries")) || (rc = list_dim_check(corpus, "corpus"))) return rc;
+    if ((rc = ensure_device())) return rc;
+    if (keff == 0) return PMM_OK;
+    cudaStream_t s = host_stream();
+    Uploaded uq, uc;
+    if ((rc = upload(queries, s, &uq)) || (rc = upload(corpus, s, &uc))) return rc;
+    DevBuf d_idx, d_sc;
+    const size_t cnt = (size_t)queries->n_rows * keff;
+    CUDA_TRY(d_idx.alloc(cnt * 4, s));
+    CUDA_TRY(d_sc.alloc(cnt * 8, s));
+    TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
+    if ((rc = dev_topk_impl(&uq.dm, &uc.dm, nullptr, corpus->dtype, k, m, 0, o, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    stat_add("d2h_bytes", (double)cnt * 12);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
+    int rc;
+    if ((rc = check_matrix(left, "left")) || (rc = check_matrix(right, "right"))) return rc;
+    if (left->n_rows == 0) return PMM_OK;  // src/matmul.rs:297-305
+    if ((rc = check_pair(left, right))) return rc;
+    if ((rc = list_dim_check(left, "left")) || (rc = list_dim_check(right, "right"))) return rc;
+    if ((rc = ensure_device())) return rc;
+    cudaStream_t s = host_stream();
+    Uploaded ul, ur;
+    if ((rc = upload(left, s, &ul)) || (rc = upload(right, s, &ur))) return rc;
+    const int wd = pmm_working_dtype(left->dtype, right->dtype);
+    const size_t bytes = (size_t)left->n_rows * right->n_rows * (wd == PMM_DTYPE_F64 ? 8 : 4);
+    DevBuf d_out;
+    CUDA_TRY(d_out.alloc(bytes, s));
+    if ((rc = dev_matmul_impl(&ul.dm, &ur.dm, d_out.p, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, s));
+    stat_add("d2h_bytes", (double)bytes);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- resident corpus
+int pmm_corpus_create(const pmm_matrix_t *corpus, int32_t query_dtype, pmm_corpus_t **out) {
+    int rc;
+    if (!out) return fail(PMM_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    if ((rc = check_matrix(corpus, "corpus"))) return rc;
+    if (corpus->n_rows == 0) return fail(PMM_ERR_INVALID, "Empty series");
+    if (corpus->dim == 0) return fail(PMM_ERR_INVALID, "Zero-dimensional vectors");
+    if ((rc = list_dim_check(corpus, "corpus"))) return rc;
+    if ((rc = ensure_device())) return rc;
+    cudaStream_t s = host_stream();
+    Uploaded uc;
+    if ((rc = upload(corpus, s, &uc))) return rc;
+    pmm_corpus *h = new pmm_corpus();
+    cudaGetDevice(&h->device);
+    h->storage_dtype = corpus->dtype;
+    h->query_dtype = query_dtype;
+    h->stream = s;
+    PathChoice pc = choose_path(query_dtype, corpus->dtype, 1);
+    DevBuf err;
+    cudaError_t e = err.alloc(sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(err.p, 0, sizeof(int), s);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(PMM_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+    }
+    rc = prepare(uc.dm, pc.mode, pc.f64, TC_TILE_N, true, true, err.as<int>(), s, &h->prep);
+    if (!rc) rc = finish_error_flag(err.as<int>(), s);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return PMM_OK;
+}
+
+int pmm_corpus_destroy(pmm_corpus_t *corpus) {
+    if (!corpus) return PMM_OK;
+    cudaStreamSynchronize(corpus->stream);
+    delete corpus;
+    return PMM_OK;
+}
+
+int64_t pmm_corpus_rows(const pmm_corpus_t *corpus) { return corpus ? corpus->prep.n_rows : 0; }
+
+int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *corpus, int64_t k, const char *metric,
+                    uint32_t *out_index, double *out_score, int64_t *k_actual) {
+    int rc;
+    if (!corpus) return fail(PMM_ERR_INVALID, "null corpus handle");
+    if ((rc = check_matrix(queries, "queries"))) return rc;
+    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative (can't convert negative int to unsigned)");
+    const int64_t N = corpus->prep.n_rows;
+    const int64_t keff = k < N ? k : N;
+    if (k_actual) *k_actual = keff;
+    if (queries->n_rows == 0) return PMM_OK;
+    int32_t m;
+    if ((rc = pmm_metric_from_str(metric, &m))) return rc;
+    if (queries->dim == 0) return fail(PMM_ERR_INVALID, "Zero-dimensional vectors");
+    if (queries->dim != corpus->prep.dim)
+        return fail(PMM_ERR_INVALID, "Dimension mismatch: left has %lld dimensional vectors, right has %lld dimensional vectors",
+                    (long long)queries->dim, (long long)corpus->prep.dim);
+    if ((rc = list_dim_check(queries, "queries"))) return rc;
+    if ((rc = ensure_device())) return rc;
+    if (keff == 0) return PMM_OK;
+    cudaStream_t s = host_stream();
+    Uploaded uq;
+    if ((rc = upload(queries, s, &uq))) return rc;
+    DevBuf d_idx, d_sc;
+    const size_t cnt = (size_t)queries->n_rows * keff;
+    CUDA_TRY(d_idx.alloc(cnt * 4, s));
+    CUDA_TRY(d_sc.alloc(cnt * 8, s));
+    TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
+    if ((rc = dev_topk_impl(&uq.dm, nullptr, &corpus->prep, corpus->storage_dtype, k, m, 0, o, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    stat_add("d2h_bytes", (double)cnt * 12);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+}  // extern "C"

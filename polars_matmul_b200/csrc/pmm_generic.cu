@@ -1,0 +1,268 @@
+// pmm_generic.cu — precision-exact SIMT path: score slab + per-row exact top-k.
+//
+// Used for f64 working precision (tcgen05 has no f64 kind), for k > 128, and as the on-device
+// cross-check of the tensor-core path.  It restates, on the GPU,
+//   * C = A*B^T (src/metrics.rs:40-97, :204-255) with ONE FMA per element, sequential in the vector
+//     dimension for every output — the same order as the CPU oracle, so scores are bit-identical to it;
+//   * the cosine / euclidean pass (src/metrics.rs:267-308, :323-362), fused into the epilogue;
+//   * select_topk_with_scores[_f32] (src/topk.rs:6-75) as radix select + ordered tie collection +
+//     bitonic sort under the total order (better score, then lower index; NaN last).
+#include "pmm_common.cuh"
+#include "pmm_kernels.h"
+
+namespace pmm {
+
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// 64x64 output tile, 16-deep k slices, 256 threads, 4x4 outputs per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) scores_kernel(const T *__restrict__ q, const T *__restrict__ c,
+                                                     const T *__restrict__ qa, const T *__restrict__ ca,
+                                                     int64_t nq, int64_t n, int64_t d, int metric,
+                                                     T *__restrict__ out, int64_t ldo) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ T As[BK][BM + 4];
+    __shared__ T Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;  // loader: row lr, k offset lk..lk+3
+
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = (T)0;
+
+    for (int64_t k0 = 0; k0 < d; k0 += BK) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int64_t kk = k0 + lk + u;
+            T av = (T)0, bv = (T)0;
+            if (kk < d) {
+                if (m0 + lr < nq) av = __ldg(q + (m0 + lr) * d + kk);
+                if (n0 + lr < n) bv = __ldg(c + (n0 + lr) * d + kk);
+            }
+            As[lk + u][lr] = av;
+            Bs[lk + u][lr] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma_rn(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t r = m0 + ty * 4 + i;
+        if (r >= nq) continue;
+        T qav = (metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN) ? qa[r] : (T)0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t cc = n0 + tx * 4 + j;
+            if (cc >= n) continue;
+            T v = acc[i][j];
+            if (metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN) v = metric_finish(v, metric, qav, ca[cc]);
+            out[r * ldo + cc] = v;
+        }
+    }
+}
+
+template <typename T>
+static cudaError_t launch_scores_t(const T *q, const T *c, const T *qa, const T *ca, int64_t nq, int64_t n,
+                                   int64_t d, int metric, T *out, int64_t ldo, cudaStream_t s) {
+    if (nq <= 0 || n <= 0) return cudaSuccess;
+    // gridDim.y <= 65535: callers chunk queries so nq/64 stays below that
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((nq + 63) / 64));
+    scores_kernel<T><<<grid, 256, 0, s>>>(q, c, qa, ca, nq, n, d, metric, out, ldo);
+    return cudaGetLastError();
+}
+cudaError_t launch_scores_f32(const float *q, const float *c, const float *qa, const float *ca, int64_t nq,
+                              int64_t n, int64_t d, int metric, float *out, int64_t ldo, cudaStream_t s) {
+    return launch_scores_t<float>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
+}
+cudaError_t launch_scores_f64(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
+                              int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s) {
+    return launch_scores_t<double>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact per-row top-k. One 256-thread block per query row.
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> { typedef uint32_t type; static constexpr int bits = 32; };
+template <> struct KeyOf<double> { typedef uint64_t type; static constexpr int bits = 64; };
+
+int select_kpad(int64_t k) {
+    int p = 32;
+    while (p < k) p <<= 1;
+    return p;
+}
+int select_smem_kpad_limit(bool f64) { return f64 ? 2048 : 4096; }  // 12 B resp. 8+4 B per entry
+
+template <typename K>
+__device__ __forceinline__ bool entry_before(K ka, uint32_t ia, K kb, uint32_t ib) {
+    return ka > kb || (ka == kb && ia < ib);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) select_topk_kernel(const T *__restrict__ scores, int64_t ld, int64_t n,
+                                                          int k, int kpad, bool higher, int64_t index_base,
+                                                          uint32_t *__restrict__ out_idx,
+                                                          double *__restrict__ out_score,
+                                                          uint64_t *__restrict__ out_cand, void *scratch,
+                                                          int use_global) {
+    typedef typename KeyOf<T>::type K;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int warp_tot[8];
+    __shared__ unsigned int sh_gt, sh_eq_base;
+    __shared__ K sh_prefix;
+    __shared__ unsigned int sh_remaining;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t row = blockIdx.x;
+    const T *s = scores + row * ld;
+
+    K *skeys;
+    uint32_t *sidx;
+    if (use_global) {
+        skeys = (K *)((unsigned char *)scratch + (size_t)row * kpad * (sizeof(K) + 4));
+        sidx = (uint32_t *)(skeys + kpad);
+    } else {
+        skeys = (K *)dyn_smem;
+        sidx = (uint32_t *)(skeys + kpad);
+    }
+
+    // ---- 1. radix select: K-th largest key, 8 bits per pass from the top
+    K prefix = 0, mask = 0;
+    unsigned int remaining = (unsigned int)k;
+    for (int shift = KeyOf<T>::bits - 8; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int64_t j = tid; j < n; j += 256) {
+            K key = score_key(s[j], higher);
+            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xff)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int cum = 0;
+            int digit = 0;
+            for (int dgt = 255; dgt >= 0; --dgt) {
+                unsigned int h = hist[dgt];
+                if (cum + h >= remaining) { digit = dgt; break; }
+                cum += h;
+            }
+            sh_remaining = remaining - cum;
+            sh_prefix = prefix | ((K)digit << shift);
+        }
+        __syncthreads();
+        remaining = sh_remaining;
+        prefix = sh_prefix;
+        mask |= (K)0xff << shift;
+        __syncthreads();
+    }
+    const K kth = prefix;                 // key of the k-th best entry
+    const unsigned int need_eq = remaining;  // how many entries equal to kth belong to the result (>= 1)
+    const unsigned int n_gt = (unsigned int)k - need_eq;
+
+    // ---- 2. collect: every key > kth, plus the first need_eq keys == kth in index order
+    if (tid == 0) { sh_gt = 0; sh_eq_base = 0; }
+    for (int t = tid; t < kpad; t += 256) { skeys[t] = 0; sidx[t] = 0xffffffffu; }
+    __syncthreads();
+    for (int64_t j0 = 0; j0 < n; j0 += 256) {
+        int64_t j = j0 + tid;
+        K key = 0;
+        bool valid = j < n;
+        if (valid) key = score_key(s[j], higher);
+        bool is_gt = valid && key > kth;
+        bool is_eq = valid && key == kth;
+        if (is_gt) {
+            unsigned int pos = atomicAdd(&sh_gt, 1u);
+            skeys[pos] = key;
+            sidx[pos] = (uint32_t)j;
+        }
+        unsigned int bal = __ballot_sync(0xffffffffu, is_eq);
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        unsigned int before = sh_eq_base, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            unsigned int c = warp_tot[w];
+            if (w < wid) before += c;
+            total += c;
+        }
+        if (is_eq) {
+            unsigned int pos = before + __popc(bal & ((1u << lane) - 1u));
+            if (pos < need_eq) { skeys[n_gt + pos] = key; sidx[n_gt + pos] = (uint32_t)j; }
+        }
+        __syncthreads();
+        if (tid == 0) sh_eq_base += total;
+        __syncthreads();
+    }
+
+    // ---- 3. bitonic sort of kpad entries, best first
+    for (int size = 2; size <= kpad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < kpad; t += 256) {
+                int p = t ^ stride;
+                if (p > t) {
+                    bool desc = (t & size) == 0;
+                    K ka = skeys[t], kb = skeys[p];
+                    uint32_t ia = sidx[t], ib = sidx[p];
+                    bool a_first = entry_before<K>(ka, ia, kb, ib);
+                    if (a_first != desc) { skeys[t] = kb; skeys[p] = ka; sidx[t] = ib; sidx[p] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 4. emit
+    for (int t = tid; t < k; t += 256) {
+        K key = skeys[t];
+        uint32_t idx = sidx[t] + (uint32_t)index_base;
+        if (out_idx) out_idx[row * k + t] = idx;
+        if (out_score) out_score[row * k + t] = (double)key_score(key, higher);
+        if (sizeof(K) == 4 && out_cand) out_cand[row * k + t] = pack_candidate((uint32_t)key, idx);
+    }
+}
+
+template <typename T>
+static cudaError_t launch_select_t(const T *scores, int64_t ld, int64_t nq, int64_t n, int64_t k, bool higher,
+                                   int64_t index_base, uint32_t *out_idx, double *out_score, uint64_t *out_cand,
+                                   void *scratch, cudaStream_t s) {
+    typedef typename KeyOf<T>::type K;
+    if (nq <= 0 || k <= 0) return cudaSuccess;
+    int kpad = select_kpad(k);
+    int use_global = kpad > select_smem_kpad_limit(sizeof(T) == 8);
+    size_t smem = use_global ? 0 : (size_t)kpad * (sizeof(K) + 4);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(select_topk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    select_topk_kernel<T><<<(unsigned)nq, 256, smem, s>>>(scores, ld, n, (int)k, kpad, higher, index_base, out_idx,
+                                                          out_score, out_cand, scratch, use_global);
+    return cudaGetLastError();
+}
+cudaError_t launch_select_f32(const float *scores, int64_t ld, int64_t nq, int64_t n, int64_t k, bool higher,
+                              int64_t index_base, uint32_t *out_idx, double *out_score, uint64_t *out_cand,
+                              void *scratch, cudaStream_t s) {
+    return launch_select_t<float>(scores, ld, nq, n, k, higher, index_base, out_idx, out_score, out_cand, scratch, s);
+}
+cudaError_t launch_select_f64(const double *scores, int64_t ld, int64_t nq, int64_t n, int64_t k, bool higher,
+                              int64_t index_base, uint32_t *out_idx, double *out_score, void *scratch,
+                              cudaStream_t s) {
+    return launch_select_t<double>(scores, ld, nq, n, k, higher, index_base, out_idx, out_score, nullptr, scratch, s);
+}
+
+}  // namespace pmm

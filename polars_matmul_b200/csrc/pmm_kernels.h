@@ -1,0 +1,103 @@
+// pmm_kernels.h — internal launcher interface between the kernel translation units and pmm_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pmm {
+
+// ---- prep (pmm_prep.cu) -------------------------------------------------------------------------
+struct PrepArgs {
+    const void *values;           // device, storage dtype
+    const int64_t *offsets;       // device or NULL
+    const uint8_t *validity;      // device or NULL
+    const uint8_t *row_validity;  // device or NULL
+    int64_t n_rows;               // real rows
+    int64_t dim;                  // real vector length
+    int64_t rows_out;             // rows written (>= n_rows; padding rows are zeros)
+    int64_t ld_out;               // leading dimension of the planes (>= dim; padding columns zeros)
+    void *out0;                   // dense / hi plane / f16 plane
+    void *out1;                   // lo plane (MODE_TF32) or NULL
+    void *norm_out;               // [rows_out] working type or NULL
+    void *sqnorm_out;             // [rows_out] working type or NULL
+    int *error_flag;              // set to 1 when a list row is longer than dim
+};
+enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2 };
+cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s);
+cudaError_t launch_norms(const PrepArgs &a, int src_dtype, cudaStream_t s);
+
+// ---- generic SIMT path (pmm_generic.cu) -----------------------------------------------------------
+// scores[i*ldo + j] = metric(dot(q_i, c_j)); metric < 0 => raw dot. Sequential FMA over the vector
+// dimension per output (same order as the oracle).
+cudaError_t launch_scores_f32(const float *q, const float *c, const float *qa, const float *ca, int64_t nq,
+                              int64_t n, int64_t d, int metric, float *out, int64_t ldo, cudaStream_t s);
+cudaError_t launch_scores_f64(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
+                              int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s);
+// Per-row exact top-k of a score slab (radix select + ordered tie collection + bitonic sort).
+// scratch: nq * kpad * 12 bytes when kpad > select_smem_kpad_limit(), else unused.
+int select_kpad(int64_t k);
+int select_smem_kpad_limit(bool f64);
+cudaError_t launch_select_f32(const float *scores, int64_t ld, int64_t nq, int64_t n, int64_t k, bool higher,
+                              int64_t index_base, uint32_t *out_idx, double *out_score, uint64_t *out_cand,
+                              void *scratch, cudaStream_t s);
+cudaError_t launch_select_f64(const double *scores, int64_t ld, int64_t nq, int64_t n, int64_t k, bool higher,
+                              int64_t index_base, uint32_t *out_idx, double *out_score, void *scratch,
+                              cudaStream_t s);
+
+// ---- candidate merge (pmm_merge.cu) ---------------------------------------------------------------
+// Regular layout: list l of query q starts at lists + l*list_stride + q*row_stride, k_in entries.
+cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t list_stride, int64_t row_stride,
+                                 int64_t nq, int k_in, int k_out, bool higher, uint32_t *out_idx,
+                                 double *out_score, uint64_t *out_cand, cudaStream_t s);
+// ---- tensor-core path (pmm_tc_kernels.cu) ----------------------------------------------------------
+constexpr int TC_TILE_M = 128;   // query rows per CTA tile
+constexpr int TC_TILE_N = 256;   // corpus rows per tile
+
+// Closed-form persistent schedule shared by the fused kernel and the merge that follows it.
+// Work is done in rounds. In a full round `mc` query tiles are in flight, each scanned by `g` CTAs
+// that take corpus tiles rank, rank+g, ... (so all CTAs sweep the corpus in lockstep and a corpus tile
+// is fetched from HBM once per round and re-read from L2). The last round spreads the remaining
+// `m_rem` query tiles over `g_rem` CTAs each.
+struct TcSchedule {
+    int m_tiles, n_tiles;
+    int num_ctas;   // grid size
+    int g;          // CTAs per query tile in full rounds
+    int mc;         // query tiles in flight in a full round (= num_ctas / g)
+    int rounds;     // full rounds
+    int m_full;     // = rounds * mc
+    int m_rem;      // = m_tiles - m_full
+    int g_rem;      // CTAs per query tile in the last round (0 when m_rem == 0)
+    __host__ __device__ int pieces(int m_tile) const { return m_tile < m_full ? g : g_rem; }
+    __host__ __device__ int64_t slot_base(int m_tile) const {
+        return m_tile < m_full ? (int64_t)m_tile * g : (int64_t)m_full * g + (int64_t)(m_tile - m_full) * g_rem;
+    }
+    __host__ __device__ int64_t total_slots() const { return (int64_t)m_full * g + (int64_t)m_rem * g_rem; }
+};
+TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_sms, int group);
+
+// Partial lists written by the fused kernel: [slot][row_in_tile (128)][kp].
+cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int kp, int64_t nq, int k_out, bool higher,
+                               uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s);
+
+struct TcArgs {
+    const void *q_hi, *q_lo;       // planes [q_rows_pad x dim_pad]  (f16 mode: q_hi only)
+    const void *c_hi, *c_lo;       // planes [c_rows_pad x dim_pad]
+    int64_t q_rows_pad, c_rows_pad, dim_pad;
+    int64_t nq, n;                 // real rows
+    int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
+    TcSchedule sched;
+    // top-k mode
+    const float *q_aux, *c_aux;    // norms (cosine) / squared norms (euclidean) / NULL (dot)
+    int64_t index_base;
+    int metric;
+    int k;                         // <= 128
+    int kp;                        // 32, 64 or 128
+    uint64_t *partial;             // [sched.total_slots()][128][kp]
+    // matmul mode
+    float *out;                    // [nq x n] row-major
+};
+bool tc_supported();               // driver exposes cuTensorMapEncodeTiled and the device is sm_100
+cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s);
+cudaError_t launch_tc_matmul(const TcArgs &a, cudaStream_t s);
+const char *tc_last_error();
+
+}  // namespace pmm

@@ -1,0 +1,240 @@
+// pmm_prep.cu — the norm-precompute / marshalling kernel (HBM-bound, streaming).
+//
+// Replaces, on device, the reference's
+//   * Series -> dense matrix marshalling: array_chunked_to_matrix_* / list_chunked_to_matrix_*
+//     (src/matmul.rs:167-286): fixed-size rows or i64 list offsets, null element -> 0, null row ->
+//     zeros, short row zero padded (a LONGER row sets an error flag; the reference panics);
+//   * row norms: compute_norms_* / compute_squared_norms_* (src/metrics.rs:367-393).  The reduction
+//     follows ndarray 0.16 `unrolled_dot` exactly: 8 partial sums p0..p7 over chunks of 8 with a
+//     separate multiply and add, combined as (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then the tail
+//     sequentially — so norms are bit-identical to the oracle's.
+// and emits, in the same pass, the operand planes the tensor-core contraction reads:
+//   MODE_DENSE : dense [n_rows x dim] copy in the working type (f32 or f64) for the SIMT path;
+//   MODE_TF32  : hi/lo TF32 planes [rows_pad x dim_pad] for the 3xTF32 split
+//                (hi = rna_tf32(x), lo = rna_tf32(x - hi); x = hi + lo to ~2^-24 relative);
+//   MODE_F16   : f16 plane [rows_pad x dim_pad] for f16-stored input (exact upcast, kind::f16 MMA).
+// Padding rows/columns are written as zeros so TMA tiles never see garbage.
+//
+// Thread mapping: 8 lanes own one row (lane j of the group owns partial sum p_j), 4 rows per warp,
+// 8 warps per block.  Each step the 8 lanes touch one 32-byte sector of the row; steps are unrolled
+// so several sectors per row are in flight.
+#include "pmm_common.cuh"
+#include "pmm_kernels.h"
+
+namespace pmm {
+
+template <typename SRC> struct SrcLoad;
+template <> struct SrcLoad<float> { template <typename W> static __device__ __forceinline__ W get(const float *p) { return (W)__ldg(p); } };
+template <> struct SrcLoad<double> { template <typename W> static __device__ __forceinline__ W get(const double *p) { return (W)__ldg(p); } };
+template <> struct SrcLoad<__half> { template <typename W> static __device__ __forceinline__ W get(const __half *p) { return (W)__half2float(__ldg(p)); } };
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+
+// Split x into two TF32-representable floats. Non-finite x: hi = x, lo = 0.
+__device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
+    uint32_t xb = __float_as_uint(x);
+    if ((xb & 0x7f800000u) == 0x7f800000u) { hi = x; lo = 0.0f; return; }
+    uint32_t hb = tf32_rna(x);
+    if ((hb & 0x7f800000u) == 0x7f800000u) hb = xb & 0xffffe000u;  // rounding overflowed: truncate
+    hi = __uint_as_float(hb);
+    lo = __uint_as_float(tf32_rna(__fsub_rn(x, hi)));
+}
+
+enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2 };
+
+template <typename SRC, typename W, int MODE>
+__global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 7;
+    const int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    const unsigned gmask = 0xffu << (lane & 24);
+    if (row >= a.rows_out) return;  // whole 8-lane group leaves together
+
+    const SRC *values = (const SRC *)a.values;
+    const int64_t dim = a.dim;
+    int64_t base = 0, len = 0;
+    if (row < a.n_rows) {
+        bool row_ok = !a.row_validity || ((a.row_validity[row >> 3] >> (row & 7)) & 1);
+        if (a.offsets) {
+            base = a.offsets[row];
+            len = a.offsets[row + 1] - base;
+            if (len > dim) {  // reference: ndarray index out of bounds panic
+                if (sub == 0) atomicExch(a.error_flag, 1);
+                len = dim;
+            }
+        } else {
+            base = row * dim;
+            len = dim;
+        }
+        if (!row_ok) len = 0;
+    }
+
+    W *dense = (W *)a.out0;
+    float *hi = (float *)a.out0, *lo = (float *)a.out1;
+    __half *hp = (__half *)a.out0;
+    const int64_t ld = a.ld_out;
+
+    auto fetch = [&](int64_t i) -> W {
+        if (i >= len) return (W)0;
+        int64_t p = base + i;
+        if (a.validity && !((a.validity[p >> 3] >> (p & 7)) & 1)) return (W)0;
+        return SrcLoad<SRC>::template get<W>(values + p);
+    };
+    auto emit = [&](int64_t i, W x) {
+        if (MODE == MODE_DENSE) {
+            dense[row * ld + i] = x;
+        } else if (MODE == MODE_TF32) {
+            float h, l;
+            tf32_split((float)x, h, l);
+            hi[row * ld + i] = h;
+            lo[row * ld + i] = l;
+        } else {
+            hp[row * ld + i] = __float2half_rn((float)x);  // exact: x came from an f16
+        }
+    };
+
+    const int64_t d8 = dim & ~(int64_t)7;
+    W p = (W)0;
+    int64_t t = 0;
+    for (; t + 32 <= d8; t += 32) {  // 4 sectors in flight
+        W x0 = fetch(t + sub), x1 = fetch(t + 8 + sub), x2 = fetch(t + 16 + sub), x3 = fetch(t + 24 + sub);
+        p = add_rn(p, mul_rn(x0, x0));
+        p = add_rn(p, mul_rn(x1, x1));
+        p = add_rn(p, mul_rn(x2, x2));
+        p = add_rn(p, mul_rn(x3, x3));
+        emit(t + sub, x0);
+        emit(t + 8 + sub, x1);
+        emit(t + 16 + sub, x2);
+        emit(t + 24 + sub, x3);
+    }
+    for (; t < d8; t += 8) {
+        W x = fetch(t + sub);
+        p = add_rn(p, mul_rn(x, x));
+        emit(t + sub, x);
+    }
+    // (p0+p4), (p1+p5), (p2+p6), (p3+p7) then a sequential sum, as ndarray's unrolled_dot
+    const int gbase = lane & 24;
+    W other = __shfl_sync(gmask, p, gbase + ((sub + 4) & 7));
+    W pair = add_rn(p, other);  // valid on sub 0..3
+    W s0 = __shfl_sync(gmask, pair, gbase + 0), s1 = __shfl_sync(gmask, pair, gbase + 1);
+    W s2 = __shfl_sync(gmask, pair, gbase + 2), s3 = __shfl_sync(gmask, pair, gbase + 3);
+    W sum = add_rn((W)0, s0);
+    sum = add_rn(sum, s1);
+    sum = add_rn(sum, s2);
+    sum = add_rn(sum, s3);
+    for (int64_t i = d8; i < dim; ++i) {  // tail (< 8 elements), every lane redundantly
+        W x = fetch(i);
+        sum = add_rn(sum, mul_rn(x, x));
+        if (sub == (int)(i - d8)) emit(i, x);
+    }
+    if (MODE != MODE_DENSE) {
+        for (int64_t i = dim + sub; i < ld; i += 8) {  // zero the padding columns
+            if (MODE == MODE_TF32) { hi[row * ld + i] = 0.0f; lo[row * ld + i] = 0.0f; }
+            else hp[row * ld + i] = __float2half_rn(0.0f);
+        }
+    }
+    if (sub == 0) {
+        if (a.sqnorm_out) ((W *)a.sqnorm_out)[row] = sum;
+        if (a.norm_out) ((W *)a.norm_out)[row] = sqrt_rn(sum);
+    }
+}
+
+template <typename SRC, typename W, int MODE>
+static cudaError_t launch_prep_t(const PrepArgs &a, cudaStream_t s) {
+    int64_t groups = (a.rows_out + 31) / 32;
+    if (groups <= 0) return cudaSuccess;
+    prep_kernel<SRC, W, MODE><<<(unsigned)groups, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// src_dtype: PMM_DTYPE_* of `values`; mode selects the product; working type: MODE_DENSE uses
+// `work_f64` (0: f32, 1: f64), the plane modes are f32 by construction.
+cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s) {
+    if (mode == MODE_TF32) {
+        if (src_dtype == 1) return launch_prep_t<float, float, MODE_TF32>(a, s);
+        if (src_dtype == 0) return launch_prep_t<__half, float, MODE_TF32>(a, s);
+        return cudaErrorInvalidValue;
+    }
+    if (mode == MODE_F16) {
+        if (src_dtype == 0) return launch_prep_t<__half, float, MODE_F16>(a, s);
+        return cudaErrorInvalidValue;
+    }
+    if (work_f64) {
+        if (src_dtype == 0) return launch_prep_t<__half, double, MODE_DENSE>(a, s);
+        if (src_dtype == 1) return launch_prep_t<float, double, MODE_DENSE>(a, s);
+        return launch_prep_t<double, double, MODE_DENSE>(a, s);
+    }
+    if (src_dtype == 0) return launch_prep_t<__half, float, MODE_DENSE>(a, s);
+    if (src_dtype == 1) return launch_prep_t<float, float, MODE_DENSE>(a, s);
+    return cudaErrorInvalidValue;
+}
+
+// Norms only (pmm_dev_norms): same reduction, no planes written.
+template <typename SRC, typename W>
+__global__ void __launch_bounds__(256) norms_kernel(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 7;
+    const int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    const unsigned gmask = 0xffu << (lane & 24);
+    if (row >= a.n_rows) return;
+    const SRC *values = (const SRC *)a.values;
+    const int64_t dim = a.dim;
+    int64_t base, len;
+    bool row_ok = !a.row_validity || ((a.row_validity[row >> 3] >> (row & 7)) & 1);
+    if (a.offsets) { base = a.offsets[row]; len = a.offsets[row + 1] - base; if (len > dim) len = dim; }
+    else { base = row * dim; len = dim; }
+    if (!row_ok) len = 0;
+    auto fetch = [&](int64_t i) -> W {
+        if (i >= len) return (W)0;
+        int64_t p = base + i;
+        if (a.validity && !((a.validity[p >> 3] >> (p & 7)) & 1)) return (W)0;
+        return SrcLoad<SRC>::template get<W>(values + p);
+    };
+    const int64_t d8 = dim & ~(int64_t)7;
+    W p = (W)0;
+    int64_t t = 0;
+    for (; t + 64 <= d8; t += 64) {  // 8 sectors in flight per row
+        W x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = fetch(t + 8 * u + sub);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p = add_rn(p, mul_rn(x[u], x[u]));
+    }
+    for (; t < d8; t += 8) { W x = fetch(t + sub); p = add_rn(p, mul_rn(x, x)); }
+    const int gbase = lane & 24;
+    W other = __shfl_sync(gmask, p, gbase + ((sub + 4) & 7));
+    W pair = add_rn(p, other);
+    W s0 = __shfl_sync(gmask, pair, gbase + 0), s1 = __shfl_sync(gmask, pair, gbase + 1);
+    W s2 = __shfl_sync(gmask, pair, gbase + 2), s3 = __shfl_sync(gmask, pair, gbase + 3);
+    W sum = add_rn((W)0, s0);
+    sum = add_rn(sum, s1);
+    sum = add_rn(sum, s2);
+    sum = add_rn(sum, s3);
+    for (int64_t i = d8; i < dim; ++i) { W x = fetch(i); sum = add_rn(sum, mul_rn(x, x)); }
+    if (sub == 0) {
+        if (a.sqnorm_out) ((W *)a.sqnorm_out)[row] = sum;
+        if (a.norm_out) ((W *)a.norm_out)[row] = sqrt_rn(sum);
+    }
+}
+
+cudaError_t launch_norms(const PrepArgs &a, int src_dtype, cudaStream_t s) {
+    int64_t groups = (a.n_rows + 31) / 32;
+    if (groups <= 0) return cudaSuccess;
+    if (src_dtype == 0) norms_kernel<__half, float><<<(unsigned)groups, 256, 0, s>>>(a);
+    else if (src_dtype == 1) norms_kernel<float, float><<<(unsigned)groups, 256, 0, s>>>(a);
+    else norms_kernel<double, double><<<(unsigned)groups, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace pmm

@@ -1,0 +1,476 @@
+// pmm_tc_kernels.cu — the hot path on 5th-gen tensor cores (sm_100a): TMA -> shared memory ->
+// tcgen05.mma -> TMEM -> fused epilogue.
+//
+// One persistent, warp-specialised kernel, two epilogues:
+//   * top-k  : replaces matmul_f32 + the cosine/euclidean pass + select_topk_with_scores_f32
+//              (src/metrics.rs:204-255, :314-365, src/topk.rs:42-75).  The Q x N score matrix the
+//              reference materialises (src/metrics.rs:211, :354) never leaves the SM: each epilogue
+//              thread owns one query row of the 128 x 256 accumulator tile in TMEM, applies the metric
+//              in f32 exactly as the reference does, packs (score key, ~index) into a u64 and keeps
+//              only candidates that beat the row's current k-th best.
+//   * matmul : replaces matmul_slice_f32 (src/metrics.rs:160-202): 128-bit stores of the tile rows.
+//
+// Precision: f32 inputs use the 3xTF32 split (hi*hi + hi*lo + lo*hi with hi/lo planes from
+// pmm_prep.cu; f32 accumulation in TMEM); f16-stored inputs use kind::f16 directly (products of two
+// f16 values are exact in f32, so only the summation order differs from the reference's upcast path).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane group = warp % 4).  Two accumulator buffers of 256
+// TMEM columns let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Running top-k: per row a threshold (the k-th best packed candidate so far) and a 16-slot staging
+// buffer in shared memory; the sorted list of KP = 32/64/128 candidates lives in global memory
+// (L2-resident).  When a row's staging buffer fills, its warp sorts the staged candidates with
+// shuffles, bitonic-merges them into the list (KP/32 registers per lane) and refreshes the threshold.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "pmm_common.cuh"
+#include "pmm_kernels.h"
+#include "pmm_tc.cuh"
+
+namespace pmm {
+using namespace tc;
+
+namespace {
+
+constexpr int BM = TC_TILE_M;
+constexpr int BN = TC_TILE_N;
+constexpr int NUM_THREADS = 192;
+constexpr int STAGE_SLOTS = 16;          // staged candidates per row before a flush is forced
+constexpr int FLUSH_AT = STAGE_SLOTS - 8;  // checked every 8 scores
+
+template <bool F16>
+struct TcCfg {
+    static constexpr int PLANES = F16 ? 1 : 2;
+    static constexpr int BK = F16 ? 64 : 32;       // elements per 128-byte smem row
+    static constexpr int KSTEPS = 4;               // 32 bytes of K per tcgen05.mma
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = F16 ? 4 : 2;
+    static constexpr int STAGING_BYTES = STAGE_SLOTS * BM * 8;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+};
+
+struct TcKParams {
+    TcSchedule sched;
+    int num_kb;
+    const float *q_aux, *c_aux;
+    int64_t nq, n;
+    int64_t index_base;
+    int metric;
+    int k;
+    uint64_t *partial;
+    float *out;
+};
+
+enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
+
+// Work of CTA `cta` in round `it`. Returns false when the CTA idles in that round.
+__device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int it, int &m_tile, int &n_start,
+                                              int &n_step, int64_t &slot) {
+    if (it < s.rounds) {
+        if (cta >= s.mc * s.g) return false;
+        int grp = cta / s.g, rank = cta - grp * s.g;
+        m_tile = it * s.mc + grp;
+        n_start = rank;
+        n_step = s.g;
+        slot = (int64_t)m_tile * s.g + rank;
+        return true;
+    }
+    if (cta >= s.m_rem * s.g_rem) return false;
+    int grp = cta / s.g_rem, rank = cta - grp * s.g_rem;
+    m_tile = s.m_full + grp;
+    n_start = rank;
+    n_step = s.g_rem;
+    slot = (int64_t)s.m_full * s.g + (int64_t)grp * s.g_rem + rank;
+    return true;
+}
+
+// Merge the staged candidates of the rows in `rows` (bit i = lane i's row) into their lists.
+template <int R>
+__device__ __forceinline__ void flush_rows(unsigned rows, uint64_t *stage_buf, uint64_t *list_base /* lane group's 32 lists */,
+                                           int row0, int lane, int k, uint64_t &thr, int &cnt) {
+    constexpr int KP = 32 * R;
+    __syncwarp();
+    while (rows) {
+        const int src = __ffs(rows) - 1;
+        rows &= rows - 1;
+        const int c = __shfl_sync(0xffffffffu, cnt, src);
+        uint64_t v = (lane < c) ? stage_buf[lane * BM + row0 + src] : 0ull;
+        v = warp_sort_desc(v, lane);
+        uint64_t *list = list_base + (int64_t)src * KP;
+        uint64_t L[R], M[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            L[r] = list[32 * r + lane];
+            M[r] = 0ull;
+        }
+        M[R - 1] = __shfl_sync(0xffffffffu, v, 31 - lane);  // staged list, reversed, sits at the tail
+        warp_merge_topk_desc<R>(L, M, lane);
+#pragma unroll
+        for (int r = 0; r < R; ++r) list[32 * r + lane] = L[r];
+        uint64_t kreg = L[R - 1];  // register holding list element k-1 (k <= 32*R)
+#pragma unroll
+        for (int r = 0; r < R - 1; ++r)
+            if (r == ((k - 1) >> 5)) kreg = L[r];
+        const uint64_t kth = __shfl_sync(0xffffffffu, kreg, (k - 1) & 31);
+        if (lane == src) {
+            thr = kth;
+            cnt = 0;
+        }
+    }
+    __syncwarp();
+}
+
+template <bool F16, int EPI, int R>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+          const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo, const TcKParams p) {
+    typedef TcCfg<F16> Cfg;
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    uint64_t *stage_buf = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
+    volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(bars + 2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const TcSchedule &S = p.sched;
+    const int total_rounds = S.rounds + (S.m_rem > 0 ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tm_qhi);
+        prefetch_tensormap(&tm_chi);
+        if (!F16) {
+            prefetch_tensormap(&tm_qlo);
+            prefetch_tensormap(&tm_clo);
+        }
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(smem_u32((const void *)tmem_ptr_smem), 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < total_rounds; ++it) {
+                int m_tile, n_start, n_step;
+                int64_t slot;
+                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+                for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t fb = full_bar(stage);
+                        mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &tm_qhi, fb, kb * Cfg::BK, m_tile * BM);
+                        if (!F16) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, m_tile * BM);
+                        tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, nt * BN);
+                        if (!F16)
+                            tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, nt * BN);
+                        if (++stage == Cfg::STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_instr_desc(F16 ? 0 : 2, BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int abuf = 0;
+            uint32_t aphase = 0;
+            for (int it = 0; it < total_rounds; ++it) {
+                int m_tile, n_start, n_step;
+                int64_t slot;
+                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+                for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                    mbar_wait(tempty_bar(abuf), aphase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(abuf * BN);
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t a_hi = sa, a_lo = sa + Cfg::A_BYTES;
+                        const uint32_t b_hi = sa + Cfg::PLANES * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                            const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
+                            const uint64_t dah = umma_smem_desc(a_hi + ks * 32), dbh = umma_smem_desc(b_hi + ks * 32);
+                            if (F16) {
+                                umma<1, true>(tmem_d, dah, dbh, idesc, acc);
+                            } else {
+                                const uint64_t dal = umma_smem_desc(a_lo + ks * 32), dbl = umma_smem_desc(b_lo + ks * 32);
+                                umma<1, false>(tmem_d, dal, dbh, idesc, acc);  // small terms first
+                                umma<1, false>(tmem_d, dah, dbl, idesc, 1u);
+                                umma<1, false>(tmem_d, dah, dbh, idesc, 1u);
+                            }
+                        }
+                        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                        if (++stage == Cfg::STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit(tfull_bar(abuf));  // accumulator tile complete
+                    abuf ^= 1;
+                    if (abuf == 0) aphase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int lg = warp & 3;          // TMEM lane group this warp may read
+        const int row0 = lg * 32;         // first tile row of the warp
+        const int row = row0 + lane;      // tile row owned by this thread
+        const bool higher = higher_is_better(p.metric);
+        const bool need_aux = (p.metric == METRIC_COSINE || p.metric == METRIC_EUCLIDEAN);
+        int abuf = 0;
+        uint32_t aphase = 0;
+        for (int it = 0; it < total_rounds; ++it) {
+            int m_tile, n_start, n_step;
+            int64_t slot;
+            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+            const int64_t qrow = (int64_t)m_tile * BM + row;
+            uint64_t thr = 0ull;
+            int cnt = 0;
+            float qa = 0.0f;
+            uint64_t *list_base = nullptr;
+            if (EPI == EPI_TOPK) {
+                constexpr int KP = 32 * R;
+                list_base = p.partial + (slot * BM + row0) * KP;
+                for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
+                if (need_aux) qa = p.q_aux[qrow];  // q_aux is padded to the tile grid
+                __syncwarp();
+            }
+            for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                mbar_wait(tfull_bar(abuf), aphase);
+                tc_fence_after();
+                const int64_t col_tile = (int64_t)nt * BN;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)row0 << 16) + (uint32_t)(abuf * BN + ch * 32), v);
+                    tmem_ld_wait();
+                    if (ch == BN / 32 - 1) {  // all TMEM reads of this buffer are done: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(abuf));
+                    }
+                    const int64_t col0 = col_tile + ch * 32;
+                    if (EPI == EPI_MATMUL) {
+                        if (qrow < p.nq) {
+                            float *dst = p.out + qrow * p.n + col0;
+                            if ((p.n & 3) == 0 && col0 + 32 <= p.n) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4 *>(dst + j) =
+                                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j8 = 0; j8 < 32; j8 += 8) {
+#pragma unroll
+                            for (int j = j8; j < j8 + 8; ++j) {
+                                const int64_t col = col0 + j;
+                                float sc = __uint_as_float(v[j]);
+                                if (need_aux) sc = metric_finish(sc, p.metric, qa, __ldg(p.c_aux + col));
+                                uint64_t cand = pack_candidate(score_key(sc, higher), (uint32_t)(p.index_base + col));
+                                if (col >= p.n) cand = 0ull;  // tile padding
+                                if (cand > thr) {
+                                    stage_buf[cnt * BM + row] = cand;
+                                    ++cnt;
+                                }
+                            }
+                            const unsigned over = __ballot_sync(0xffffffffu, cnt > FLUSH_AT);
+                            if (over) flush_rows<R>(over, stage_buf, list_base, row0, lane, p.k, thr, cnt);
+                        }
+                    }
+                }
+                abuf ^= 1;
+                if (abuf == 0) aphase ^= 1u;
+            }
+            if (EPI == EPI_TOPK) {
+                const unsigned pending = __ballot_sync(0xffffffffu, cnt > 0);
+                if (pending) flush_rows<R>(pending, stage_buf, list_base, row0, lane, p.k, thr, cnt);
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+thread_local char g_tc_err[256] = "";
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+// [rows x cols] row-major plane, box = box_rows x 128 bytes, SWIZZLE_128B.
+bool make_plane_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int box_rows, bool f16) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled not available from the driver");
+        return false;
+    }
+    const int esz = f16 ? 2 : 4;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base),
+                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return false;
+    }
+    return true;
+}
+
+template <bool F16, int EPI, int R>
+cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
+    typedef TcCfg<F16> Cfg;
+    CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
+    if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, BN, F16)) return cudaErrorInvalidValue;
+    if (F16) {
+        tq_lo = tq_hi;
+        tc_lo = tc_hi;
+    } else {
+        if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, BN, false)) return cudaErrorInvalidValue;
+    }
+    TcKParams p;
+    p.sched = a.sched;
+    p.num_kb = (int)(a.dim_pad / Cfg::BK);
+    p.q_aux = a.q_aux;
+    p.c_aux = a.c_aux;
+    p.nq = a.nq;
+    p.n = a.n;
+    p.index_base = a.index_base;
+    p.metric = a.metric;
+    p.k = a.k;
+    p.partial = a.partial;
+    p.out = a.out;
+    auto kern = tc_kernel<F16, EPI, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    kern<<<a.sched.num_ctas, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(tq_hi, tq_lo, tc_hi, tc_lo, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+const char *tc_last_error() { return g_tc_err; }
+
+bool tc_supported() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return false;
+    return prop.major == 10 && get_encode_fn() != nullptr;
+}
+
+TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_sms, int group) {
+    TcSchedule s;
+    s.m_tiles = (int)((q_rows + BM - 1) / BM);
+    s.n_tiles = (int)((c_rows + BN - 1) / BN);
+    int G = num_sms > 0 ? num_sms : 1;
+    s.g = group < 1 ? 1 : group;
+    if (s.g > s.n_tiles) s.g = s.n_tiles;
+    if (s.g > G) s.g = G;
+    s.mc = G / s.g;
+    s.rounds = s.m_tiles / s.mc;
+    s.m_full = s.rounds * s.mc;
+    s.m_rem = s.m_tiles - s.m_full;
+    s.g_rem = 0;
+    if (s.m_rem > 0) {
+        s.g_rem = G / s.m_rem;
+        if (s.g_rem > s.n_tiles) s.g_rem = s.n_tiles;
+        if (s.g_rem < 1) s.g_rem = 1;
+    }
+    int used_full = s.rounds > 0 ? s.mc * s.g : 0;
+    int used_rem = s.m_rem * s.g_rem;
+    s.num_ctas = used_full > used_rem ? used_full : used_rem;
+    if (s.num_ctas < 1) s.num_ctas = 1;
+    return s;
+}
+
+cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s) {
+    if (a.k < 1 || a.k > 128) return cudaErrorInvalidValue;
+    if (a.f16) {
+        if (a.kp == 32) return launch_t<true, EPI_TOPK, 1>(a, s);
+        if (a.kp == 64) return launch_t<true, EPI_TOPK, 2>(a, s);
+        if (a.kp == 128) return launch_t<true, EPI_TOPK, 4>(a, s);
+    } else {
+        if (a.kp == 32) return launch_t<false, EPI_TOPK, 1>(a, s);
+        if (a.kp == 64) return launch_t<false, EPI_TOPK, 2>(a, s);
+        if (a.kp == 128) return launch_t<false, EPI_TOPK, 4>(a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_tc_matmul(const TcArgs &a, cudaStream_t s) {
+    if (a.f16) return launch_t<true, EPI_MATMUL, 1>(a, s);
+    return launch_t<false, EPI_MATMUL, 1>(a, s);
+}
+
+}  // namespace pmm

@@ -1,0 +1,115 @@
+"""
+Multi-GPU driver for the top-k path: one process per GPU, corpus rows sharded contiguously, queries
+replicated (BASELINE.json north_star item 6).
+
+The reference has no distributed code at all; the corpus partitions naturally, so every rank runs the
+fused kernel on its shard with global row numbers (index_base), the ranks exchange only Q x k packed
+candidates (8 bytes each) with one NCCL all-gather over NVLink, and every rank merges the gathered lists
+with the same merge kernel the single-GPU path uses between corpus pieces.  Because the packed order
+(score key, then lower index) is a total order, the result does not depend on the number of shards.
+
+torch / torch.distributed are plumbing here (device buffers, the NCCL communicator, streams); the
+compute is libpmm_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _native
+
+
+def shard_bounds(n_rows: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous row ranges: rank g owns [g*ceil(N/G), min(N, (g+1)*ceil(N/G)))."""
+    per = -(-n_rows // world_size) if world_size > 0 else n_rows
+    return [(min(n_rows, g * per), min(n_rows, (g + 1) * per)) for g in range(world_size)]
+
+
+# ---- packed candidate format (host mirror of pmm_common.cuh pack_candidate / score_key) ------------
+def pack_candidates(index: np.ndarray, score_f32: np.ndarray, higher_is_better: bool) -> np.ndarray:
+    """(u32 index, f32 score) -> u64 candidates: (ordered key << 32) | ~index. Data-format helper."""
+    s = np.asarray(score_f32, np.float32) + np.float32(0.0)            # -0.0 -> +0.0
+    u = s.view(np.uint32)
+    key = np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+    if not higher_is_better:
+        key = ~key
+    key = np.where(np.isnan(s), np.uint32(0), key).astype(np.uint64)
+    return (key << np.uint64(32)) | (~np.asarray(index, np.uint32)).astype(np.uint64)
+
+
+def unpack_candidates(cand: np.ndarray, higher_is_better: bool):
+    """u64 candidates -> (u32 index, f64 score). Empty slots (0) decode to index 2^32-1, score NaN."""
+    cand = np.asarray(cand, np.uint64)
+    index = ~(cand & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    key = (cand >> np.uint64(32)).astype(np.uint32)
+    u = key if higher_is_better else ~key
+    bits = np.where(u & np.uint32(0x80000000), u ^ np.uint32(0x80000000), ~u).astype(np.uint32)
+    score = bits.view(np.float32).astype(np.float64)
+    score = np.where(key == 0, np.nan, score)
+    return index, score
+
+
+def all_gather_candidates(cand, group=None):
+    """[Q, k] int64 tensor per rank -> [G, Q, k] on every rank (NCCL on GPU tensors, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(cand.shape), dtype=cand.dtype, device=cand.device)
+    if cand.is_cuda:
+        dist.all_gather_into_tensor(out, cand.contiguous(), group=group)
+    else:  # gloo has no all_gather_into_tensor for every build: use the list form
+        parts = [torch.empty_like(cand) for _ in range(world)]
+        dist.all_gather(parts, cand.contiguous(), group=group)
+        out = torch.stack(parts, 0)
+    return out
+
+
+class ShardedTopk:
+    """Top-k of replicated queries against a corpus sharded over the ranks of `group`."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def topk_device(self, d_queries, d_corpus_shard, index_base: int, n_total: int, k: int, metric: str):
+        """d_queries [Q, D], d_corpus_shard [n_local, D]: CUDA tensors (f32 or f16) on this rank's GPU.
+        Returns (index int32-as-u32 [Q, k_eff], score f64 [Q, k_eff]) CUDA tensors, identical on every rank."""
+        import torch
+        m = _native.metric_from_str(metric)
+        Q, D = d_queries.shape
+        n_local = d_corpus_shard.shape[0]
+        k_eff = min(int(k), int(n_total))
+        if k_eff > 128:
+            raise _native.PmmError(_native.PMM_ERR_UNSUPPORTED, "sharded top-k supports k <= 128")
+        code = {torch.float16: _native.DTYPE_F16, torch.float32: _native.DTYPE_F32}[d_queries.dtype]
+        ccode = {torch.float16: _native.DTYPE_F16, torch.float32: _native.DTYPE_F32}[d_corpus_shard.dtype]
+        stream = torch.cuda.current_stream().cuda_stream
+        k_local = min(k_eff, n_local)
+        cand = torch.zeros((Q, k_eff), dtype=torch.int64, device=d_queries.device)  # 0 = empty slot
+        if k_local > 0:
+            local = cand if k_local == k_eff else torch.empty((Q, k_local), dtype=torch.int64, device=d_queries.device)
+            _native.dev_topk(_native.dev_matrix(d_queries.data_ptr(), Q, D, code),
+                             _native.dev_matrix(d_corpus_shard.data_ptr(), n_local, D, ccode),
+                             k_local, m, index_base=index_base, cand_ptr=local.data_ptr(), stream=stream)
+            if local is not cand:
+                cand[:, :k_local] = local
+        gathered = all_gather_candidates(cand, self.group) if self.world > 1 else cand.unsqueeze(0)
+        idx = torch.empty((Q, k_eff), dtype=torch.int32, device=d_queries.device)
+        sc = torch.empty((Q, k_eff), dtype=torch.float64, device=d_queries.device)
+        _native.dev_merge_candidates(gathered.data_ptr(), gathered.shape[0], Q, k_eff, k_eff, m,
+                                     idx.data_ptr(), sc.data_ptr(), stream=stream)
+        return idx, sc
+
+    def topk_host(self, queries: np.ndarray, corpus_shard: np.ndarray, index_base: int, n_total: int, k: int,
+                  metric: str, pinned_q=None, pinned_c=None):
+        """End-to-end variant: host buffers in (pinned tensors are copied without staging), host arrays out."""
+        import torch
+        tq = pinned_q if pinned_q is not None else torch.from_numpy(queries)
+        tc = pinned_c if pinned_c is not None else torch.from_numpy(corpus_shard)
+        dq = tq.to("cuda", non_blocking=True)
+        dc = tc.to("cuda", non_blocking=True)
+        idx, sc = self.topk_device(dq, dc, index_base, n_total, k, metric)
+        return idx.cpu().numpy().view(np.uint32), sc.cpu().numpy()

@@ -1,0 +1,382 @@
+"""
+GPU parity tests: the CUDA path, called through the C ABI (include/pmm.h), against the CPU oracle on
+the same seeded inputs, plus the committed golden fixtures.  Run on the B200 box: pytest -m gpu.
+Tolerances are stated in tests/parity.py (1e-5 relative f32, 1e-12 f64; indices exact up to near-ties).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native():
+    from polars_matmul_b200 import _native
+    _native.lib()
+    if _native.device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu tests must run on the GPU box")
+    _native.set_option("force_generic", 0)
+    return _native
+
+
+@pytest.fixture(scope="module")
+def pmm():
+    import polars_matmul_b200
+    return polars_matmul_b200
+
+
+def _randn(rng, *shape, dtype=np.float32):
+    return rng.standard_normal(shape).astype(dtype)
+
+
+def _hm(a):
+    from polars_matmul_b200.arrow import to_host_matrix
+    return to_host_matrix(a)
+
+
+# ---------------------------------------------------------------------------------------------- golden vectors
+def test_reference_known_answers_topk(native, oracle, golden_dir):
+    known = json.load(open(os.path.join(golden_dir, "reference_known_answers.json")))
+    for case in known["topk"]:
+        for dt in (np.float64, np.float32):
+            q, c = np.array(case["query"], dt), np.array(case["corpus"], dt)
+            idx, sc = native.topk(_hm(q), _hm(c), case["k"], case["metric"])
+            assert idx.shape[1] == case["n_results"], case["src"]
+            assert idx[:, 0].tolist() == case["top1_index"], case["src"]
+            np.testing.assert_allclose(sc[:, 0], case["top1_score"], atol=case["atol"])
+            parity.check_topk(idx, sc, q, c, case["k"], case["metric"], oracle)
+
+
+def test_reference_known_answers_matmul(native, oracle, golden_dir):
+    known = json.load(open(os.path.join(golden_dir, "reference_known_answers.json")))
+    for case in known["matmul"]:
+        dt = np.float32 if case["dtype"] == "f32" else np.float64
+        out = native.matmul(_hm(np.array(case["left"], dt)), _hm(np.array(case["right"], dt)))
+        assert out.dtype == dt
+        np.testing.assert_allclose(out, np.array(case["expect"]), rtol=case["rtol"])
+        if "flat" in case:
+            np.testing.assert_allclose(out.reshape(-1), case["flat"], rtol=case["rtol"])
+
+
+def test_reference_errors(native, golden_dir):
+    known = json.load(open(os.path.join(golden_dir, "reference_known_answers.json")))
+    for case in known["errors"]:
+        q = np.array(case["query"], np.float64).reshape(len(case["query"]), -1)
+        c = np.array(case["corpus"], np.float64).reshape(len(case["corpus"]), -1 if case["corpus"] else q.shape[1])
+        with pytest.raises(RuntimeError, match=case["match"]):
+            if case["call"] == "topk":
+                native.topk(_hm(q), _hm(c), case["k"], case["metric"])
+            else:
+                native.matmul(_hm(q), _hm(c))
+
+
+def test_seeded_numpy_fixtures(native, oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "matmul_seed42_10x20x32_f64.npz"))
+    out = native.matmul(_hm(g["left"]), _hm(g["right"]))
+    np.testing.assert_allclose(out, g["expect"], rtol=float(g["rtol"]))
+    g = np.load(os.path.join(golden_dir, "cosine_seed42_5x20x16_f64.npz"))
+    idx, sc = native.topk(_hm(g["query"]), _hm(g["corpus"]), int(g["k"]), "cosine")
+    np.testing.assert_allclose(sc, g["expect_sorted_desc"], rtol=float(g["rtol"]))
+    g = np.load(os.path.join(golden_dir, "bench_selfcheck_seed42_100x500x64_f64.npz"))
+    for dt in (np.float64, np.float32):
+        idx, sc = native.topk(_hm(g["query"].astype(dt)), _hm(g["corpus"].astype(dt)), int(g["k"]), "cosine")
+        np.testing.assert_allclose(sc, g["expect_topk_scores"], rtol=float(g["rtol"]))
+
+
+# ---------------------------------------------------------------------------------------------- SIMT path: bit-exact
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_generic_path_bit_exact(native, oracle, metric, dtype):
+    rng = np.random.default_rng(7)
+    q, c = _randn(rng, 37, 50, dtype=dtype), _randn(rng, 1000, 50, dtype=dtype)
+    native.set_option("force_generic", 1)
+    try:
+        idx, sc = native.topk(_hm(q), _hm(c), 17, metric)
+    finally:
+        native.set_option("force_generic", 0)
+    parity.check_topk(idx, sc, q, c, 17, metric, oracle, exact=True)
+
+
+def test_generic_path_large_k_and_clamp(native, oracle):
+    rng = np.random.default_rng(8)
+    q, c = _randn(rng, 9, 24), _randn(rng, 700, 24)
+    for k in (129, 300, 700, 5000):  # > 128 routes to the SIMT path; 5000 clamps to N (src/matmul.rs:443)
+        idx, sc = native.topk(_hm(q), _hm(c), k, "dot")
+        assert idx.shape == (9, min(k, 700))
+        parity.check_topk(idx, sc, q, c, k, "dot", oracle, exact=True)
+
+
+def test_f64_path(native, oracle):
+    rng = np.random.default_rng(9)
+    q, c = _randn(rng, 64, 64, dtype=np.float64), _randn(rng, 2000, 64, dtype=np.float64)
+    for metric in ("cosine", "dot", "euclidean"):
+        idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
+        parity.check_topk(idx, sc, q, c, 10, metric, oracle, exact=True)
+    out = native.matmul(_hm(q), _hm(c))
+    assert out.dtype == np.float64
+    assert np.array_equal(out, oracle.matmul(q, c))
+
+
+def test_mixed_dtype_uses_f64(native, oracle):
+    rng = np.random.default_rng(10)
+    q, c = _randn(rng, 5, 16, dtype=np.float32), _randn(rng, 40, 16, dtype=np.float64)
+    out = native.matmul(_hm(q), _hm(c))
+    assert out.dtype == np.float64 and np.array_equal(out, oracle.matmul(q, c))
+    idx, sc = native.topk(_hm(q), _hm(c), 3, "cosine")
+    parity.check_topk(idx, sc, q, c, 3, "cosine", oracle, exact=True)
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core path
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+@pytest.mark.parametrize("shape", [(300, 5000, 96, 10), (257, 3000, 100, 100), (64, 9000, 768, 128),
+                                   (1, 300, 8, 1), (130, 257, 33, 64)])
+def test_tc_topk_f32(native, oracle, metric, shape):
+    nq, n, d, k = shape
+    rng = np.random.default_rng(nq + n + d)
+    q, c = _randn(rng, nq, d), _randn(rng, n, d)
+    idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+    frac = parity.check_topk(idx, sc, q, c, k, metric, oracle)
+    assert frac > 0.999, f"only {frac:.4f} of indices equal the oracle's"
+
+
+def test_tc_readme_config_c1(native, oracle):
+    # BASELINE.json configs[0]: 1000 x 10000, 256-d f32, cosine, k=10; same generator as
+    # examples/benchmark_topk.py:69-71
+    np.random.seed(42)
+    q = np.random.randn(1000, 256).astype(np.float32)
+    c = np.random.randn(10000, 256).astype(np.float32)
+    idx, sc = native.topk(_hm(q), _hm(c), 10, "cosine")
+    frac = parity.check_topk(idx, sc, q, c, 10, "cosine", oracle)
+    assert frac == 1.0
+    # and against the reference's own NumPy comparator (sorted scores, rtol 1e-4, benchmark_topk.py:122-138)
+    _, ns = oracle.numpy_topk_cosine(q, c, 10)
+    np.testing.assert_allclose(sc, ns, rtol=1e-4)
+
+
+def test_tc_matmul_f32_c2(native, oracle):
+    # BASELINE.json configs[1]: raw matmul 1000 x 10000 x 256
+    np.random.seed(42)
+    q = np.random.randn(1000, 256).astype(np.float32)
+    c = np.random.randn(10000, 256).astype(np.float32)
+    out = native.matmul(_hm(q), _hm(c))
+    assert out.dtype == np.float32 and out.shape == (1000, 10000)
+    parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float32)
+    q64, c64 = q[:200].astype(np.float64), c[:3000].astype(np.float64)
+    out = native.matmul(_hm(q64), _hm(c64))
+    assert np.array_equal(out, oracle.matmul(q64, c64))
+
+
+@pytest.mark.parametrize("shape", [(7, 13, 5), (129, 1000, 257), (300, 257, 64)])
+def test_tc_matmul_odd_shapes(native, oracle, shape):
+    nq, n, d = shape
+    rng = np.random.default_rng(nq * n)
+    q, c = _randn(rng, nq, d), _randn(rng, n, d)
+    out = native.matmul(_hm(q), _hm(c))
+    parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float32)
+
+
+def test_tie_stress(native, oracle):
+    # exact ties: duplicated corpus rows, small-integer vectors, zero vectors (north_star tie rule)
+    rng = np.random.default_rng(3)
+    base = rng.integers(-3, 4, size=(50, 32)).astype(np.float32)
+    c = np.concatenate([base, base, np.zeros((5, 32), np.float32), base[:10]], 0)   # many duplicates
+    q = np.concatenate([base[:20], np.zeros((2, 32), np.float32)], 0)
+    for metric in ("cosine", "dot", "euclidean"):
+        for k in (1, 7, 40, 115):
+            idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+            # integer-valued data: every product and partial sum is exact in f32, so the tensor-core path
+            # must reproduce the oracle's indices exactly, ties included
+            oi, osc = oracle.topk(q, c, k, metric)
+            assert np.array_equal(idx, oi), (metric, k, np.argwhere(idx != oi)[:4].tolist())
+            parity.check_topk(idx, sc, q, c, k, metric, oracle)
+
+
+def test_nan_and_inf_rank_last(native, oracle):
+    c = np.ones((300, 16), np.float32)
+    c[5, 0] = np.nan
+    c[9, 3] = np.inf
+    c[11] *= 2
+    q = np.ones((3, 16), np.float32)
+    idx, sc = native.topk(_hm(q), _hm(c), 300, "dot")          # k > 128: SIMT path, IEEE semantics throughout
+    oi, osc = oracle.topk(q, c, 300, "dot")
+    assert np.array_equal(idx, oi)
+    assert np.isnan(sc[:, -1]).all() and idx[0, 0] == 9 and idx[0, 1] == 11
+    # tensor-core path: NaN ranks last as well (an infinite INPUT turns into NaN under the 3xTF32 split,
+    # 0 * inf in the lo*hi term — documented deviation)
+    c[9, 3] = 1.0
+    idx, sc = native.topk(_hm(q), _hm(c), 100, "dot")
+    oi, osc = oracle.topk(q, c, 100, "dot")
+    assert np.array_equal(idx, oi) and idx[0, 0] == 11
+    idx, sc = native.topk(_hm(q), _hm(c[:40]), 40, "dot")
+    assert idx[0, -1] == 5 and np.isnan(sc[0, -1])
+
+
+def test_zero_norm_cosine(native, oracle):
+    c = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 2, 0, 0]], np.float32)
+    q = np.array([[1, 1, 0, 0], [0, 0, 0, 0]], np.float32)
+    idx, sc = native.topk(_hm(q), _hm(c), 3, "cosine")
+    oi, osc = oracle.topk(q, c, 3, "cosine")
+    assert np.array_equal(idx, oi) and np.array_equal(sc, osc)
+
+
+# ---------------------------------------------------------------------------------------------- containers / dtypes
+def test_list_input_with_nulls_and_short_rows(pmm, native, oracle):
+    import pyarrow as pa
+    rng = np.random.default_rng(5)
+    dense = _randn(rng, 40, 12)
+    rows = [r.tolist() for r in dense]
+    rows[3] = rows[3][:7]            # short row -> zero padded (src/matmul.rs:247-254)
+    rows[5][2] = None                # null element -> 0.0
+    rows[8] = None                   # null row -> zeros
+    arr = pa.array(rows, type=pa.large_list(pa.float32()))
+    dense[3, 7:] = 0
+    dense[5, 2] = 0
+    dense[8] = 0
+    q = _randn(rng, 6, 12)
+    idx, sc = pmm.topk_arrays(q, arr, 5, "dot")
+    parity.check_topk(idx, sc, q, dense, 5, "dot", oracle)
+    out = pmm.matmul_array(arr, q)
+    parity.check_matmul(out, dense, q, oracle.matmul(dense, q), np.float32)
+    # Array (fixed-size list) container and int32 offsets
+    fsl = pa.FixedSizeListArray.from_arrays(pa.array(dense.reshape(-1)), 12)
+    idx2, sc2 = pmm.topk_arrays(q, fsl, 5, "dot")
+    assert np.array_equal(idx, idx2)
+    with pytest.raises(RuntimeError, match="ragged"):
+        bad = pa.array([[1.0, 2.0], [1.0, 2.0, 3.0]], type=pa.list_(pa.float32()))
+        pmm.topk_arrays(np.ones((1, 2), np.float32), bad, 1, "dot")
+
+
+def test_integer_columns_are_cast_to_f64(pmm, oracle):
+    import pyarrow as pa
+    arr = pa.array([[1, 2], [3, 4], [5, 6]], type=pa.list_(pa.int64()))
+    out = pmm.matmul_array(arr, arr)
+    assert out.dtype == np.float64
+    assert out.tolist() == [[5, 11, 17], [11, 25, 39], [17, 39, 61]]
+
+
+def test_f16_storage(native, oracle):
+    rng = np.random.default_rng(11)
+    q16, c16 = _randn(rng, 70, 128).astype(np.float16), _randn(rng, 4000, 128).astype(np.float16)
+    q32, c32 = q16.astype(np.float32), c16.astype(np.float32)   # reference contract: exact upcast, then f32 path
+    for metric in ("cosine", "dot", "euclidean"):
+        idx, sc = native.topk(_hm(q16), _hm(c16), 10, metric)
+        frac = parity.check_topk(idx, sc, q32, c32, 10, metric, oracle, working_dtype=np.float32)
+        assert frac > 0.999
+    out = native.matmul(_hm(q16), _hm(c16))
+    assert out.dtype == np.float32
+    parity.check_matmul(out, q32, c32, oracle.matmul(q32, c32), np.float32)
+    # mixed f16 / f32 stays on the f32 path
+    idx, sc = native.topk(_hm(q32), _hm(c16), 10, "cosine")
+    parity.check_topk(idx, sc, q32, c32, 10, "cosine", oracle, working_dtype=np.float32)
+
+
+def test_result_containers(pmm):
+    import pyarrow as pa
+    q = np.eye(3, dtype=np.float32)
+    c = np.eye(3, dtype=np.float32)[[2, 0, 1]]
+    r = pmm._topk(q, c, 2, "cosine")
+    assert r.type == pa.large_list(pa.struct([("index", pa.uint32()), ("score", pa.float64())]))
+    assert [x[0]["index"] for x in r.to_pylist()] == [1, 2, 0]
+    m = pmm._matmul(q, c)
+    assert m.type == pa.list_(pa.float32(), 3)
+    assert pmm._matmul(np.empty((0, 3), np.float32), c).type == pa.large_list(pa.float32())
+    assert len(pmm._topk(np.empty((0, 3)), c, 2, "not-a-metric")) == 0   # empty query short-circuits first
+    assert len(pmm._topk(q, c, 0, "dot").to_pylist()[0]) == 0             # k = 0 -> empty lists
+
+
+def test_resident_corpus_handle(native, oracle):
+    rng = np.random.default_rng(12)
+    q, c = _randn(rng, 50, 64), _randn(rng, 3000, 64)
+    h = native.ResidentCorpus(_hm(c), native.DTYPE_F32)
+    try:
+        for metric in ("cosine", "euclidean", "dot"):
+            idx, sc = h.topk(_hm(q), 10, metric)
+            i2, s2 = native.topk(_hm(q), _hm(c), 10, metric)
+            assert np.array_equal(idx, i2) and np.array_equal(sc, s2)
+    finally:
+        h.close()
+
+
+# ---------------------------------------------------------------------------------------------- device entry points
+def test_device_level_shards_merge(native, oracle):
+    """Two corpus shards on one GPU -> packed candidates with global indices -> merge == unsharded."""
+    import torch
+    rng = np.random.default_rng(13)
+    q, c = _randn(rng, 200, 96), _randn(rng, 6000, 96)
+    dq = torch.from_numpy(q).cuda()
+    k = 20
+    for metric_name, metric in (("cosine", 0), ("dot", 1), ("euclidean", 2)):
+        lists = torch.zeros((2, 200, k), dtype=torch.int64, device="cuda")
+        bounds = [(0, 2500), (2500, 6000)]
+        for s, (lo, hi) in enumerate(bounds):
+            dc = torch.from_numpy(c[lo:hi]).cuda()
+            native.dev_topk(native.dev_matrix(dq.data_ptr(), 200, 96, native.DTYPE_F32),
+                            native.dev_matrix(dc.data_ptr(), hi - lo, 96, native.DTYPE_F32), k, metric,
+                            index_base=lo, cand_ptr=lists[s].data_ptr(),
+                            stream=torch.cuda.current_stream().cuda_stream)
+        idx = torch.empty((200, k), dtype=torch.int32, device="cuda")
+        sc = torch.empty((200, k), dtype=torch.float64, device="cuda")
+        native.dev_merge_candidates(lists.data_ptr(), 2, 200, k, k, metric, idx.data_ptr(), sc.data_ptr(),
+                                    stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        i_np = idx.cpu().numpy().view(np.uint32)
+        parity.check_topk(i_np, sc.cpu().numpy(), q, c, k, metric_name, oracle)
+        i1, s1 = native.topk(_hm(q), _hm(c), k, metric_name)
+        assert np.array_equal(i1, i_np) and np.array_equal(s1, sc.cpu().numpy())
+
+
+def test_device_norms_bit_exact(native, oracle):
+    import torch
+    rng = np.random.default_rng(14)
+    for dt, tdt, code in ((np.float32, torch.float32, 1), (np.float64, torch.float64, 2)):
+        x = _randn(rng, 777, 203, dtype=dt)
+        dx = torch.from_numpy(x).cuda()
+        out = torch.empty(777, dtype=tdt, device="cuda")
+        for squared in (False, True):
+            native.dev_norms(native.dev_matrix(dx.data_ptr(), 777, 203, code), squared, out.data_ptr(),
+                             stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), oracle.norms(x, squared=squared))
+
+
+def test_full_size_c3_properties(native, oracle):
+    """BASELINE.json configs[2] at full size (100k x 1M x 768, k=100): too large for the oracle as a
+    whole, so check size-independent properties plus the oracle on a query sample."""
+    import torch
+    Q, N, D, k = 100_000, 1_000_000, 768, 100
+    g = torch.Generator(device="cuda").manual_seed(42)
+    dq = torch.randn((Q, D), generator=g, device="cuda", dtype=torch.float32)
+    dc = torch.randn((N, D), generator=g, device="cuda", dtype=torch.float32)
+    idx = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    sc = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+    for metric_name, metric in (("dot", 1), ("euclidean", 2)):
+        native.dev_topk(native.dev_matrix(dq.data_ptr(), Q, D, 1), native.dev_matrix(dc.data_ptr(), N, D, 1), k, metric,
+                        index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(),
+                        stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        i64 = idx.long() & 0xFFFFFFFF
+        # sorted best-first, indices in range and unique per row
+        d = sc[:, 1:] - sc[:, :-1]
+        assert bool((d <= 0).all()) if metric == 1 else bool((d >= 0).all())
+        assert int(i64.max()) < N
+        srt, _ = torch.sort(i64, dim=1)
+        assert bool((srt[:, 1:] > srt[:, :-1]).all())
+        # scores recomputed in f64 from the returned indices (a checksum that does not need the oracle)
+        rows = torch.arange(0, Q, 997, device="cuda")
+        cq = dq[rows].double()
+        cc = dc[i64[rows]].double()                              # [r, k, D]
+        dot = torch.einsum("rd,rkd->rk", cq, cc)
+        ref = dot if metric == 1 else torch.sqrt(torch.clamp((cq * cq).sum(1)[:, None] + (cc * cc).sum(2) - 2 * dot, min=0))
+        assert torch.allclose(sc[rows], ref, rtol=1e-5, atol=0)
+        # oracle on a sample of queries against the FULL corpus
+        sample = np.arange(0, Q, Q // 16)[:16]
+        qs = dq[torch.from_numpy(sample).cuda()].cpu().numpy()
+        ch = dc.cpu().numpy()
+        frac = parity.check_topk(idx[torch.from_numpy(sample).cuda()].cpu().numpy().view(np.uint32),
+                                 sc[torch.from_numpy(sample).cuda()].cpu().numpy(), qs, ch, k, metric_name, oracle)
+        assert frac > 0.995
