@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny shapes for a functional check (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--q", type=int, default=None, help="override the query count (profiling runs only)")
+    ap.add_argument("--n", type=int, default=None, help="override the corpus rows per GPU (profiling runs only)")
     ap.add_argument("--metric", default=None)
     ap.add_argument("--k", type=int, default=None)
     args = ap.parse_args()
@@ -190,6 +192,10 @@ def main():
     W = dict(WORKLOAD)
     if args.small:
         W.update(Q=2000, N=50_000)
+    if args.q:
+        W["Q"] = args.q
+    if args.n:
+        W["N"] = args.n
     if args.metric:
         W["metric"] = args.metric
     if args.k:
@@ -260,7 +266,7 @@ def main():
     kname = "tc_topk_tf32x3"
     k_ms = _native.get_stat(kname + "_ms")
     k_launches = _native.get_stat(kname + "_launches")
-    stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps) for n in ("prep", kname, "merge")}
+    stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps) for n in ("prep", kname, "merge", "rescore")}
     _native.set_option("profile", 0)
     value = world * Q / (ms_step / 1000.0)
 

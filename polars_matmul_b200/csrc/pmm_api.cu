@@ -274,9 +274,25 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
     return PMM_OK;
 }
 
-// Tensor-core path on prepared PLANES.
-int topk_tc(const Prepared &q, const Prepared &c, int64_t keff, int metric, int64_t index_base, TopkOut o,
-            cudaStream_t s) {
+RawMatrix raw_of(const pmm_matrix_t &m) {
+    RawMatrix r;
+    r.values = m.values;
+    r.offsets = m.offsets;
+    r.validity = m.validity;
+    r.row_validity = m.row_validity;
+    r.n_rows = m.n_rows;
+    r.dim = m.dim;
+    r.dtype = m.dtype;
+    return r;
+}
+
+// List capacity of the tensor-core filter: at least 8 more candidates than requested are kept, so the
+// exact re-scoring can reorder near-ties across the k-th position.
+int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : keff <= 120 ? 128 : 256; }
+
+// Tensor-core path on prepared PLANES: fused filter -> merge of corpus pieces -> exact re-scoring.
+int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
+            int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -291,21 +307,28 @@ int topk_tc(const Prepared &q, const Prepared &c, int64_t keff, int metric, int6
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
     a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms, g_tc_group.load());
-    a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
-    a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
+    const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
+    const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
+    a.q_aux = q_aux;
+    a.c_aux = c_aux;
     a.index_base = index_base;
     a.metric = metric;
-    a.k = (int)keff;
-    a.kp = keff <= 32 ? 32 : keff <= 64 ? 64 : 128;
-    DevBuf partial;
+    a.kp = tc_list_capacity(keff);
+    a.k = a.kp;
+    DevBuf partial, kept;
     CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * TC_TILE_M * a.kp * 8, s));
+    CUDA_TRY(kept.alloc((size_t)q.n_rows * a.kp * 8, s));
     a.partial = partial.as<uint64_t>();
     cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : "tc_topk_tf32x3", s, [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
+    const bool higher = metric != PMM_METRIC_EUCLIDEAN;
     CUDA_TRY(launch_counted("merge", s, [&] {
-        return launch_merge_tiles(a.partial, a.sched, a.kp, q.n_rows, (int)keff, metric != PMM_METRIC_EUCLIDEAN, o.index,
-                                  o.score, o.cand, s);
+        return launch_merge_tiles(a.partial, a.sched, a.kp, q.n_rows, a.kp, higher, nullptr, nullptr, kept.as<uint64_t>(), s);
+    }));
+    CUDA_TRY(launch_counted("rescore", s, [&] {
+        return launch_rescore(kept.as<uint64_t>(), a.kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base,
+                              (int)keff, o.index, o.score, o.cand, s);
     }));
     return PMM_OK;
 }
@@ -326,6 +349,8 @@ PathChoice choose_path(int q_dtype, int c_dtype, int64_t keff) {
 // All pointers device-resident. `pc_corpus`: an already prepared corpus or NULL.
 int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared *pc_corpus, int corpus_dtype, int64_t k,
                   int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
+    // dc: the raw corpus column on the device (always needed: the exact re-scoring reads it);
+    // pc_corpus: optional operands already prepared from it (resident corpus handle).
     const int64_t N = pc_corpus ? pc_corpus->n_rows : dc->n_rows;
     const int64_t keff = k < N ? k : N;
     if (keff == 0) return PMM_OK;
@@ -346,9 +371,9 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
         if (rc) return rc;
         c = &c_local;
     }
-    rc = pc.tc ? topk_tc(q, *c, keff, metric, index_base, o, s) : topk_generic(q, *c, keff, metric, index_base, o, s);
+    rc = pc.tc ? topk_tc(q, *c, *dq, *dc, keff, metric, index_base, o, s) : topk_generic(q, *c, keff, metric, index_base, o, s);
     if (rc) return rc;
-    if (dq->offsets || (dc && dc->offsets)) return finish_error_flag(err.as<int>(), s);
+    if (dq->offsets || dc->offsets) return finish_error_flag(err.as<int>(), s);
     return PMM_OK;
 }
 
@@ -472,6 +497,7 @@ int list_dim_check(const pmm_matrix_t *m, const char *) {
 }  // namespace
 
 struct pmm_corpus {
+    Uploaded raw;   // the raw column stays on the device: the exact re-scoring reads candidate rows from it
     Prepared prep;
     int device = 0;
     int storage_dtype = PMM_DTYPE_F32;
@@ -668,9 +694,12 @@ int pmm_corpus_create(const pmm_matrix_t *corpus, int32_t query_dtype, pmm_corpu
     if ((rc = list_dim_check(corpus, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
     cudaStream_t s = host_stream();
-    Uploaded uc;
-    if ((rc = upload(corpus, s, &uc))) return rc;
     pmm_corpus *h = new pmm_corpus();
+    Uploaded &uc = h->raw;
+    if ((rc = upload(corpus, s, &uc))) {
+        delete h;
+        return rc;
+    }
     cudaGetDevice(&h->device);
     h->storage_dtype = corpus->dtype;
     h->query_dtype = query_dtype;
@@ -729,7 +758,7 @@ int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *corpus, int
     CUDA_TRY(d_idx.alloc(cnt * 4, s));
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
-    if ((rc = dev_topk_impl(&uq.dm, nullptr, &corpus->prep, corpus->storage_dtype, k, m, 0, o, s))) return rc;
+    if ((rc = dev_topk_impl(&uq.dm, &corpus->raw.dm, &corpus->prep, corpus->storage_dtype, k, m, 0, o, s))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
     stat_add("d2h_bytes", (double)cnt * 12);

@@ -48,6 +48,20 @@ cudaError_t launch_select_f64(const double *scores, int64_t ld, int64_t nq, int6
 cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t list_stride, int64_t row_stride,
                                  int64_t nq, int k_in, int k_out, bool higher, uint32_t *out_idx,
                                  double *out_score, uint64_t *out_cand, cudaStream_t s);
+// ---- exact re-scoring of kept candidates (pmm_rescore.cu) ---------------------------------------------
+struct RawMatrix {               // a device-resident column in Arrow layout (pmm_matrix_t with device pointers)
+    const void *values;
+    const int64_t *offsets;
+    const uint8_t *validity;
+    const uint8_t *row_validity;
+    int64_t n_rows, dim;
+    int dtype;                   // 0 f16, 1 f32
+};
+// cand [n_queries][kp_in] packed candidates (approximate keys, global indices) -> exact top-k_out.
+cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
+                           const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
+                           uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s);
+
 // ---- tensor-core path (pmm_tc_kernels.cu) ----------------------------------------------------------
 constexpr int TC_TILE_M = 128;   // query rows per CTA tile
 constexpr int TC_TILE_N = 256;   // corpus rows per tile
@@ -89,8 +103,8 @@ struct TcArgs {
     const float *q_aux, *c_aux;    // norms (cosine) / squared norms (euclidean) / NULL (dot)
     int64_t index_base;
     int metric;
-    int k;                         // <= 128
-    int kp;                        // 32, 64 or 128
+    int k;                         // candidates kept per query and piece: the list position that sets the threshold (<= kp)
+    int kp;                        // list capacity: 32, 64, 128 or 256
     uint64_t *partial;             // [sched.total_slots()][128][kp]
     // matmul mode
     float *out;                    // [nq x n] row-major

@@ -72,9 +72,11 @@ cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t
                                  int64_t nq, int k_in, int k_out, bool higher, uint32_t *out_idx,
                                  double *out_score, uint64_t *out_cand, cudaStream_t s) {
     if (nq <= 0 || k_out <= 0) return cudaSuccess;
-    if (k_in > 128 || k_out > k_in) return cudaErrorInvalidValue;
+    if (k_in > 256 || k_out > k_in) return cudaErrorInvalidValue;
     unsigned grid = (unsigned)((nq + 7) / 8);
-    if (k_in <= 32)
+    if (k_in > 128)
+        merge_regular_kernel<8><<<grid, 256, 0, s>>>(lists, (int)n_lists, list_stride, row_stride, nq, k_in, k_out, higher, out_idx, out_score, out_cand);
+    else if (k_in <= 32)
         merge_regular_kernel<1><<<grid, 256, 0, s>>>(lists, (int)n_lists, list_stride, row_stride, nq, k_in, k_out, higher, out_idx, out_score, out_cand);
     else if (k_in <= 64)
         merge_regular_kernel<2><<<grid, 256, 0, s>>>(lists, (int)n_lists, list_stride, row_stride, nq, k_in, k_out, higher, out_idx, out_score, out_cand);
@@ -93,6 +95,8 @@ cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int kp, 
         merge_tiles_kernel<2><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 128)
         merge_tiles_kernel<4><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
+    else if (kp == 256)
+        merge_tiles_kernel<8><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

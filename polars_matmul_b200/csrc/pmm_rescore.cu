@@ -1,0 +1,146 @@
+// pmm_rescore.cu — exact f32 re-scoring of the candidates the tensor-core kernel kept.
+//
+// Why: tcgen05.mma accumulates in f32 with truncation; over the 3 x D/8 accumulate steps of a 3xTF32
+// contraction the bias reaches ~1e-5 relative at D = 768 (measured), i.e. the stated
+// tolerance.  So the fused kernel is used as a FILTER that keeps KP >= k + 8 candidates per query
+// under its approximate scores, and this kernel recomputes the score of each kept candidate with the
+// reference's arithmetic: one FMA per element, sequential in the vector dimension
+// (src/metrics.rs:204-255 as restated by the oracle), then the metric pass of src/metrics.rs:323-362
+// with the exact norms from pmm_prep.cu, then the final best-first order of src/topk.rs:42-75 under
+// (score, lower index first).  Output scores are therefore bit-identical to the SIMT path's.
+//
+// One block per query, one thread per candidate; the query row sits in shared memory, each thread
+// streams its candidate's corpus row (L1 keeps the sector remainder between iterations).
+#include "pmm_common.cuh"
+#include "pmm_kernels.h"
+
+namespace pmm {
+
+template <typename SRC> struct RsLoad;
+template <> struct RsLoad<float> { static __device__ __forceinline__ float get(const void *v, int64_t p) { return __ldg((const float *)v + p); } };
+template <> struct RsLoad<__half> { static __device__ __forceinline__ float get(const void *v, int64_t p) { return __half2float(__ldg((const __half *)v + p)); } };
+
+template <typename SRC>
+__device__ __forceinline__ float raw_fetch(const RawMatrix &m, int64_t base, int64_t len, int64_t i) {
+    if (i >= len) return 0.0f;
+    const int64_t p = base + i;
+    if (m.validity && !((m.validity[p >> 3] >> (p & 7)) & 1)) return 0.0f;
+    return RsLoad<SRC>::get(m.values, p);
+}
+
+__device__ __forceinline__ void raw_row(const RawMatrix &m, int64_t row, int64_t &base, int64_t &len) {
+    if (m.offsets) {
+        base = m.offsets[row];
+        len = m.offsets[row + 1] - base;
+        if (len > m.dim) len = m.dim;
+    } else {
+        base = row * m.dim;
+        len = m.dim;
+    }
+    if (m.row_validity && !((m.row_validity[row >> 3] >> (row & 7)) & 1)) len = 0;
+}
+
+template <typename CSRC, int NT>
+__global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict__ cand, int kp_in, RawMatrix qm,
+                                                     RawMatrix cm, const float *__restrict__ q_aux,
+                                                     const float *__restrict__ c_aux, int metric,
+                                                     int64_t index_base, int k_out, uint32_t *out_idx,
+                                                     double *out_score, uint64_t *out_cand) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t *sortbuf = (uint64_t *)rs_smem;            // NT entries
+    float *qs = (float *)(rs_smem + NT * 8);            // dim floats
+    const int64_t q = blockIdx.x;
+    const int t = threadIdx.x;
+    const int dim = (int)qm.dim;
+    {
+        int64_t qb, ql;
+        raw_row(qm, q, qb, ql);
+        for (int i = t; i < dim; i += NT)
+            qs[i] = qm.dtype == 0 ? raw_fetch<__half>(qm, qb, ql, i) : raw_fetch<float>(qm, qb, ql, i);
+    }
+    __syncthreads();
+    const bool higher = higher_is_better(metric);
+    uint64_t packed = 0ull;
+    const uint64_t c = (t < kp_in) ? cand[q * kp_in + t] : 0ull;
+    if (c != 0ull) {
+        const uint32_t gidx = candidate_index(c);
+        const int64_t row = (int64_t)gidx - index_base;
+        int64_t cb, cl;
+        raw_row(cm, row, cb, cl);
+        float acc = 0.0f;
+        const bool fast = sizeof(CSRC) == 4 && !cm.validity && cl == dim && (dim & 3) == 0 &&
+                          ((((uintptr_t)cm.values) + (size_t)cb * 4) & 15) == 0;
+        if (fast) {
+            const float4 *rp = (const float4 *)((const float *)cm.values + cb);
+#pragma unroll 4
+            for (int i = 0; i < dim / 4; ++i) {
+                const float4 v = __ldg(rp + i);
+                acc = __fmaf_rn(qs[4 * i + 0], v.x, acc);
+                acc = __fmaf_rn(qs[4 * i + 1], v.y, acc);
+                acc = __fmaf_rn(qs[4 * i + 2], v.z, acc);
+                acc = __fmaf_rn(qs[4 * i + 3], v.w, acc);
+            }
+        } else {
+            for (int i = 0; i < dim; ++i) acc = __fmaf_rn(qs[i], raw_fetch<CSRC>(cm, cb, cl, i), acc);
+        }
+        float sc = acc;
+        if (metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN) sc = metric_finish(acc, metric, q_aux[q], c_aux[row]);
+        packed = pack_candidate(score_key(sc, higher), gidx);
+    }
+    sortbuf[t] = packed;
+    __syncthreads();
+    for (int size = 2; size <= NT; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int p = t ^ stride;
+            if (p > t) {
+                const bool desc = (t & size) == 0;
+                const uint64_t a = sortbuf[t], b = sortbuf[p];
+                if ((a > b) != desc) { sortbuf[t] = b; sortbuf[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (t < k_out) {
+        const uint64_t r = sortbuf[t];
+        if (out_idx) out_idx[q * k_out + t] = candidate_index(r);
+        if (out_score) out_score[q * k_out + t] = (double)key_score(candidate_key(r), higher);
+        if (out_cand) out_cand[q * k_out + t] = r;
+    }
+}
+
+template <typename CSRC>
+static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
+                                    const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
+                                    uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
+    const unsigned grid = (unsigned)qm.n_rows;
+    const size_t smem_q = (size_t)qm.dim * 4;
+#define PMM_RS(NT)                                                                                                  \
+    {                                                                                                               \
+        size_t smem = NT * 8 + smem_q;                                                                              \
+        if (smem > 48 * 1024) {                                                                                     \
+            cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                         \
+        }                                                                                                           \
+        rescore_kernel<CSRC, NT><<<grid, NT, smem, s>>>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, \
+                                                        out_idx, out_score, out_cand);                              \
+    }
+    if (kp_in <= 32) PMM_RS(32)
+    else if (kp_in <= 64) PMM_RS(64)
+    else if (kp_in <= 128) PMM_RS(128)
+    else if (kp_in <= 256) PMM_RS(256)
+    else return cudaErrorInvalidValue;
+#undef PMM_RS
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
+                           const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
+                           uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
+    if (qm.n_rows <= 0 || k_out <= 0) return cudaSuccess;
+    if (qm.dim * 4 > 200 * 1024) return cudaErrorInvalidValue;  // query row must fit shared memory
+    if (cm.dtype == 0)
+        return launch_rescore_t<__half>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, s);
+    return launch_rescore_t<float>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, s);
+}
+
+}  // namespace pmm

@@ -455,15 +455,17 @@ TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_sms, int gro
 }
 
 cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s) {
-    if (a.k < 1 || a.k > 128) return cudaErrorInvalidValue;
+    if (a.k < 1 || a.k > a.kp) return cudaErrorInvalidValue;
     if (a.f16) {
         if (a.kp == 32) return launch_t<true, EPI_TOPK, 1>(a, s);
         if (a.kp == 64) return launch_t<true, EPI_TOPK, 2>(a, s);
         if (a.kp == 128) return launch_t<true, EPI_TOPK, 4>(a, s);
+        if (a.kp == 256) return launch_t<true, EPI_TOPK, 8>(a, s);
     } else {
         if (a.kp == 32) return launch_t<false, EPI_TOPK, 1>(a, s);
         if (a.kp == 64) return launch_t<false, EPI_TOPK, 2>(a, s);
         if (a.kp == 128) return launch_t<false, EPI_TOPK, 4>(a, s);
+        if (a.kp == 256) return launch_t<false, EPI_TOPK, 8>(a, s);
     }
     return cudaErrorInvalidValue;
 }
