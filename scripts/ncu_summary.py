@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Summarises an .ncu-rep (one kernel launch) into a small markdown table for profiles/."""
+import csv
+import subprocess
+import sys
+
+rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "sm__cycles_active.avg",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+]
+with open(out, "w") as f:
+    f.write(f"# {title}\n\nSource: `{rep}` (`ncu --set full --clock-control none --import-source on`, one launch).\n\n")
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        f.write(f"Kernel: `{name[:120]}`\n\n| metric | value | unit |\n|---|---|---|\n")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                f.write(f"| {k} | {r[i]} | {units[i]} |\n")
+        f.write("\n")
+print(open(out).read())
