@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{4};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{1}, g_tc_rowb{128};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -306,6 +306,7 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.nq = q.n_rows;
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
+    a.rowb = g_tc_rowb.load();
     a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms, g_tc_group.load());
     const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
@@ -402,6 +403,7 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         a.nq = Q;
         a.n = N;
         a.f16 = pc.mode == PREP_F16 ? 1 : 0;
+        a.rowb = g_tc_rowb.load();
         a.sched = make_tc_schedule(Q, N, di.num_sms, g_tc_group.load());
         a.metric = PMM_METRIC_DOT;
         a.k = 1;
@@ -553,6 +555,7 @@ int pmm_set_option(const char *key, int64_t value) {
     if (k == "force_generic") g_force_generic.store((int)value);
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 1 ? 1 : (int)value);
+    else if (k == "tc_rowb") g_tc_rowb.store(value == 64 ? 64 : 128);
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
     else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
     return PMM_OK;

@@ -98,6 +98,7 @@ struct TcArgs {
     int64_t q_rows_pad, c_rows_pad, dim_pad;
     int64_t nq, n;                 // real rows
     int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
+    int rowb;                      // 128 or 64: bytes of K per smem row (pipeline: 2 or 4 stages for f32)
     TcSchedule sched;
     // top-k mode
     const float *q_aux, *c_aux;    // norms (cosine) / squared norms (euclidean) / NULL (dot)

@@ -102,13 +102,15 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
 
 // Shared-memory matrix descriptor: K-major tile, 128-byte rows, SWIZZLE_128B (8-row x 128 B atoms,
 // 1024 B between atoms along M/N). Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor).
+// ROWB = 128: SWIZZLE_128B (layout type 2); ROWB = 64: SWIZZLE_64B (layout type 4); 8-row atoms.
+template <int ROWB>
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);        // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for SW128 K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;               // stride byte offset (next 8-row atom), bits [32,46)
     d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;           // layout type
     return d;
 }
 // Instruction descriptor (cute InstrDescriptor): f32 accumulate, K-major A and B.

@@ -40,17 +40,20 @@ constexpr int NUM_THREADS = 192;
 constexpr int STAGE_SLOTS = 16;          // staged candidates per row before a flush is forced
 constexpr int FLUSH_AT = STAGE_SLOTS - 8;  // checked every 8 scores
 
-template <bool F16>
+// ROWB = bytes of K per shared-memory row (= the swizzle span): 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
+// Smaller rows give twice as many, half as large pipeline stages in the same shared memory.
+template <bool F16, int ROWB>
 struct TcCfg {
     static constexpr int PLANES = F16 ? 1 : 2;
-    static constexpr int BK = F16 ? 64 : 32;       // elements per 128-byte smem row
-    static constexpr int KSTEPS = 4;               // 32 bytes of K per tcgen05.mma
-    static constexpr int A_BYTES = BM * 128;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int BK = ROWB / (F16 ? 2 : 4);  // elements of K per stage
+    static constexpr int KSTEPS = ROWB / 32;         // 32 bytes of K per tcgen05.mma
+    static constexpr int A_BYTES = BM * ROWB;
+    static constexpr int B_BYTES = BN * ROWB;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = F16 ? 4 : 2;
+    static constexpr int STAGES = (F16 ? 4 : 2) * (128 / ROWB);
     static constexpr int STAGING_BYTES = STAGE_SLOTS * BM * 8;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+    static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of the tile
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + AUX_BYTES + 256 + 1024;
 };
 
 struct TcKParams {
@@ -89,9 +92,11 @@ __device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int 
 }
 
 // Merge the staged candidates of the rows in `rows` (bit i = lane i's row) into their lists.
+// thr = packed k-th best of the row's list (0 while the list is not full); thr_f = its filter value
+// as a float, NaN while the list is not full (so that `!(f <= thr_f)` admits everything).
 template <int R>
 __device__ __forceinline__ void flush_rows(unsigned rows, uint64_t *stage_buf, uint64_t *list_base /* lane group's 32 lists */,
-                                           int row0, int lane, int k, uint64_t &thr, int &cnt) {
+                                           int row0, int lane, int k, uint64_t &thr, float &thr_f, int &cnt) {
     constexpr int KP = 32 * R;
     __syncwarp();
     while (rows) {
@@ -118,23 +123,71 @@ __device__ __forceinline__ void flush_rows(unsigned rows, uint64_t *stage_buf, u
         const uint64_t kth = __shfl_sync(0xffffffffu, kreg, (k - 1) & 31);
         if (lane == src) {
             thr = kth;
+            thr_f = kth == 0ull ? __uint_as_float(0x7fc00000u) : key_score(candidate_key(kth), true);
             cnt = 0;
         }
     }
     __syncwarp();
 }
 
-template <bool F16, int EPI, int R>
+// Filter value of one accumulator: a float that is LARGER for a BETTER candidate of this query row and
+// monotone in the reference's score (the exact score is recomputed later by pmm_rescore.cu):
+//   dot       f = acc
+//   cosine    f = acc * inv_cn[col] * rowmul          (row constant 1/qn dropped; zero norms -> 0)
+//   euclidean f = -max((csq[col] - 2 acc) + qsq, 0)   (sqrt dropped)
+template <int METRIC>
+__device__ __forceinline__ float filter_value(float acc, float aux, float rowc) {
+    if (METRIC == METRIC_COSINE) return (acc * aux) * rowc;
+    if (METRIC == METRIC_EUCLIDEAN) return -fmaxf(fmaf(-2.0f, acc, aux) + rowc, 0.0f);
+    return acc;
+}
+
+// One 32-column chunk of the accumulator tile for this thread's row.
+template <int METRIC, int R>
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const float *aux_s /* 32 floats, smem */, float rowc,
+                                             int64_t col0, int64_t n, int64_t index_base, uint64_t *stage_buf,
+                                             uint64_t *list_base, int row, int row0, int lane, int k, uint64_t &thr,
+                                             float &thr_f, int &cnt) {
+#pragma unroll
+    for (int j8 = 0; j8 < 32; j8 += 8) {
+        float aux[8];
+        if (METRIC != METRIC_DOT) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(aux_s + j8);
+            const float4 a1 = *reinterpret_cast<const float4 *>(aux_s + j8 + 4);
+            aux[0] = a0.x; aux[1] = a0.y; aux[2] = a0.z; aux[3] = a0.w;
+            aux[4] = a1.x; aux[5] = a1.y; aux[6] = a1.z; aux[7] = a1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float f = filter_value<METRIC>(__uint_as_float(v[j8 + j]), METRIC != METRIC_DOT ? aux[j] : 0.0f, rowc);
+            if (!(f <= thr_f)) {  // rare: better than the row's k-th best (or the list is not full, or NaN)
+                const int64_t col = col0 + j8 + j;
+                if (col < n) {
+                    const uint64_t cand = pack_candidate(score_key(f, true), (uint32_t)(index_base + col));
+                    if (cand > thr) {
+                        stage_buf[cnt * BM + row] = cand;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+        const unsigned over = __ballot_sync(0xffffffffu, cnt > FLUSH_AT);
+        if (over) flush_rows<R>(over, stage_buf, list_base, row0, lane, k, thr, thr_f, cnt);
+    }
+}
+
+template <bool F16, int EPI, int R, int ROWB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
           const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo, const TcKParams p) {
-    typedef TcCfg<F16> Cfg;
+    typedef TcCfg<F16, ROWB> Cfg;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
     uint64_t *stage_buf = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    float *aux_tiles = (float *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + Cfg::AUX_BYTES);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -226,11 +279,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
 #pragma unroll
                         for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
                             const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-                            const uint64_t dah = umma_smem_desc(a_hi + ks * 32), dbh = umma_smem_desc(b_hi + ks * 32);
+                            const uint64_t dah = umma_smem_desc<ROWB>(a_hi + ks * 32), dbh = umma_smem_desc<ROWB>(b_hi + ks * 32);
                             if (F16) {
                                 umma<1, true>(tmem_d, dah, dbh, idesc, acc);
                             } else {
-                                const uint64_t dal = umma_smem_desc(a_lo + ks * 32), dbl = umma_smem_desc(b_lo + ks * 32);
+                                const uint64_t dal = umma_smem_desc<ROWB>(a_lo + ks * 32), dbl = umma_smem_desc<ROWB>(b_lo + ks * 32);
                                 umma<1, false>(tmem_d, dal, dbh, idesc, acc);  // small terms first
                                 umma<1, false>(tmem_d, dah, dbl, idesc, 1u);
                                 umma<1, false>(tmem_d, dah, dbh, idesc, 1u);
@@ -253,8 +306,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         const int lg = warp & 3;          // TMEM lane group this warp may read
         const int row0 = lg * 32;         // first tile row of the warp
         const int row = row0 + lane;      // tile row owned by this thread
-        const bool higher = higher_is_better(p.metric);
-        const bool need_aux = (p.metric == METRIC_COSINE || p.metric == METRIC_EUCLIDEAN);
+        float *aux_s = aux_tiles + lg * BN;
         int abuf = 0;
         uint32_t aphase = 0;
         for (int it = 0; it < total_rounds; ++it) {
@@ -263,20 +315,32 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
             const int64_t qrow = (int64_t)m_tile * BM + row;
             uint64_t thr = 0ull;
+            float thr_f = __uint_as_float(0x7fc00000u);
             int cnt = 0;
-            float qa = 0.0f;
+            float rowc = 0.0f;
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
                 list_base = p.partial + (slot * BM + row0) * KP;
                 for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
-                if (need_aux) qa = p.q_aux[qrow];  // q_aux is padded to the tile grid
+                // q_aux is padded to the tile grid. cosine: 1 unless the query norm is ~0; euclidean: |q|^2
+                if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > 1e-6f ? 1.0f : 0.0f;
+                if (p.metric == METRIC_EUCLIDEAN) rowc = p.q_aux[qrow];
                 __syncwarp();
             }
             for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                const int64_t col_tile = (int64_t)nt * BN;
+                if (EPI == EPI_TOPK && p.metric != METRIC_DOT) {  // stage this tile's corpus aux values (per warp)
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < BN / 32; ++i) {
+                        const float a = __ldg(p.c_aux + col_tile + i * 32 + lane);  // c_aux is padded to the tile grid
+                        aux_s[i * 32 + lane] = p.metric == METRIC_COSINE ? (a > 1e-6f ? __frcp_rn(a) : 0.0f) : a;
+                    }
+                    __syncwarp();
+                }
                 mbar_wait(tfull_bar(abuf), aphase);
                 tc_fence_after();
-                const int64_t col_tile = (int64_t)nt * BN;
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     uint32_t v[32];
@@ -303,24 +367,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                                     if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
                             }
                         }
+                    } else if (p.metric == METRIC_DOT) {
+                        filter_chunk<METRIC_DOT, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf, list_base, row,
+                                                    row0, lane, p.k, thr, thr_f, cnt);
+                    } else if (p.metric == METRIC_COSINE) {
+                        filter_chunk<METRIC_COSINE, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf, list_base,
+                                                       row, row0, lane, p.k, thr, thr_f, cnt);
                     } else {
-#pragma unroll
-                        for (int j8 = 0; j8 < 32; j8 += 8) {
-#pragma unroll
-                            for (int j = j8; j < j8 + 8; ++j) {
-                                const int64_t col = col0 + j;
-                                float sc = __uint_as_float(v[j]);
-                                if (need_aux) sc = metric_finish(sc, p.metric, qa, __ldg(p.c_aux + col));
-                                uint64_t cand = pack_candidate(score_key(sc, higher), (uint32_t)(p.index_base + col));
-                                if (col >= p.n) cand = 0ull;  // tile padding
-                                if (cand > thr) {
-                                    stage_buf[cnt * BM + row] = cand;
-                                    ++cnt;
-                                }
-                            }
-                            const unsigned over = __ballot_sync(0xffffffffu, cnt > FLUSH_AT);
-                            if (over) flush_rows<R>(over, stage_buf, list_base, row0, lane, p.k, thr, cnt);
-                        }
+                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf,
+                                                          list_base, row, row0, lane, p.k, thr, thr_f, cnt);
                     }
                 }
                 abuf ^= 1;
@@ -328,7 +383,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             }
             if (EPI == EPI_TOPK) {
                 const unsigned pending = __ballot_sync(0xffffffffu, cnt > 0);
-                if (pending) flush_rows<R>(pending, stage_buf, list_base, row0, lane, p.k, thr, cnt);
+                if (pending) flush_rows<R>(pending, stage_buf, list_base, row0, lane, p.k, thr, thr_f, cnt);
             }
         }
     }
@@ -364,7 +419,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // [rows x cols] row-major plane, box = box_rows x 128 bytes, SWIZZLE_128B.
-bool make_plane_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int box_rows, bool f16) {
+bool make_plane_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int box_rows, bool f16, int rowb) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled not available from the driver");
@@ -373,10 +428,11 @@ bool make_plane_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols
     const int esz = f16 ? 2 : 4;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)cols * esz};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(rowb / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base),
-                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -385,18 +441,18 @@ bool make_plane_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols
     return true;
 }
 
-template <bool F16, int EPI, int R>
-cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
-    typedef TcCfg<F16> Cfg;
+template <bool F16, int EPI, int R, int ROWB>
+cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
+    typedef TcCfg<F16, ROWB> Cfg;
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
-    if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, BN, F16)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, BN, F16, ROWB)) return cudaErrorInvalidValue;
     if (F16) {
         tq_lo = tq_hi;
         tc_lo = tc_hi;
     } else {
-        if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false)) return cudaErrorInvalidValue;
-        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, BN, false)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false, ROWB)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, BN, false, ROWB)) return cudaErrorInvalidValue;
     }
     TcKParams p;
     p.sched = a.sched;
@@ -410,11 +466,18 @@ cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
     p.k = a.k;
     p.partial = a.partial;
     p.out = a.out;
-    auto kern = tc_kernel<F16, EPI, R>;
+    auto kern = tc_kernel<F16, EPI, R, ROWB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     kern<<<a.sched.num_ctas, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(tq_hi, tq_lo, tc_hi, tc_lo, p);
     return cudaGetLastError();
+}
+
+template <bool F16, int EPI, int R>
+cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
+    // the narrow-row variant needs dim_pad to be a multiple of its (smaller) K block: always true
+    if (a.rowb == 64) return launch_t2<F16, EPI, R, 64>(a, s);
+    return launch_t2<F16, EPI, R, 128>(a, s);
 }
 
 }  // namespace
