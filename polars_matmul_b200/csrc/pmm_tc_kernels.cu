@@ -37,8 +37,9 @@ namespace {
 constexpr int BM = TC_TILE_M;
 constexpr int BN = TC_TILE_N;
 constexpr int NUM_THREADS = 192;
-constexpr int STAGE_SLOTS = 16;          // staged candidates per row before a flush is forced
-constexpr int FLUSH_AT = STAGE_SLOTS - 8;  // checked every 8 scores
+constexpr int STAGE_SLOTS = 24;            // staged candidates per row (shared memory)
+constexpr int EMERGENCY_AT = STAGE_SLOTS - 8;  // mid-tile flush only above this (checked every 8 scores)
+constexpr int FLUSH_AT = 8;                // end-of-tile flush above this: happens AFTER the TMEM buffer was released
 
 // ROWB = bytes of K per shared-memory row (= the swizzle span): 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
 // Smaller rows give twice as many, half as large pipeline stages in the same shared memory.
@@ -103,15 +104,15 @@ __device__ __forceinline__ void flush_rows(unsigned rows, uint64_t *stage_buf, u
         const int src = __ffs(rows) - 1;
         rows &= rows - 1;
         const int c = __shfl_sync(0xffffffffu, cnt, src);
-        uint64_t v = (lane < c) ? stage_buf[lane * BM + row0 + src] : 0ull;
-        v = warp_sort_desc(v, lane);
         uint64_t *list = list_base + (int64_t)src * KP;
         uint64_t L[R], M[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < R; ++r) {  // issue the list loads first: their L2 latency overlaps the sort below
             L[r] = list[32 * r + lane];
             M[r] = 0ull;
         }
+        uint64_t v = (lane < c) ? stage_buf[lane * BM + row0 + src] : 0ull;
+        v = warp_sort_desc(v, lane);
         M[R - 1] = __shfl_sync(0xffffffffu, v, 31 - lane);  // staged list, reversed, sits at the tail
         warp_merge_topk_desc<R>(L, M, lane);
 #pragma unroll
@@ -171,7 +172,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
                 }
             }
         }
-        const unsigned over = __ballot_sync(0xffffffffu, cnt > FLUSH_AT);
+        const unsigned over = __ballot_sync(0xffffffffu, cnt > EMERGENCY_AT);
         if (over) flush_rows<R>(over, stage_buf, list_base, row0, lane, k, thr, thr_f, cnt);
     }
 }
@@ -377,6 +378,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf,
                                                           list_base, row, row0, lane, p.k, thr, thr_f, cnt);
                     }
+                }
+                if (EPI == EPI_TOPK) {  // regular flush: the TMEM buffer is already back with the MMA warp
+                    const unsigned due = __ballot_sync(0xffffffffu, cnt > FLUSH_AT);
+                    if (due) flush_rows<R>(due, stage_buf, list_base, row0, lane, p.k, thr, thr_f, cnt);
                 }
                 abuf ^= 1;
                 if (abuf == 0) aphase ^= 1u;
