@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
                                                      double *out_score, uint64_t *out_cand) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t *sortbuf = (uint64_t *)rs_smem;            // NT entries
-    float *qs = (float *)(rs_smem + NT * 8);            // dim floats
+    float *qs = (float *)(rs_smem + NT * 8);            // dim floats, then one 32x33 transpose tile per warp
     const int64_t q = blockIdx.x;
     const int t = threadIdx.x;
     const int dim = (int)qm.dim;
@@ -60,29 +60,35 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     }
     __syncthreads();
     const bool higher = higher_is_better(metric);
-    uint64_t packed = 0ull;
+    const int lane = t & 31, wrp = t >> 5;
+    float (*tile)[33] = (float (*)[33])(rs_smem + NT * 8 + (size_t)((dim + 3) & ~3) * 4 + (size_t)wrp * 32 * 33 * 4);
     const uint64_t c = (t < kp_in) ? cand[q * kp_in + t] : 0ull;
-    if (c != 0ull) {
-        const uint32_t gidx = candidate_index(c);
-        const int64_t row = (int64_t)gidx - index_base;
-        int64_t cb, cl;
-        raw_row(cm, row, cb, cl);
-        float acc = 0.0f;
-        const bool fast = sizeof(CSRC) == 4 && !cm.validity && cl == dim && (dim & 3) == 0 &&
-                          ((((uintptr_t)cm.values) + (size_t)cb * 4) & 15) == 0;
-        if (fast) {
-            const float4 *rp = (const float4 *)((const float *)cm.values + cb);
-#pragma unroll 4
-            for (int i = 0; i < dim / 4; ++i) {
-                const float4 v = __ldg(rp + i);
-                acc = __fmaf_rn(qs[4 * i + 0], v.x, acc);
-                acc = __fmaf_rn(qs[4 * i + 1], v.y, acc);
-                acc = __fmaf_rn(qs[4 * i + 2], v.z, acc);
-                acc = __fmaf_rn(qs[4 * i + 3], v.w, acc);
-            }
-        } else {
-            for (int i = 0; i < dim; ++i) acc = __fmaf_rn(qs[i], raw_fetch<CSRC>(cm, cb, cl, i), acc);
+    const uint32_t gidx = candidate_index(c);
+    const int64_t row = (int64_t)gidx - index_base;
+    int64_t cb = 0, cl = 0;
+    if (c != 0ull) raw_row(cm, row, cb, cl);
+    // Each warp walks the vector dimension 32 elements at a time: candidate rows are read with coalesced
+    // 128-byte requests (lane = element), transposed through shared memory, and every thread then
+    // accumulates ITS candidate sequentially in d — the reference's order.
+    float acc = 0.0f;
+    for (int d0 = 0; d0 < dim; d0 += 32) {
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
+            tile[i][lane] = raw_fetch<CSRC>(cm, cbi, cli, d0 + lane);
         }
+        __syncwarp();
+        const int jn = dim - d0 < 32 ? dim - d0 : 32;
+        if (jn == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = __fmaf_rn(qs[d0 + j], tile[lane][j], acc);
+        } else {
+            for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile[lane][j], acc);
+        }
+        __syncwarp();
+    }
+    uint64_t packed = 0ull;
+    if (c != 0ull) {
         float sc = acc;
         if (metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN) sc = metric_finish(acc, metric, q_aux[q], c_aux[row]);
         packed = pack_candidate(score_key(sc, higher), gidx);
@@ -113,10 +119,10 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
                                     const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
                                     uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
     const unsigned grid = (unsigned)qm.n_rows;
-    const size_t smem_q = (size_t)qm.dim * 4;
+    const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
 #define PMM_RS(NT)                                                                                                  \
     {                                                                                                               \
-        size_t smem = NT * 8 + smem_q;                                                                              \
+        size_t smem = NT * 8 + smem_q + (size_t)(NT / 32) * 32 * 33 * 4;                                                                              \
         if (smem > 48 * 1024) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                         \
@@ -137,7 +143,7 @@ cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm,
                            const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
                            uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
     if (qm.n_rows <= 0 || k_out <= 0) return cudaSuccess;
-    if (qm.dim * 4 > 200 * 1024) return cudaErrorInvalidValue;  // query row must fit shared memory
+    if (qm.dim * 4 > 160 * 1024) return cudaErrorInvalidValue;  // query row must fit shared memory
     if (cm.dtype == 0)
         return launch_rescore_t<__half>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, s);
     return launch_rescore_t<float>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, s);

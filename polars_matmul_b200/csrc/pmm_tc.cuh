@@ -70,6 +70,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void *
         : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async group of the issuing thread). Out-of-bounds parts of the
+// box are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ------------------------------------------------------------------------------
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t cols) {

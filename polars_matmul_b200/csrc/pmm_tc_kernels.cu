@@ -54,7 +54,9 @@ struct TcCfg {
     static constexpr int STAGES = (F16 ? 4 : 2) * (128 / ROWB);
     static constexpr int STAGING_BYTES = STAGE_SLOTS * BM * 8;
     static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of the tile
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + AUX_BYTES + 256 + 1024;
+    static constexpr int STORE_BYTES = 4 * 2 * 4096; // matmul epilogue: per warp two 32x32 f32 TMA-store tiles
+    static constexpr int EPI_BYTES = (STAGING_BYTES + AUX_BYTES) > STORE_BYTES ? (STAGING_BYTES + AUX_BYTES) : STORE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
 };
 
 struct TcKParams {
@@ -67,6 +69,7 @@ struct TcKParams {
     int k;
     uint64_t *partial;
     float *out;
+    int out_tma;   // 1: matmul epilogue stores through TMA (row pitch is a multiple of 16 bytes)
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
@@ -180,7 +183,8 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
 template <bool F16, int EPI, int R, int ROWB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
-          const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo, const TcKParams p) {
+          const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo,
+          const __grid_constant__ CUtensorMap tm_out, const TcKParams p) {
     typedef TcCfg<F16, ROWB> Cfg;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -188,7 +192,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     const uint32_t smem_base = smem_u32(smem);
     uint64_t *stage_buf = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
     float *aux_tiles = (float *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
-    uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + Cfg::AUX_BYTES);
+    uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -354,19 +358,30 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     }
                     const int64_t col0 = col_tile + ch * 32;
                     if (EPI == EPI_MATMUL) {
-                        if (qrow < p.nq) {
-                            float *dst = p.out + qrow * p.n + col0;
-                            if ((p.n & 3) == 0 && col0 + 32 <= p.n) {
+                        if (p.out_tma) {
+                            // registers -> swizzled 32x32 smem tile -> one TMA store per warp and chunk: full 128-byte
+                            // lines, bounds clipped by the hardware
+                            const uint32_t sbuf = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (uint32_t)((lg * 2 + (ch & 1)) * 4096);
+                            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+                            __syncwarp();
 #pragma unroll
-                                for (int j = 0; j < 32; j += 4)
-                                    *reinterpret_cast<float4 *>(dst + j) =
-                                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
+                            for (int c = 0; c < 8; ++c) {
+                                const uint32_t dst = sbuf + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4));
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                                             "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                                             : "memory");
                             }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tm_out, sbuf, (int32_t)col0, (int32_t)(m_tile * BM + row0));
+                                tma_store_commit();
+                            }
+                        } else if (qrow < p.nq) {
+                            float *dst = p.out + qrow * p.n + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
                         }
                     } else if (p.metric == METRIC_DOT) {
                         filter_chunk<METRIC_DOT, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf, list_base, row,
@@ -393,6 +408,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         }
     }
 
+    if (EPI == EPI_MATMUL && warp >= 2 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
     __syncwarp();
     tc_fence_before();
     __syncthreads();
@@ -446,6 +462,24 @@ bool make_plane_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols
     return true;
 }
 
+// [rows x cols] f32 row-major output, box 32 x 32, SWIZZLE_128B (matmul epilogue TMA store).
+bool make_out_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled(out) failed with CUresult %d", (int)r);
+        return false;
+    }
+    return true;
+}
+
 template <bool F16, int EPI, int R, int ROWB>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     typedef TcCfg<F16, ROWB> Cfg;
@@ -459,7 +493,14 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
         if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false, ROWB)) return cudaErrorInvalidValue;
         if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, BN, false, ROWB)) return cudaErrorInvalidValue;
     }
+    CUtensorMap t_out = tq_hi;  // placeholder for the top-k kernels
+    int out_tma = 0;
+    if (EPI == EPI_MATMUL && (a.n % 4) == 0 && (((uintptr_t)a.out) & 15) == 0) {
+        if (!make_out_map(&t_out, a.out, a.nq, a.n)) return cudaErrorInvalidValue;
+        out_tma = 1;
+    }
     TcKParams p;
+    p.out_tma = out_tma;
     p.sched = a.sched;
     p.num_kb = (int)(a.dim_pad / Cfg::BK);
     p.q_aux = a.q_aux;
@@ -474,7 +515,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     auto kern = tc_kernel<F16, EPI, R, ROWB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    kern<<<a.sched.num_ctas, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(tq_hi, tq_lo, tc_hi, tc_lo, p);
+    kern<<<a.sched.num_ctas, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(tq_hi, tq_lo, tc_hi, tc_lo, t_out, p);
     return cudaGetLastError();
 }
 
