@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{2}, g_tc_rowb{128};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{4}, g_tc_cg{2};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -306,8 +306,8 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.nq = q.n_rows;
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
-    a.rowb = g_tc_rowb.load();
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms, g_tc_group.load());
+    a.cg = g_tc_cg.load();
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg, g_tc_group.load(), a.cg);
     const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.q_aux = q_aux;
@@ -317,7 +317,7 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.kp = tc_list_capacity(keff);
     a.k = a.kp;
     DevBuf partial, kept;
-    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * TC_TILE_M * a.kp * 8, s));
+    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * a.cg * TC_TILE_M * a.kp * 8, s));
     CUDA_TRY(kept.alloc((size_t)q.n_rows * a.kp * 8, s));
     a.partial = partial.as<uint64_t>();
     cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : "tc_topk_tf32x3", s, [&] { return launch_tc_topk(a, s); });
@@ -325,7 +325,7 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
     const bool higher = metric != PMM_METRIC_EUCLIDEAN;
     CUDA_TRY(launch_counted("merge", s, [&] {
-        return launch_merge_tiles(a.partial, a.sched, a.kp, q.n_rows, a.kp, higher, nullptr, nullptr, kept.as<uint64_t>(), s);
+        return launch_merge_tiles(a.partial, a.sched, a.cg, a.kp, q.n_rows, a.kp, higher, nullptr, nullptr, kept.as<uint64_t>(), s);
     }));
     CUDA_TRY(launch_counted("rescore", s, [&] {
         return launch_rescore(kept.as<uint64_t>(), a.kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base,
@@ -364,7 +364,7 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared q, c_local;
-    int rc = prepare(*dq, pc.mode, pc.f64, TC_TILE_M, want_norm, want_sq, err.as<int>(), s, &q);
+    int rc = prepare(*dq, pc.mode, pc.f64, 2 * TC_TILE_M, want_norm, want_sq, err.as<int>(), s, &q);
     if (rc) return rc;
     const Prepared *c = pc_corpus;
     if (!c) {
@@ -384,7 +384,7 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared l, r;
-    int rc = prepare(*dl, pc.mode, pc.f64, TC_TILE_M, false, false, err.as<int>(), s, &l);
+    int rc = prepare(*dl, pc.mode, pc.f64, 2 * TC_TILE_M, false, false, err.as<int>(), s, &l);
     if (rc) return rc;
     rc = prepare(*dr, pc.mode, pc.f64, TC_TILE_N, false, false, err.as<int>(), s, &r);
     if (rc) return rc;
@@ -403,8 +403,8 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         a.nq = Q;
         a.n = N;
         a.f16 = pc.mode == PREP_F16 ? 1 : 0;
-        a.rowb = g_tc_rowb.load();
-        a.sched = make_tc_schedule(Q, N, di.num_sms, g_tc_group.load());
+        a.cg = g_tc_cg.load();
+        a.sched = make_tc_schedule(Q, N, di.num_sms / a.cg, g_tc_group.load(), a.cg);
         a.metric = PMM_METRIC_DOT;
         a.k = 1;
         a.kp = 32;
@@ -555,7 +555,7 @@ int pmm_set_option(const char *key, int64_t value) {
     if (k == "force_generic") g_force_generic.store((int)value);
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 1 ? 1 : (int)value);
-    else if (k == "tc_rowb") g_tc_rowb.store(value == 64 ? 64 : 128);
+    else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
     else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
     return PMM_OK;

@@ -73,7 +73,7 @@ constexpr int TC_TILE_N = 256;   // corpus rows per tile
 // `m_rem` query tiles over `g_rem` CTAs each.
 struct TcSchedule {
     int m_tiles, n_tiles;
-    int num_ctas;   // grid size
+    int num_ctas;   // scheduling units launched (CTAs, or CTA pairs for cta_group::2)
     int g;          // CTAs per query tile in full rounds
     int mc;         // query tiles in flight in a full round (= num_ctas / g)
     int rounds;     // full rounds
@@ -86,10 +86,10 @@ struct TcSchedule {
     }
     __host__ __device__ int64_t total_slots() const { return (int64_t)m_full * g + (int64_t)m_rem * g_rem; }
 };
-TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_sms, int group);
+TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg);
 
-// Partial lists written by the fused kernel: [slot][row_in_tile (128)][kp].
-cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int kp, int64_t nq, int k_out, bool higher,
+// Partial lists written by the fused kernel: [slot][cta of the group (cg)][row_in_tile (128)][kp].
+cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int kp, int64_t nq, int k_out, bool higher,
                                uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s);
 
 struct TcArgs {
@@ -98,7 +98,7 @@ struct TcArgs {
     int64_t q_rows_pad, c_rows_pad, dim_pad;
     int64_t nq, n;                 // real rows
     int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
-    int rowb;                      // 128 or 64: bytes of K per smem row (pipeline: 2 or 4 stages for f32)
+    int cg;                        // tcgen05 cta_group: 1, or 2 (CTA pairs, UMMA M=256)
     TcSchedule sched;
     // top-k mode
     const float *q_aux, *c_aux;    // norms (cosine) / squared norms (euclidean) / NULL (dot)
@@ -106,7 +106,7 @@ struct TcArgs {
     int metric;
     int k;                         // candidates kept per query and piece: the list position that sets the threshold (<= kp)
     int kp;                        // list capacity: 32, 64, 128 or 256
-    uint64_t *partial;             // [sched.total_slots()][128][kp]
+    uint64_t *partial;             // [sched.total_slots()][cg][128][kp]
     // matmul mode
     float *out;                    // [nq x n] row-major
 };

@@ -54,16 +54,17 @@ __global__ void __launch_bounds__(256) merge_regular_kernel(const uint64_t *__re
 }
 
 template <int R>
-__global__ void __launch_bounds__(256) merge_tiles_kernel(const uint64_t *__restrict__ lists, TcSchedule sched,
+__global__ void __launch_bounds__(256) merge_tiles_kernel(const uint64_t *__restrict__ lists, TcSchedule sched, int cg,
                                                           int64_t nq, int k_out, bool higher, uint32_t *out_idx,
                                                           double *out_score, uint64_t *out_cand) {
     constexpr int KP = 32 * R;
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= nq) return;
-    const int mt = (int)(q / TC_TILE_M), r = (int)(q % TC_TILE_M);
-    const uint64_t *base = lists + (sched.slot_base(mt) * TC_TILE_M + r) * KP;
-    const int64_t piece_stride = (int64_t)TC_TILE_M * KP;
+    const int tile_rows = TC_TILE_M * cg;
+    const int mt = (int)(q / tile_rows), r = (int)(q % tile_rows);  // r = cta_in_group * 128 + row
+    const uint64_t *base = lists + (sched.slot_base(mt) * tile_rows + r) * KP;
+    const int64_t piece_stride = (int64_t)tile_rows * KP;
     auto ptr = [&](int l) { return base + l * piece_stride; };
     merge_query<R>(ptr, sched.pieces(mt), KP, k_out, higher, q, out_idx, out_score, out_cand, lane);
 }
@@ -85,18 +86,18 @@ cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int kp, int64_t nq, int k_out, bool higher,
+cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int kp, int64_t nq, int k_out, bool higher,
                                uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
     if (nq <= 0 || k_out <= 0) return cudaSuccess;
     unsigned grid = (unsigned)((nq + 7) / 8);
     if (kp == 32)
-        merge_tiles_kernel<1><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<1><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 64)
-        merge_tiles_kernel<2><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<2><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 128)
-        merge_tiles_kernel<4><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<4><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 256)
-        merge_tiles_kernel<8><<<grid, 256, 0, s>>>(lists, sched, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<8><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

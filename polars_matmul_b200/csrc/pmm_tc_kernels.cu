@@ -24,6 +24,7 @@
 // shuffles, bitonic-merges them into the list (KP/32 registers per lane) and refreshes the threshold.
 #include <cuda.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "pmm_common.cuh"
 #include "pmm_kernels.h"
@@ -42,20 +43,23 @@ constexpr int EMERGENCY_AT = STAGE_SLOTS - 8;  // mid-tile flush only above this
 constexpr int FLUSH_AT = 8;                // end-of-tile flush above this: happens AFTER the TMEM buffer was released
 
 // ROWB = bytes of K per shared-memory row (= the swizzle span): 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
-// Smaller rows give twice as many, half as large pipeline stages in the same shared memory.
-template <bool F16, int ROWB>
+// CG   = tcgen05 cta_group: 1 = one CTA per 128 x 256 tile; 2 = a CTA pair (cluster of 2) computes a
+//        256 x 256 tile with UMMA M=256: each CTA holds 128 query rows and HALF of the corpus tile
+//        (128 rows), so corpus bytes per SM halve and a third pipeline stage fits.
+template <bool F16, int ROWB, int CG>
 struct TcCfg {
     static constexpr int PLANES = F16 ? 1 : 2;
     static constexpr int BK = ROWB / (F16 ? 2 : 4);  // elements of K per stage
     static constexpr int KSTEPS = ROWB / 32;         // 32 bytes of K per tcgen05.mma
+    static constexpr int B_ROWS = BN / CG;           // corpus rows this CTA stages per tile
     static constexpr int A_BYTES = BM * ROWB;
-    static constexpr int B_BYTES = BN * ROWB;
+    static constexpr int B_BYTES = B_ROWS * ROWB;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = (F16 ? 4 : 2) * (128 / ROWB);
     static constexpr int STAGING_BYTES = STAGE_SLOTS * BM * 8;
     static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of the tile
     static constexpr int STORE_BYTES = 4 * 2 * 4096; // matmul epilogue: per warp two 32x32 f32 TMA-store tiles
     static constexpr int EPI_BYTES = (STAGING_BYTES + AUX_BYTES) > STORE_BYTES ? (STAGING_BYTES + AUX_BYTES) : STORE_BYTES;
+    static constexpr int STAGES = (232448 - EPI_BYTES - 256 - 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
 };
 
@@ -180,12 +184,12 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     }
 }
 
-template <bool F16, int EPI, int R, int ROWB>
+template <bool F16, int EPI, int R, int ROWB, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
           const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo,
           const __grid_constant__ CUtensorMap tm_out, const TcKParams p) {
-    typedef TcCfg<F16, ROWB> Cfg;
+    typedef TcCfg<F16, ROWB, CG> Cfg;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -201,7 +205,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(bars + 2 * Cfg::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cta = blockIdx.x;
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair; 0 = leader (issues the MMAs)
+    const int cta = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // scheduling unit: CTA or CTA pair
     const TcSchedule &S = p.sched;
     const int total_rounds = S.rounds + (S.m_rem > 0 ? 1 : 0);
 
@@ -218,16 +223,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 4);
+            mbar_init(tempty_bar(b), 4 * CG);  // one arrival per epilogue warp of every CTA of the group
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc<1>(smem_u32((const void *)tmem_ptr_smem), 512);
-        tmem_relinquish<1>();
+        tmem_alloc<CG>(smem_u32((const void *)tmem_ptr_smem), 512);
+        tmem_relinquish<CG>();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -244,13 +249,26 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     for (int kb = 0; kb < p.num_kb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint32_t fb = full_bar(stage);
-                        mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-                        tma_load_2d(sa, &tm_qhi, fb, kb * Cfg::BK, m_tile * BM);
-                        if (!F16) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, m_tile * BM);
-                        tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, nt * BN);
-                        if (!F16)
-                            tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, nt * BN);
+                        const int32_t arow = (m_tile * CG + (int)crank) * BM;            // this CTA's 128 query rows
+                        const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
+                        if (CG == 1) {
+                            const uint32_t fb = full_bar(stage);
+                            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                            tma_load_2d(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
+                            if (!F16) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
+                            tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, brow);
+                            if (!F16) tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
+                        } else {
+                            // both CTAs of the pair load into their own shared memory; all bytes are counted on the
+                            // LEADER's full barrier, which its MMA thread waits on
+                            const uint32_t fb = mapa_u32(full_bar(stage), 0u);
+                            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+                            tma_load_2d_pair(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
+                            if (!F16) tma_load_2d_pair(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
+                            tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, brow);
+                            if (!F16)
+                                tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
+                        }
                         if (++stage == Cfg::STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -261,8 +279,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_instr_desc(F16 ? 0 : 2, BM, BN);
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = umma_instr_desc(F16 ? 0 : 2, BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int abuf = 0;
@@ -286,21 +304,23 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
                             const uint64_t dah = umma_smem_desc<ROWB>(a_hi + ks * 32), dbh = umma_smem_desc<ROWB>(b_hi + ks * 32);
                             if (F16) {
-                                umma<1, true>(tmem_d, dah, dbh, idesc, acc);
+                                umma<CG, true>(tmem_d, dah, dbh, idesc, acc);
                             } else {
                                 const uint64_t dal = umma_smem_desc<ROWB>(a_lo + ks * 32), dbl = umma_smem_desc<ROWB>(b_lo + ks * 32);
-                                umma<1, false>(tmem_d, dal, dbh, idesc, acc);  // small terms first
-                                umma<1, false>(tmem_d, dah, dbl, idesc, 1u);
-                                umma<1, false>(tmem_d, dah, dbh, idesc, 1u);
+                                umma<CG, false>(tmem_d, dal, dbh, idesc, acc);  // small terms first
+                                umma<CG, false>(tmem_d, dah, dbl, idesc, 1u);
+                                umma<CG, false>(tmem_d, dah, dbh, idesc, 1u);
                             }
                         }
-                        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                        if (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_pair(empty_bar(stage), 3);
                         if (++stage == Cfg::STAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
                     }
-                    umma_commit(tfull_bar(abuf));  // accumulator tile complete
+                    // accumulator tile complete (each CTA of a pair holds its 128 rows of it)
+                    if (CG == 1) umma_commit(tfull_bar(abuf)); else umma_commit_pair(tfull_bar(abuf), 3);
                     abuf ^= 1;
                     if (abuf == 0) aphase ^= 1u;
                 }
@@ -318,7 +338,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             int m_tile, n_start, n_step;
             int64_t slot;
             if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
-            const int64_t qrow = (int64_t)m_tile * BM + row;
+            const int64_t qrow = ((int64_t)m_tile * CG + crank) * BM + row;
             uint64_t thr = 0ull;
             float thr_f = __uint_as_float(0x7fc00000u);
             int cnt = 0;
@@ -326,7 +346,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
-                list_base = p.partial + (slot * BM + row0) * KP;
+                list_base = p.partial + ((slot * CG + crank) * BM + row0) * KP;
                 for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
                 // q_aux is padded to the tile grid. cosine: 1 unless the query norm is ~0; euclidean: |q|^2
                 if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > 1e-6f ? 1.0f : 0.0f;
@@ -354,7 +374,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     if (ch == BN / 32 - 1) {  // all TMEM reads of this buffer are done: hand it back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(abuf));
+                        if (lane == 0) {
+                            if (CG == 1) mbar_arrive(tempty_bar(abuf)); else mbar_arrive_cluster(tempty_bar(abuf), 0u);
+                        }
                     }
                     const int64_t col0 = col_tile + ch * 32;
                     if (EPI == EPI_MATMUL) {
@@ -374,7 +396,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&tm_out, sbuf, (int32_t)col0, (int32_t)(m_tile * BM + row0));
+                                tma_store_2d(&tm_out, sbuf, (int32_t)col0, (int32_t)((m_tile * CG + (int)crank) * BM + row0));
                                 tma_store_commit();
                             }
                         } else if (qrow < p.nq) {
@@ -411,10 +433,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     if (EPI == EPI_MATMUL && warp >= 2 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
     __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<1>(tmem_base, 512);
+        tmem_dealloc<CG>(tmem_base, 512);
     }
 }
 
@@ -480,18 +502,18 @@ bool make_out_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols) 
     return true;
 }
 
-template <bool F16, int EPI, int R, int ROWB>
+template <bool F16, int EPI, int R, int ROWB, int CG>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
-    typedef TcCfg<F16, ROWB> Cfg;
+    typedef TcCfg<F16, ROWB, CG> Cfg;
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, BN, F16, ROWB)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS, F16, ROWB)) return cudaErrorInvalidValue;
     if (F16) {
         tq_lo = tq_hi;
         tc_lo = tc_hi;
     } else {
         if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false, ROWB)) return cudaErrorInvalidValue;
-        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, BN, false, ROWB)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS, false, ROWB)) return cudaErrorInvalidValue;
     }
     CUtensorMap t_out = tq_hi;  // placeholder for the top-k kernels
     int out_tma = 0;
@@ -512,18 +534,29 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.k = a.k;
     p.partial = a.partial;
     p.out = a.out;
-    auto kern = tc_kernel<F16, EPI, R, ROWB>;
+    auto kern = tc_kernel<F16, EPI, R, ROWB, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    kern<<<a.sched.num_ctas, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(tq_hi, tq_lo, tc_hi, tc_lo, t_out, p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(a.sched.num_ctas * CG));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, tq_hi, tq_lo, tc_hi, tc_lo, t_out, p);
 }
 
 template <bool F16, int EPI, int R>
 cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
-    // the narrow-row variant needs dim_pad to be a multiple of its (smaller) K block: always true
-    if (a.rowb == 64) return launch_t2<F16, EPI, R, 64>(a, s);
-    return launch_t2<F16, EPI, R, 128>(a, s);
+    if (a.cg == 2) return launch_t2<F16, EPI, R, 128, 2>(a, s);
+    return launch_t2<F16, EPI, R, 128, 1>(a, s);
 }
 
 }  // namespace
@@ -538,11 +571,12 @@ bool tc_supported() {
     return prop.major == 10 && get_encode_fn() != nullptr;
 }
 
-TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_sms, int group) {
+TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg) {
     TcSchedule s;
-    s.m_tiles = (int)((q_rows + BM - 1) / BM);
+    const int tile_m = BM * cg;   // query rows per scheduling unit (CTA or CTA pair)
+    s.m_tiles = (int)((q_rows + tile_m - 1) / tile_m);
     s.n_tiles = (int)((c_rows + BN - 1) / BN);
-    int G = num_sms > 0 ? num_sms : 1;
+    int G = num_units > 0 ? num_units : 1;
     s.g = group < 1 ? 1 : group;
     if (s.g > s.n_tiles) s.g = s.n_tiles;
     if (s.g > G) s.g = G;
