@@ -176,7 +176,9 @@ PMM_API void pmm_reset_kernel_launch_count(void);
 
 /* Tuning / diagnostics. Known keys: "force_generic" (0/1: route f32 top-k through the SIMT
  * scores+select path), "profile" (0/1: bracket kernels with CUDA events on the launching stream
- * and accumulate per-kernel milliseconds, read back with pmm_get_stat). */
+ * and accumulate per-kernel milliseconds, read back with pmm_get_stat), "tc_cg" (1|2: tcgen05
+ * cta_group of the fused kernels, default 2), "tc_group" (CTA groups sharing a query tile, 0 = auto),
+ * "generic_workspace_mb" (score slab of the SIMT path). */
 PMM_API int pmm_set_option(const char *key, int64_t value);
 /* Accumulated statistics since the last pmm_reset_stats(): "<kernel>_ms", "<kernel>_launches",
  * "h2d_bytes", "d2h_bytes". Unknown name -> 0. */

@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{4}, g_tc_cg{2};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -286,6 +286,17 @@ RawMatrix raw_of(const pmm_matrix_t &m) {
     return r;
 }
 
+// CTAs (or CTA pairs) that share one query tile. More sharers shrink the set of query tiles in flight (L2
+// footprint of the query planes) but every sharer pays the warm-up of its own candidate lists, so short
+// corpus sweeps get fewer: one sharer per ~800 corpus tiles, at most 4 (measured: profiles/sweep_r1.md).
+int tc_group_for(int64_t corpus_rows) {
+    int g = g_tc_group.load();
+    if (g > 0) return g;
+    int64_t n_tiles = (corpus_rows + TC_TILE_N - 1) / TC_TILE_N;
+    g = (int)(n_tiles / 800);
+    return g < 1 ? 1 : g > 4 ? 4 : g;
+}
+
 // List capacity of the tensor-core filter: at least 8 more candidates than requested are kept, so the
 // exact re-scoring can reorder near-ties across the k-th position.
 int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : keff <= 120 ? 128 : 256; }
@@ -307,7 +318,7 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
     a.cg = g_tc_cg.load();
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg, g_tc_group.load(), a.cg);
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg, tc_group_for(c.n_rows), a.cg);
     const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.q_aux = q_aux;
@@ -404,7 +415,7 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         a.n = N;
         a.f16 = pc.mode == PREP_F16 ? 1 : 0;
         a.cg = g_tc_cg.load();
-        a.sched = make_tc_schedule(Q, N, di.num_sms / a.cg, g_tc_group.load(), a.cg);
+        a.sched = make_tc_schedule(Q, N, di.num_sms / a.cg, 1, a.cg);
         a.metric = PMM_METRIC_DOT;
         a.k = 1;
         a.kp = 32;
@@ -554,7 +565,7 @@ int pmm_set_option(const char *key, int64_t value) {
     std::string k(key);
     if (k == "force_generic") g_force_generic.store((int)value);
     else if (k == "profile") g_profile.store((int)value);
-    else if (k == "tc_group") g_tc_group.store(value < 1 ? 1 : (int)value);
+    else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
     else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);

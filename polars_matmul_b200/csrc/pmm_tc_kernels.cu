@@ -238,19 +238,21 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < total_rounds; ++it) {
-                int m_tile, n_start, n_step;
-                int64_t slot;
-                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
-                for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const int32_t arow = (m_tile * CG + (int)crank) * BM;            // this CTA's 128 query rows
-                        const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
+        // The whole warp walks the schedule (warp-uniform control flow and addresses); one elected lane issues.
+        const bool issuer = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < total_rounds; ++it) {
+            int m_tile, n_start, n_step;
+            int64_t slot;
+            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+            const int32_t arow = (m_tile * CG + (int)crank) * BM;                // this CTA's 128 query rows
+            for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    if (issuer) {
                         if (CG == 1) {
                             const uint32_t fb = full_bar(stage);
                             mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
@@ -260,7 +262,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             if (!F16) tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
                         } else {
                             // both CTAs of the pair load into their own shared memory; all bytes are counted on the
-                            // LEADER's full barrier, which its MMA thread waits on
+                            // LEADER's full barrier, which its MMA warp waits on
                             const uint32_t fb = mapa_u32(full_bar(stage), 0u);
                             if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
                             tma_load_2d_pair(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
@@ -269,18 +271,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             if (!F16)
                                 tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
                         }
-                        if (++stage == Cfg::STAGES) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                    }
+                    __syncwarp();
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0 && crank == 0) {
+        // Warp-uniform loop (all lanes wait on the barriers and compute descriptors in uniform registers);
+        // one elected lane issues tcgen05.mma / tcgen05.commit.  Only the leader CTA of a pair issues.
+        if (crank == 0) {
             constexpr uint32_t idesc = umma_instr_desc(F16 ? 0 : 2, BM * CG, BN);
+            const bool issuer = elect_one();
             int stage = 0;
             uint32_t phase = 0;
             int abuf = 0;
@@ -297,30 +303,36 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint32_t a_hi = sa, a_lo = sa + Cfg::A_BYTES;
-                        const uint32_t b_hi = sa + Cfg::PLANES * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+                        // descriptors of the stage's four tiles; a K-step of 32 bytes adds 2 to the address field
+                        const uint64_t d_ah = umma_smem_desc<ROWB>(sa);
+                        const uint64_t d_al = d_ah + (uint64_t)(Cfg::A_BYTES >> 4);
+                        const uint64_t d_bh = d_ah + (uint64_t)((Cfg::PLANES * Cfg::A_BYTES) >> 4);
+                        const uint64_t d_bl = d_bh + (uint64_t)(Cfg::B_BYTES >> 4);
+                        if (issuer) {
 #pragma unroll
-                        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-                            const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-                            const uint64_t dah = umma_smem_desc<ROWB>(a_hi + ks * 32), dbh = umma_smem_desc<ROWB>(b_hi + ks * 32);
-                            if (F16) {
-                                umma<CG, true>(tmem_d, dah, dbh, idesc, acc);
-                            } else {
-                                const uint64_t dal = umma_smem_desc<ROWB>(a_lo + ks * 32), dbl = umma_smem_desc<ROWB>(b_lo + ks * 32);
-                                umma<CG, false>(tmem_d, dal, dbh, idesc, acc);  // small terms first
-                                umma<CG, false>(tmem_d, dah, dbl, idesc, 1u);
-                                umma<CG, false>(tmem_d, dah, dbh, idesc, 1u);
+                            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                                const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
+                                if (F16) {
+                                    umma<CG, true>(tmem_d, d_ah + 2 * ks, d_bh + 2 * ks, idesc, acc);
+                                } else {
+                                    umma<CG, false>(tmem_d, d_al + 2 * ks, d_bh + 2 * ks, idesc, acc);  // small terms first
+                                    umma<CG, false>(tmem_d, d_ah + 2 * ks, d_bl + 2 * ks, idesc, 1u);
+                                    umma<CG, false>(tmem_d, d_ah + 2 * ks, d_bh + 2 * ks, idesc, 1u);
+                                }
                             }
+                            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                            if (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_pair(empty_bar(stage), 3);
                         }
-                        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-                        if (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_pair(empty_bar(stage), 3);
+                        __syncwarp();
                         if (++stage == Cfg::STAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
                     }
-                    // accumulator tile complete (each CTA of a pair holds its 128 rows of it)
-                    if (CG == 1) umma_commit(tfull_bar(abuf)); else umma_commit_pair(tfull_bar(abuf), 3);
+                    if (issuer) {  // accumulator tile complete (each CTA of a pair holds its 128 rows of it)
+                        if (CG == 1) umma_commit(tfull_bar(abuf)); else umma_commit_pair(tfull_bar(abuf), 3);
+                    }
+                    __syncwarp();
                     abuf ^= 1;
                     if (abuf == 0) aphase ^= 1u;
                 }

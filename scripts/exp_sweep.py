@@ -36,7 +36,7 @@ def run():
     _native.dev_topk(_native.dev_matrix(dq.data_ptr(), Q, D, 1), _native.dev_matrix(dc.data_ptr(), N, D, 1), k, 1,
                      index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(), stream=st)
 res = []
-configs = [(1, 2), (2, 1), (2, 2), (2, 4), (1, 1)]
+configs = [(2, 4), (2, 2), (2, 8), (1, 2)]
 for rowb, grp in configs:
     _native.set_option("tc_cg", rowb); _native.set_option("tc_group", grp)
     run(); torch.cuda.synchronize()
