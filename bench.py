@@ -40,6 +40,17 @@ METRIC_NAME = "topk_queries_per_sec"
 UNIT = "queries/s"
 
 
+def load_traffic(kernel: str, workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        e = d.get(f"{kernel}@{workload}")
+        if e:
+            return e
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,8 +314,11 @@ def main():
         # 3xTF32: three tcgen05 TF32 MMAs per logical MAC and TF32 runs at half the bf16 rate, so the
         # tensor pipe peak for ALGORITHMIC f32 flops is the measured bf16 peak / 6.
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")) / 6.0
+        tr = load_traffic(kname, f"{W['name']}:{Q}x{N}x{D}:k{k}")
         roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "frac": (achieved / peak) if achieved else None,
+                    "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                    "traffic_note": tr["source"] if tr else "no ncu capture committed for this workload",
                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms,
                     "kernel_share_of_step": (k_avg_ms / ms_step) if ms_step else None,
                     "peak_note": f"{peak_src}: bf16_tflops_sustained / 6 (TF32 = 1/2 bf16 rate, 3 MMAs per MAC); "

@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_round_sync{1};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -327,8 +327,14 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.metric = metric;
     a.kp = tc_list_capacity(keff);
     a.k = a.kp;
-    DevBuf partial, kept;
+    DevBuf partial, kept, rsync;
     CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * a.cg * TC_TILE_M * a.kp * 8, s));
+    if (g_tc_round_sync.load()) {
+        const size_t nb = (size_t)(a.sched.rounds + 2) * sizeof(unsigned int);
+        CUDA_TRY(rsync.alloc(nb, s));
+        CUDA_TRY(cudaMemsetAsync(rsync.p, 0, nb, s));
+        a.round_sync = rsync.as<unsigned int>();
+    }
     CUDA_TRY(kept.alloc((size_t)q.n_rows * a.kp * 8, s));
     a.partial = partial.as<uint64_t>();
     cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : "tc_topk_tf32x3", s, [&] { return launch_tc_topk(a, s); });
@@ -567,6 +573,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
+    else if (k == "tc_round_sync") g_tc_round_sync.store(value ? 1 : 0);
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
     else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
     return PMM_OK;

@@ -109,6 +109,7 @@ struct TcArgs {
     uint64_t *partial;             // [sched.total_slots()][cg][128][kp]
     // matmul mode
     float *out;                    // [nq x n] row-major
+    unsigned int *round_sync;      // [rounds + 1] zeroed device counters (grid-wide round barrier) or NULL
 };
 bool tc_supported();               // driver exposes cuTensorMapEncodeTiled and the device is sm_100
 cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s);

