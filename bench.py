@@ -109,7 +109,7 @@ def cpu_baseline_sample(q_host: np.ndarray, c_host: np.ndarray, k: int, metric: 
     """Times the oracle port on a bounded query sample against the full corpus shard."""
     from oracle import pmm_oracle as oracle
     oracle.build()
-    n_cal = 8
+    n_cal = 8 * max(1, oracle.num_threads())      # the oracle parallelises over blocks of 8 queries
     t0 = time.perf_counter()
     oracle.topk(q_host[:n_cal], c_host, k, metric)
     t_cal = time.perf_counter() - t0
@@ -135,7 +135,7 @@ def run_reference(args):
         W.update(Q=2000, N=50_000)
     rng = np.random.default_rng(42)
     # bounded sample: the oracle scans the FULL corpus for a subset of the queries
-    n_probe = 8
+    n_probe = 8 * max(1, oracle.num_threads())    # the oracle parallelises over blocks of 8 queries
     c = rng.standard_normal((W["N"], W["D"]), dtype=np.float32)
     q = rng.standard_normal((4096, W["D"]), dtype=np.float32)
     t0 = time.perf_counter()

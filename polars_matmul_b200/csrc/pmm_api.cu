@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_round_sync{1};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -286,15 +286,15 @@ RawMatrix raw_of(const pmm_matrix_t &m) {
     return r;
 }
 
-// CTAs (or CTA pairs) that share one query tile. More sharers shrink the set of query tiles in flight (L2
-// footprint of the query planes) but every sharer pays the warm-up of its own candidate lists, so short
-// corpus sweeps get fewer: one sharer per ~800 corpus tiles, at most 4 (measured: profiles/sweep_r1.md).
+// CTA pairs that share one query tile (they take corpus tiles rank, rank+g, ...). More sharers shrink the
+// set of query tiles in flight (L2 footprint of the query planes) but every sharer pays the warm-up of its
+// own candidate lists. Measured with the pacing barriers on (profiles/sweep_r1.md): 2 is best for long
+// corpus sweeps, 1 for short ones.
 int tc_group_for(int64_t corpus_rows) {
     int g = g_tc_group.load();
     if (g > 0) return g;
     int64_t n_tiles = (corpus_rows + TC_TILE_N - 1) / TC_TILE_N;
-    g = (int)(n_tiles / 800);
-    return g < 1 ? 1 : g > 4 ? 4 : g;
+    return n_tiles >= 1600 ? 2 : 1;
 }
 
 // List capacity of the tensor-core filter: at least 8 more candidates than requested are kept, so the
@@ -329,8 +329,9 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.k = a.kp;
     DevBuf partial, kept, rsync;
     CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * a.cg * TC_TILE_M * a.kp * 8, s));
-    if (g_tc_round_sync.load()) {
-        const size_t nb = (size_t)(a.sched.rounds + 2) * sizeof(unsigned int);
+    if (g_tc_sync_tiles.load() > 0) {
+        a.sync_tiles = g_tc_sync_tiles.load();
+        const size_t nb = (size_t)tc_sync_counters(a.sched, a.sync_tiles) * sizeof(unsigned int);
         CUDA_TRY(rsync.alloc(nb, s));
         CUDA_TRY(cudaMemsetAsync(rsync.p, 0, nb, s));
         a.round_sync = rsync.as<unsigned int>();
@@ -573,7 +574,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
-    else if (k == "tc_round_sync") g_tc_round_sync.store(value ? 1 : 0);
+    else if (k == "tc_sync_tiles") g_tc_sync_tiles.store(value < 0 ? 0 : (int)value);  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
     else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
     return PMM_OK;

@@ -87,6 +87,7 @@ struct TcSchedule {
     __host__ __device__ int64_t total_slots() const { return (int64_t)m_full * g + (int64_t)m_rem * g_rem; }
 };
 TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg);
+int64_t tc_sync_counters(const TcSchedule &s, int sync_tiles);  // number of pacing counters a launch needs
 
 // Partial lists written by the fused kernel: [slot][cta of the group (cg)][row_in_tile (128)][kp].
 cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int kp, int64_t nq, int k_out, bool higher,
@@ -109,7 +110,8 @@ struct TcArgs {
     uint64_t *partial;             // [sched.total_slots()][cg][128][kp]
     // matmul mode
     float *out;                    // [nq x n] row-major
-    unsigned int *round_sync;      // [rounds + 1] zeroed device counters (grid-wide round barrier) or NULL
+    unsigned int *round_sync;      // zeroed device counters for the producers' pacing barriers (tc_sync_counters()) or NULL
+    int sync_tiles;                // corpus tiles between two pacing barriers
 };
 bool tc_supported();               // driver exposes cuTensorMapEncodeTiled and the device is sm_100
 cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s);

@@ -74,7 +74,8 @@ struct TcKParams {
     uint64_t *partial;
     float *out;
     int out_tma;   // 1: matmul epilogue stores through TMA (row pitch is a multiple of 16 bytes)
-    unsigned int *round_sync;  // [rounds + 1] zeroed counters: producers of all CTAs meet at every round start
+    unsigned int *round_sync;  // zeroed counters: producers of all CTAs meet every `sync_tiles` corpus tiles (NULL: off)
+    int sync_tiles;
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
@@ -243,29 +244,42 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         const bool issuer = elect_one();
         int stage = 0;
         uint32_t phase = 0;
+        const int n_sync_full = p.round_sync ? ((S.n_tiles + S.g - 1) / S.g + p.sync_tiles - 1) / p.sync_tiles : 0;
         for (int it = 0; it < total_rounds; ++it) {
-            // All CTAs are co-resident (persistent grid <= #SMs), so their producers can meet: every round starts
-            // with all groups at corpus tile 0, which keeps the groups sweeping the corpus in lockstep and a
-            // corpus tile is read from HBM once per round instead of once per group (measured 16x less DRAM traffic).
-            if (it > 0 && p.round_sync) {
-                if (issuer) {
-                    atomicAdd(p.round_sync + it, 1u);
-                    const long long t0 = clock64();
-                    // best-effort pacing, never a correctness dependency: give up after ~4 ms (e.g. when another
-                    // kernel holds some SMs and part of this grid is not resident yet)
-                    while (ld_acquire_u32(p.round_sync + it) < gridDim.x) {
-                        __nanosleep(200);
-                        if (clock64() - t0 > 8000000ll) break;
-                    }
-                }
-                __syncwarp();
-            }
+            // Pacing. All CTAs are co-resident (persistent grid <= #SMs), so their producers can meet: every
+            // `sync_tiles` corpus tiles of a round all producers wait for each other, which keeps the groups
+            // sweeping the corpus in lockstep so that a corpus tile is read from HBM once per round instead of
+            // once per group.  Sync points of a round are numbered identically in every CTA; a CTA that has
+            // fewer tiles (or none) in the round still arrives at all of them.
+            const int step_r = it < S.rounds ? S.g : S.g_rem;
+            const int n_sync = p.round_sync ? ((S.n_tiles + step_r - 1) / step_r + p.sync_tiles - 1) / p.sync_tiles : 0;
+            unsigned int *sync_base = p.round_sync + (it < S.rounds ? it * n_sync_full : S.rounds * n_sync_full);
             int m_tile, n_start, n_step;
             int64_t slot;
-            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) {
+                if (issuer)
+                    for (int sp = 0; sp < n_sync; ++sp) atomicAdd(sync_base + sp, 1u);
+                __syncwarp();
+                continue;
+            }
             const int32_t arow = (m_tile * CG + (int)crank) * BM;                // this CTA's 128 query rows
-            for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+            int j = 0;  // tile counter of this CTA inside the round
+            for (int nt = n_start; nt < S.n_tiles; nt += n_step, ++j) {
                 const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
+                if (n_sync && j % p.sync_tiles == 0) {
+                    if (issuer) {
+                        unsigned int *ctr = sync_base + j / p.sync_tiles;
+                        atomicAdd(ctr, 1u);
+                        const long long t0 = clock64();
+                        // best-effort, never a correctness dependency: give up after ~4 ms (e.g. when another
+                        // kernel holds some SMs and part of this grid is not resident yet)
+                        while (ld_acquire_u32(ctr) < gridDim.x) {
+                            __nanosleep(100);
+                            if (clock64() - t0 > 8000000ll) break;
+                        }
+                    }
+                    __syncwarp();
+                }
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -295,6 +309,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         phase ^= 1u;
                     }
                 }
+            }
+            if (n_sync) {  // sync points of this round that lie beyond this CTA's last tile
+                if (issuer)
+                    for (int sp = (j + p.sync_tiles - 1) / p.sync_tiles; sp < n_sync; ++sp) atomicAdd(sync_base + sp, 1u);
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -564,6 +583,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.partial = a.partial;
     p.out = a.out;
     p.round_sync = a.round_sync;
+    p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
     auto kern = tc_kernel<F16, EPI, R, ROWB, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -625,6 +645,12 @@ TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int g
     s.num_ctas = used_full > used_rem ? used_full : used_rem;
     if (s.num_ctas < 1) s.num_ctas = 1;
     return s;
+}
+
+int64_t tc_sync_counters(const TcSchedule &s, int sync_tiles) {
+    if (sync_tiles < 1) sync_tiles = 1;
+    auto per_round = [&](int step) { return step > 0 ? ((s.n_tiles + step - 1) / step + sync_tiles - 1) / sync_tiles : 0; };
+    return (int64_t)s.rounds * per_round(s.g) + (s.m_rem > 0 ? per_round(s.g_rem) : 0) + 1;
 }
 
 cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s) {
