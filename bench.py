@@ -322,7 +322,10 @@ def main():
                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms,
                     "kernel_share_of_step": (k_avg_ms / ms_step) if ms_step else None,
                     "peak_note": f"{peak_src}: bf16_tflops_sustained / 6 (TF32 = 1/2 bf16 rate, 3 MMAs per MAC); "
-                                 f"raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}",
+                                 f"raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}. "
+                                 "frac can exceed 1: the denominator is a power-capped cuBLAS run (profiles/peaks_r1e.json: "
+                                 "cuBLAS TF32 744 burst / 613 sustained on the same box, i.e. 248 / 204 per 3xTF32 flop); "
+                                 "the nominal 3xTF32 ceiling at 1965 MHz is 375 TFLOP/s",
                     "per_kernel_ms_per_step": stats}
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:

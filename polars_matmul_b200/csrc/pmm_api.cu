@@ -287,14 +287,18 @@ RawMatrix raw_of(const pmm_matrix_t &m) {
 }
 
 // CTA pairs that share one query tile (they take corpus tiles rank, rank+g, ...). More sharers shrink the
-// set of query tiles in flight (L2 footprint of the query planes) but every sharer pays the warm-up of its
-// own candidate lists. Measured with the pacing barriers on (profiles/sweep_r1.md): 2 is best for long
-// corpus sweeps, 1 for short ones.
-int tc_group_for(int64_t corpus_rows) {
+// set of query tiles in flight — whose operand planes must stay L2-resident, they are re-read for every
+// corpus tile — but every sharer pays the warm-up of its own candidate lists. Rule (measured with the
+// pacing barriers on, profiles/sweep_r1.md): the smallest g in {1,2,4} that keeps the in-flight query
+// planes under 64 MB, as long as every sharer still sweeps >= 200 corpus tiles.
+int tc_group_for(int64_t corpus_rows, int64_t dim_pad, bool f16, int units, int cg) {
     int g = g_tc_group.load();
     if (g > 0) return g;
-    int64_t n_tiles = (corpus_rows + TC_TILE_N - 1) / TC_TILE_N;
-    return n_tiles >= 1600 ? 2 : 1;
+    const int64_t n_tiles = (corpus_rows + TC_TILE_N - 1) / TC_TILE_N;
+    const int64_t tile_bytes = (int64_t)TC_TILE_M * cg * dim_pad * (f16 ? 2 : 8);  // hi+lo planes for f32
+    g = 1;
+    while (g < 4 && (units / g) * tile_bytes > (64ll << 20) && n_tiles / (2 * g) >= 200) g *= 2;
+    return g;
 }
 
 // List capacity of the tensor-core filter: at least 8 more candidates than requested are kept, so the
@@ -318,7 +322,7 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
     a.cg = g_tc_cg.load();
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg, tc_group_for(c.n_rows), a.cg);
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg, tc_group_for(c.n_rows, q.ld, a.f16 != 0, di.num_sms / a.cg, a.cg), a.cg);
     const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.q_aux = q_aux;
