@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -290,14 +290,14 @@ RawMatrix raw_of(const pmm_matrix_t &m) {
 // set of query tiles in flight — whose operand planes must stay L2-resident, they are re-read for every
 // corpus tile — but every sharer pays the warm-up of its own candidate lists. Rule (measured with the
 // pacing barriers on, profiles/sweep_r1.md): the smallest g in {1,2,4} that keeps the in-flight query
-// planes under 64 MB, as long as every sharer still sweeps >= 200 corpus tiles.
+// planes under 64 MB, as long as every sharer still sweeps >= 64 corpus tiles.
 int tc_group_for(int64_t corpus_rows, int64_t dim_pad, bool f16, int units, int cg) {
     int g = g_tc_group.load();
     if (g > 0) return g;
     const int64_t n_tiles = (corpus_rows + TC_TILE_N - 1) / TC_TILE_N;
     const int64_t tile_bytes = (int64_t)TC_TILE_M * cg * dim_pad * (f16 ? 2 : 8);  // hi+lo planes for f32
     g = 1;
-    while (g < 4 && (units / g) * tile_bytes > (64ll << 20) && n_tiles / (2 * g) >= 200) g *= 2;
+    while (g < 4 && (units / g) * tile_bytes > (64ll << 20) && n_tiles / (2 * g) >= 64) g *= 2;
     return g;
 }
 
@@ -305,9 +305,11 @@ int tc_group_for(int64_t corpus_rows, int64_t dim_pad, bool f16, int units, int 
 // exact re-scoring can reorder near-ties across the k-th position.
 int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : keff <= 120 ? 128 : 256; }
 
-// Tensor-core path on prepared PLANES: fused filter -> merge of corpus pieces -> exact re-scoring.
-int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
-            int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
+// Tensor-core filter on prepared PLANES: fused kernel -> merge of the corpus pieces of every query tile.
+// kept [Q x kp]: per query the kp best candidates under the kernel's filter value (approximate keys,
+// comparable across corpus chunks and shards of the same query), indices = index_base + corpus row.
+int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
+              cudaStream_t s) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -322,16 +324,15 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
     a.cg = g_tc_cg.load();
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg, tc_group_for(c.n_rows, q.ld, a.f16 != 0, di.num_sms / a.cg, a.cg), a.cg);
-    const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
-    const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
-    a.q_aux = q_aux;
-    a.c_aux = c_aux;
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg,
+                               tc_group_for(c.n_rows, q.ld, a.f16 != 0, di.num_sms / a.cg, a.cg), a.cg);
+    a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
+    a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.index_base = index_base;
     a.metric = metric;
-    a.kp = tc_list_capacity(keff);
-    a.k = a.kp;
-    DevBuf partial, kept, rsync;
+    a.kp = kp;
+    a.k = kp;
+    DevBuf partial, rsync;
     CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * a.cg * TC_TILE_M * a.kp * 8, s));
     if (g_tc_sync_tiles.load() > 0) {
         a.sync_tiles = g_tc_sync_tiles.load();
@@ -340,17 +341,28 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
         CUDA_TRY(cudaMemsetAsync(rsync.p, 0, nb, s));
         a.round_sync = rsync.as<unsigned int>();
     }
-    CUDA_TRY(kept.alloc((size_t)q.n_rows * a.kp * 8, s));
     a.partial = partial.as<uint64_t>();
     cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : "tc_topk_tf32x3", s, [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
-    const bool higher = metric != PMM_METRIC_EUCLIDEAN;
     CUDA_TRY(launch_counted("merge", s, [&] {
-        return launch_merge_tiles(a.partial, a.sched, a.cg, a.kp, q.n_rows, a.kp, higher, nullptr, nullptr, kept.as<uint64_t>(), s);
+        return launch_merge_tiles(a.partial, a.sched, a.cg, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
     }));
+    return PMM_OK;
+}
+
+// Tensor-core path: filter -> exact re-scoring of the kept candidates.
+int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
+            int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
+    const int kp = tc_list_capacity(keff);
+    DevBuf kept;
+    CUDA_TRY(kept.alloc((size_t)q.n_rows * kp * 8, s));
+    int rc = tc_filter(q, c, kp, metric, index_base, kept.as<uint64_t>(), s);
+    if (rc) return rc;
+    const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
+    const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     CUDA_TRY(launch_counted("rescore", s, [&] {
-        return launch_rescore(kept.as<uint64_t>(), a.kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base,
+        return launch_rescore(kept.as<uint64_t>(), kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base,
                               (int)keff, o.index, o.score, o.cand, s);
     }));
     return PMM_OK;
@@ -518,6 +530,138 @@ int list_dim_check(const pmm_matrix_t *m, const char *) {
     return PMM_OK;
 }
 
+cudaStream_t copy_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    static thread_local int dev_of_stream = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!s || dev_of_stream != dev) {
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        dev_of_stream = dev;
+    }
+    return s;
+}
+
+// Host top-k on the tensor-core path with the corpus upload overlapped with compute (north_star item 5:
+// the Arrow buffer feeds H2D copies directly). The corpus is cut into row chunks; chunk i+1 is copied on
+// a second stream while chunk i runs prep + the fused filter; the per-chunk candidate lists are merged
+// and re-scored once against the whole (now resident) corpus. A small first chunk starts the tensor
+// cores early; the rest of the upload hides behind it.
+int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t keff, int metric, PathChoice pc,
+                      uint32_t *out_index, double *out_score) {
+    cudaStream_t s = host_stream(), cs = copy_stream();
+    const int64_t Q = queries->n_rows, N = corpus->n_rows, D = corpus->dim;
+    const int es = esize(corpus->dtype);
+    // chunk boundaries in rows (multiples of 256 so bitmaps can be re-based by whole bytes)
+    std::vector<int64_t> cut{0};
+    int64_t first = (N / 8) / 256 * 256;
+    if (first < 16384) first = 16384;
+    if (first < N) cut.push_back(first);
+    cut.push_back(N);
+    const int n_chunks = (int)cut.size() - 1;
+
+    Uploaded uq;
+    int rc = upload(queries, s, &uq);
+    if (rc) return rc;
+    // corpus metadata now, values chunk by chunk
+    Uploaded uc;
+    uc.dm = *corpus;
+    int64_t pos0 = 0, pos1 = N * D;
+    if (corpus->offsets) {
+        pos0 = corpus->offsets[0];
+        pos1 = corpus->offsets[N];
+        if (pos1 < pos0) return fail(PMM_ERR_INVALID, "list offsets are not monotonic");
+        CUDA_TRY(uc.offsets.alloc((size_t)(N + 1) * 8, s));
+        CUDA_TRY(cudaMemcpyAsync(uc.offsets.p, corpus->offsets, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, s));
+        uc.dm.offsets = uc.offsets.as<int64_t>();
+        stat_add("h2d_bytes", (double)(N + 1) * 8);
+    }
+    CUDA_TRY(uc.values.alloc((size_t)(pos1 - pos0) * es, s));
+    uc.dm.values = (const char *)uc.values.p - (size_t)pos0 * es;
+    if (corpus->validity) {
+        const size_t nb = (size_t)((pos1 + 7) / 8);
+        CUDA_TRY(uc.validity.alloc(nb, s));
+        CUDA_TRY(cudaMemcpyAsync(uc.validity.p, corpus->validity, nb, cudaMemcpyHostToDevice, s));
+        uc.dm.validity = uc.validity.as<uint8_t>();
+    }
+    if (corpus->row_validity) {
+        const size_t nb = (size_t)((N + 7) / 8);
+        CUDA_TRY(uc.row_validity.alloc(nb, s));
+        CUDA_TRY(cudaMemcpyAsync(uc.row_validity.p, corpus->row_validity, nb, cudaMemcpyHostToDevice, s));
+        uc.dm.row_validity = uc.row_validity.as<uint8_t>();
+    }
+    cudaEvent_t ready;
+    CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ready, s));
+    CUDA_TRY(cudaStreamWaitEvent(cs, ready, 0));  // the copy stream may touch the buffers once they exist
+    std::vector<cudaEvent_t> ev(n_chunks);
+    for (int i = 0; i < n_chunks; ++i) {
+        const int64_t a = corpus->offsets ? corpus->offsets[cut[i]] : cut[i] * D;
+        const int64_t b = corpus->offsets ? corpus->offsets[cut[i + 1]] : cut[i + 1] * D;
+        if (b > a)
+            CUDA_TRY(cudaMemcpyAsync((char *)uc.values.p + (size_t)(a - pos0) * es, (const char *)corpus->values + (size_t)a * es,
+                                     (size_t)(b - a) * es, cudaMemcpyHostToDevice, cs));
+        stat_add("h2d_bytes", (double)(b - a) * es);
+        CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ev[i], cs));
+    }
+
+    const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
+    DevBuf err, kept_all, kept, c_aux_all, d_idx, d_sc;
+    CUDA_TRY(err.alloc(sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    Prepared q;
+    if ((rc = prepare(uq.dm, pc.mode, false, 2 * TC_TILE_M, want_norm, want_sq, err.as<int>(), s, &q))) return rc;
+    const int kp = tc_list_capacity(keff);
+    CUDA_TRY(kept_all.alloc((size_t)n_chunks * Q * kp * 8, s));
+    CUDA_TRY(kept.alloc((size_t)Q * kp * 8, s));
+    if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)N * 4, s));
+    for (int i = 0; i < n_chunks; ++i) {
+        CUDA_TRY(cudaStreamWaitEvent(s, ev[i], 0));
+        const int64_t r0 = cut[i], rows = cut[i + 1] - cut[i];
+        pmm_matrix_t dm = uc.dm;
+        dm.n_rows = rows;
+        if (dm.offsets) {
+            dm.offsets += r0;  // offsets hold absolute child positions: values / validity stay as they are
+        } else {
+            dm.values = (const char *)dm.values + (size_t)r0 * D * es;
+            if (dm.validity) dm.validity += (r0 * D) / 8;  // r0 is a multiple of 256
+        }
+        if (dm.row_validity) dm.row_validity += r0 / 8;
+        Prepared c;
+        if ((rc = prepare(dm, pc.mode, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c))) return rc;
+        if (want_norm || want_sq)
+            CUDA_TRY(cudaMemcpyAsync(c_aux_all.as<float>() + r0, want_norm ? c.norm.p : c.sqnorm.p, (size_t)rows * 4,
+                                     cudaMemcpyDeviceToDevice, s));
+        if ((rc = tc_filter(q, c, kp, metric, r0, kept_all.as<uint64_t>() + (size_t)i * Q * kp, s))) return rc;
+    }
+    const uint64_t *kept_ptr = kept_all.as<uint64_t>();
+    if (n_chunks > 1) {
+        CUDA_TRY(launch_counted("merge", s, [&] {
+            return launch_merge_regular(kept_all.as<uint64_t>(), n_chunks, Q * kp, kp, Q, kp, kp, true, nullptr, nullptr,
+                                        kept.as<uint64_t>(), s);
+        }));
+        kept_ptr = kept.as<uint64_t>();
+    }
+    const size_t cnt = (size_t)Q * keff;
+    CUDA_TRY(d_idx.alloc(cnt * 4, s));
+    CUDA_TRY(d_sc.alloc(cnt * 8, s));
+    const float *q_aux = want_norm ? q.norm.as<float>() : want_sq ? q.sqnorm.as<float>() : nullptr;
+    CUDA_TRY(launch_counted("rescore", s, [&] {
+        return launch_rescore(kept_ptr, kp, raw_of(uq.dm), raw_of(uc.dm), q_aux, c_aux_all.as<float>(), metric, 0, (int)keff,
+                              d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr, s);
+    }));
+    CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    stat_add("d2h_bytes", (double)cnt * 12);
+    if (queries->offsets || corpus->offsets) rc = finish_error_flag(err.as<int>(), s);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    cudaEventDestroy(ready);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 }  // namespace
 
 struct pmm_corpus {
@@ -578,6 +722,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
+    else if (k == "host_chunked") g_host_chunked.store(value ? 1 : 0);
     else if (k == "tc_sync_tiles") g_tc_sync_tiles.store(value < 0 ? 0 : (int)value);  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
     else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
@@ -673,6 +818,11 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     if ((rc = ensure_device())) return rc;
     if (keff == 0) return PMM_OK;
     cudaStream_t s = host_stream();
+    {
+        PathChoice pc = choose_path(queries->dtype, corpus->dtype, keff);
+        if (pc.tc && g_host_chunked.load() && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 64e6)
+            return host_topk_chunked(queries, corpus, keff, m, pc, out_index, out_score);
+    }
     Uploaded uq, uc;
     if ((rc = upload(queries, s, &uq)) || (rc = upload(corpus, s, &uc))) return rc;
     DevBuf d_idx, d_sc;

@@ -300,6 +300,38 @@ def test_resident_corpus_handle(native, oracle):
         h.close()
 
 
+def test_host_chunked_upload_path(pmm, native, oracle):
+    """Corpora >= 64 MB take the chunked host path (upload of chunk i+1 overlaps compute of chunk i):
+    same result as the oracle, for fixed-size rows and for list offsets with nulls."""
+    import pyarrow as pa
+    rng = np.random.default_rng(77)
+    q, c = _randn(rng, 200, 192), _randn(rng, 90_000, 192)          # 69 MB corpus -> 2 chunks
+    c[20_000] = c[3]                                                  # an exact tie across the chunk boundary
+    for metric in ("cosine", "dot", "euclidean"):
+        idx, sc = native.topk(_hm(q), _hm(c), 20, metric)
+        parity.check_topk(idx, sc, q, c, 20, metric, oracle, exact=True)
+    native.set_option("host_chunked", 0)
+    try:
+        i0, s0 = native.topk(_hm(q), _hm(c), 20, "cosine")
+    finally:
+        native.set_option("host_chunked", 1)
+    i1, s1 = native.topk(_hm(q), _hm(c), 20, "cosine")
+    assert np.array_equal(i0, i1) and np.array_equal(s0, s1)
+    # list layout: offsets + a null row + a null element + a short row, spread over both chunks
+    flat = pa.array(c.reshape(-1))
+    offsets = np.arange(0, (c.shape[0] + 1) * 192, 192, dtype=np.int64)
+    lst = pa.LargeListArray.from_arrays(pa.array(offsets), flat)
+    rows = lst.to_pylist()[:3]
+    dense = c.copy()
+    mask = np.ones(c.shape[0], bool)
+    mask[[5, 50_000]] = False                                         # null rows -> zeros
+    lst = pa.LargeListArray.from_arrays(pa.array(offsets), flat, mask=pa.array(~mask))
+    dense[[5, 50_000]] = 0
+    del rows
+    idx, sc = pmm.topk_arrays(q, lst, 20, "dot")
+    parity.check_topk(idx, sc, q, dense, 20, "dot", oracle, exact=True)
+
+
 # ---------------------------------------------------------------------------------------------- device entry points
 def test_device_level_shards_merge(native, oracle):
     """Two corpus shards on one GPU -> packed candidates with global indices -> merge == unsharded."""
