@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -254,9 +254,11 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
         double *os = o.score ? o.score + q0 * keff : nullptr;
         uint64_t *oc = o.cand ? o.cand + q0 * keff : nullptr;
         if (f64) {
-            CUDA_TRY(launch_counted("scores_f64", s, [&] {
-                return launch_scores_f64(q.p0.as<double>() + q0 * D, c.p0.as<double>(), qa ? (const double *)qa + q0 : nullptr,
-                                         (const double *)ca, nq, N, D, metric, slab.as<double>(), N, s);
+            const bool simt = g_f64_simt.load() != 0;
+            CUDA_TRY(launch_counted(simt ? "scores_f64" : "scores_f64_dmma", s, [&] {
+                return (simt ? launch_scores_f64 : launch_scores_f64_dmma)(
+                    q.p0.as<double>() + q0 * D, c.p0.as<double>(), qa ? (const double *)qa + q0 : nullptr, (const double *)ca, nq,
+                    N, D, metric, slab.as<double>(), N, s);
             }));
             CUDA_TRY(launch_counted("select_f64", s, [&] {
                 return launch_select_f64(slab.as<double>(), N, nq, N, keff, higher, index_base, oi, os, scratch.p, s);
@@ -449,9 +451,11 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
     } else if (pc.f64) {
         for (int64_t q0 = 0; q0 < Q; q0 += (1 << 20)) {
             int64_t nq = Q - q0 < (1 << 20) ? Q - q0 : (1 << 20);
-            CUDA_TRY(launch_counted("scores_f64", s, [&] {
-                return launch_scores_f64(l.p0.as<double>() + q0 * D, r.p0.as<double>(), nullptr, nullptr, nq, N, D, PMM_METRIC_DOT,
-                                         (double *)d_out + q0 * N, N, s);
+            const bool simt = g_f64_simt.load() != 0;
+            CUDA_TRY(launch_counted(simt ? "scores_f64" : "scores_f64_dmma", s, [&] {
+                return (simt ? launch_scores_f64 : launch_scores_f64_dmma)(l.p0.as<double>() + q0 * D, r.p0.as<double>(), nullptr,
+                                                                           nullptr, nq, N, D, PMM_METRIC_DOT,
+                                                                           (double *)d_out + q0 * N, N, s);
             }));
         }
     } else {
@@ -722,6 +726,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
+    else if (k == "f64_simt") g_f64_simt.store(value ? 1 : 0);  // 1: bit-exact sequential-FMA f64 instead of DMMA
     else if (k == "host_chunked") g_host_chunked.store(value ? 1 : 0);
     else if (k == "tc_sync_tiles") g_tc_sync_tiles.store(value < 0 ? 0 : (int)value);  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);

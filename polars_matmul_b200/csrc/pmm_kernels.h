@@ -32,6 +32,9 @@ cudaError_t launch_scores_f32(const float *q, const float *c, const float *qa, c
                               int64_t n, int64_t d, int metric, float *out, int64_t ldo, cudaStream_t s);
 cudaError_t launch_scores_f64(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
                               int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s);
+// Same contract on the FP64 tensor path (mma.sync.m8n8k4.f64); agrees to ~1e-15 relative, not bit for bit.
+cudaError_t launch_scores_f64_dmma(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
+                                   int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s);
 // Per-row exact top-k of a score slab (radix select + ordered tie collection + bitonic sort).
 // scratch: nq * kpad * 12 bytes when kpad > select_smem_kpad_limit(), else unused.
 int select_kpad(int64_t k);

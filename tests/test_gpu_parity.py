@@ -95,10 +95,12 @@ def test_generic_path_bit_exact(native, oracle, metric, dtype):
     rng = np.random.default_rng(7)
     q, c = _randn(rng, 37, 50, dtype=dtype), _randn(rng, 1000, 50, dtype=dtype)
     native.set_option("force_generic", 1)
+    native.set_option("f64_simt", 1)          # f64: sequential-FMA kernel instead of DMMA
     try:
         idx, sc = native.topk(_hm(q), _hm(c), 17, metric)
     finally:
         native.set_option("force_generic", 0)
+        native.set_option("f64_simt", 0)
     parity.check_topk(idx, sc, q, c, 17, metric, oracle, exact=True)
 
 
@@ -114,21 +116,36 @@ def test_generic_path_large_k_and_clamp(native, oracle):
 def test_f64_path(native, oracle):
     rng = np.random.default_rng(9)
     q, c = _randn(rng, 64, 64, dtype=np.float64), _randn(rng, 2000, 64, dtype=np.float64)
+    # default: DMMA (mma.sync.m8n8k4.f64) — within 1e-12 relative of the oracle, indices equal up to near-ties
     for metric in ("cosine", "dot", "euclidean"):
         idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
-        parity.check_topk(idx, sc, q, c, 10, metric, oracle, exact=True)
+        frac = parity.check_topk(idx, sc, q, c, 10, metric, oracle)
+        assert frac == 1.0
     out = native.matmul(_hm(q), _hm(c))
     assert out.dtype == np.float64
-    assert np.array_equal(out, oracle.matmul(q, c))
+    parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float64)
+    # odd shapes through the DMMA tiles (row/column/k tails)
+    q2, c2 = _randn(rng, 131, 37, dtype=np.float64), _randn(rng, 77, 37, dtype=np.float64)
+    parity.check_matmul(native.matmul(_hm(q2), _hm(c2)), q2, c2, oracle.matmul(q2, c2), np.float64)
+    # sequential-FMA kernel: bit-identical
+    native.set_option("f64_simt", 1)
+    try:
+        for metric in ("cosine", "dot", "euclidean"):
+            idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
+            parity.check_topk(idx, sc, q, c, 10, metric, oracle, exact=True)
+        assert np.array_equal(native.matmul(_hm(q), _hm(c)), oracle.matmul(q, c))
+    finally:
+        native.set_option("f64_simt", 0)
 
 
 def test_mixed_dtype_uses_f64(native, oracle):
     rng = np.random.default_rng(10)
     q, c = _randn(rng, 5, 16, dtype=np.float32), _randn(rng, 40, 16, dtype=np.float64)
     out = native.matmul(_hm(q), _hm(c))
-    assert out.dtype == np.float64 and np.array_equal(out, oracle.matmul(q, c))
+    assert out.dtype == np.float64
+    parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float64)
     idx, sc = native.topk(_hm(q), _hm(c), 3, "cosine")
-    parity.check_topk(idx, sc, q, c, 3, "cosine", oracle, exact=True)
+    assert parity.check_topk(idx, sc, q, c, 3, "cosine", oracle) == 1.0
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core path
@@ -167,7 +184,7 @@ def test_tc_matmul_f32_c2(native, oracle):
     parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float32)
     q64, c64 = q[:200].astype(np.float64), c[:3000].astype(np.float64)
     out = native.matmul(_hm(q64), _hm(c64))
-    assert np.array_equal(out, oracle.matmul(q64, c64))
+    parity.check_matmul(out, q64, c64, oracle.matmul(q64, c64), np.float64)
 
 
 @pytest.mark.parametrize("shape", [(7, 13, 5), (129, 1000, 257), (300, 257, 64)])
