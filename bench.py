@@ -278,6 +278,7 @@ def main():
     k_ms = _native.get_stat(kname + "_ms")
     k_launches = _native.get_stat(kname + "_launches")
     stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps) for n in ("prep", kname, "merge", "rescore")}
+    stats["fallback_queries_per_step"] = _native.get_stat("fallback_queries") / max(1, args.steps)
     _native.set_option("profile", 0)
     value = world * Q / (ms_step / 1000.0)
 

@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -150,12 +150,13 @@ struct Prepared {
     int mode = PREP_DENSE;   // PREP_*
     bool f64 = false;
     int64_t n_rows = 0, dim = 0, rows_pad = 0, ld = 0;
-    DevBuf p0, p1, norm, sqnorm;
+    DevBuf p0, p1, norm, sqnorm, max_sq;
+    unsigned int *max_sq_ptr = nullptr;  // own (max_sq) or shared across corpus chunks
 };
 
 // Runs the prep kernel on a device-resident matrix. row_tile: pad rows to this multiple (planes only).
 int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool want_norm, bool want_sq, int *d_err,
-            cudaStream_t s, Prepared *out) {
+            cudaStream_t s, Prepared *out, bool want_max = false, unsigned int *shared_max = nullptr) {
     out->mode = mode;
     out->f64 = f64;
     out->n_rows = m.n_rows;
@@ -175,6 +176,12 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     }
     if (want_norm) CUDA_TRY(out->norm.alloc((size_t)(out->rows_pad * wsz), s));
     if (want_sq) CUDA_TRY(out->sqnorm.alloc((size_t)(out->rows_pad * wsz), s));
+    out->max_sq_ptr = shared_max;
+    if (want_max && !shared_max) {
+        CUDA_TRY(out->max_sq.alloc(sizeof(unsigned int), s));
+        CUDA_TRY(cudaMemsetAsync(out->max_sq.p, 0, sizeof(unsigned int), s));
+        out->max_sq_ptr = out->max_sq.as<unsigned int>();
+    }
     PrepArgs a;
     a.values = m.values;
     a.offsets = m.offsets;
@@ -188,6 +195,7 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     a.out1 = out->p1.p;
     a.norm_out = out->norm.p;
     a.sqnorm_out = out->sqnorm.p;
+    a.max_sq_out = out->max_sq_ptr;
     a.error_flag = d_err;
     CUDA_TRY(launch_counted("prep", s, [&] { return launch_prep(a, m.dtype, mode, f64 ? 1 : 0, s); }));
     return PMM_OK;
@@ -353,7 +361,84 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     return PMM_OK;
 }
 
-// Tensor-core path: filter -> exact re-scoring of the kept candidates.
+int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric, int64_t index_base, TopkOut o,
+                 cudaStream_t s);
+
+// Relative error bound of the tensor-core filter value against the exact f32 score, per |q||c|:
+// one f32 ulp of truncation per tcgen05 accumulate step (3*D/8 of them for 3xTF32), the TF32 split
+// residue, and the worst-case rounding of the exact sequential-FMA sum itself (D * 2^-24).
+float filter_eps(int64_t dim) { return 1.1e-7f * (float)dim + 2e-6f; }
+
+// Exact re-scoring of the kept candidates + the losslessness check; queries the check cannot clear are
+// recomputed on the exact SIMT path (gather -> scores + select -> scatter). May synchronise the stream.
+int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, const float *q_aux,
+                       const float *c_aux, const float *q_sq, const unsigned int *c_max_sq, int metric, int64_t index_base,
+                       int64_t keff, TopkOut o, cudaStream_t s) {
+    const int64_t Q = raw_q.n_rows;
+    DevBuf flags, count;
+    RescoreCheck chk;
+    memset(&chk, 0, sizeof(chk));
+    const bool verify = g_verify.load() && q_sq && c_max_sq;
+    if (verify) {
+        CUDA_TRY(flags.alloc((size_t)Q, s));
+        CUDA_TRY(count.alloc(sizeof(unsigned int), s));
+        CUDA_TRY(cudaMemsetAsync(flags.p, 0, (size_t)Q, s));
+        CUDA_TRY(cudaMemsetAsync(count.p, 0, sizeof(unsigned int), s));
+        chk.q_sq = q_sq;
+        chk.c_max_sq = c_max_sq;
+        chk.eps = filter_eps(raw_q.dim);
+        chk.flags = flags.as<unsigned char>();
+        chk.flag_count = count.as<unsigned int>();
+    }
+    CUDA_TRY(launch_counted("rescore", s, [&] {
+        return launch_rescore(kept, kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base, (int)keff, o.index,
+                              o.score, o.cand, chk, s);
+    }));
+    if (!verify) return PMM_OK;
+    unsigned int n_flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_flag, count.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (n_flag == 0) return PMM_OK;
+    stat_add("fallback_queries", (double)n_flag);
+    // ---- exact path for the flagged queries
+    std::vector<unsigned char> hflags((size_t)Q);
+    CUDA_TRY(cudaMemcpy(hflags.data(), flags.p, (size_t)Q, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> ids;
+    ids.reserve(n_flag);
+    for (int64_t i = 0; i < Q; ++i)
+        if (hflags[(size_t)i]) ids.push_back(i);
+    const int64_t F = (int64_t)ids.size();
+    DevBuf d_ids, dense_q, t_idx, t_sc, t_cand, err;
+    CUDA_TRY(d_ids.alloc((size_t)F * 8, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ids.p, ids.data(), (size_t)F * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(dense_q.alloc((size_t)F * raw_q.dim * 4, s));
+    CUDA_TRY(launch_counted("gather", s, [&] { return launch_gather_rows(raw_of(raw_q), d_ids.as<int64_t>(), F, dense_q.as<float>(), s); }));
+    pmm_matrix_t qd;
+    memset(&qd, 0, sizeof(qd));
+    qd.values = dense_q.p;
+    qd.n_rows = F;
+    qd.dim = raw_q.dim;
+    qd.dtype = PMM_DTYPE_F32;
+    CUDA_TRY(err.alloc(sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
+    Prepared qf, cf;
+    int rc = prepare(qd, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &qf);
+    if (rc) return rc;
+    if ((rc = prepare(raw_c, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
+    CUDA_TRY(t_idx.alloc((size_t)F * keff * 4, s));
+    CUDA_TRY(t_sc.alloc((size_t)F * keff * 8, s));
+    CUDA_TRY(t_cand.alloc((size_t)F * keff * 8, s));
+    TopkOut t{t_idx.as<uint32_t>(), t_sc.as<double>(), t_cand.as<uint64_t>()};
+    if ((rc = topk_generic(qf, cf, keff, metric, index_base, t, s))) return rc;
+    CUDA_TRY(launch_counted("scatter", s, [&] {
+        return launch_scatter_results(d_ids.as<int64_t>(), F, (int)keff, t.index, t.score, t.cand, o.index, o.score, o.cand, s);
+    }));
+    CUDA_TRY(cudaStreamSynchronize(s));  // ids (host vector) and temporaries stay alive until the work is done
+    return PMM_OK;
+}
+
+// Tensor-core path: filter -> exact re-scoring of the kept candidates (+ verification).
 int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
             int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
     const int kp = tc_list_capacity(keff);
@@ -363,11 +448,8 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     if (rc) return rc;
     const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
-    CUDA_TRY(launch_counted("rescore", s, [&] {
-        return launch_rescore(kept.as<uint64_t>(), kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base,
-                              (int)keff, o.index, o.score, o.cand, s);
-    }));
-    return PMM_OK;
+    return rescore_and_verify(kept.as<uint64_t>(), kp, raw_q, raw_c, q_aux, c_aux, q.sqnorm.as<float>(), c.max_sq_ptr, metric,
+                              index_base, keff, o, s);
 }
 
 struct PathChoice {
@@ -400,11 +482,12 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared q, c_local;
-    int rc = prepare(*dq, pc.mode, pc.f64, 2 * TC_TILE_M, want_norm, want_sq, err.as<int>(), s, &q);
+    // the tensor-core path always needs squared norms (error bound of the losslessness check)
+    int rc = prepare(*dq, pc.mode, pc.f64, 2 * TC_TILE_M, want_norm, want_sq || pc.tc, err.as<int>(), s, &q);
     if (rc) return rc;
     const Prepared *c = pc_corpus;
     if (!c) {
-        rc = prepare(*dc, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c_local);
+        rc = prepare(*dc, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c_local, pc.tc);
         if (rc) return rc;
         c = &c_local;
     }
@@ -615,7 +698,10 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared q;
-    if ((rc = prepare(uq.dm, pc.mode, false, 2 * TC_TILE_M, want_norm, want_sq, err.as<int>(), s, &q))) return rc;
+    if ((rc = prepare(uq.dm, pc.mode, false, 2 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
+    DevBuf c_max;
+    CUDA_TRY(c_max.alloc(sizeof(unsigned int), s));
+    CUDA_TRY(cudaMemsetAsync(c_max.p, 0, sizeof(unsigned int), s));
     const int kp = tc_list_capacity(keff);
     CUDA_TRY(kept_all.alloc((size_t)n_chunks * Q * kp * 8, s));
     CUDA_TRY(kept.alloc((size_t)Q * kp * 8, s));
@@ -633,7 +719,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         }
         if (dm.row_validity) dm.row_validity += r0 / 8;
         Prepared c;
-        if ((rc = prepare(dm, pc.mode, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c))) return rc;
+        if ((rc = prepare(dm, pc.mode, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
         if (want_norm || want_sq)
             CUDA_TRY(cudaMemcpyAsync(c_aux_all.as<float>() + r0, want_norm ? c.norm.p : c.sqnorm.p, (size_t)rows * 4,
                                      cudaMemcpyDeviceToDevice, s));
@@ -651,10 +737,10 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(d_idx.alloc(cnt * 4, s));
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     const float *q_aux = want_norm ? q.norm.as<float>() : want_sq ? q.sqnorm.as<float>() : nullptr;
-    CUDA_TRY(launch_counted("rescore", s, [&] {
-        return launch_rescore(kept_ptr, kp, raw_of(uq.dm), raw_of(uc.dm), q_aux, c_aux_all.as<float>(), metric, 0, (int)keff,
-                              d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr, s);
-    }));
+    TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
+    if ((rc = rescore_and_verify(kept_ptr, kp, uq.dm, uc.dm, q_aux, c_aux_all.as<float>(), q.sqnorm.as<float>(),
+                                 c_max.as<unsigned int>(), metric, 0, keff, o, s)))
+        return rc;
     CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
     stat_add("d2h_bytes", (double)cnt * 12);
@@ -726,6 +812,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
+    else if (k == "verify") g_verify.store(value ? 1 : 0);  // 0: skip the filter-losslessness check (and its fallback)
     else if (k == "f64_simt") g_f64_simt.store(value ? 1 : 0);  // 1: bit-exact sequential-FMA f64 instead of DMMA
     else if (k == "host_chunked") g_host_chunked.store(value ? 1 : 0);
     else if (k == "tc_sync_tiles") g_tc_sync_tiles.store(value < 0 ? 0 : (int)value);  // 0 = no pacing barriers
@@ -893,7 +980,7 @@ int pmm_corpus_create(const pmm_matrix_t *corpus, int32_t query_dtype, pmm_corpu
         delete h;
         return fail(PMM_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
     }
-    rc = prepare(uc.dm, pc.mode, pc.f64, TC_TILE_N, true, true, err.as<int>(), s, &h->prep);
+    rc = prepare(uc.dm, pc.mode, pc.f64, TC_TILE_N, true, true, err.as<int>(), s, &h->prep, pc.tc);
     if (!rc) rc = finish_error_flag(err.as<int>(), s);
     if (rc) {
         delete h;

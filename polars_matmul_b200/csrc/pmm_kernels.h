@@ -19,6 +19,7 @@ struct PrepArgs {
     void *out1;                   // lo plane (MODE_TF32) or NULL
     void *norm_out;               // [rows_out] working type or NULL
     void *sqnorm_out;             // [rows_out] working type or NULL
+    unsigned int *max_sq_out;     // f32 working type only: atomicMax of the squared norms' bit patterns, or NULL
     int *error_flag;              // set to 1 when a list row is longer than dim
 };
 enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2 };
@@ -60,10 +61,22 @@ struct RawMatrix {               // a device-resident column in Arrow layout (pm
     int64_t n_rows, dim;
     int dtype;                   // 0 f16, 1 f32
 };
+// Inputs of the "was the filter lossless for this query" check (all device pointers; flags == NULL: no check).
+struct RescoreCheck {
+    const float *q_sq;             // [n_queries] squared query norms
+    const unsigned int *c_max_sq;  // bits of the largest squared corpus norm (float >= 0, compared as uint)
+    float eps;                     // relative error bound of the filter value vs the exact score, per |q||c|
+    unsigned char *flags;          // [n_queries] set to 1 when not provable
+    unsigned int *flag_count;
+};
 // cand [n_queries][kp_in] packed candidates (approximate keys, global indices) -> exact top-k_out.
 cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
                            const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
-                           uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s);
+                           uint32_t *out_idx, double *out_score, uint64_t *out_cand, const RescoreCheck &chk,
+                           cudaStream_t s);
+cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, float *out, cudaStream_t s);
+cudaError_t launch_scatter_results(const int64_t *ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,
+                                   const uint64_t *sc, uint32_t *di, double *ds, uint64_t *dc, cudaStream_t s);
 
 // ---- tensor-core path (pmm_tc_kernels.cu) ----------------------------------------------------------
 constexpr int TC_TILE_M = 128;   // query rows per CTA tile

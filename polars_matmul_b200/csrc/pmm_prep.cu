@@ -148,6 +148,13 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
         if (a.sqnorm_out) ((W *)a.sqnorm_out)[row] = sum;
         if (a.norm_out) ((W *)a.norm_out)[row] = sqrt_rn(sum);
     }
+    if (sizeof(W) == 4 && a.max_sq_out) {  // largest squared norm of the column: one atomic per warp
+        const float fs = (float)sum;
+        unsigned int bits = (sub == 0 && row < a.n_rows && fs == fs) ? __float_as_uint(fs) : 0u;  // >= 0: orders like uint
+        const unsigned am = __activemask();
+        bits = __reduce_max_sync(am, bits);
+        if (lane == __ffs(am) - 1 && bits) atomicMax(a.max_sq_out, bits);
+    }
 }
 
 template <typename SRC, typename W, int MODE>

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
                                                      RawMatrix cm, const float *__restrict__ q_aux,
                                                      const float *__restrict__ c_aux, int metric,
                                                      int64_t index_base, int k_out, uint32_t *out_idx,
-                                                     double *out_score, uint64_t *out_cand) {
+                                                     double *out_score, uint64_t *out_cand, RescoreCheck chk) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t *sortbuf = (uint64_t *)rs_smem;            // NT entries
     float *qs = (float *)(rs_smem + NT * 8);            // dim floats, then one 32x33 transpose tile per warp
@@ -106,6 +106,33 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             __syncthreads();
         }
     }
+    // ---- was the filter provably lossless for this query?  Every candidate the filter dropped has a filter
+    // value <= f_last (the worst kept one). Its exact score can exceed what f_last maps to by at most the
+    // filter's error bound; if the exact k-th score is not strictly better than that, a dropped candidate
+    // might belong to (or tie into) the top-k: flag the query, the host recomputes it on the exact path.
+    if (t == 0 && chk.flags) {
+        const uint64_t last = cand[q * kp_in + kp_in - 1];   // 0: fewer than kp_in candidates exist -> nothing dropped
+        bool ok = true;
+        if (last != 0ull && k_out > 0) {
+            const float f_last = key_score(candidate_key(last), true);
+            const float tk = key_score(candidate_key(sortbuf[k_out - 1]), higher);
+            const float qn = sqrtf(chk.q_sq[q]);
+            const float cmax = sqrtf(__uint_as_float(*chk.c_max_sq));
+            if (metric == METRIC_DOT) {
+                ok = tk > f_last + chk.eps * qn * cmax;
+            } else if (metric == METRIC_COSINE) {
+                ok = qn > 1e-6f && tk > f_last / qn + chk.eps + 1e-6f;
+            } else {  // filter value = -(squared distance)
+                const float sq_floor = -f_last - 2.0f * chk.eps * qn * cmax - 1e-6f * (qn * qn + cmax * cmax);
+                ok = sq_floor > 0.0f && tk < sqrtf(sq_floor) * (1.0f - 1e-6f);
+            }
+            if (!(ok)) ok = false;  // NaN anywhere -> not provable
+        }
+        if (!ok) {
+            chk.flags[q] = 1;
+            atomicAdd(chk.flag_count, 1u);
+        }
+    }
     if (t < k_out) {
         const uint64_t r = sortbuf[t];
         if (out_idx) out_idx[q * k_out + t] = candidate_index(r);
@@ -117,7 +144,8 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
 template <typename CSRC>
 static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
                                     const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
-                                    uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
+                                    uint32_t *out_idx, double *out_score, uint64_t *out_cand, const RescoreCheck &chk,
+                                    cudaStream_t s) {
     const unsigned grid = (unsigned)qm.n_rows;
     const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
 #define PMM_RS(NT)                                                                                                  \
@@ -128,7 +156,7 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
             if (e != cudaSuccess) return e;                                                                         \
         }                                                                                                           \
         rescore_kernel<CSRC, NT><<<grid, NT, smem, s>>>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, \
-                                                        out_idx, out_score, out_cand);                              \
+                                                        out_idx, out_score, out_cand, chk);                         \
     }
     if (kp_in <= 32) PMM_RS(32)
     else if (kp_in <= 64) PMM_RS(64)
@@ -141,12 +169,46 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
 
 cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
                            const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
-                           uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
+                           uint32_t *out_idx, double *out_score, uint64_t *out_cand, const RescoreCheck &chk, cudaStream_t s) {
     if (qm.n_rows <= 0 || k_out <= 0) return cudaSuccess;
     if (qm.dim * 4 > 160 * 1024) return cudaErrorInvalidValue;  // query row must fit shared memory
     if (cm.dtype == 0)
-        return launch_rescore_t<__half>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, s);
-    return launch_rescore_t<float>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, s);
+        return launch_rescore_t<__half>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, chk, s);
+    return launch_rescore_t<float>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, out_score, out_cand, chk, s);
+}
+
+
+// ---- fallback plumbing: gather flagged query rows into a dense f32 matrix, scatter their results back ----
+template <typename SRC>
+__global__ void gather_rows_kernel(RawMatrix qm, const int64_t *__restrict__ ids, int64_t n_ids, float *__restrict__ out) {
+    const int64_t r = blockIdx.x;
+    if (r >= n_ids) return;
+    int64_t b, l;
+    raw_row(qm, ids[r], b, l);
+    for (int64_t i = threadIdx.x; i < qm.dim; i += blockDim.x) out[r * qm.dim + i] = raw_fetch<SRC>(qm, b, l, i);
+}
+cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, float *out, cudaStream_t s) {
+    if (n_ids <= 0) return cudaSuccess;
+    if (qm.dtype == 0) gather_rows_kernel<__half><<<(unsigned)n_ids, 128, 0, s>>>(qm, ids, n_ids, out);
+    else gather_rows_kernel<float><<<(unsigned)n_ids, 128, 0, s>>>(qm, ids, n_ids, out);
+    return cudaGetLastError();
+}
+__global__ void scatter_results_kernel(const int64_t *__restrict__ ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,
+                                       const uint64_t *sc, uint32_t *di, double *ds, uint64_t *dc) {
+    const int64_t r = blockIdx.x;
+    if (r >= n_ids) return;
+    const int64_t q = ids[r];
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        if (di) di[q * k + t] = si[r * k + t];
+        if (ds) ds[q * k + t] = ss[r * k + t];
+        if (dc) dc[q * k + t] = sc[r * k + t];
+    }
+}
+cudaError_t launch_scatter_results(const int64_t *ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,
+                                   const uint64_t *sc, uint32_t *di, double *ds, uint64_t *dc, cudaStream_t s) {
+    if (n_ids <= 0 || k <= 0) return cudaSuccess;
+    scatter_results_kernel<<<(unsigned)n_ids, 128, 0, s>>>(ids, n_ids, k, si, ss, sc, di, ds, dc);
+    return cudaGetLastError();
 }
 
 }  // namespace pmm
