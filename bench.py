@@ -123,7 +123,7 @@ def cpu_baseline_sample(q_host: np.ndarray, c_host: np.ndarray, k: int, metric: 
                       f"oracle/pmm_oracle.c (OpenMP, -O3 -mavx2 -mfma); the reference (Rust/faer) cannot be built in this image"}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: oracle port on host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -164,10 +164,20 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    # Libraries (NCCL, torchrun) print to stdout; the contract is ONE JSON line there. Route fd 1 to stderr for
+    # the duration of the run and write the JSON line to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -182,7 +192,7 @@ def main():
     ap.add_argument("--k", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -290,7 +300,7 @@ def main():
         def step_e2e():
             if world == 1:
                 return _native.topk(hq, hc, k, metric)
-            return driver.topk_host(None, None, rank * N, n_total, k, metric, pinned_q=q_pin, pinned_c=c_pin)
+            return driver.topk_host(hq, hc, rank * N, n_total, k, metric)
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
@@ -345,7 +355,7 @@ def main():
             "queries_per_sec_global_corpus": Q / (ms_step / 1000.0),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -150,6 +150,12 @@ PMM_API int pmm_dev_topk(const pmm_matrix_t *d_queries, const pmm_matrix_t *d_co
                  int64_t index_base, uint32_t *d_index, double *d_score, uint64_t *d_candidates,
                  void *stream);
 
+/* Host inputs (this rank's corpus shard, replicated queries) -> this rank's exact local top-k as packed
+ * candidates [Q * min(k, shard rows)] LEFT IN DEVICE MEMORY at d_candidates, ready for the all-gather.
+ * The shard upload overlaps the compute (chunked H2D). Synchronous: the candidates are complete on return. */
+PMM_API int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard, int64_t k, int32_t metric,
+                           int64_t index_base, uint64_t *d_candidates);
+
 /* K-way merge of `n_lists` candidate lists laid out [n_lists][n_queries][k_in] (each sorted best
  * first, as pmm_dev_topk writes them; e.g. the all-gathered shards) into the final
  * [n_queries * k_out] index/score buffers.  k_out <= k_in <= 128. */

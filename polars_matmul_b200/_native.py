@@ -75,6 +75,7 @@ def lib() -> ctypes.CDLL:
         "pmm_corpus_rows": (i64, [vp]),
         "pmm_topk_corpus": (ctypes.c_int, [P, vp, i64, ctypes.c_char_p, vp, vp, ctypes.POINTER(i64)]),
         "pmm_dev_topk": (ctypes.c_int, [P, P, i64, i32, i64, vp, vp, vp, vp]),
+        "pmm_topk_shard": (ctypes.c_int, [P, P, i64, i32, i64, vp]),
         "pmm_dev_merge_candidates": (ctypes.c_int, [vp, i64, i64, i64, i64, i32, vp, vp, vp]),
         "pmm_dev_matmul": (ctypes.c_int, [P, P, vp, vp]),
         "pmm_dev_norms": (ctypes.c_int, [P, i32, vp, vp]),
@@ -98,7 +99,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "pmm_metric_from_str", "pmm_higher_is_better", "pmm_working_dtype", "pmm_topk", "pmm_matmul",
-    "pmm_corpus_create", "pmm_corpus_destroy", "pmm_corpus_rows", "pmm_topk_corpus", "pmm_dev_topk",
+    "pmm_corpus_create", "pmm_corpus_destroy", "pmm_corpus_rows", "pmm_topk_corpus", "pmm_dev_topk", "pmm_topk_shard",
     "pmm_dev_merge_candidates", "pmm_dev_matmul", "pmm_dev_norms", "pmm_last_error", "pmm_version",
     "pmm_device_count", "pmm_set_device", "pmm_kernel_launch_count", "pmm_reset_kernel_launch_count",
     "pmm_set_option", "pmm_get_stat", "pmm_reset_stats",
@@ -209,6 +210,12 @@ def dev_topk(dq: PmmMatrix, dc: PmmMatrix, k: int, metric: int, index_base: int 
              score_ptr: int = 0, cand_ptr: int = 0, stream: int = 0) -> None:
     check(lib().pmm_dev_topk(ctypes.byref(dq), ctypes.byref(dc), k, metric, index_base, index_ptr or None,
                              score_ptr or None, cand_ptr or None, stream or None))
+
+
+def topk_shard(queries: HostMatrix, corpus_shard: HostMatrix, k: int, metric: int, index_base: int, cand_ptr: int) -> None:
+    """pmm_topk_shard: host buffers in, exact packed candidates left on the device at cand_ptr."""
+    q, c = queries.c_struct(), corpus_shard.c_struct()
+    check(lib().pmm_topk_shard(ctypes.byref(q), ctypes.byref(c), int(k), int(metric), int(index_base), cand_ptr))
 
 
 def dev_merge_candidates(lists_ptr: int, n_lists: int, n_queries: int, k_in: int, k_out: int, metric: int,

@@ -634,8 +634,10 @@ cudaStream_t copy_stream() {
 // a second stream while chunk i runs prep + the fused filter; the per-chunk candidate lists are merged
 // and re-scored once against the whole (now resident) corpus. A small first chunk starts the tensor
 // cores early; the rest of the upload hides behind it.
+// Outputs: host index/score buffers and/or exact packed candidates left on the device (d_cand, for the
+// multi-GPU exchange); corpus row j is reported as index_base + j.
 int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t keff, int metric, PathChoice pc,
-                      uint32_t *out_index, double *out_score) {
+                      int64_t index_base, uint32_t *out_index, double *out_score, uint64_t *d_cand) {
     cudaStream_t s = host_stream(), cs = copy_stream();
     const int64_t Q = queries->n_rows, N = corpus->n_rows, D = corpus->dim;
     const int es = esize(corpus->dtype);
@@ -723,7 +725,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         if (want_norm || want_sq)
             CUDA_TRY(cudaMemcpyAsync(c_aux_all.as<float>() + r0, want_norm ? c.norm.p : c.sqnorm.p, (size_t)rows * 4,
                                      cudaMemcpyDeviceToDevice, s));
-        if ((rc = tc_filter(q, c, kp, metric, r0, kept_all.as<uint64_t>() + (size_t)i * Q * kp, s))) return rc;
+        if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept_all.as<uint64_t>() + (size_t)i * Q * kp, s))) return rc;
     }
     const uint64_t *kept_ptr = kept_all.as<uint64_t>();
     if (n_chunks > 1) {
@@ -737,13 +739,13 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(d_idx.alloc(cnt * 4, s));
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     const float *q_aux = want_norm ? q.norm.as<float>() : want_sq ? q.sqnorm.as<float>() : nullptr;
-    TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
+    TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), d_cand};
     if ((rc = rescore_and_verify(kept_ptr, kp, uq.dm, uc.dm, q_aux, c_aux_all.as<float>(), q.sqnorm.as<float>(),
-                                 c_max.as<unsigned int>(), metric, 0, keff, o, s)))
+                                 c_max.as<unsigned int>(), metric, index_base, keff, o, s)))
         return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
-    stat_add("d2h_bytes", (double)cnt * 12);
+    if (out_index) CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
+    if (out_score) CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    if (out_index || out_score) stat_add("d2h_bytes", (double)cnt * 12);
     if (queries->offsets || corpus->offsets) rc = finish_error_flag(err.as<int>(), s);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(cs));
@@ -913,7 +915,7 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     {
         PathChoice pc = choose_path(queries->dtype, corpus->dtype, keff);
         if (pc.tc && g_host_chunked.load() && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 64e6)
-            return host_topk_chunked(queries, corpus, keff, m, pc, out_index, out_score);
+            return host_topk_chunked(queries, corpus, keff, m, pc, 0, out_index, out_score, nullptr);
     }
     Uploaded uq, uc;
     if ((rc = upload(queries, s, &uq)) || (rc = upload(corpus, s, &uc))) return rc;
@@ -926,6 +928,32 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
     stat_add("d2h_bytes", (double)cnt * 12);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard, int64_t k, int32_t metric,
+                   int64_t index_base, uint64_t *d_candidates) {
+    int rc;
+    if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus_shard, "corpus"))) return rc;
+    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative");
+    if (queries->n_rows == 0) return PMM_OK;
+    if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
+    if ((rc = check_pair(queries, corpus_shard))) return rc;
+    if ((rc = list_dim_check(queries, "queries")) || (rc = list_dim_check(corpus_shard, "corpus"))) return rc;
+    if ((rc = ensure_device())) return rc;
+    const int64_t keff = k < corpus_shard->n_rows ? k : corpus_shard->n_rows;
+    if (keff == 0) return PMM_OK;
+    PathChoice pc = choose_path(queries->dtype, corpus_shard->dtype, keff);
+    if (pc.f64) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
+    if (pc.tc && g_host_chunked.load() &&
+        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 64e6)
+        return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
+    cudaStream_t s = host_stream();
+    Uploaded uq, uc;
+    if ((rc = upload(queries, s, &uq)) || (rc = upload(corpus_shard, s, &uc))) return rc;
+    TopkOut o{nullptr, nullptr, d_candidates};
+    if ((rc = dev_topk_impl(&uq.dm, &uc.dm, nullptr, corpus_shard->dtype, k, metric, index_base, o, s))) return rc;
     CUDA_TRY(cudaStreamSynchronize(s));
     return PMM_OK;
 }

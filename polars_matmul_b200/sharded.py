@@ -103,13 +103,30 @@ class ShardedTopk:
                                      idx.data_ptr(), sc.data_ptr(), stream=stream)
         return idx, sc
 
-    def topk_host(self, queries: np.ndarray, corpus_shard: np.ndarray, index_base: int, n_total: int, k: int,
-                  metric: str, pinned_q=None, pinned_c=None):
-        """End-to-end variant: host buffers in (pinned tensors are copied without staging), host arrays out."""
+    def topk_host(self, queries, corpus_shard, index_base: int, n_total: int, k: int, metric: str):
+        """End-to-end variant: host buffers in (NumPy / Arrow / HostMatrix; pinned memory is copied without
+        staging), host arrays out. The shard upload overlaps the fused kernel inside libpmm_b200
+        (pmm_topk_shard); only the Q x k candidates cross NVLink."""
         import torch
-        tq = pinned_q if pinned_q is not None else torch.from_numpy(queries)
-        tc = pinned_c if pinned_c is not None else torch.from_numpy(corpus_shard)
-        dq = tq.to("cuda", non_blocking=True)
-        dc = tc.to("cuda", non_blocking=True)
-        idx, sc = self.topk_device(dq, dc, index_base, n_total, k, metric)
+        from .arrow import to_host_matrix
+        m = _native.metric_from_str(metric)
+        q, c = to_host_matrix(queries), to_host_matrix(corpus_shard)
+        Q = q.n_rows
+        k_eff = min(int(k), int(n_total))
+        if k_eff > 128:
+            raise _native.PmmError(_native.PMM_ERR_UNSUPPORTED, "sharded top-k supports k <= 128")
+        k_local = min(k_eff, c.n_rows)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        cand = torch.zeros((Q, k_eff), dtype=torch.int64, device=dev)
+        if k_local > 0:
+            local = cand if k_local == k_eff else torch.empty((Q, k_local), dtype=torch.int64, device=dev)
+            torch.cuda.current_stream().synchronize()          # cand is zeroed before the library writes it
+            _native.topk_shard(q, c, k_local, m, index_base, local.data_ptr())
+            if local is not cand:
+                cand[:, :k_local] = local
+        gathered = all_gather_candidates(cand, self.group) if self.world > 1 else cand.unsqueeze(0)
+        idx = torch.empty((Q, k_eff), dtype=torch.int32, device=dev)
+        sc = torch.empty((Q, k_eff), dtype=torch.float64, device=dev)
+        _native.dev_merge_candidates(gathered.data_ptr(), gathered.shape[0], Q, k_eff, k_eff, m,
+                                     idx.data_ptr(), sc.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
         return idx.cpu().numpy().view(np.uint32), sc.cpu().numpy()

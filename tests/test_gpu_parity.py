@@ -377,6 +377,32 @@ def test_device_level_shards_merge(native, oracle):
         assert np.array_equal(i1, i_np) and np.array_equal(s1, sc.cpu().numpy())
 
 
+def test_host_shard_entry_point(native, oracle):
+    """pmm_topk_shard: host shard in, exact candidates on the device; two shards merged == unsharded oracle.
+    The second shard is large enough (>= 64 MB) to take the chunked/overlapped upload path."""
+    import torch
+    from polars_matmul_b200.sharded import ShardedTopk, shard_bounds
+    rng = np.random.default_rng(31)
+    q, c = _randn(rng, 150, 256), _randn(rng, 80_000, 256)
+    k = 12
+    bounds = [(0, 10_000), (10_000, 80_000)]                     # 10 MB (simple path) + 72 MB (chunked path)
+    for metric_name, metric in (("cosine", 0), ("euclidean", 2)):
+        lists = torch.zeros((2, 150, k), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        for s_, (lo, hi) in enumerate(bounds):
+            native.topk_shard(_hm(q), _hm(c[lo:hi]), k, metric, lo, lists[s_].data_ptr())
+        idx = torch.empty((150, k), dtype=torch.int32, device="cuda")
+        sc = torch.empty((150, k), dtype=torch.float64, device="cuda")
+        native.dev_merge_candidates(lists.data_ptr(), 2, 150, k, k, metric, idx.data_ptr(), sc.data_ptr(),
+                                    stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        parity.check_topk(idx.cpu().numpy().view(np.uint32), sc.cpu().numpy(), q, c, k, metric_name, oracle, exact=True)
+    # the single-rank driver (world size 1) end to end
+    i2, s2 = ShardedTopk().topk_host(q, c, 0, c.shape[0], k, "cosine")
+    parity.check_topk(i2, s2, q, c, k, "cosine", oracle, exact=True)
+    assert shard_bounds(80_000, 2) == [(0, 40_000), (40_000, 80_000)]
+
+
 def test_device_norms_bit_exact(native, oracle):
     import torch
     rng = np.random.default_rng(14)
