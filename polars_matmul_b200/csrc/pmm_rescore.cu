@@ -72,11 +72,14 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     // accumulates ITS candidate sequentially in d — the reference's order.
     float acc = 0.0f;
     for (int d0 = 0; d0 < dim; d0 += 32) {
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {  // 32 independent row reads in flight per lane before anything is consumed
             const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
-            tile[i][lane] = raw_fetch<CSRC>(cm, cbi, cli, d0 + lane);
+            x[i] = raw_fetch<CSRC>(cm, cbi, cli, d0 + lane);
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[i][lane] = x[i];
         __syncwarp();
         const int jn = dim - d0 < 32 ? dim - d0 : 32;
         if (jn == 32) {
