@@ -71,6 +71,35 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     // 128-byte requests (lane = element), transposed through shared memory, and every thread then
     // accumulates ITS candidate sequentially in d — the reference's order.
     float acc = 0.0f;
+    // f16 rows without nulls: 64 elements per step, one half2 per lane (128-byte requests per row)
+    const bool wide16 = sizeof(CSRC) == 2 && !cm.offsets && !cm.validity && (dim & 1) == 0;
+    if (wide16) {
+        float (*tile2)[65] = (float (*)[65])(rs_smem + NT * 8 + (size_t)((dim + 3) & ~3) * 4 + (size_t)wrp * 32 * 65 * 4);
+        const __half2 *vals = (const __half2 *)cm.values;
+        for (int d0 = 0; d0 < dim; d0 += 64) {
+            float2 x[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
+                const int e = d0 + 2 * lane;
+                x[i] = e < cli ? __half22float2(__ldg(vals + ((cbi + e) >> 1))) : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                tile2[i][2 * lane] = x[i].x;
+                tile2[i][2 * lane + 1] = x[i].y;
+            }
+            __syncwarp();
+            const int jn = dim - d0 < 64 ? dim - d0 : 64;
+            if (jn == 64) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) acc = __fmaf_rn(qs[d0 + j], tile2[lane][j], acc);
+            } else {
+                for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile2[lane][j], acc);
+            }
+            __syncwarp();
+        }
+    } else
     for (int d0 = 0; d0 < dim; d0 += 32) {
         float x[32];
 #pragma unroll
@@ -153,7 +182,7 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
     const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
 #define PMM_RS(NT)                                                                                                  \
     {                                                                                                               \
-        size_t smem = NT * 8 + smem_q + (size_t)(NT / 32) * 32 * 33 * 4;                                                                              \
+        size_t smem = NT * 8 + smem_q + (size_t)(NT / 32) * 32 * (sizeof(CSRC) == 2 ? 65 : 33) * 4;                                                                              \
         if (smem > 48 * 1024) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                         \
