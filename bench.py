@@ -284,10 +284,13 @@ def main():
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = _native.kernel_launch_count()
-    kname = "tc_topk_tf32x3"
+    kname = max(("tc_topk_tf32x1", "tc_topk_tf32x3"), key=lambda n: _native.get_stat(n + "_ms"))
     k_ms = _native.get_stat(kname + "_ms")
     k_launches = _native.get_stat(kname + "_launches")
-    stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps) for n in ("prep", kname, "merge", "rescore")}
+    stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps)
+             for n in ("prep", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge", "rescore", "gather", "scatter", "scores_f32", "select_f32")
+             if _native.get_stat(n + "_ms") > 0}
+    stats["requeried_tf32x3_per_step"] = _native.get_stat("requeried_tf32x3") / max(1, args.steps)
     stats["fallback_queries_per_step"] = _native.get_stat("fallback_queries") / max(1, args.steps)
     _native.set_option("profile", 0)
     value = world * Q / (ms_step / 1000.0)
@@ -322,9 +325,10 @@ def main():
         flops_per_launch = 2.0 * Q * N * D
         k_avg_ms = k_ms / max(1.0, k_launches)
         achieved = flops_per_launch / (k_avg_ms / 1000.0) / 1e12 if k_avg_ms > 0 else None
-        # 3xTF32: three tcgen05 TF32 MMAs per logical MAC and TF32 runs at half the bf16 rate, so the
-        # tensor pipe peak for ALGORITHMIC f32 flops is the measured bf16 peak / 6.
-        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")) / 6.0
+        # Tensor-pipe peak for ALGORITHMIC f32 flops: TF32 runs at half the bf16 rate; the first-level filter issues one
+        # TF32 MMA per MAC (bf16 / 2), the 3xTF32 split three (bf16 / 6).
+        terms = 1 if kname.endswith("x1") else 3
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")) / (2.0 * terms)
         tr = load_traffic(kname, f"{W['name']}:{Q}x{N}x{D}:k{k}")
         roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None,
@@ -332,11 +336,10 @@ def main():
                     "traffic_note": tr["source"] if tr else "no ncu capture committed for this workload",
                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms,
                     "kernel_share_of_step": (k_avg_ms / ms_step) if ms_step else None,
-                    "peak_note": f"{peak_src}: bf16_tflops_sustained / 6 (TF32 = 1/2 bf16 rate, 3 MMAs per MAC); "
-                                 f"raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}. "
-                                 "frac can exceed 1: the denominator is a power-capped cuBLAS run (profiles/peaks_r1e.json: "
-                                 "cuBLAS TF32 744 burst / 613 sustained on the same box, i.e. 248 / 204 per 3xTF32 flop); "
-                                 "the nominal 3xTF32 ceiling at 1965 MHz is 375 TFLOP/s",
+                    "peak_note": f"{peak_src}: bf16_tflops_sustained / {2 * terms} (TF32 = 1/2 bf16 rate, {terms} TF32 MMA(s) per MAC "
+                                 f"in {kname}); raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}. "
+                                 "The exact f32 result comes from the re-scoring kernel; queries whose filter is not provably "
+                                 "lossless are re-run with 3xTF32 (requeried_tf32x3_per_step) or on the SIMT path",
                     "per_kernel_ms_per_step": stats}
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
@@ -350,7 +353,8 @@ def main():
                                    "candidates merged after one NCCL all-gather" if world > 1 else "single GPU",
                        "value_definition": "n_gpus * Q / step time: every rank scans its own shard for all Q queries",
                        "l2": "inputs (3.4 GB per rank) are far larger than the 126 MB L2; no explicit flush",
-                       "arithmetic": "3xTF32 tcgen05 (hi*hi + hi*lo + lo*hi), f32 accumulate in TMEM"},
+                       "arithmetic": "tcgen05 kind::tf32 filter (x1 first level, 3xTF32 hi/lo split on demand), f32 accumulate in "
+                                     "TMEM; exact f32 re-scoring + per-query losslessness proof"},
             "tflops_effective": 2.0 * Q * n_total * D / (ms_step / 1000.0) / 1e12,
             "queries_per_sec_global_corpus": Q / (ms_step / 1000.0),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

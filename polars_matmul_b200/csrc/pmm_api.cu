@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -319,7 +319,7 @@ int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : 
 // kept [Q x kp]: per query the kp best candidates under the kernel's filter value (approximate keys,
 // comparable across corpus chunks and shards of the same query), indices = index_base + corpus row.
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
-              cudaStream_t s) {
+              cudaStream_t s, int terms) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -333,9 +333,10 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.nq = q.n_rows;
     a.n = c.n_rows;
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
-    a.cg = g_tc_cg.load();
+    a.terms = a.f16 ? 1 : terms;
+    a.cg = (a.terms == 1 && !a.f16) ? 2 : g_tc_cg.load();
     a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg,
-                               tc_group_for(c.n_rows, q.ld, a.f16 != 0, di.num_sms / a.cg, a.cg), a.cg);
+                               tc_group_for(c.n_rows, q.ld, a.f16 != 0 || a.terms == 1, di.num_sms / a.cg, a.cg), a.cg);
     a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.index_base = index_base;
@@ -352,7 +353,8 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
         a.round_sync = rsync.as<unsigned int>();
     }
     a.partial = partial.as<uint64_t>();
-    cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : "tc_topk_tf32x3", s, [&] { return launch_tc_topk(a, s); });
+    cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : a.terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3", s,
+                                   [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
     CUDA_TRY(launch_counted("merge", s, [&] {
@@ -364,17 +366,30 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
 int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric, int64_t index_base, TopkOut o,
                  cudaStream_t s);
 
-// Relative error bound of the tensor-core filter value against the exact f32 score, per |q||c|:
-// one f32 ulp of truncation per tcgen05 accumulate step (3*D/8 of them for 3xTF32), the TF32 split
-// residue, and the worst-case rounding of the exact sequential-FMA sum itself (D * 2^-24).
-float filter_eps(int64_t dim) { return 1.1e-7f * (float)dim + 2e-6f; }
+// Relative error bound (per |q||c|) of the tensor-core filter value against the exact f32 score:
+//   operand rounding: TF32 x1 keeps 11 significant bits per operand (rna) -> 2^-11 on the product sum
+//                     (Cauchy-Schwarz); the 3xTF32 split leaves 2^-21; f16 planes are exact;
+//   accumulation    : one f32 ulp of truncation per tcgen05 accumulate step (terms * D / 8 steps);
+//   the exact sum   : worst-case rounding of the sequential-FMA reference itself, D * 2^-24.
+float filter_eps(int64_t dim, int terms, bool f16) {
+    const float split = f16 ? 0.0f : terms == 1 ? 4.9e-4f : 4.8e-7f;
+    return split + (float)dim * (1.5e-8f * (float)terms + 6.0e-8f) + 1e-6f;
+}
 
-// Exact re-scoring of the kept candidates + the losslessness check; queries the check cannot clear are
-// recomputed on the exact SIMT path (gather -> scores + select -> scatter). May synchronise the stream.
-int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, const float *q_aux,
-                       const float *c_aux, const float *q_sq, const unsigned int *c_max_sq, int metric, int64_t index_base,
-                       int64_t keff, TopkOut o, cudaStream_t s) {
+int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
+                     const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
+                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s);
+
+// Exact re-scoring of the kept candidates + the losslessness check. Queries the check cannot clear are
+// gathered and recomputed one level up: after the TF32 x1 filter by the 3xTF32 filter (next_terms = 3),
+// after that (or for f16 planes) on the exact SIMT path (next_terms = 0). May synchronise the stream.
+int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, const float *q_sq,
+                       const float *q_norm, const Prepared *c_planes, const float *c_norm, const float *c_sq,
+                       const unsigned int *c_max_sq, float eps, int next_terms, int metric, int64_t index_base, int64_t keff,
+                       TopkOut o, cudaStream_t s) {
     const int64_t Q = raw_q.n_rows;
+    const float *q_aux = metric == PMM_METRIC_COSINE ? q_norm : metric == PMM_METRIC_EUCLIDEAN ? q_sq : nullptr;
+    const float *c_aux = metric == PMM_METRIC_COSINE ? c_norm : metric == PMM_METRIC_EUCLIDEAN ? c_sq : nullptr;
     DevBuf flags, count;
     RescoreCheck chk;
     memset(&chk, 0, sizeof(chk));
@@ -386,7 +401,7 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
         CUDA_TRY(cudaMemsetAsync(count.p, 0, sizeof(unsigned int), s));
         chk.q_sq = q_sq;
         chk.c_max_sq = c_max_sq;
-        chk.eps = filter_eps(raw_q.dim);
+        chk.eps = eps;
         chk.flags = flags.as<unsigned char>();
         chk.flag_count = count.as<unsigned int>();
     }
@@ -399,8 +414,8 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     CUDA_TRY(cudaMemcpyAsync(&n_flag, count.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (n_flag == 0) return PMM_OK;
-    stat_add("fallback_queries", (double)n_flag);
-    // ---- exact path for the flagged queries
+    stat_add(next_terms == 3 ? "requeried_tf32x3" : "fallback_queries", (double)n_flag);
+    // ---- gather the flagged queries into a dense f32 matrix
     std::vector<unsigned char> hflags((size_t)Q);
     CUDA_TRY(cudaMemcpy(hflags.data(), flags.p, (size_t)Q, cudaMemcpyDeviceToHost));
     std::vector<int64_t> ids;
@@ -421,16 +436,28 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     qd.dtype = PMM_DTYPE_F32;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
-    const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
-    Prepared qf, cf;
-    int rc = prepare(qd, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &qf);
-    if (rc) return rc;
-    if ((rc = prepare(raw_c, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
     CUDA_TRY(t_idx.alloc((size_t)F * keff * 4, s));
     CUDA_TRY(t_sc.alloc((size_t)F * keff * 8, s));
     CUDA_TRY(t_cand.alloc((size_t)F * keff * 8, s));
     TopkOut t{t_idx.as<uint32_t>(), t_sc.as<double>(), t_cand.as<uint64_t>()};
-    if ((rc = topk_generic(qf, cf, keff, metric, index_base, t, s))) return rc;
+    const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
+    int rc;
+    if (next_terms == 3) {
+        // one level up on the tensor cores: 3xTF32 planes of the flagged queries against the corpus planes
+        Prepared qf, cf;
+        if ((rc = prepare(qd, PREP_TF32, false, 2 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
+        const Prepared *cp = c_planes;
+        if (!cp) {  // chunked upload: the per-chunk planes are gone, rebuild them from the resident raw corpus
+            if ((rc = prepare(raw_c, PREP_TF32, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
+            cp = &cf;
+        }
+        if ((rc = tc_topk_verified(qf, cp, qd, raw_c, c_norm, c_sq, c_max_sq, 3, keff, metric, index_base, nullptr, t, s))) return rc;
+    } else {
+        Prepared qf, cf;
+        if ((rc = prepare(qd, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &qf))) return rc;
+        if ((rc = prepare(raw_c, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
+        if ((rc = topk_generic(qf, cf, keff, metric, index_base, t, s))) return rc;
+    }
     CUDA_TRY(launch_counted("scatter", s, [&] {
         return launch_scatter_results(d_ids.as<int64_t>(), F, (int)keff, t.index, t.score, t.cand, o.index, o.score, o.cand, s);
     }));
@@ -438,18 +465,36 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     return PMM_OK;
 }
 
-// Tensor-core path: filter -> exact re-scoring of the kept candidates (+ verification).
+// Filter at `terms` (unless the kept lists are supplied) -> exact re-scoring -> verification -> next level.
+// c may be NULL only when kept_in is given. c_norm / c_sq / c_max_sq describe the whole corpus (index_base-relative).
+int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
+                     const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
+                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s) {
+    const int kp = tc_list_capacity(keff);
+    const bool f16 = q.mode == PREP_F16;
+    DevBuf kept;
+    const uint64_t *kept_ptr = kept_in;
+    if (!kept_ptr) {
+        CUDA_TRY(kept.alloc((size_t)q.n_rows * kp * 8, s));
+        int rc = tc_filter(q, *c, kp, metric, index_base, kept.as<uint64_t>(), s, terms);
+        if (rc) return rc;
+        kept_ptr = kept.as<uint64_t>();
+    }
+    const int next_terms = (!f16 && terms == 1) ? 3 : 0;
+    return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), c, c_norm, c_sq, c_max_sq,
+                              filter_eps(raw_q.dim, terms, f16), next_terms, metric, index_base, keff, o, s);
+}
+
+// First filter level for f32 planes: TF32 x1 unless switched off ("tc_levels" = 1) or cta_group::1 was forced.
+int first_level_terms(const Prepared &q) {
+    return (q.mode == PREP_TF32 && g_tc_levels.load() >= 2 && g_tc_cg.load() == 2) ? 1 : 3;
+}
+
+// Tensor-core path: filter -> exact re-scoring of the kept candidates -> verification (-> next level).
 int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
             int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
-    const int kp = tc_list_capacity(keff);
-    DevBuf kept;
-    CUDA_TRY(kept.alloc((size_t)q.n_rows * kp * 8, s));
-    int rc = tc_filter(q, c, kp, metric, index_base, kept.as<uint64_t>(), s);
-    if (rc) return rc;
-    const float *q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
-    const float *c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
-    return rescore_and_verify(kept.as<uint64_t>(), kp, raw_q, raw_c, q_aux, c_aux, q.sqnorm.as<float>(), c.max_sq_ptr, metric,
-                              index_base, keff, o, s);
+    return tc_topk_verified(q, &c, raw_q, raw_c, c.norm.as<float>(), c.sqnorm.as<float>(), c.max_sq_ptr, first_level_terms(q),
+                            keff, metric, index_base, nullptr, o, s);
 }
 
 struct PathChoice {
@@ -705,6 +750,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(c_max.alloc(sizeof(unsigned int), s));
     CUDA_TRY(cudaMemsetAsync(c_max.p, 0, sizeof(unsigned int), s));
     const int kp = tc_list_capacity(keff);
+    const int terms0 = first_level_terms(q);
     CUDA_TRY(kept_all.alloc((size_t)n_chunks * Q * kp * 8, s));
     CUDA_TRY(kept.alloc((size_t)Q * kp * 8, s));
     if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)N * 4, s));
@@ -725,7 +771,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         if (want_norm || want_sq)
             CUDA_TRY(cudaMemcpyAsync(c_aux_all.as<float>() + r0, want_norm ? c.norm.p : c.sqnorm.p, (size_t)rows * 4,
                                      cudaMemcpyDeviceToDevice, s));
-        if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept_all.as<uint64_t>() + (size_t)i * Q * kp, s))) return rc;
+        if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept_all.as<uint64_t>() + (size_t)i * Q * kp, s, terms0))) return rc;
     }
     const uint64_t *kept_ptr = kept_all.as<uint64_t>();
     if (n_chunks > 1) {
@@ -738,10 +784,10 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     const size_t cnt = (size_t)Q * keff;
     CUDA_TRY(d_idx.alloc(cnt * 4, s));
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
-    const float *q_aux = want_norm ? q.norm.as<float>() : want_sq ? q.sqnorm.as<float>() : nullptr;
     TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), d_cand};
-    if ((rc = rescore_and_verify(kept_ptr, kp, uq.dm, uc.dm, q_aux, c_aux_all.as<float>(), q.sqnorm.as<float>(),
-                                 c_max.as<unsigned int>(), metric, index_base, keff, o, s)))
+    // c_aux_all holds the corpus norms (cosine) or squared norms (euclidean) of the whole corpus
+    if ((rc = tc_topk_verified(q, nullptr, uq.dm, uc.dm, c_aux_all.as<float>(), c_aux_all.as<float>(), c_max.as<unsigned int>(),
+                               terms0, keff, metric, index_base, kept_ptr, o, s)))
         return rc;
     if (out_index) CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
     if (out_score) CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
@@ -814,6 +860,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
+    else if (k == "tc_levels") g_tc_levels.store(value >= 2 ? 2 : 1);  // 2: TF32 x1 first-level filter, 3xTF32 on demand
     else if (k == "verify") g_verify.store(value ? 1 : 0);  // 0: skip the filter-losslessness check (and its fallback)
     else if (k == "f64_simt") g_f64_simt.store(value ? 1 : 0);  // 1: bit-exact sequential-FMA f64 instead of DMMA
     else if (k == "host_chunked") g_host_chunked.store(value ? 1 : 0);

@@ -46,9 +46,11 @@ constexpr int FLUSH_AT = 8;                // end-of-tile flush above this: happ
 // CG   = tcgen05 cta_group: 1 = one CTA per 128 x 256 tile; 2 = a CTA pair (cluster of 2) computes a
 //        256 x 256 tile with UMMA M=256: each CTA holds 128 query rows and HALF of the corpus tile
 //        (128 rows), so corpus bytes per SM halve and a third pipeline stage fits.
-template <bool F16, int ROWB, int CG>
+// TERMS = tcgen05 MMAs per K-step for f32 data: 3 = the 3xTF32 split (hi/lo planes), 1 = hi*hi only (TF32
+//         precision, |error| <= 2^-11 |q||c|; used as the first-level filter, see pmm_api.cu).
+template <bool F16, int ROWB, int CG, int TERMS>
 struct TcCfg {
-    static constexpr int PLANES = F16 ? 1 : 2;
+    static constexpr int PLANES = (F16 || TERMS == 1) ? 1 : 2;
     static constexpr int BK = ROWB / (F16 ? 2 : 4);  // elements of K per stage
     static constexpr int KSTEPS = ROWB / 32;         // 32 bytes of K per tcgen05.mma
     static constexpr int B_ROWS = BN / CG;           // corpus rows this CTA stages per tile
@@ -186,12 +188,13 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     }
 }
 
-template <bool F16, int EPI, int R, int ROWB, int CG>
+template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
           const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo,
           const __grid_constant__ CUtensorMap tm_out, const TcKParams p) {
-    typedef TcCfg<F16, ROWB, CG> Cfg;
+    typedef TcCfg<F16, ROWB, CG, TERMS> Cfg;
+    constexpr bool ONE = F16 || TERMS == 1;   // one operand plane per matrix, one MMA per K-step
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -215,7 +218,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_qhi);
         prefetch_tensormap(&tm_chi);
-        if (!F16) {
+        if (!ONE) {
             prefetch_tensormap(&tm_qlo);
             prefetch_tensormap(&tm_clo);
         }
@@ -288,18 +291,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             const uint32_t fb = full_bar(stage);
                             mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
                             tma_load_2d(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
-                            if (!F16) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
+                            if (!ONE) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
                             tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, brow);
-                            if (!F16) tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
+                            if (!ONE) tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
                         } else {
                             // both CTAs of the pair load into their own shared memory; all bytes are counted on the
                             // LEADER's full barrier, which its MMA warp waits on
                             const uint32_t fb = mapa_u32(full_bar(stage), 0u);
                             if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
                             tma_load_2d_pair(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
-                            if (!F16) tma_load_2d_pair(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
+                            if (!ONE) tma_load_2d_pair(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
                             tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, brow);
-                            if (!F16)
+                            if (!ONE)
                                 tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
                         }
                     }
@@ -350,6 +353,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                                 const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
                                 if (F16) {
                                     umma<CG, true>(tmem_d, d_ah + 2 * ks, d_bh + 2 * ks, idesc, acc);
+                                } else if (TERMS == 1) {
+                                    umma<CG, false>(tmem_d, d_ah + 2 * ks, d_bh + 2 * ks, idesc, acc);
                                 } else {
                                     umma<CG, false>(tmem_d, d_al + 2 * ks, d_bh + 2 * ks, idesc, acc);  // small terms first
                                     umma<CG, false>(tmem_d, d_ah + 2 * ks, d_bl + 2 * ks, idesc, 1u);
@@ -550,13 +555,14 @@ bool make_out_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols) 
     return true;
 }
 
-template <bool F16, int EPI, int R, int ROWB, int CG>
+template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
-    typedef TcCfg<F16, ROWB, CG> Cfg;
+    typedef TcCfg<F16, ROWB, CG, TERMS> Cfg;
+    constexpr bool ONE = F16 || TERMS == 1;
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
     if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS, F16, ROWB)) return cudaErrorInvalidValue;
-    if (F16) {
+    if (ONE) {
         tq_lo = tq_hi;
         tc_lo = tc_hi;
     } else {
@@ -584,7 +590,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.out = a.out;
     p.round_sync = a.round_sync;
     p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
-    auto kern = tc_kernel<F16, EPI, R, ROWB, CG>;
+    auto kern = tc_kernel<F16, EPI, R, ROWB, CG, TERMS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
@@ -605,8 +611,11 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
 
 template <bool F16, int EPI, int R>
 cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
-    if (a.cg == 2) return launch_t2<F16, EPI, R, 128, 2>(a, s);
-    return launch_t2<F16, EPI, R, 128, 1>(a, s);
+    if (!F16 && EPI == EPI_TOPK && a.terms == 1) {   // first-level filter: TF32 x1 (cta_group::2 only)
+        return launch_t2<false, EPI, R, 128, 2, 1>(a, s);
+    }
+    if (a.cg == 2) return launch_t2<F16, EPI, R, 128, 2, 3>(a, s);
+    return launch_t2<F16, EPI, R, 128, 1, 3>(a, s);
 }
 
 }  // namespace

@@ -36,15 +36,16 @@ def run():
     _native.dev_topk(_native.dev_matrix(dq.data_ptr(), Q, D, 1), _native.dev_matrix(dc.data_ptr(), N, D, 1), k, 1,
                      index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(), stream=st)
 res = []
-configs = [(2, 4, 32), (2, 4, 100000), (2, 4, 8), (2, 4, 128), (2, 2, 32), (2, 2, 8), (2, 1, 32), (2, 4, 0)]
-for rowb, grp, rs in configs:
-    _native.set_option("tc_cg", rowb); _native.set_option("tc_group", grp); _native.set_option("tc_sync_tiles", rs)
+configs = [(2, 0, 32, 2), (2, 0, 32, 1), (2, 2, 32, 2), (2, 4, 32, 2), (2, 1, 32, 2), (2, 2, 16, 2)]
+for rowb, grp, rs, lv in configs:
+    _native.set_option("tc_cg", rowb); _native.set_option("tc_group", grp); _native.set_option("tc_sync_tiles", rs); _native.set_option("tc_levels", lv)
     run(); torch.cuda.synchronize()
     _native.set_option("profile", 1); _native.reset_stats()
     run(); run(); torch.cuda.synchronize()
-    ms = _native.get_stat("tc_topk_tf32x3_ms") / 2
+    ms = (_native.get_stat("tc_topk_tf32x3_ms") + _native.get_stat("tc_topk_tf32x1_ms")) / 2
+    rq = _native.get_stat("requeried_tf32x3") / 2
     _native.set_option("profile", 0)
     tf = 2.0 * Q * N * D / ms / 1e9
-    res.append({"cg": rowb, "sync_tiles": rs, "group": grp, "kernel_ms": ms, "tflops": tf})
+    res.append({"cg": rowb, "sync_tiles": rs, "levels": lv, "requeried": rq, "group": grp, "kernel_ms": ms, "tflops": tf})
     print(res[-1], flush=True)
 json.dump(res, open("gpurun_out/sweep.json", "w"), indent=1)

@@ -212,6 +212,46 @@ def test_tie_stress(native, oracle):
             parity.check_topk(idx, sc, q, c, k, metric, oracle)
 
 
+def test_filter_levels_and_fallback_are_exercised(native, oracle):
+    """TF32 x1 filter -> 3xTF32 re-query -> exact SIMT fallback: craft inputs that need each level and check
+    via the library's statistics that the level actually ran; the result must still equal the oracle."""
+    rng = np.random.default_rng(123)
+    d, n, k = 64, 4000, 10
+    # (a) well separated scores: level 0 suffices
+    q = _randn(rng, 64, d)
+    c = _randn(rng, n, d)
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q), _hm(c), k, "dot")
+    parity.check_topk(idx, sc, q, c, k, "dot", oracle, exact=True)
+    assert native.get_stat("requeried_tf32x3") == 0 and native.get_stat("fallback_queries") == 0
+    # (b) 60 corpus rows within ~1e-5 relative of each other at the top: TF32 cannot separate them (needs 3xTF32),
+    #     3xTF32 can (gaps are ~10x its error bound)
+    base = _randn(rng, 1, d)
+    c2 = c.copy()
+    c2[:60] = base * (1.0 + 3e-5 * np.arange(60, dtype=np.float32)[:, None]) * 3.0
+    q2 = np.repeat(base, 8, axis=0) + 1e-3 * _randn(rng, 8, d)
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q2), _hm(c2), k, "dot")
+    parity.check_topk(idx, sc, q2, c2, k, "dot", oracle, exact=True)
+    assert native.get_stat("requeried_tf32x3") > 0
+    # (c) 60 exact duplicates at the top: no filter can prove anything about exact ties -> exact SIMT path
+    c3 = c.copy()
+    c3[100:160] = base * 3.0
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q2), _hm(c3), k, "cosine")
+    parity.check_topk(idx, sc, q2, c3, k, "cosine", oracle, exact=True)
+    assert native.get_stat("fallback_queries") > 0
+    assert (idx[:, 0] == 100).all()          # lowest index among the exact ties first
+    # (d) single level (3xTF32 first) gives the same answers
+    native.set_option("tc_levels", 1)
+    try:
+        i1, s1 = native.topk(_hm(q2), _hm(c2), k, "dot")
+    finally:
+        native.set_option("tc_levels", 2)
+    i2, s2 = native.topk(_hm(q2), _hm(c2), k, "dot")
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+
+
 def test_nan_and_inf_rank_last(native, oracle):
     c = np.ones((300, 16), np.float32)
     c[5, 0] = np.nan
