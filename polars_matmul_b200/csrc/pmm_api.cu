@@ -367,12 +367,14 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
                  cudaStream_t s);
 
 // Relative error bound (per |q||c|) of the tensor-core filter value against the exact f32 score:
-//   operand rounding: TF32 x1 keeps 11 significant bits per operand (rna) -> 2^-11 on the product sum
-//                     (Cauchy-Schwarz); the 3xTF32 split leaves 2^-21; f16 planes are exact;
+//   operand rounding: TF32 has 11 significant bits, unit roundoff u = 2^-11 per operand (cvt.rna), so a TF32 x1
+//                     product is off by <= 2u + u^2 ~ 2^-10 and so is the sum (Cauchy-Schwarz);
+//                     3xTF32: each operand keeps a residue <= 2^-22 and the lo*lo term (<= 2^-22) is dropped:
+//                     <= 3 * 2^-22; f16 planes are exact;
 //   accumulation    : one f32 ulp of truncation per tcgen05 accumulate step (terms * D / 8 steps);
 //   the exact sum   : worst-case rounding of the sequential-FMA reference itself, D * 2^-24.
 float filter_eps(int64_t dim, int terms, bool f16) {
-    const float split = f16 ? 0.0f : terms == 1 ? 4.9e-4f : 4.8e-7f;
+    const float split = f16 ? 0.0f : terms == 1 ? 9.8e-4f : 7.5e-7f;
     return split + (float)dim * (1.5e-8f * (float)terms + 6.0e-8f) + 1e-6f;
 }
 

@@ -224,11 +224,11 @@ def test_filter_levels_and_fallback_are_exercised(native, oracle):
     idx, sc = native.topk(_hm(q), _hm(c), k, "dot")
     parity.check_topk(idx, sc, q, c, k, "dot", oracle, exact=True)
     assert native.get_stat("requeried_tf32x3") == 0 and native.get_stat("fallback_queries") == 0
-    # (b) 60 corpus rows within ~1e-5 relative of each other at the top: TF32 cannot separate them (needs 3xTF32),
-    #     3xTF32 can (gaps are ~10x its error bound)
+    # (b) 60 corpus rows spaced 1e-5 relative at the top: rank 10 and rank 32 are 2.2e-4 apart, below the TF32 x1
+    #     bound (~1e-3) but far above the 3xTF32 bound (~1e-5): level 0 must hand these queries to level 1
     base = _randn(rng, 1, d)
     c2 = c.copy()
-    c2[:60] = base * (1.0 + 3e-5 * np.arange(60, dtype=np.float32)[:, None]) * 3.0
+    c2[:60] = base * (1.0 + 1e-5 * np.arange(60, dtype=np.float32)[:, None]) * 3.0
     q2 = np.repeat(base, 8, axis=0) + 1e-3 * _randn(rng, 8, d)
     native.reset_stats()
     idx, sc = native.topk(_hm(q2), _hm(c2), k, "dot")
