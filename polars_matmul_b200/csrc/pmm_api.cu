@@ -40,7 +40,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -335,8 +335,12 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.f16 = q.mode == PREP_F16 ? 1 : 0;
     a.terms = a.f16 ? 1 : terms;
     a.cg = (a.terms == 1 && !a.f16) ? 2 : g_tc_cg.load();
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, di.num_sms / a.cg,
-                               tc_group_for(c.n_rows, q.ld, a.f16 != 0 || a.terms == 1, di.num_sms / a.cg, a.cg), a.cg);
+    a.clm = (a.cg == 2 && g_tc_clm.load() == 2) ? 2 : 1;
+    a.cluster4 = g_tc_cluster4.load();
+    const int gs = a.cg * a.clm;   // CTAs per scheduling unit
+    int units = di.num_sms / gs;
+    if (g_tc_max_units.load() > 0 && units > g_tc_max_units.load()) units = g_tc_max_units.load();
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, units, tc_group_for(c.n_rows, q.ld, a.f16 != 0 || a.terms == 1, units, gs), gs);
     a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.index_base = index_base;
@@ -344,7 +348,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.kp = kp;
     a.k = kp;
     DevBuf partial, rsync;
-    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * a.cg * TC_TILE_M * a.kp * 8, s));
+    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * gs * TC_TILE_M * a.kp * 8, s));
     if (g_tc_sync_tiles.load() > 0) {
         a.sync_tiles = g_tc_sync_tiles.load();
         const size_t nb = (size_t)tc_sync_counters(a.sched, a.sync_tiles) * sizeof(unsigned int);
@@ -358,7 +362,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
     CUDA_TRY(launch_counted("merge", s, [&] {
-        return launch_merge_tiles(a.partial, a.sched, a.cg, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
+        return launch_merge_tiles(a.partial, a.sched, gs, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
     }));
     return PMM_OK;
 }
@@ -447,7 +451,7 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     if (next_terms == 3) {
         // one level up on the tensor cores: 3xTF32 planes of the flagged queries against the corpus planes
         Prepared qf, cf;
-        if ((rc = prepare(qd, PREP_TF32, false, 2 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
+        if ((rc = prepare(qd, PREP_TF32, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
         const Prepared *cp = c_planes;
         if (!cp) {  // chunked upload: the per-chunk planes are gone, rebuild them from the resident raw corpus
             if ((rc = prepare(raw_c, PREP_TF32, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
@@ -530,7 +534,7 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared q, c_local;
     // the tensor-core path always needs squared norms (error bound of the losslessness check)
-    int rc = prepare(*dq, pc.mode, pc.f64, 2 * TC_TILE_M, want_norm, want_sq || pc.tc, err.as<int>(), s, &q);
+    int rc = prepare(*dq, pc.mode, pc.f64, 4 * TC_TILE_M, want_norm, want_sq || pc.tc, err.as<int>(), s, &q);
     if (rc) return rc;
     const Prepared *c = pc_corpus;
     if (!c) {
@@ -747,7 +751,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared q;
-    if ((rc = prepare(uq.dm, pc.mode, false, 2 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
+    if ((rc = prepare(uq.dm, pc.mode, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
     DevBuf c_max;
     CUDA_TRY(c_max.alloc(sizeof(unsigned int), s));
     CUDA_TRY(cudaMemsetAsync(c_max.p, 0, sizeof(unsigned int), s));
@@ -862,6 +866,9 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "profile") g_profile.store((int)value);
     else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
+    else if (k == "tc_max_units") g_tc_max_units.store((int)value);
+    else if (k == "tc_cluster4") g_tc_cluster4.store(value ? 1 : 0);
+    else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast
     else if (k == "tc_levels") g_tc_levels.store(value >= 2 ? 2 : 1);  // 2: TF32 x1 first-level filter, 3xTF32 on demand
     else if (k == "verify") g_verify.store(value ? 1 : 0);  // 0: skip the filter-losslessness check (and its fallback)
     else if (k == "f64_simt") g_f64_simt.store(value ? 1 : 0);  // 1: bit-exact sequential-FMA f64 instead of DMMA

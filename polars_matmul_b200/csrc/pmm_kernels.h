@@ -116,6 +116,8 @@ struct TcArgs {
     int64_t nq, n;                 // real rows
     int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
     int cg;                        // tcgen05 cta_group: 1, or 2 (CTA pairs, UMMA M=256)
+    int cluster4;                  // cg == 2, clm == 1: launch two independent pairs per cluster of 4
+    int clm;                       // CTA pairs per cluster: 1, or 2 (corpus tile multicast; needs cg == 2)
     int terms;                     // f32 top-k: 3 = 3xTF32 split, 1 = hi*hi only (first-level filter, needs cg == 2)
     TcSchedule sched;
     // top-k mode

@@ -67,6 +67,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void *tmap,
         "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// Multicast form: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and the bytes are
+// counted on the mbarrier at the same CTA-relative offset in each of those CTAs.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void *tmap, uint32_t bar, int32_t c0, int32_t c1,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
 // Same, issued by either CTA of a cta_group::2 pair; bytes are counted on the barrier at `bar` in the
 // LEADER CTA (peer bit cleared), the data lands in the issuing CTA's shared memory.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void *tmap, uint32_t bar_cluster, int32_t c0, int32_t c1) {

@@ -48,7 +48,10 @@ constexpr int FLUSH_AT = 8;                // end-of-tile flush above this: happ
 //        (128 rows), so corpus bytes per SM halve and a third pipeline stage fits.
 // TERMS = tcgen05 MMAs per K-step for f32 data: 3 = the 3xTF32 split (hi/lo planes), 1 = hi*hi only (TF32
 //         precision, |error| <= 2^-11 |q||c|; used as the first-level filter, see pmm_api.cu).
-template <bool F16, int ROWB, int CG, int TERMS>
+// CLM  = CTA pairs per cluster (cta_group::2 only): 2 = a cluster of 4 CTAs works on two query tiles against the
+//        SAME corpus tile; each CTA fetches a quarter of the corpus tile and TMA-multicasts it to the CTA of the
+//        other pair that needs the same half, so corpus bytes L2 -> shared memory halve again.
+template <bool F16, int ROWB, int CG, int TERMS, int CLM = 1>
 struct TcCfg {
     static constexpr int PLANES = (F16 || TERMS == 1) ? 1 : 2;
     static constexpr int BK = ROWB / (F16 ? 2 : 4);  // elements of K per stage
@@ -188,13 +191,15 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     }
 }
 
-template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS>
+template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
           const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo,
           const __grid_constant__ CUtensorMap tm_out, const TcKParams p) {
-    typedef TcCfg<F16, ROWB, CG, TERMS> Cfg;
+    typedef TcCfg<F16, ROWB, CG, TERMS, CLM> Cfg;
     constexpr bool ONE = F16 || TERMS == 1;   // one operand plane per matrix, one MMA per K-step
+    constexpr int GS = CG * CLM;              // CTAs per scheduling unit (= cluster size)
+    static_assert(CLM == 1 || CG == 2, "corpus multicast is built on CTA pairs");
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -207,11 +212,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
-    volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(bars + 2 * Cfg::STAGES + 4);
+    auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };  // CLM == 2: "peer CTA's stage landed"
+    volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(bars + 3 * Cfg::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair; 0 = leader (issues the MMAs)
-    const int cta = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // scheduling unit: CTA or CTA pair
+    const uint32_t crank4 = GS > 1 ? cluster_ctarank() : 0u;    // rank inside the cluster
+    const uint32_t crank = crank4 & (uint32_t)(CG - 1);          // rank inside the CTA pair; 0 = leader (issues the MMAs)
+    const uint32_t pairc = CLM == 2 ? (crank4 >> 1) : 0u;        // which pair of the cluster
+    const uint32_t leader_rank = crank4 & ~1u;                   // cluster rank of this pair's leader
+    const int cta = (int)(blockIdx.x / GS);                      // scheduling unit: CTA, CTA pair or cluster of two pairs
     const TcSchedule &S = p.sched;
     const int total_rounds = S.rounds + (S.m_rem > 0 ? 1 : 0);
 
@@ -224,7 +233,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         }
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CLM);   // every pair that reads (or multicasts into) the slot releases it
+            mbar_init(pfull_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
@@ -237,7 +247,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         tmem_relinquish<CG>();
     }
     tc_fence_before();
-    if (CG == 2) cluster_sync(); else __syncthreads();
+    if (GS > 1) cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -265,7 +275,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                 __syncwarp();
                 continue;
             }
-            const int32_t arow = (m_tile * CG + (int)crank) * BM;                // this CTA's 128 query rows
+            const int32_t arow = ((m_tile * CLM + (int)pairc) * CG + (int)crank) * BM;   // this CTA's 128 query rows
             int j = 0;  // tile counter of this CTA inside the round
             for (int nt = n_start; nt < S.n_tiles; nt += n_step, ++j) {
                 const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
@@ -294,16 +304,31 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             if (!ONE) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
                             tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, brow);
                             if (!ONE) tma_load_2d(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
-                        } else {
+                        } else if (CLM == 1) {
                             // both CTAs of the pair load into their own shared memory; all bytes are counted on the
                             // LEADER's full barrier, which its MMA warp waits on
-                            const uint32_t fb = mapa_u32(full_bar(stage), 0u);
+                            const uint32_t fb = mapa_u32(full_bar(stage), leader_rank);
                             if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
                             tma_load_2d_pair(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
                             if (!ONE) tma_load_2d_pair(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
                             tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES, &tm_chi, fb, kb * Cfg::BK, brow);
                             if (!ONE)
                                 tma_load_2d_pair(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &tm_clo, fb, kb * Cfg::BK, brow);
+                        } else {
+                            // cluster of two pairs: every CTA arms ITS OWN full barrier with the bytes that land in its
+                            // shared memory (own query tile + the whole corpus half, a quarter of which arrives from the
+                            // other pair's CTA by multicast) and fetches its quarter of the corpus tile for both.
+                            const uint32_t fb = full_bar(stage);
+                            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                            tma_load_2d(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
+                            if (!ONE) tma_load_2d(sa + Cfg::A_BYTES, &tm_qlo, fb, kb * Cfg::BK, arow);
+                            const uint16_t mask = (uint16_t)((1u << crank) | (1u << (2 + crank)));   // same half, both pairs
+                            const uint32_t qoff = pairc * (Cfg::B_ROWS / 2) * ROWB;                  // my quarter inside the half
+                            const int32_t qrow_b = brow + (int)pairc * (Cfg::B_ROWS / 2);
+                            tma_load_2d_mc(sa + Cfg::PLANES * Cfg::A_BYTES + qoff, &tm_chi, fb, kb * Cfg::BK, qrow_b, mask);
+                            if (!ONE)
+                                tma_load_2d_mc(sa + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES + qoff, &tm_clo, fb, kb * Cfg::BK,
+                                               qrow_b, mask);
                         }
                     }
                     __syncwarp();
@@ -340,6 +365,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     const uint32_t tmem_d = tmem_base + (uint32_t)(abuf * BN);
                     for (int kb = 0; kb < p.num_kb; ++kb) {
                         mbar_wait(full_bar(stage), phase);
+                        if (CLM == 2) mbar_wait(pfull_bar(stage), phase);   // the peer CTA's half of the stage landed too
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         // descriptors of the stage's four tiles; a K-step of 32 bytes adds 2 to the address field
@@ -361,8 +387,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                                     umma<CG, false>(tmem_d, d_ah + 2 * ks, d_bh + 2 * ks, idesc, 1u);
                                 }
                             }
-                            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-                            if (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_pair(empty_bar(stage), 3);
+                            // frees the smem slot when these MMAs retire: in both CTAs of the pair, and with multicast
+                            // in all four CTAs of the cluster (the other pair's CTAs write into this pair's slots)
+                            if (CG == 1) umma_commit(empty_bar(stage));
+                            else umma_commit_pair(empty_bar(stage), CLM == 2 ? (uint16_t)0xF : (uint16_t)(3u << leader_rank));
                         }
                         __syncwarp();
                         if (++stage == Cfg::STAGES) {
@@ -371,11 +399,32 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         }
                     }
                     if (issuer) {  // accumulator tile complete (each CTA of a pair holds its 128 rows of it)
-                        if (CG == 1) umma_commit(tfull_bar(abuf)); else umma_commit_pair(tfull_bar(abuf), 3);
+                        if (CG == 1) umma_commit(tfull_bar(abuf)); else umma_commit_pair(tfull_bar(abuf), (uint16_t)(3u << leader_rank));
                     }
                     __syncwarp();
                     abuf ^= 1;
                     if (abuf == 0) aphase ^= 1u;
+                }
+            }
+        } else if (CLM == 2) {
+            // Non-leader CTA of a pair, multicast mode: its stage bytes are counted on ITS OWN full barrier; relay
+            // "stage landed" to the pair leader, which issues the MMAs that read both CTAs' shared memory.
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < total_rounds; ++it) {
+                int m_tile, n_start, n_step;
+                int64_t slot;
+                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+                for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        if (lane == 0) mbar_arrive_cluster(pfull_bar(stage), leader_rank);
+                        __syncwarp();
+                        if (++stage == Cfg::STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
                 }
             }
         }
@@ -391,7 +440,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             int m_tile, n_start, n_step;
             int64_t slot;
             if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
-            const int64_t qrow = ((int64_t)m_tile * CG + crank) * BM + row;
+            const int64_t qrow = (((int64_t)m_tile * CLM + pairc) * CG + crank) * BM + row;
             uint64_t thr = 0ull;
             float thr_f = __uint_as_float(0x7fc00000u);
             int cnt = 0;
@@ -399,7 +448,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
-                list_base = p.partial + ((slot * CG + crank) * BM + row0) * KP;
+                list_base = p.partial + ((slot * GS + (crank4 & (uint32_t)(GS - 1))) * BM + row0) * KP;
                 for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
                 // q_aux is padded to the tile grid. cosine: 1 unless the query norm is ~0; euclidean: |q|^2
                 if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > 1e-6f ? 1.0f : 0.0f;
@@ -428,7 +477,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if (CG == 1) mbar_arrive(tempty_bar(abuf)); else mbar_arrive_cluster(tempty_bar(abuf), 0u);
+                            if (CG == 1) mbar_arrive(tempty_bar(abuf)); else mbar_arrive_cluster(tempty_bar(abuf), leader_rank);
                         }
                     }
                     const int64_t col0 = col_tile + ch * 32;
@@ -449,7 +498,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&tm_out, sbuf, (int32_t)col0, (int32_t)((m_tile * CG + (int)crank) * BM + row0));
+                                tma_store_2d(&tm_out, sbuf, (int32_t)col0, (int32_t)(((m_tile * CLM + (int)pairc) * CG + (int)crank) * BM + row0));
                                 tma_store_commit();
                             }
                         } else if (qrow < p.nq) {
@@ -486,7 +535,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     if (EPI == EPI_MATMUL && warp >= 2 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
     __syncwarp();
     tc_fence_before();
-    if (CG == 2) cluster_sync(); else __syncthreads();
+    if (GS > 1) cluster_sync(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, 512);
@@ -555,19 +604,19 @@ bool make_out_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols) 
     return true;
 }
 
-template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS>
+template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM = 1>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
-    typedef TcCfg<F16, ROWB, CG, TERMS> Cfg;
+    typedef TcCfg<F16, ROWB, CG, TERMS, CLM> Cfg;
     constexpr bool ONE = F16 || TERMS == 1;
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS, F16, ROWB)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS / CLM, F16, ROWB)) return cudaErrorInvalidValue;
     if (ONE) {
         tq_lo = tq_hi;
         tc_lo = tc_hi;
     } else {
         if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false, ROWB)) return cudaErrorInvalidValue;
-        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS, false, ROWB)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS / CLM, false, ROWB)) return cudaErrorInvalidValue;
     }
     CUtensorMap t_out = tq_hi;  // placeholder for the top-k kernels
     int out_tma = 0;
@@ -590,18 +639,19 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.out = a.out;
     p.round_sync = a.round_sync;
     p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
-    auto kern = tc_kernel<F16, EPI, R, ROWB, CG, TERMS>;
+    auto kern = tc_kernel<F16, EPI, R, ROWB, CG, TERMS, CLM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(a.sched.num_ctas * CG));
+    cfg.gridDim = dim3((unsigned)(a.sched.num_ctas * CG * CLM));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    // cluster_x: CG*CLM, or 4 for independent CTA pairs co-scheduled two per cluster (a.cluster4)
+    attr[0].val.clusterDim.x = (CG == 2 && CLM == 1 && a.cluster4 && (a.sched.num_ctas % 2) == 0) ? 4 : CG * CLM;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -611,6 +661,10 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
 
 template <bool F16, int EPI, int R>
 cudaError_t launch_t(const TcArgs &a, cudaStream_t s) {
+    if (EPI == EPI_TOPK && a.cg == 2 && a.clm == 2) {   // cluster of two pairs with corpus multicast
+        if (!F16 && a.terms == 1) return launch_t2<false, EPI, R, 128, 2, 1, 2>(a, s);
+        return launch_t2<F16, EPI, R, 128, 2, 3, 2>(a, s);
+    }
     if (!F16 && EPI == EPI_TOPK && a.terms == 1) {   // first-level filter: TF32 x1 (cta_group::2 only)
         return launch_t2<false, EPI, R, 128, 2, 1>(a, s);
     }
@@ -632,7 +686,7 @@ bool tc_supported() {
 
 TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg) {
     TcSchedule s;
-    const int tile_m = BM * cg;   // query rows per scheduling unit (CTA or CTA pair)
+    const int tile_m = BM * cg;   // query rows per scheduling unit; cg = CTAs per unit (1, 2, or 4 for a cluster of two pairs)
     s.m_tiles = (int)((q_rows + tile_m - 1) / tile_m);
     s.n_tiles = (int)((c_rows + BN - 1) / BN);
     int G = num_units > 0 ? num_units : 1;

@@ -25,7 +25,7 @@ def timed(fn, name, iters=5, warm=2, flush=None):
         fn()
     ev[1].record(); torch.cuda.synchronize()
     stats = {}
-    for k in ("prep", "norms", "tc_topk_tf32x3", "tc_topk_f16", "tc_matmul_tf32x3", "tc_matmul_f16", "scores_f32", "scores_f64", "scores_f64_dmma",
+    for k in ("prep", "norms", "tc_topk_tf32x1", "tc_topk_tf32x3", "tc_topk_f16", "tc_matmul_tf32x3", "tc_matmul_f16", "scores_f32", "scores_f64", "scores_f64_dmma",
               "select_f32", "select_f64", "merge", "rescore"):
         v = _native.get_stat(k + "_ms")
         if v:
@@ -80,9 +80,10 @@ def topk_case(Q, N, D, k, metric, dt, label, iters=2):
     s = timed(fn, label, iters=iters, warm=0)
     e1.record(); torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1) / iters
-    kern = [k_ for k_ in s if k_.startswith(("tc_topk", "scores"))][0]
+    kern = max([k_ for k_ in s if k_.startswith(("tc_topk", "scores"))], key=lambda k_: s[k_])
     out[label] = {"step_ms": total_ms, "queries_per_s": Q / total_ms * 1e3, "kernel": kern[:-3], "kernel_ms": s[kern],
-                  "kernel_TFLOPs": 2.0 * Q * N * D / s[kern] / 1e9, "per_kernel_ms": s}
+                  "kernel_TFLOPs": 2.0 * Q * N * D / s[kern] / 1e9, "per_kernel_ms": s,
+                  "requeried_tf32x3": _native.get_stat("requeried_tf32x3") / iters, "fallback_queries": _native.get_stat("fallback_queries") / iters}
 topk_case(1000, 10000, 256, 10, "cosine", torch.float32, "topk_C1_1000x10000x256_cosine_k10", iters=20)
 topk_case(100_000, 1_000_000, 768, 100, "euclidean", torch.float32, "topk_C3_euclidean")
 topk_case(100_000, 1_000_000, 768, 100, "cosine", torch.float32, "topk_C3shape_cosine")

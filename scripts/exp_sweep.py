@@ -8,8 +8,8 @@ from polars_matmul_b200 import _native
 from polars_matmul_b200.arrow import to_host_matrix
 from oracle import pmm_oracle as oracle
 
-def check(rowb):
-    _native.set_option("tc_cg", rowb)
+def check(rowb, clm=1, c4=0):
+    _native.set_option("tc_cg", rowb); _native.set_option("tc_clm", clm); _native.set_option("tc_cluster4", c4)
     rng = np.random.default_rng(1)
     q = rng.standard_normal((300, 200)).astype(np.float32)
     c = rng.standard_normal((5000, 200)).astype(np.float32)
@@ -22,9 +22,9 @@ def check(rowb):
     idx, sc = _native.topk(to_host_matrix(h), to_host_matrix(ch), 10, "cosine")
     oi, osc = oracle.topk(h.astype(np.float32), ch.astype(np.float32), 10, "cosine")
     assert np.array_equal(idx, oi) and np.array_equal(sc, osc), (rowb, "f16")
-    print("parity ok cg", rowb, flush=True)
+    print("parity ok cg", rowb, "clm", clm, flush=True)
 
-check(1); check(2)
+check(2)
 Q, N, D, k = (int(x) for x in (sys.argv[1:5] if len(sys.argv) > 4 else (100000, 1000000, 768, 100)))
 g = torch.Generator(device="cuda").manual_seed(0)
 dq = torch.randn((Q, D), generator=g, device="cuda")
@@ -36,9 +36,9 @@ def run():
     _native.dev_topk(_native.dev_matrix(dq.data_ptr(), Q, D, 1), _native.dev_matrix(dc.data_ptr(), N, D, 1), k, 1,
                      index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(), stream=st)
 res = []
-configs = [(2, 0, 32, 2), (2, 0, 32, 1), (2, 2, 32, 2), (2, 4, 32, 2), (2, 1, 32, 2), (2, 2, 16, 2)]
-for rowb, grp, rs, lv in configs:
-    _native.set_option("tc_cg", rowb); _native.set_option("tc_group", grp); _native.set_option("tc_sync_tiles", rs); _native.set_option("tc_levels", lv)
+configs = [(2, 0, 32, 2, 1, 0), (2, 0, 32, 1, 1, 0)]
+for rowb, grp, rs, lv, clm, c4 in configs:
+    _native.set_option("tc_cg", rowb); _native.set_option("tc_group", grp); _native.set_option("tc_sync_tiles", rs); _native.set_option("tc_levels", lv); _native.set_option("tc_clm", clm); _native.set_option("tc_max_units", c4)
     run(); torch.cuda.synchronize()
     _native.set_option("profile", 1); _native.reset_stats()
     run(); run(); torch.cuda.synchronize()
@@ -46,6 +46,6 @@ for rowb, grp, rs, lv in configs:
     rq = _native.get_stat("requeried_tf32x3") / 2
     _native.set_option("profile", 0)
     tf = 2.0 * Q * N * D / ms / 1e9
-    res.append({"cg": rowb, "sync_tiles": rs, "levels": lv, "requeried": rq, "group": grp, "kernel_ms": ms, "tflops": tf})
+    res.append({"cg": rowb, "sync_tiles": rs, "levels": lv, "clm": clm, "max_units": c4, "requeried": rq, "group": grp, "kernel_ms": ms, "tflops": tf})
     print(res[-1], flush=True)
 json.dump(res, open("gpurun_out/sweep.json", "w"), indent=1)
