@@ -158,27 +158,44 @@ __device__ __forceinline__ float filter_value(float acc, float aux, float rowc) 
 }
 
 // One 32-column chunk of the accumulator tile for this thread's row.
+// Common case: no score of the chunk beats any row's threshold. It costs the filter values, a max tree
+// (one FMNMX per score; fmaxf drops NaN, and NaN can only matter while a list is not full, when thr_f is NaN
+// and every test below is true) and ONE warp vote. Otherwise the warp descends group by group (8 scores),
+// again behind a vote, and only then tests single scores.
 template <int METRIC, int R>
-__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const float *aux_s /* 32 floats, smem */, float rowc,
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t aux_s /* shared address: 32 floats */, float rowc,
                                              int64_t col0, int64_t n, int64_t index_base, uint64_t *stage_buf,
                                              uint64_t *list_base, int row, int row0, int lane, int k, uint64_t &thr,
                                              float &thr_f, int &cnt) {
+    float f[32];
 #pragma unroll
-    for (int j8 = 0; j8 < 32; j8 += 8) {
-        float aux[8];
-        if (METRIC != METRIC_DOT) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(aux_s + j8);
-            const float4 a1 = *reinterpret_cast<const float4 *>(aux_s + j8 + 4);
-            aux[0] = a0.x; aux[1] = a0.y; aux[2] = a0.z; aux[3] = a0.w;
-            aux[4] = a1.x; aux[5] = a1.y; aux[6] = a1.z; aux[7] = a1.w;
-        }
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (METRIC != METRIC_DOT)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3) : "r"(aux_s + 4u * j4));
+        f[j4 + 0] = filter_value<METRIC>(__uint_as_float(v[j4 + 0]), a0, rowc);
+        f[j4 + 1] = filter_value<METRIC>(__uint_as_float(v[j4 + 1]), a1, rowc);
+        f[j4 + 2] = filter_value<METRIC>(__uint_as_float(v[j4 + 2]), a2, rowc);
+        f[j4 + 3] = filter_value<METRIC>(__uint_as_float(v[j4 + 3]), a3, rowc);
+    }
+    float gmax[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float f = filter_value<METRIC>(__uint_as_float(v[j8 + j]), METRIC != METRIC_DOT ? aux[j] : 0.0f, rowc);
-            if (!(f <= thr_f)) {  // rare: better than the row's k-th best (or the list is not full, or NaN)
-                const int64_t col = col0 + j8 + j;
+    for (int g = 0; g < 4; ++g) {
+        float m01 = fmaxf(f[8 * g + 0], f[8 * g + 1]), m23 = fmaxf(f[8 * g + 2], f[8 * g + 3]);
+        float m45 = fmaxf(f[8 * g + 4], f[8 * g + 5]), m67 = fmaxf(f[8 * g + 6], f[8 * g + 7]);
+        gmax[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+    }
+    const float cmax = fmaxf(fmaxf(gmax[0], gmax[1]), fmaxf(gmax[2], gmax[3]));
+    if (!__any_sync(0xffffffffu, !(cmax <= thr_f))) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (!__any_sync(0xffffffffu, !(gmax[g] <= thr_f))) continue;
+#pragma unroll
+        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+            if (!(f[j] <= thr_f)) {  // better than the row's k-th best (or the list is not full, or NaN)
+                const int64_t col = col0 + j;
                 if (col < n) {
-                    const uint64_t cand = pack_candidate(score_key(f, true), (uint32_t)(index_base + col));
+                    const uint64_t cand = pack_candidate(score_key(f[j], true), (uint32_t)(index_base + col));
                     if (cand > thr) {
                         stage_buf[cnt * BM + row] = cand;
                         ++cnt;
@@ -434,6 +451,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         const int row0 = lg * 32;         // first tile row of the warp
         const int row = row0 + lane;      // tile row owned by this thread
         float *aux_s = aux_tiles + lg * BN;
+        const uint32_t aux_sa = smem_u32(aux_s);
         int abuf = 0;
         uint32_t aphase = 0;
         for (int it = 0; it < total_rounds; ++it) {
@@ -508,13 +526,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                                 if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
                         }
                     } else if (p.metric == METRIC_DOT) {
-                        filter_chunk<METRIC_DOT, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf, list_base, row,
+                        filter_chunk<METRIC_DOT, R>(v, aux_sa + ch * 128, rowc, col0, p.n, p.index_base, stage_buf, list_base, row,
                                                     row0, lane, p.k, thr, thr_f, cnt);
                     } else if (p.metric == METRIC_COSINE) {
-                        filter_chunk<METRIC_COSINE, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf, list_base,
+                        filter_chunk<METRIC_COSINE, R>(v, aux_sa + ch * 128, rowc, col0, p.n, p.index_base, stage_buf, list_base,
                                                        row, row0, lane, p.k, thr, thr_f, cnt);
                     } else {
-                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_s + ch * 32, rowc, col0, p.n, p.index_base, stage_buf,
+                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + ch * 128, rowc, col0, p.n, p.index_base, stage_buf,
                                                           list_base, row, row0, lane, p.k, thr, thr_f, cnt);
                     }
                 }
