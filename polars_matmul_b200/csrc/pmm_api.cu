@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -40,7 +41,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -337,6 +338,9 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.cg = (a.terms == 1 && !a.f16) ? 2 : g_tc_cg.load();
     a.clm = (a.cg == 2 && g_tc_clm.load() == 2) ? 2 : 1;
     a.cluster4 = g_tc_cluster4.load();
+    a.debug_skip = g_tc_debug_skip.load();
+    a.sync_slack = g_tc_sync_slack.load();
+    a.max_flush = g_tc_max_flush.load();
     const int gs = a.cg * a.clm;   // CTAs per scheduling unit
     int units = di.num_sms / gs;
     if (g_tc_max_units.load() > 0 && units > g_tc_max_units.load()) units = g_tc_max_units.load();
@@ -347,8 +351,10 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.metric = metric;
     a.kp = kp;
     a.k = kp;
-    DevBuf partial, rsync;
+    DevBuf partial, rsync, staged;
     CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * gs * TC_TILE_M * a.kp * 8, s));
+    CUDA_TRY(staged.alloc((size_t)tc_staged_bytes(a.sched.num_ctas * gs), s));
+    a.staged = staged.as<uint64_t>();
     if (g_tc_sync_tiles.load() > 0) {
         a.sync_tiles = g_tc_sync_tiles.load();
         const size_t nb = (size_t)tc_sync_counters(a.sched, a.sync_tiles) * sizeof(unsigned int);
@@ -868,6 +874,9 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
     else if (k == "tc_max_units") g_tc_max_units.store((int)value);
     else if (k == "tc_cluster4") g_tc_cluster4.store(value ? 1 : 0);
+    else if (k == "tc_sync_slack") g_tc_sync_slack.store(value < 0 ? 0 : value);
+    else if (k == "tc_max_flush") g_tc_max_flush.store(value < 0 ? 0 : value);
+    else if (k == "tc_debug_skip") g_tc_debug_skip.store(value);  // measurement only: results are wrong when set
     else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast
     else if (k == "tc_levels") g_tc_levels.store(value >= 2 ? 2 : 1);  // 2: TF32 x1 first-level filter, 3xTF32 on demand
     else if (k == "verify") g_verify.store(value ? 1 : 0);  // 0: skip the filter-losslessness check (and its fallback)
@@ -881,6 +890,12 @@ int pmm_set_option(const char *key, int64_t value) {
 
 double pmm_get_stat(const char *name) {
     if (!name) return 0.0;
+    if (!strncmp(name, "tc_dbg_wait", 11)) {  // tc_dbg_wait0..3: diagnostics of the last launches with tc_debug_skip = 8
+        static unsigned long long last[52];
+        const int i = atoi(name + 11);
+        if (i == 0) tc_debug_wait_cycles(last);
+        return i >= 0 && i < 52 ? (double)last[i] : 0.0;
+    }
     std::lock_guard<std::mutex> lk(g_stat_mu);
     resolve_pending_locked();
     auto it = g_stats.find(name);

@@ -119,6 +119,39 @@ __device__ __forceinline__ uint64_t warp_sort_desc(uint64_t v, int lane) {
     return v;
 }
 
+// Full bitonic sort of 32*RS values, element e at (reg e/32, lane e%32), descending in e.
+template <int RS>
+__device__ __forceinline__ void warp_sort_regs_desc(uint64_t (&S)[RS], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * RS; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {                            // register-to-register; direction depends on r only
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    if ((r & rs) == 0) {
+                        const bool desc = ((32 * r) & size) == 0;
+                        const uint64_t a = S[r], b = S[r + rs];
+                        const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
+                        S[r] = desc ? hi : lo;
+                        S[r + rs] = desc ? lo : hi;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const uint64_t o = shfl_xor_u64(S[r], stride);
+                    const bool lower = (lane & stride) == 0;
+                    const bool desc = (((32 * r) | lane) & size) == 0;
+                    const bool keep_max = (lower == desc);
+                    S[r] = keep_max ? (S[r] > o ? S[r] : o) : (S[r] < o ? S[r] : o);
+                }
+            }
+        }
+    }
+}
+
 // L holds a BITONIC sequence of 32*R values, element e at (reg e/32, lane e%32).
 // Sorts it descending in place.
 template <int R>

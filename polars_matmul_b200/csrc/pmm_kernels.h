@@ -103,6 +103,9 @@ struct TcSchedule {
     __host__ __device__ int64_t total_slots() const { return (int64_t)m_full * g + (int64_t)m_rem * g_rem; }
 };
 TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg);
+// Diagnostics: reads and clears the wait-cycle counters filled when TcArgs::debug_skip == 8.
+void tc_debug_wait_cycles(unsigned long long out[52]);
+int64_t tc_staged_bytes(int num_ctas);  // size of TcArgs::staged
 int64_t tc_sync_counters(const TcSchedule &s, int sync_tiles);  // number of pacing counters a launch needs
 
 // Partial lists written by the fused kernel: [slot][cta of the group (cg)][row_in_tile (128)][kp].
@@ -117,6 +120,9 @@ struct TcArgs {
     int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
     int cg;                        // tcgen05 cta_group: 1, or 2 (CTA pairs, UMMA M=256)
     int cluster4;                  // cg == 2, clm == 1: launch two independent pairs per cluster of 4
+    int sync_slack;                // pacing: wait for the sync point this many points back (0 = strict lockstep)
+    int max_flush;                 // list merges per epilogue warp and tile (0 = auto from the tile's MMA time)
+    int debug_skip;                // measurement only: 1 = epilogue loads TMEM but does not filter, 2 = one load per tile
     int clm;                       // CTA pairs per cluster: 1, or 2 (corpus tile multicast; needs cg == 2)
     int terms;                     // f32 top-k: 3 = 3xTF32 split, 1 = hi*hi only (first-level filter, needs cg == 2)
     TcSchedule sched;
@@ -127,6 +133,7 @@ struct TcArgs {
     int k;                         // candidates kept per query and piece: the list position that sets the threshold (<= kp)
     int kp;                        // list capacity: 32, 64, 128 or 256
     uint64_t *partial;             // [sched.total_slots()][cg][128][kp]
+    uint64_t *staged;              // top-k: scratch of tc_staged_bytes(grid CTAs) bytes (unsorted candidates per CTA and row)
     // matmul mode
     float *out;                    // [nq x n] row-major
     unsigned int *round_sync;      // zeroed device counters for the producers' pacing barriers (tc_sync_counters()) or NULL

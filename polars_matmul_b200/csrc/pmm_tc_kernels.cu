@@ -38,9 +38,16 @@ namespace {
 constexpr int BM = TC_TILE_M;
 constexpr int BN = TC_TILE_N;
 constexpr int NUM_THREADS = 192;
-constexpr int STAGE_SLOTS = 24;            // staged candidates per row (shared memory)
-constexpr int EMERGENCY_AT = STAGE_SLOTS - 8;  // mid-tile flush only above this (checked every 8 scores)
-constexpr int FLUSH_AT = 8;                // end-of-tile flush above this: happens AFTER the TMEM buffer was released
+// Candidates that beat a row's threshold are APPENDED to a per-row staging area in global memory (L2-resident,
+// one per CTA and row, reused by every item of the CTA) and merged into the row's sorted list in batches: the
+// cost of a merge (sort the batch, one bitonic merge with the list) is the same for 10 or 100 staged
+// candidates, so batches should be large.  Thresholds only move at a merge; a stale threshold admits more
+// candidates, never fewer.
+constexpr int LOOK_PITCH = 36;             // floats per lane in the hit-lookup area (16-byte aligned, 4-way bank spread)
+constexpr int SC = 128;                    // staging capacity per row
+constexpr int HARD_AT = SC - 32;           // a 32-column chunk adds at most 32: merge inside the tile above this
+constexpr int URGENT_AT = 80;              // rows above this are always merged at the end of a tile
+constexpr int SOFT_AT = 48;                // end-of-tile merge above this (rate limited), AFTER the TMEM buffer was released
 
 // ROWB = bytes of K per shared-memory row (= the swizzle span): 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
 // CG   = tcgen05 cta_group: 1 = one CTA per 128 x 256 tile; 2 = a CTA pair (cluster of 2) computes a
@@ -60,7 +67,7 @@ struct TcCfg {
     static constexpr int A_BYTES = BM * ROWB;
     static constexpr int B_BYTES = B_ROWS * ROWB;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-    static constexpr int STAGING_BYTES = STAGE_SLOTS * BM * 8;
+    static constexpr int STAGING_BYTES = 4 * 32 * LOOK_PITCH * 4;  // per epilogue warp: one chunk of filter values (hit lookup)
     static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of the tile
     static constexpr int STORE_BYTES = 4 * 2 * 4096; // matmul epilogue: per warp two 32x32 f32 TMA-store tiles
     static constexpr int EPI_BYTES = (STAGING_BYTES + AUX_BYTES) > STORE_BYTES ? (STAGING_BYTES + AUX_BYTES) : STORE_BYTES;
@@ -77,13 +84,21 @@ struct TcKParams {
     int metric;
     int k;
     uint64_t *partial;
+    uint64_t *staged;  // top-k epilogue: grid x 128 rows x SC staged candidates
     float *out;
     int out_tma;   // 1: matmul epilogue stores through TMA (row pitch is a multiple of 16 bytes)
     unsigned int *round_sync;  // zeroed counters: producers of all CTAs meet every `sync_tiles` corpus tiles (NULL: off)
     int sync_tiles;
+    int debug_skip;  // measurement only (TcArgs::debug_skip)
+    int sync_slack;
+    int max_flush;   // row merges per warp at the end of a tile (rate limit; rows above URGENT_AT always go)
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
+
+// Diagnostics (option tc_debug_skip = 8): cycles the MMA warps spent waiting for [0] a free accumulator buffer,
+// [1] a filled operand stage, [2] in total; [3] cycles epilogue warp 2 of the leader CTAs spent in list flushes.
+__device__ unsigned long long g_tc_wait[4 + 48];  // [20 + b] / [36 + b]: epilogue warp 2 filter / flush cycles  // [4 + b]: accumulator-buffer waits at tile 2^b..2^(b+1)-1 of an item
 
 // Work of CTA `cta` in round `it`. Returns false when the CTA idles in that round.
 __device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int it, int &m_tile, int &n_start,
@@ -110,24 +125,45 @@ __device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int 
 // thr = packed k-th best of the row's list (0 while the list is not full); thr_f = its filter value
 // as a float, NaN while the list is not full (so that `!(f <= thr_f)` admits everything).
 template <int R>
-__device__ __forceinline__ void flush_rows(unsigned rows, uint64_t *stage_buf, uint64_t *list_base /* lane group's 32 lists */,
-                                           int row0, int lane, int k, uint64_t &thr, float &thr_f, int &cnt) {
+__device__ __forceinline__ void flush_rows(unsigned rows, const uint64_t *stg /* the warp's 32 staging rows */,
+                                           uint64_t *list_base /* lane group's 32 lists */, int lane, int k, uint64_t &thr,
+                                           float &thr_f, int &cnt) {
     constexpr int KP = 32 * R;
     __syncwarp();
+    if (k < 0) {  // measurement only (debug_skip == 3): drop the staged candidates
+        cnt = 0;
+        return;
+    }
     while (rows) {
         const int src = __ffs(rows) - 1;
         rows &= rows - 1;
         const int c = __shfl_sync(0xffffffffu, cnt, src);
         uint64_t *list = list_base + (int64_t)src * KP;
-        uint64_t L[R], M[R];
+        const uint64_t *sr = stg + (int64_t)src * SC;
+        uint64_t L[R], M[R], S[SC / 32];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {  // issue the list loads first: their L2 latency overlaps the sort below
-            L[r] = list[32 * r + lane];
-            M[r] = 0ull;
+        for (int r = 0; r < R; ++r) L[r] = list[32 * r + lane];  // issued first: the L2 latency overlaps the sort below
+#pragma unroll
+        for (int r = 0; r < SC / 32; ++r) S[r] = (32 * r + lane < c) ? sr[32 * r + lane] : 0ull;
+        // M = the staged candidates, sorted descending, cut or zero-padded to the list length and REVERSED:
+        // M[r] at lane l holds element 32R-1-(32r+l), i.e. register R-1-r, lane 31-l of the sorted staging area.
+        if (c <= 32) {
+            S[0] = warp_sort_desc(S[0], lane);
+#pragma unroll
+            for (int r = 0; r < R - 1; ++r) M[r] = 0ull;
+            M[R - 1] = __shfl_sync(0xffffffffu, S[0], 31 - lane);
+        } else {
+            if (c <= 64) {  // half-size network; registers 2, 3 are empty (zeros sort last)
+                uint64_t S2[2] = {S[0], S[1]};
+                warp_sort_regs_desc<2>(S2, lane);
+                S[0] = S2[0];
+                S[1] = S2[1];
+            } else {
+                warp_sort_regs_desc<SC / 32>(S, lane);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) M[r] = (R - 1 - r) < SC / 32 ? __shfl_sync(0xffffffffu, S[(R - 1 - r) < SC / 32 ? (R - 1 - r) : 0], 31 - lane) : 0ull;
         }
-        uint64_t v = (lane < c) ? stage_buf[lane * BM + row0 + src] : 0ull;
-        v = warp_sort_desc(v, lane);
-        M[R - 1] = __shfl_sync(0xffffffffu, v, 31 - lane);  // staged list, reversed, sits at the tail
         warp_merge_topk_desc<R>(L, M, lane);
 #pragma unroll
         for (int r = 0; r < R; ++r) list[32 * r + lane] = L[r];
@@ -163,10 +199,10 @@ __device__ __forceinline__ float filter_value(float acc, float aux, float rowc) 
 // and every test below is true) and ONE warp vote. Otherwise the warp descends group by group (8 scores),
 // again behind a vote, and only then tests single scores.
 template <int METRIC, int R>
-__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t aux_s /* shared address: 32 floats */, float rowc,
-                                             int64_t col0, int64_t n, int64_t index_base, uint64_t *stage_buf,
-                                             uint64_t *list_base, int row, int row0, int lane, int k, uint64_t &thr,
-                                             float &thr_f, int &cnt) {
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t aux_s /* shared address: 32 floats */,
+                                             uint32_t look_s /* shared address: the warp's 32 x LOOK_PITCH floats */, float rowc,
+                                             int64_t col0, int64_t n, int64_t index_base, uint64_t *stg /* warp's staging rows */,
+                                             uint64_t *list_base, int lane, int k, uint64_t &thr, float &thr_f, int &cnt) {
     float f[32];
 #pragma unroll
     for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -187,25 +223,37 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t a
     }
     const float cmax = fmaxf(fmaxf(gmax[0], gmax[1]), fmaxf(gmax[2], gmax[3]));
     if (!__any_sync(0xffffffffu, !(cmax <= thr_f))) return;
+    // Some row of the warp has a hit.  Each lane builds the bit mask of ITS hits without branches; lanes with
+    // hits park their 32 filter values in shared memory (so that a hit can be fetched by its run-time position)
+    // and walk their masks side by side: the loop runs max-hits-per-lane times, usually once, instead of once
+    // per column position.  A hit: better than the k-th best, or the list is not full (thr_f NaN), or NaN.
+    unsigned m = 0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (!__any_sync(0xffffffffu, !(gmax[g] <= thr_f))) continue;
+    for (int j = 0; j < 32; ++j) m |= !(f[j] <= thr_f) ? (1u << j) : 0u;
+    if (m) {
+        const uint32_t mine = look_s + (uint32_t)lane * (LOOK_PITCH * 4);
 #pragma unroll
-        for (int j = 8 * g; j < 8 * g + 8; ++j) {
-            if (!(f[j] <= thr_f)) {  // better than the row's k-th best (or the list is not full, or NaN)
-                const int64_t col = col0 + j;
-                if (col < n) {
-                    const uint64_t cand = pack_candidate(score_key(f[j], true), (uint32_t)(index_base + col));
-                    if (cand > thr) {
-                        stage_buf[cnt * BM + row] = cand;
-                        ++cnt;
-                    }
+        for (int j4 = 0; j4 < 32; j4 += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mine + 4u * j4), "f"(f[j4]), "f"(f[j4 + 1]), "f"(f[j4 + 2]),
+                         "f"(f[j4 + 3])
+                         : "memory");
+        do {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            float fv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fv) : "r"(mine + 4u * j) : "memory");
+            const int64_t col = col0 + j;
+            if (col < n) {
+                const uint64_t cand = pack_candidate(score_key(fv, true), (uint32_t)(index_base + col));
+                if (cand > thr) {
+                    stg[lane * SC + cnt] = cand;
+                    ++cnt;
                 }
             }
-        }
-        const unsigned over = __ballot_sync(0xffffffffu, cnt > EMERGENCY_AT);
-        if (over) flush_rows<R>(over, stage_buf, list_base, row0, lane, k, thr, thr_f, cnt);
+        } while (m);
     }
+    const unsigned over = __ballot_sync(0xffffffffu, cnt > HARD_AT);  // room for the next chunk's (at most) 32
+    if (over) flush_rows<R>(over, stg, list_base, lane, k, thr, thr_f, cnt);
 }
 
 template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM>
@@ -221,7 +269,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
-    uint64_t *stage_buf = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
     float *aux_tiles = (float *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
     uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
     const uint32_t bar_base = smem_u32(bars);
@@ -300,12 +347,17 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     if (issuer) {
                         unsigned int *ctr = sync_base + j / p.sync_tiles;
                         atomicAdd(ctr, 1u);
-                        const long long t0 = clock64();
-                        // best-effort, never a correctness dependency: give up after ~4 ms (e.g. when another
-                        // kernel holds some SMs and part of this grid is not resident yet)
-                        while (ld_acquire_u32(ctr) < gridDim.x) {
-                            __nanosleep(100);
-                            if (clock64() - t0 > 8000000ll) break;
+                        // wait until every producer has reached the sync point `sync_slack` points back (0: this one):
+                        // CTAs may drift apart by sync_slack + 1 segments, which absorbs epilogue jitter
+                        unsigned int *wctr = ctr - p.sync_slack;
+                        if (wctr >= p.round_sync) {
+                            const long long t0 = clock64();
+                            // best-effort, never a correctness dependency: give up after ~4 ms (e.g. when another
+                            // kernel holds some SMs and part of this grid is not resident yet)
+                            while (ld_acquire_u32(wctr) < gridDim.x) {
+                                __nanosleep(100);
+                                if (clock64() - t0 > 8000000ll) break;
+                            }
                         }
                     }
                     __syncwarp();
@@ -372,16 +424,28 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             uint32_t phase = 0;
             int abuf = 0;
             uint32_t aphase = 0;
+            const bool dbg = p.debug_skip == 8;
+            long long w_tempty = 0, w_full = 0;
+            const long long w_start = dbg ? clock64() : 0ll;
             for (int it = 0; it < total_rounds; ++it) {
                 int m_tile, n_start, n_step;
                 int64_t slot;
                 if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
-                for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                int jt = 0;
+                for (int nt = n_start; nt < S.n_tiles; nt += n_step, ++jt) {
+                    const long long w0 = dbg ? clock64() : 0ll;
                     mbar_wait(tempty_bar(abuf), aphase ^ 1u);
+                    if (dbg) {
+                        const long long w = clock64() - w0;
+                        w_tempty += w;
+                        if (issuer) atomicAdd(&g_tc_wait[4 + (31 - __clz(jt + 1))], (unsigned long long)w);
+                    }
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(abuf * BN);
                     for (int kb = 0; kb < p.num_kb; ++kb) {
+                        const long long w1 = dbg ? clock64() : 0ll;
                         mbar_wait(full_bar(stage), phase);
+                        if (dbg) w_full += clock64() - w1;
                         if (CLM == 2) mbar_wait(pfull_bar(stage), phase);   // the peer CTA's half of the stage landed too
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -423,6 +487,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     if (abuf == 0) aphase ^= 1u;
                 }
             }
+            if (dbg && issuer) {
+                atomicAdd(&g_tc_wait[0], (unsigned long long)w_tempty);
+                atomicAdd(&g_tc_wait[1], (unsigned long long)w_full);
+                atomicAdd(&g_tc_wait[2], (unsigned long long)(clock64() - w_start));
+            }
         } else if (CLM == 2) {
             // Non-leader CTA of a pair, multicast mode: its stage bytes are counted on ITS OWN full barrier; relay
             // "stage landed" to the pair leader, which issues the MMAs that read both CTAs' shared memory.
@@ -451,6 +520,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         const int row0 = lg * 32;         // first tile row of the warp
         const int row = row0 + lane;      // tile row owned by this thread
         float *aux_s = aux_tiles + lg * BN;
+        const uint32_t look_sa = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (uint32_t)(lg * 32 * LOOK_PITCH * 4);
+        uint64_t *stg = p.staged + ((int64_t)blockIdx.x * BM + row0) * SC;  // this warp's 32 staging rows
         const uint32_t aux_sa = smem_u32(aux_s);
         int abuf = 0;
         uint32_t aphase = 0;
@@ -460,8 +531,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
             const int64_t qrow = (((int64_t)m_tile * CLM + pairc) * CG + crank) * BM + row;
             uint64_t thr = 0ull;
-            float thr_f = __uint_as_float(0x7fc00000u);
+            float thr_f = p.debug_skip == 3 ? 103.0f : __uint_as_float(0x7fc00000u);  // DEBUGSKIP3
+            if (p.debug_skip == 3) thr = 1ull;
+            const int kk = p.debug_skip == 3 ? -1 : p.k;
             int cnt = 0;
+            unsigned rot = 0;
+            const int max_flush = p.max_flush;
             float rowc = 0.0f;
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
@@ -486,9 +561,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                 }
                 mbar_wait(tfull_bar(abuf), aphase);
                 tc_fence_after();
+                const bool edbg = p.debug_skip == 8 && warp == 2 && crank == 0;
+                const long long e0 = edbg ? clock64() : 0ll;
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     uint32_t v[32];
+                    if (EPI == EPI_TOPK && p.debug_skip == 2 && ch != BN / 32 - 1) continue;
                     tmem_ld_32x32(tmem_base + ((uint32_t)row0 << 16) + (uint32_t)(abuf * BN + ch * 32), v);
                     tmem_ld_wait();
                     if (ch == BN / 32 - 1) {  // all TMEM reads of this buffer are done: hand it back
@@ -499,6 +577,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         }
                     }
                     const int64_t col0 = col_tile + ch * 32;
+                    if (EPI == EPI_TOPK && (p.debug_skip == 1 || p.debug_skip == 2)) continue;
                     if (EPI == EPI_MATMUL) {
                         if (p.out_tma) {
                             // registers -> swizzled 32x32 smem tile -> one TMA store per warp and chunk: full 128-byte
@@ -526,26 +605,53 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                                 if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
                         }
                     } else if (p.metric == METRIC_DOT) {
-                        filter_chunk<METRIC_DOT, R>(v, aux_sa + ch * 128, rowc, col0, p.n, p.index_base, stage_buf, list_base, row,
-                                                    row0, lane, p.k, thr, thr_f, cnt);
+                        filter_chunk<METRIC_DOT, R>(v, aux_sa + ch * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane, kk,
+                                                    thr, thr_f, cnt);
                     } else if (p.metric == METRIC_COSINE) {
-                        filter_chunk<METRIC_COSINE, R>(v, aux_sa + ch * 128, rowc, col0, p.n, p.index_base, stage_buf, list_base,
-                                                       row, row0, lane, p.k, thr, thr_f, cnt);
+                        filter_chunk<METRIC_COSINE, R>(v, aux_sa + ch * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane,
+                                                       kk, thr, thr_f, cnt);
                     } else {
-                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + ch * 128, rowc, col0, p.n, p.index_base, stage_buf,
-                                                          list_base, row, row0, lane, p.k, thr, thr_f, cnt);
+                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + ch * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base,
+                                                          lane, kk, thr, thr_f, cnt);
                     }
                 }
+                if (edbg && lane == 0)
+                    atomicAdd(&g_tc_wait[20 + (31 - __clz((nt - n_start) / n_step + 1))], (unsigned long long)(clock64() - e0));
                 if (EPI == EPI_TOPK) {  // regular flush: the TMEM buffer is already back with the MMA warp
-                    const unsigned due = __ballot_sync(0xffffffffu, cnt > FLUSH_AT);
-                    if (due) flush_rows<R>(due, stage_buf, list_base, row0, lane, p.k, thr, thr_f, cnt);
+                    // Rows of a warp fill their staging slots at the same rate, so they come due in bursts; a burst
+                    // of 32 row merges takes several tiles' worth of MMA time and stalls the accumulator ring.
+                    // Spread it: at most `max_flush` rows per tile (rows that are nearly full first), the rest
+                    // keep staging (EMERGENCY_AT still bounds them).
+                    unsigned due = __ballot_sync(0xffffffffu, cnt > SOFT_AT);
+                    if (__popc(due) > max_flush) {
+                        unsigned pick = __ballot_sync(0xffffffffu, cnt > URGENT_AT);
+                        unsigned rest = due & ~pick;
+                        rest = __funnelshift_r(rest, rest, rot);  // rotate so that no row is always last
+                        int room = max_flush - __popc(pick);
+                        while (room > 0 && rest) {
+                            const unsigned low = rest & (0u - rest);
+                            pick |= __funnelshift_l(low, low, rot);
+                            rest ^= low;
+                            --room;
+                        }
+                        due = pick;
+                        rot = (rot + 7) & 31;
+                    }
+                    if (due) {
+                        const long long f0 = p.debug_skip == 8 ? clock64() : 0ll;
+                        flush_rows<R>(due, stg, list_base, lane, kk, thr, thr_f, cnt);
+                        if (edbg && lane == 0) {
+                            atomicAdd(&g_tc_wait[3], (unsigned long long)(clock64() - f0));
+                            atomicAdd(&g_tc_wait[36 + (31 - __clz((nt - n_start) / n_step + 1))], (unsigned long long)(clock64() - f0));
+                        }
+                    }
                 }
                 abuf ^= 1;
                 if (abuf == 0) aphase ^= 1u;
             }
             if (EPI == EPI_TOPK) {
                 const unsigned pending = __ballot_sync(0xffffffffu, cnt > 0);
-                if (pending) flush_rows<R>(pending, stage_buf, list_base, row0, lane, p.k, thr, thr_f, cnt);
+                if (pending) flush_rows<R>(pending, stg, list_base, lane, kk, thr, thr_f, cnt);
             }
         }
     }
@@ -654,9 +760,14 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.metric = a.metric;
     p.k = a.k;
     p.partial = a.partial;
+    p.staged = a.staged;
     p.out = a.out;
     p.round_sync = a.round_sync;
     p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
+    p.debug_skip = a.debug_skip;
+    // merges that fit beside one tile's MMA time: a merge costs about as much as 8 k-blocks of one plane
+    p.max_flush = a.max_flush > 0 ? a.max_flush : (p.num_kb * a.terms / 8 > 1 ? p.num_kb * a.terms / 8 : 1);
+    p.sync_slack = a.sync_slack > 0 ? a.sync_slack : 0;
     auto kern = tc_kernel<F16, EPI, R, ROWB, CG, TERMS, CLM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -727,6 +838,15 @@ TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int g
     if (s.num_ctas < 1) s.num_ctas = 1;
     return s;
 }
+
+void tc_debug_wait_cycles(unsigned long long out[52]) {
+    unsigned long long zero[52] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_tc_wait, sizeof(zero));
+    cudaMemcpyToSymbol(g_tc_wait, zero, sizeof(zero));
+}
+
+int64_t tc_staged_bytes(int num_ctas) { return (int64_t)num_ctas * BM * SC * 8; }
 
 int64_t tc_sync_counters(const TcSchedule &s, int sync_tiles) {
     if (sync_tiles < 1) sync_tiles = 1;
