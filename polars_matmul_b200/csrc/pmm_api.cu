@@ -352,8 +352,9 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.kp = kp;
     a.k = kp;
     DevBuf partial, rsync, staged;
-    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * gs * TC_TILE_M * a.kp * 8, s));
-    CUDA_TRY(staged.alloc((size_t)tc_staged_bytes(a.sched.num_ctas * gs), s));
+    const int esets = tc_epilogue_sets(a.f16, a.terms);
+    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * esets * gs * TC_TILE_M * a.kp * 8, s));
+    CUDA_TRY(staged.alloc((size_t)tc_staged_bytes(a.sched.num_ctas * gs, esets), s));
     a.staged = staged.as<uint64_t>();
     if (g_tc_sync_tiles.load() > 0) {
         a.sync_tiles = g_tc_sync_tiles.load();
@@ -368,7 +369,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
     CUDA_TRY(launch_counted("merge", s, [&] {
-        return launch_merge_tiles(a.partial, a.sched, gs, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
+        return launch_merge_tiles(a.partial, a.sched, gs, esets, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
     }));
     return PMM_OK;
 }

@@ -113,7 +113,7 @@ __device__ __forceinline__ uint64_t warp_sort_desc(uint64_t v, int lane) {
             bool lower = (lane & stride) == 0;            // I hold the lower-indexed slot of the pair
             bool desc = (lane & size) == 0;               // this sub-sequence sorts descending
             bool keep_max = (lower == desc);
-            v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+            v = ((v > o) != keep_max) ? o : v;            // one compare: take the partner's value unless mine is the one to keep
         }
     }
     return v;
@@ -145,7 +145,7 @@ __device__ __forceinline__ void warp_sort_regs_desc(uint64_t (&S)[RS], int lane)
                     const bool lower = (lane & stride) == 0;
                     const bool desc = (((32 * r) | lane) & size) == 0;
                     const bool keep_max = (lower == desc);
-                    S[r] = keep_max ? (S[r] > o ? S[r] : o) : (S[r] < o ? S[r] : o);
+                    S[r] = ((S[r] > o) != keep_max) ? o : S[r];
                 }
             }
         }
@@ -173,7 +173,7 @@ __device__ __forceinline__ void warp_bitonic_merge_desc(uint64_t (&L)[R], int la
         for (int r = 0; r < R; ++r) {
             uint64_t o = shfl_xor_u64(L[r], stride);
             bool lower = (lane & stride) == 0;
-            L[r] = lower ? (L[r] > o ? L[r] : o) : (L[r] < o ? L[r] : o);
+            L[r] = ((L[r] > o) != lower) ? o : L[r];
         }
     }
 }

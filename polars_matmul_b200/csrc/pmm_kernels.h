@@ -105,11 +105,12 @@ struct TcSchedule {
 TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg);
 // Diagnostics: reads and clears the wait-cycle counters filled when TcArgs::debug_skip == 8.
 void tc_debug_wait_cycles(unsigned long long out[52]);
-int64_t tc_staged_bytes(int num_ctas);  // size of TcArgs::staged
+int tc_epilogue_sets(int f16, int terms);  // epilogue warp sets of the top-k kernel variant: lists per (slot, row)
+int64_t tc_staged_bytes(int num_ctas, int esets);  // size of TcArgs::staged
 int64_t tc_sync_counters(const TcSchedule &s, int sync_tiles);  // number of pacing counters a launch needs
 
 // Partial lists written by the fused kernel: [slot][cta of the group (cg)][row_in_tile (128)][kp].
-cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int kp, int64_t nq, int k_out, bool higher,
+cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int esets, int kp, int64_t nq, int k_out, bool higher,
                                uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s);
 
 struct TcArgs {
@@ -132,7 +133,7 @@ struct TcArgs {
     int metric;
     int k;                         // candidates kept per query and piece: the list position that sets the threshold (<= kp)
     int kp;                        // list capacity: 32, 64, 128 or 256
-    uint64_t *partial;             // [sched.total_slots()][cg][128][kp]
+    uint64_t *partial;             // [sched.total_slots()][tc_epilogue_sets()][cg][128][kp]
     uint64_t *staged;              // top-k: scratch of tc_staged_bytes(grid CTAs) bytes (unsorted candidates per CTA and row)
     // matmul mode
     float *out;                    // [nq x n] row-major

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) merge_regular_kernel(const uint64_t *__re
 }
 
 template <int R>
-__global__ void __launch_bounds__(256) merge_tiles_kernel(const uint64_t *__restrict__ lists, TcSchedule sched, int cg,
+__global__ void __launch_bounds__(256) merge_tiles_kernel(const uint64_t *__restrict__ lists, TcSchedule sched, int cg, int esets,
                                                           int64_t nq, int k_out, bool higher, uint32_t *out_idx,
                                                           double *out_score, uint64_t *out_cand) {
     constexpr int KP = 32 * R;
@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(256) merge_tiles_kernel(const uint64_t *__rest
     if (q >= nq) return;
     const int tile_rows = TC_TILE_M * cg;
     const int mt = (int)(q / tile_rows), r = (int)(q % tile_rows);  // r = cta_in_group * 128 + row
-    const uint64_t *base = lists + (sched.slot_base(mt) * tile_rows + r) * KP;
+    // lists of one query: [piece][epilogue set], a regular stride apart
+    const uint64_t *base = lists + (sched.slot_base(mt) * esets * tile_rows + r) * KP;
     const int64_t piece_stride = (int64_t)tile_rows * KP;
     auto ptr = [&](int l) { return base + l * piece_stride; };
-    merge_query<R>(ptr, sched.pieces(mt), KP, k_out, higher, q, out_idx, out_score, out_cand, lane);
+    merge_query<R>(ptr, sched.pieces(mt) * esets, KP, k_out, higher, q, out_idx, out_score, out_cand, lane);
 }
 
 cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t list_stride, int64_t row_stride,
@@ -86,18 +87,18 @@ cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int kp, int64_t nq, int k_out, bool higher,
+cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int esets, int kp, int64_t nq, int k_out, bool higher,
                                uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
     if (nq <= 0 || k_out <= 0) return cudaSuccess;
     unsigned grid = (unsigned)((nq + 7) / 8);
     if (kp == 32)
-        merge_tiles_kernel<1><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<1><<<grid, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 64)
-        merge_tiles_kernel<2><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<2><<<grid, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 128)
-        merge_tiles_kernel<4><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<4><<<grid, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
     else if (kp == 256)
-        merge_tiles_kernel<8><<<grid, 256, 0, s>>>(lists, sched, cg, nq, k_out, higher, out_idx, out_score, out_cand);
+        merge_tiles_kernel<8><<<grid, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

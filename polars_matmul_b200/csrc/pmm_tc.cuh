@@ -30,6 +30,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
         : "memory");
 }
+// Same without release semantics: for handing back a TMEM buffer whose tcgen05.ld's have completed
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order the tensor-memory side).  A releasing arrive
+// makes the warp drain all its outstanding global stores first (MEMBAR.ALL.CTA), which the candidate-list
+// writes of the epilogue make expensive.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+        : "memory");
+}
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
     uint32_t r;

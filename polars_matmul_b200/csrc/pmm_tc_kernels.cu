@@ -37,7 +37,13 @@ namespace {
 
 constexpr int BM = TC_TILE_M;
 constexpr int BN = TC_TILE_N;
-constexpr int NUM_THREADS = 192;
+// Epilogue warp sets. The top-k kernels with ONE operand plane (f16, TF32 x1) spend about as long filtering a tile
+// as multiplying it, so they run two sets of four epilogue warps: set e owns columns [e*128, e*128+128) of every
+// accumulator tile and keeps its own candidate lists (merged with the others by pmm_merge.cu).  Two warps per
+// scheduler also hide each other's TMEM-load and dependent-issue latencies.  The 3xTF32 and matmul kernels are
+// MMA- resp. store-bound and keep one set (and the deeper operand pipeline).
+__host__ __device__ constexpr int tc_esets(bool f16, int epi, int terms) { return (epi == 0 && f16) ? 2 : 1; }
+__host__ __device__ constexpr int tc_threads(int esets) { return 64 + 128 * esets; }
 // Candidates that beat a row's threshold are APPENDED to a per-row staging area in global memory (L2-resident,
 // one per CTA and row, reused by every item of the CTA) and merged into the row's sorted list in batches: the
 // cost of a merge (sort the batch, one bitonic merge with the list) is the same for 10 or 100 staged
@@ -47,7 +53,9 @@ constexpr int LOOK_PITCH = 36;             // floats per lane in the hit-lookup 
 constexpr int SC = 128;                    // staging capacity per row
 constexpr int HARD_AT = SC - 32;           // a 32-column chunk adds at most 32: merge inside the tile above this
 constexpr int URGENT_AT = 80;              // rows above this are always merged at the end of a tile
-constexpr int SOFT_AT = 48;                // end-of-tile merge above this (rate limited), AFTER the TMEM buffer was released
+// end-of-tile merge above this (rate limited after the first tiles), AFTER the TMEM buffer was released.  Smaller
+// batches for short lists were measured and lose: a merge has a high fixed cost (f16 C5, k=10: 192 -> 197 ms).
+constexpr int SOFT_AT = 48;
 
 // ROWB = bytes of K per shared-memory row (= the swizzle span): 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
 // CG   = tcgen05 cta_group: 1 = one CTA per 128 x 256 tile; 2 = a CTA pair (cluster of 2) computes a
@@ -58,7 +66,7 @@ constexpr int SOFT_AT = 48;                // end-of-tile merge above this (rate
 // CLM  = CTA pairs per cluster (cta_group::2 only): 2 = a cluster of 4 CTAs works on two query tiles against the
 //        SAME corpus tile; each CTA fetches a quarter of the corpus tile and TMA-multicasts it to the CTA of the
 //        other pair that needs the same half, so corpus bytes L2 -> shared memory halve again.
-template <bool F16, int ROWB, int CG, int TERMS, int CLM = 1>
+template <bool F16, int ROWB, int CG, int TERMS, int CLM = 1, int ESETS = 1>
 struct TcCfg {
     static constexpr int PLANES = (F16 || TERMS == 1) ? 1 : 2;
     static constexpr int BK = ROWB / (F16 ? 2 : 4);  // elements of K per stage
@@ -67,8 +75,8 @@ struct TcCfg {
     static constexpr int A_BYTES = BM * ROWB;
     static constexpr int B_BYTES = B_ROWS * ROWB;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-    static constexpr int STAGING_BYTES = 4 * 32 * LOOK_PITCH * 4;  // per epilogue warp: one chunk of filter values (hit lookup)
-    static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of the tile
+    static constexpr int STAGING_BYTES = ESETS * 4 * 32 * LOOK_PITCH * 4;  // per epilogue warp: one chunk of filter values (hit lookup)
+    static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of its columns of the tile
     static constexpr int STORE_BYTES = 4 * 2 * 4096; // matmul epilogue: per warp two 32x32 f32 TMA-store tiles
     static constexpr int EPI_BYTES = (STAGING_BYTES + AUX_BYTES) > STORE_BYTES ? (STAGING_BYTES + AUX_BYTES) : STORE_BYTES;
     static constexpr int STAGES = (232448 - EPI_BYTES - 256 - 1024) / STAGE_BYTES;
@@ -257,11 +265,13 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t a
 }
 
 template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(tc_esets(F16, EPI, TERMS)), 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
           const __grid_constant__ CUtensorMap tm_chi, const __grid_constant__ CUtensorMap tm_clo,
           const __grid_constant__ CUtensorMap tm_out, const TcKParams p) {
-    typedef TcCfg<F16, ROWB, CG, TERMS, CLM> Cfg;
+    constexpr int ESETS = tc_esets(F16, EPI, TERMS);
+    constexpr int CPS = BN / 32 / ESETS;      // 32-column chunks of a tile per epilogue warp
+    typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS> Cfg;
     constexpr bool ONE = F16 || TERMS == 1;   // one operand plane per matrix, one MMA per K-step
     constexpr int GS = CG * CLM;              // CTAs per scheduling unit (= cluster size)
     static_assert(CLM == 1 || CG == 2, "corpus multicast is built on CTA pairs");
@@ -302,7 +312,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 4 * CG);  // one arrival per epilogue warp of every CTA of the group
+            mbar_init(tempty_bar(b), 4 * ESETS * CG);  // one arrival per epilogue warp of every CTA of the group
         }
         fence_barrier_init();
     }
@@ -519,9 +529,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         const int lg = warp & 3;          // TMEM lane group this warp may read
         const int row0 = lg * 32;         // first tile row of the warp
         const int row = row0 + lane;      // tile row owned by this thread
-        float *aux_s = aux_tiles + lg * BN;
-        const uint32_t look_sa = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (uint32_t)(lg * 32 * LOOK_PITCH * 4);
-        uint64_t *stg = p.staged + ((int64_t)blockIdx.x * BM + row0) * SC;  // this warp's 32 staging rows
+        const int eset = (warp - 2) >> 2;  // epilogue set: columns [eset * BN / ESETS, (eset + 1) * BN / ESETS) of every tile
+        const int ch0 = eset * CPS;
+        float *aux_s = aux_tiles + (warp - 2) * (BN / ESETS);
+        const uint32_t look_sa = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (uint32_t)((warp - 2) * 32 * LOOK_PITCH * 4);
+        // this warp's 32 staging rows
+        uint64_t *stg = EPI == EPI_TOPK ? p.staged + (((int64_t)blockIdx.x * ESETS + eset) * BM + row0) * SC : nullptr;
         const uint32_t aux_sa = smem_u32(aux_s);
         int abuf = 0;
         uint32_t aphase = 0;
@@ -541,7 +554,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
-                list_base = p.partial + ((slot * GS + (crank4 & (uint32_t)(GS - 1))) * BM + row0) * KP;
+                list_base = p.partial + (((slot * ESETS + eset) * GS + (crank4 & (uint32_t)(GS - 1))) * BM + row0) * KP;
                 for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
                 // q_aux is padded to the tile grid. cosine: 1 unless the query norm is ~0; euclidean: |q|^2
                 if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > 1e-6f ? 1.0f : 0.0f;
@@ -553,8 +566,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                 if (EPI == EPI_TOPK && p.metric != METRIC_DOT) {  // stage this tile's corpus aux values (per warp)
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < BN / 32; ++i) {
-                        const float a = __ldg(p.c_aux + col_tile + i * 32 + lane);  // c_aux is padded to the tile grid
+                    for (int i = 0; i < CPS; ++i) {
+                        const float a = __ldg(p.c_aux + col_tile + (ch0 + i) * 32 + lane);  // c_aux is padded to the tile grid
                         aux_s[i * 32 + lane] = p.metric == METRIC_COSINE ? (a > 1e-6f ? __frcp_rn(a) : 0.0f) : a;
                     }
                     __syncwarp();
@@ -564,16 +577,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                 const bool edbg = p.debug_skip == 8 && warp == 2 && crank == 0;
                 const long long e0 = edbg ? clock64() : 0ll;
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
+                for (int ch = ch0; ch < ch0 + CPS; ++ch) {
                     uint32_t v[32];
-                    if (EPI == EPI_TOPK && p.debug_skip == 2 && ch != BN / 32 - 1) continue;
+                    if (EPI == EPI_TOPK && p.debug_skip == 2 && ch != ch0 + CPS - 1) continue;
                     tmem_ld_32x32(tmem_base + ((uint32_t)row0 << 16) + (uint32_t)(abuf * BN + ch * 32), v);
                     tmem_ld_wait();
-                    if (ch == BN / 32 - 1) {  // all TMEM reads of this buffer are done: hand it back
+                    if (ch == ch0 + CPS - 1) {  // this warp's TMEM reads of the buffer are done: hand it back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if (CG == 1) mbar_arrive(tempty_bar(abuf)); else mbar_arrive_cluster(tempty_bar(abuf), leader_rank);
+                            if (CG == 1) mbar_arrive(tempty_bar(abuf)); else mbar_arrive_cluster_relaxed(tempty_bar(abuf), leader_rank);
                         }
                     }
                     const int64_t col0 = col_tile + ch * 32;
@@ -605,13 +618,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                                 if (col0 + j < p.n) dst[j] = __uint_as_float(v[j]);
                         }
                     } else if (p.metric == METRIC_DOT) {
-                        filter_chunk<METRIC_DOT, R>(v, aux_sa + ch * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane, kk,
+                        filter_chunk<METRIC_DOT, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane, kk,
                                                     thr, thr_f, cnt);
                     } else if (p.metric == METRIC_COSINE) {
-                        filter_chunk<METRIC_COSINE, R>(v, aux_sa + ch * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane,
+                        filter_chunk<METRIC_COSINE, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane,
                                                        kk, thr, thr_f, cnt);
                     } else {
-                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + ch * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base,
+                        filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base,
                                                           lane, kk, thr, thr_f, cnt);
                     }
                 }
@@ -623,7 +636,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     // Spread it: at most `max_flush` rows per tile (rows that are nearly full first), the rest
                     // keep staging (EMERGENCY_AT still bounds them).
                     unsigned due = __ballot_sync(0xffffffffu, cnt > SOFT_AT);
-                    if (__popc(due) > max_flush) {
+                    if (__popc(due) > max_flush && nt - n_start >= 32 * n_step) {  // (early tiles: thresholds move fast, merge all)
                         unsigned pick = __ballot_sync(0xffffffffu, cnt > URGENT_AT);
                         unsigned rest = due & ~pick;
                         rest = __funnelshift_r(rest, rest, rot);  // rotate so that no row is always last
@@ -730,7 +743,8 @@ bool make_out_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols) 
 
 template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM = 1>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
-    typedef TcCfg<F16, ROWB, CG, TERMS, CLM> Cfg;
+    constexpr int ESETS = tc_esets(F16, EPI, TERMS);
+    typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS> Cfg;
     constexpr bool ONE = F16 || TERMS == 1;
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
@@ -774,7 +788,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(a.sched.num_ctas * CG * CLM));
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(tc_threads(ESETS));
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -846,7 +860,9 @@ void tc_debug_wait_cycles(unsigned long long out[52]) {
     cudaMemcpyToSymbol(g_tc_wait, zero, sizeof(zero));
 }
 
-int64_t tc_staged_bytes(int num_ctas) { return (int64_t)num_ctas * BM * SC * 8; }
+int tc_epilogue_sets(int f16, int terms) { return tc_esets(f16 != 0, EPI_TOPK, terms); }
+
+int64_t tc_staged_bytes(int num_ctas, int esets) { return (int64_t)num_ctas * esets * BM * SC * 8; }
 
 int64_t tc_sync_counters(const TcSchedule &s, int sync_tiles) {
     if (sync_tiles < 1) sync_tiles = 1;
