@@ -16,6 +16,11 @@
 
 namespace pmm {
 
+// floats per candidate row of a warp's transpose tile: 16-byte aligned rows whose float4 reads (one row per lane)
+// and per-element writes (one column per lane) are both free of bank conflicts (pitch = 4 mod 32)
+constexpr int RS_PITCH32 = 36;  // 32 elements per step
+constexpr int RS_PITCH16 = 68;  // f16 rows: 64 elements per step
+
 template <typename SRC> struct RsLoad;
 template <> struct RsLoad<float> { static __device__ __forceinline__ float get(const void *v, int64_t p) { return __ldg((const float *)v + p); } };
 template <> struct RsLoad<__half> { static __device__ __forceinline__ float get(const void *v, int64_t p) { return __half2float(__ldg((const __half *)v + p)); } };
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
                                                      double *out_score, uint64_t *out_cand, RescoreCheck chk) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t *sortbuf = (uint64_t *)rs_smem;            // NT entries
-    float *qs = (float *)(rs_smem + NT * 8);            // dim floats, then one 32x33 transpose tile per warp
+    float *qs = (float *)(rs_smem + NT * 8);            // dim floats, then one transpose tile per warp
     const int64_t q = blockIdx.x;
     const int t = threadIdx.x;
     const int dim = (int)qm.dim;
@@ -61,63 +66,115 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     __syncthreads();
     const bool higher = higher_is_better(metric);
     const int lane = t & 31, wrp = t >> 5;
-    float (*tile)[33] = (float (*)[33])(rs_smem + NT * 8 + (size_t)((dim + 3) & ~3) * 4 + (size_t)wrp * 32 * 33 * 4);
-    const uint64_t c = (t < kp_in) ? cand[q * kp_in + t] : 0ull;
+    uint64_t c_in = (t < kp_in) ? cand[q * kp_in + t] : 0ull;
+    // Candidates that cannot reach the top k are not re-scored (their corpus rows are never fetched): the list is
+    // sorted by filter value f, |exact - f| <= E (the same bound the losslessness check below uses), so a candidate
+    // with f < f_k - 2E (f_k = k-th best filter value) is strictly worse than k others.  With exact-product filters
+    // (f16 planes) this leaves about k of the KP candidates.
+    if (chk.q_sq && chk.c_max_sq && k_out > 0 && t >= k_out && k_out <= kp_in && c_in != 0ull) {
+        const uint64_t ck = cand[q * kp_in + k_out - 1];
+        if (ck != 0ull) {
+            const float f_k = key_score(candidate_key(ck), true), f_j = key_score(candidate_key(c_in), true);
+            const float qn = sqrtf(chk.q_sq[q]);
+            const float cmax = sqrtf(__uint_as_float(*chk.c_max_sq));
+            const float e = metric == METRIC_DOT      ? chk.eps * qn * cmax
+                            : metric == METRIC_COSINE ? (chk.eps + 1e-6f) * qn
+                                                      : 2.0f * chk.eps * qn * cmax + 1e-6f * (qn * qn + cmax * cmax);
+            if (f_j < f_k - 2.0f * e - 1e-6f * fabsf(f_k)) c_in = 0ull;  // (NaN anywhere: keep)
+        }
+    }
+    const uint64_t c = c_in;
     const uint32_t gidx = candidate_index(c);
     const int64_t row = (int64_t)gidx - index_base;
     int64_t cb = 0, cl = 0;
     if (c != 0ull) raw_row(cm, row, cb, cl);
-    // Each warp walks the vector dimension 32 elements at a time: candidate rows are read with coalesced
-    // 128-byte requests (lane = element), transposed through shared memory, and every thread then
-    // accumulates ITS candidate sequentially in d — the reference's order.
+    // Each warp walks the vector dimension 32 (f16: 64) elements at a time: candidate rows are read with
+    // coalesced 128-byte requests (lane = element), transposed through shared memory, and every thread then
+    // accumulates ITS candidate sequentially in d — the reference's order.  Candidates are sorted best first and
+    // the skipped ones sit at the end, so the warp only fetches rows [0, n_act).
+    const int n_act = 32 - __clz(__ballot_sync(0xffffffffu, c != 0ull));
     float acc = 0.0f;
+    unsigned char *tile_base = rs_smem + NT * 8 + (size_t)((dim + 3) & ~3) * 4;
     // f16 rows without nulls: 64 elements per step, one half2 per lane (128-byte requests per row)
     const bool wide16 = sizeof(CSRC) == 2 && !cm.offsets && !cm.validity && (dim & 1) == 0;
     if (wide16) {
-        float (*tile2)[65] = (float (*)[65])(rs_smem + NT * 8 + (size_t)((dim + 3) & ~3) * 4 + (size_t)wrp * 32 * 65 * 4);
+        float (*tile2)[RS_PITCH16] = (float (*)[RS_PITCH16])(tile_base + (size_t)wrp * 32 * RS_PITCH16 * 4);
         const __half2 *vals = (const __half2 *)cm.values;
         for (int d0 = 0; d0 < dim; d0 += 64) {
             float2 x[32];
+            // row reads are issued in batches of 8 candidates (a warp-uniform guard per batch, no branch per row):
+            // every batch is in flight before the first value is consumed
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
-                const int e = d0 + 2 * lane;
-                x[i] = e < cli ? __half22float2(__ldg(vals + ((cbi + e) >> 1))) : make_float2(0.0f, 0.0f);
+            for (int g = 0; g < 32; g += 8) {
+                if (g < n_act) {
+#pragma unroll
+                    for (int i = g; i < g + 8; ++i) {
+                        const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
+                        const int e = d0 + 2 * lane;
+                        x[i] = e < cli ? __half22float2(__ldg(vals + ((cbi + e) >> 1))) : make_float2(0.0f, 0.0f);
+                    }
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                tile2[i][2 * lane] = x[i].x;
-                tile2[i][2 * lane + 1] = x[i].y;
+            for (int g = 0; g < 32; g += 8) {
+                if (g < n_act) {
+#pragma unroll
+                    for (int i = g; i < g + 8; ++i) *(float2 *)&tile2[i][2 * lane] = x[i];
+                }
             }
             __syncwarp();
             const int jn = dim - d0 < 64 ? dim - d0 : 64;
             if (jn == 64) {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) acc = __fmaf_rn(qs[d0 + j], tile2[lane][j], acc);
+                for (int j = 0; j < 64; j += 4) {
+                    const float4 qv = *(const float4 *)&qs[d0 + j], cv = *(const float4 *)&tile2[lane][j];
+                    acc = __fmaf_rn(qv.x, cv.x, acc);
+                    acc = __fmaf_rn(qv.y, cv.y, acc);
+                    acc = __fmaf_rn(qv.z, cv.z, acc);
+                    acc = __fmaf_rn(qv.w, cv.w, acc);
+                }
             } else {
                 for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile2[lane][j], acc);
             }
             __syncwarp();
         }
-    } else
-    for (int d0 = 0; d0 < dim; d0 += 32) {
-        float x[32];
+    } else {
+        float (*tile)[RS_PITCH32] = (float (*)[RS_PITCH32])(tile_base + (size_t)wrp * 32 * RS_PITCH32 * 4);
+        for (int d0 = 0; d0 < dim; d0 += 32) {
+            float x[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {  // 32 independent row reads in flight per lane before anything is consumed
-            const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
-            x[i] = raw_fetch<CSRC>(cm, cbi, cli, d0 + lane);
+            for (int g = 0; g < 32; g += 8) {  // up to 32 independent row reads in flight per lane before anything is consumed
+                if (g < n_act) {
+#pragma unroll
+                    for (int i = g; i < g + 8; ++i) {
+                        const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
+                        x[i] = raw_fetch<CSRC>(cm, cbi, cli, d0 + lane);
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 32; g += 8) {
+                if (g < n_act) {
+#pragma unroll
+                    for (int i = g; i < g + 8; ++i) tile[i][lane] = x[i];
+                }
+            }
+            __syncwarp();
+            const int jn = dim - d0 < 32 ? dim - d0 : 32;
+            if (jn == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 qv = *(const float4 *)&qs[d0 + j], cv = *(const float4 *)&tile[lane][j];
+                    acc = __fmaf_rn(qv.x, cv.x, acc);
+                    acc = __fmaf_rn(qv.y, cv.y, acc);
+                    acc = __fmaf_rn(qv.z, cv.z, acc);
+                    acc = __fmaf_rn(qv.w, cv.w, acc);
+                }
+            } else {
+                for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile[lane][j], acc);
+            }
+            __syncwarp();
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tile[i][lane] = x[i];
-        __syncwarp();
-        const int jn = dim - d0 < 32 ? dim - d0 : 32;
-        if (jn == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc = __fmaf_rn(qs[d0 + j], tile[lane][j], acc);
-        } else {
-            for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile[lane][j], acc);
-        }
-        __syncwarp();
     }
     uint64_t packed = 0ull;
     if (c != 0ull) {
@@ -182,7 +239,7 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
     const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
 #define PMM_RS(NT)                                                                                                  \
     {                                                                                                               \
-        size_t smem = NT * 8 + smem_q + (size_t)(NT / 32) * 32 * (sizeof(CSRC) == 2 ? 65 : 33) * 4;                                                                              \
+        size_t smem = NT * 8 + smem_q + (size_t)(NT / 32) * 32 * (sizeof(CSRC) == 2 ? RS_PITCH16 : RS_PITCH32) * 4;                                                                              \
         if (smem > 48 * 1024) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                         \
