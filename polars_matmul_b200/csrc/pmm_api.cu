@@ -41,7 +41,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -122,22 +122,87 @@ int ensure_device() {
     return PMM_OK;
 }
 
+// Large blocks (>= 32 MB) that a thread frees are parked here and handed to the next request of a similar size on
+// the same stream and device, instead of going back to the CUDA memory pool.  Why: the host path allocates
+// multi-GB buffers (raw corpus, operand planes) in a different interleaving every call; the pool then has the
+// bytes but not as one range and re-maps physical memory to serve the request, which showed up as 0.3-1.5 s stalls
+// in 1 of 5 end-to-end calls.  Reuse on the SAME stream keeps stream order (like cudaFreeAsync + cudaMallocAsync).
+// pmm_set_option("release_workspace", 1) returns the parked blocks to the pool.
+struct BlockCache {
+    struct Entry {
+        void *p;
+        size_t cap;
+        cudaStream_t s;
+        int dev;
+    };
+    std::vector<Entry> free_blocks;
+    size_t bytes = 0;
+    static constexpr size_t kMinBlock = (size_t)32 << 20, kMaxBytes = (size_t)48 << 30;
+    void *take(size_t want, cudaStream_t s, int dev, size_t *cap) {
+        int best = -1;
+        for (int i = 0; i < (int)free_blocks.size(); ++i) {
+            const Entry &e = free_blocks[i];
+            if (e.s == s && e.dev == dev && e.cap >= want && e.cap <= want + want / 2 &&
+                (best < 0 || e.cap < free_blocks[best].cap))
+                best = i;
+        }
+        if (best < 0) return nullptr;
+        void *p = free_blocks[best].p;
+        *cap = free_blocks[best].cap;
+        bytes -= free_blocks[best].cap;
+        free_blocks.erase(free_blocks.begin() + best);
+        return p;
+    }
+    bool park(void *p, size_t cap, cudaStream_t s, int dev) {
+        if (cap < kMinBlock || bytes + cap > kMaxBytes) return false;
+        free_blocks.push_back(Entry{p, cap, s, dev});
+        bytes += cap;
+        return true;
+    }
+    void clear() {
+        for (const Entry &e : free_blocks) cudaFreeAsync(e.p, e.s);
+        free_blocks.clear();
+        bytes = 0;
+    }
+    ~BlockCache() { clear(); }
+};
+thread_local BlockCache g_block_cache;
+
 // Stream-ordered device buffer.
+// alloc() on a buffer that is already large enough (same stream) keeps it: loops over corpus chunks reuse their
+// scratch instead of cycling differently sized blocks.
 struct DevBuf {
     void *p = nullptr;
+    size_t cap = 0;
     cudaStream_t s = nullptr;
+    int dev = 0;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        if (bytes == 0) bytes = 16;
+        if (p && cap >= bytes && s == stream) return cudaSuccess;
         release();
         s = stream;
-        if (bytes == 0) bytes = 16;
-        return cudaMallocAsync(&p, bytes, stream);
+        cudaGetDevice(&dev);
+        if (bytes >= BlockCache::kMinBlock) {
+            bytes = (bytes + BlockCache::kMinBlock - 1) / BlockCache::kMinBlock * BlockCache::kMinBlock;
+            if ((p = g_block_cache.take(bytes, stream, dev, &cap))) return cudaSuccess;
+        }
+        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        if (e != cudaSuccess && g_block_cache.bytes) {  // out of memory with blocks parked: give them back and retry
+            cudaGetLastError();
+            g_block_cache.clear();
+            e = cudaMallocAsync(&p, bytes, stream);
+        }
+        cap = e == cudaSuccess ? bytes : 0;
+        if (e != cudaSuccess) p = nullptr;
+        return e;
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && !g_block_cache.park(p, cap, s, dev)) cudaFreeAsync(p, s);
         p = nullptr;
+        cap = 0;
     }
     ~DevBuf() { release(); }
     template <typename T> T *as() const { return (T *)p; }
@@ -154,6 +219,12 @@ struct Prepared {
     DevBuf p0, p1, norm, sqnorm, max_sq;
     unsigned int *max_sq_ptr = nullptr;  // own (max_sq) or shared across corpus chunks
 };
+
+// Bytes of one operand plane prepare() allocates for `rows` x `dim` (tensor-core modes).
+size_t plane_bytes(int mode, int64_t rows, int64_t dim, int64_t row_tile) {
+    const int64_t kq = mode == PREP_F16 ? 64 : 32, es = mode == PREP_F16 ? 2 : 4;
+    return (size_t)(round_up(rows, row_tile) * round_up(dim, kq) * es);
+}
 
 // Runs the prep kernel on a device-resident matrix. row_tile: pad rows to this multiple (planes only).
 int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool want_norm, bool want_sq, int *d_err,
@@ -319,8 +390,19 @@ int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : 
 // Tensor-core filter on prepared PLANES: fused kernel -> merge of the corpus pieces of every query tile.
 // kept [Q x kp]: per query the kp best candidates under the kernel's filter value (approximate keys,
 // comparable across corpus chunks and shards of the same query), indices = index_base + corpus row.
+// Corpus in chunks (host path): `carry` keeps the per-row candidate lists between the launches, so a later chunk
+// starts with full lists and tight thresholds instead of paying the list warm-up again, and the lists of all
+// chunks never have to be merged.  All launches of one carry use the schedule group of the WHOLE corpus
+// (`corpus_rows_total`), which fixes the list layout.  phase bit 0: first launch (fresh lists), bit 1: last launch
+// (merge the pieces of every query tile into `kept`).
+struct TcCarry {
+    DevBuf partial;
+    int64_t corpus_rows_total = 0;
+    int64_t layout_rows = 0;  // rows of the smallest chunk (caps the sharing factors of every launch alike)
+};
+
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
-              cudaStream_t s, int terms) {
+              cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -344,16 +426,20 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     const int gs = a.cg * a.clm;   // CTAs per scheduling unit
     int units = di.num_sms / gs;
     if (g_tc_max_units.load() > 0 && units > g_tc_max_units.load()) units = g_tc_max_units.load();
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, units, tc_group_for(c.n_rows, q.ld, a.f16 != 0 || a.terms == 1, units, gs), gs);
+    const int64_t group_rows = carry ? carry->corpus_rows_total : c.n_rows;
+    a.sched = make_tc_schedule(q.n_rows, c.n_rows, units, tc_group_for(group_rows, q.ld, a.f16 != 0 || a.terms == 1, units, gs), gs,
+                               carry ? carry->layout_rows : 0);
     a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
     a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
     a.index_base = index_base;
     a.metric = metric;
     a.kp = kp;
     a.k = kp;
-    DevBuf partial, rsync, staged;
+    DevBuf own_partial, rsync, staged;
+    DevBuf &partial = carry ? carry->partial : own_partial;
     const int esets = tc_epilogue_sets(a.f16, a.terms);
-    CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * esets * gs * TC_TILE_M * a.kp * 8, s));
+    if (!carry || (phase & 1)) CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * esets * gs * TC_TILE_M * a.kp * 8, s));
+    a.resume = (carry && !(phase & 1)) ? 1 : 0;
     CUDA_TRY(staged.alloc((size_t)tc_staged_bytes(a.sched.num_ctas * gs, esets), s));
     a.staged = staged.as<uint64_t>();
     if (g_tc_sync_tiles.load() > 0) {
@@ -368,9 +454,10 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
                                    [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
-    CUDA_TRY(launch_counted("merge", s, [&] {
-        return launch_merge_tiles(a.partial, a.sched, gs, esets, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
-    }));
+    if (phase & 2)
+        CUDA_TRY(launch_counted("merge", s, [&] {
+            return launch_merge_tiles(a.partial, a.sched, gs, esets, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
+        }));
     return PMM_OK;
 }
 
@@ -387,6 +474,25 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
 float filter_eps(int64_t dim, int terms, bool f16) {
     const float split = f16 ? 0.0f : terms == 1 ? 9.8e-4f : 7.5e-7f;
     return split + (float)dim * (1.5e-8f * (float)terms + 6.0e-8f) + 1e-6f;
+}
+
+int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
+                     const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
+                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s);
+
+// Rows [r0, r0 + rows) of a device-resident matrix as a matrix of its own. r0 must be a multiple of 256 (element
+// validity bitmaps are re-based by whole bytes).
+pmm_matrix_t slice_rows(const pmm_matrix_t &m, int64_t r0, int64_t rows) {
+    pmm_matrix_t dm = m;
+    dm.n_rows = rows;
+    if (dm.offsets) {
+        dm.offsets += r0;  // offsets hold absolute child positions: values / validity stay as they are
+    } else {
+        dm.values = (const char *)dm.values + (size_t)r0 * m.dim * esize(m.dtype);
+        if (dm.validity) dm.validity += (r0 * m.dim) / 8;
+    }
+    if (dm.row_validity) dm.row_validity += r0 / 8;
+    return dm;
 }
 
 int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
@@ -459,12 +565,33 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
         // one level up on the tensor cores: 3xTF32 planes of the flagged queries against the corpus planes
         Prepared qf, cf;
         if ((rc = prepare(qd, PREP_TF32, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
-        const Prepared *cp = c_planes;
-        if (!cp) {  // chunked upload: the per-chunk planes are gone, rebuild them from the resident raw corpus
-            if ((rc = prepare(raw_c, PREP_TF32, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
-            cp = &cf;
+        if (c_planes) {
+            if ((rc = tc_topk_verified(qf, c_planes, qd, raw_c, c_norm, c_sq, c_max_sq, 3, keff, metric, index_base, nullptr, t, s)))
+                return rc;
+        } else {
+            // Chunked upload: the per-chunk planes are gone. Rebuild them from the resident raw corpus piece by piece
+            // (planes of at most 128k rows: bounded, equally sized scratch that the memory pool hands back without
+            // mapping new memory — a 2 x corpus-size request after the chunk-sized frees stalled for 0.3-1.5 s),
+            // carrying the candidate lists from piece to piece.
+            const int64_t N = raw_c.n_rows, step = 131072;
+            const int kp1 = tc_list_capacity(keff);
+            DevBuf kept1;
+            CUDA_TRY(kept1.alloc((size_t)F * kp1 * 8, s));
+            TcCarry carry;
+            carry.corpus_rows_total = N;
+            carry.layout_rows = N < step ? N : (N % step ? N % step : step);
+            Prepared cpiece;  // plane buffers of the first (largest) piece are reused by the others
+            for (int64_t r0 = 0; r0 < N; r0 += step) {
+                const int64_t rows = N - r0 < step ? N - r0 : step;
+                if ((rc = prepare(slice_rows(raw_c, r0, rows), PREP_TF32, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &cpiece)))
+                    return rc;
+                if ((rc = tc_filter(qf, cpiece, kp1, metric, index_base + r0, kept1.as<uint64_t>(), s, 3, &carry,
+                                    (r0 == 0 ? 1 : 0) | (r0 + rows >= N ? 2 : 0))))
+                    return rc;
+            }
+            if ((rc = tc_topk_verified(qf, nullptr, qd, raw_c, c_norm, c_sq, c_max_sq, 3, keff, metric, index_base, kept1.as<uint64_t>(), t, s)))
+                return rc;
         }
-        if ((rc = tc_topk_verified(qf, cp, qd, raw_c, c_norm, c_sq, c_max_sq, 3, keff, metric, index_base, nullptr, t, s))) return rc;
     } else {
         Prepared qf, cf;
         if ((rc = prepare(qd, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &qf))) return rc;
@@ -699,12 +826,32 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     cudaStream_t s = host_stream(), cs = copy_stream();
     const int64_t Q = queries->n_rows, N = corpus->n_rows, D = corpus->dim;
     const int es = esize(corpus->dtype);
-    // chunk boundaries in rows (multiples of 256 so bitmaps can be re-based by whole bytes)
+    // Chunk boundaries in rows (multiples of 256 so bitmaps can be re-based by whole bytes).  The filter of chunk i
+    // runs while chunk i+1 is copied, so only the first copy is exposed: start small (N/16) and let the chunks grow
+    // by the ratio of filter time to copy time per row (2 Q / tensor rate vs element size / PCIe rate, about 3.5 at
+    // Q = 100k f32), so that each copy finishes just before the filter wants it.  Copy-bound shapes (few queries)
+    // get equal chunks instead.
     std::vector<int64_t> cut{0};
-    int64_t first = (N / 8) / 256 * 256;
-    if (first < 16384) first = 16384;
-    if (first < N) cut.push_back(first);
-    cut.push_back(N);
+    {
+        const double rate = corpus->dtype == PMM_DTYPE_F16 ? 1.2e15 : 7.0e14;   // sustained filter FLOP/s, measured
+        double ratio = 0.8 * (2.0 * (double)Q / rate) / ((double)es / 4.0e10);  // 40 GB/s host -> device, 20 % margin
+        if (g_host_chunk_ratio_pct.load() > 0) ratio = g_host_chunk_ratio_pct.load() / 100.0;
+        const int max_chunks = 8;
+        const int first_div = g_host_chunk_first_div.load() > 0 ? g_host_chunk_first_div.load() : 32;
+        int64_t size = (N / (ratio < 1.5 ? max_chunks : first_div)) / 256 * 256;
+        if (ratio < 1.5) ratio = 1.0;
+        if (ratio > 4.0) ratio = 4.0;
+        if (size < 16384) size = 16384;
+        int64_t at = 0;
+        while (at + size < N && (int)cut.size() < max_chunks) {
+            at += size;
+            cut.push_back(at);
+            size = (int64_t)((double)size * ratio) / 256 * 256;
+        }
+        // a small remainder joins the previous chunk
+        if (cut.size() > 2 && N - cut.back() < (cut.back() - cut[cut.size() - 2]) / 4) cut.pop_back();
+        cut.push_back(N);
+    }
     const int n_chunks = (int)cut.size() - 1;
 
     Uploaded uq;
@@ -764,36 +911,36 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(cudaMemsetAsync(c_max.p, 0, sizeof(unsigned int), s));
     const int kp = tc_list_capacity(keff);
     const int terms0 = first_level_terms(q);
-    CUDA_TRY(kept_all.alloc((size_t)n_chunks * Q * kp * 8, s));
+    TcCarry carry;
+    carry.corpus_rows_total = N;
+    carry.layout_rows = N;
+    for (int i = 0; i < n_chunks; ++i) carry.layout_rows = std::min<int64_t>(carry.layout_rows, cut[i + 1] - cut[i]);
     CUDA_TRY(kept.alloc((size_t)Q * kp * 8, s));
     if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)N * 4, s));
+    // one set of plane buffers, sized for the largest chunk and reused by all of them
+    Prepared c;
+    {
+        int64_t max_rows = 0;
+        for (int i = 0; i < n_chunks; ++i) max_rows = std::max<int64_t>(max_rows, cut[i + 1] - cut[i]);
+        CUDA_TRY(c.p0.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));
+        if (pc.mode == PREP_TF32) CUDA_TRY(c.p1.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));
+        if (want_norm) CUDA_TRY(c.norm.alloc((size_t)round_up(max_rows, TC_TILE_N) * 4, s));
+        if (want_sq) CUDA_TRY(c.sqnorm.alloc((size_t)round_up(max_rows, TC_TILE_N) * 4, s));
+    }
     for (int i = 0; i < n_chunks; ++i) {
         CUDA_TRY(cudaStreamWaitEvent(s, ev[i], 0));
         const int64_t r0 = cut[i], rows = cut[i + 1] - cut[i];
-        pmm_matrix_t dm = uc.dm;
-        dm.n_rows = rows;
-        if (dm.offsets) {
-            dm.offsets += r0;  // offsets hold absolute child positions: values / validity stay as they are
-        } else {
-            dm.values = (const char *)dm.values + (size_t)r0 * D * es;
-            if (dm.validity) dm.validity += (r0 * D) / 8;  // r0 is a multiple of 256
-        }
-        if (dm.row_validity) dm.row_validity += r0 / 8;
-        Prepared c;
+        const pmm_matrix_t dm = slice_rows(uc.dm, r0, rows);  // r0 is a multiple of 256
         if ((rc = prepare(dm, pc.mode, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
         if (want_norm || want_sq)
             CUDA_TRY(cudaMemcpyAsync(c_aux_all.as<float>() + r0, want_norm ? c.norm.p : c.sqnorm.p, (size_t)rows * 4,
                                      cudaMemcpyDeviceToDevice, s));
-        if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept_all.as<uint64_t>() + (size_t)i * Q * kp, s, terms0))) return rc;
+        // the candidate lists are carried from chunk to chunk; the last launch merges them into `kept`
+        if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept.as<uint64_t>(), s, terms0, &carry,
+                            (i == 0 ? 1 : 0) | (i == n_chunks - 1 ? 2 : 0))))
+            return rc;
     }
-    const uint64_t *kept_ptr = kept_all.as<uint64_t>();
-    if (n_chunks > 1) {
-        CUDA_TRY(launch_counted("merge", s, [&] {
-            return launch_merge_regular(kept_all.as<uint64_t>(), n_chunks, Q * kp, kp, Q, kp, kp, true, nullptr, nullptr,
-                                        kept.as<uint64_t>(), s);
-        }));
-        kept_ptr = kept.as<uint64_t>();
-    }
+    const uint64_t *kept_ptr = kept.as<uint64_t>();
     const size_t cnt = (size_t)Q * keff;
     CUDA_TRY(d_idx.alloc(cnt * 4, s));
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
@@ -876,6 +1023,9 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "tc_max_units") g_tc_max_units.store((int)value);
     else if (k == "tc_cluster4") g_tc_cluster4.store(value ? 1 : 0);
     else if (k == "tc_sync_slack") g_tc_sync_slack.store(value < 0 ? 0 : value);
+    else if (k == "release_workspace") g_block_cache.clear();  // this thread's parked device blocks go back to the pool
+    else if (k == "host_chunk_ratio_pct") g_host_chunk_ratio_pct.store(value);  // 0 = auto
+    else if (k == "host_chunk_first_div") g_host_chunk_first_div.store(value);  // first chunk = N / this (0 = 32)
     else if (k == "tc_max_flush") g_tc_max_flush.store(value < 0 ? 0 : value);
     else if (k == "tc_debug_skip") g_tc_debug_skip.store(value);  // measurement only: results are wrong when set
     else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast

@@ -102,7 +102,7 @@ struct TcSchedule {
     }
     __host__ __device__ int64_t total_slots() const { return (int64_t)m_full * g + (int64_t)m_rem * g_rem; }
 };
-TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg);
+TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg, int64_t layout_rows = 0);
 // Diagnostics: reads and clears the wait-cycle counters filled when TcArgs::debug_skip == 8.
 void tc_debug_wait_cycles(unsigned long long out[52]);
 int tc_epilogue_sets(int f16, int terms);  // epilogue warp sets of the top-k kernel variant: lists per (slot, row)
@@ -121,6 +121,7 @@ struct TcArgs {
     int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
     int cg;                        // tcgen05 cta_group: 1, or 2 (CTA pairs, UMMA M=256)
     int cluster4;                  // cg == 2, clm == 1: launch two independent pairs per cluster of 4
+    int resume;                    // 1: keep the lists in `partial` (same schedule layout) and continue from their thresholds
     int sync_slack;                // pacing: wait for the sync point this many points back (0 = strict lockstep)
     int max_flush;                 // list merges per epilogue warp and tile (0 = auto from the tile's MMA time)
     int debug_skip;                // measurement only: 1 = epilogue loads TMEM but does not filter, 2 = one load per tile

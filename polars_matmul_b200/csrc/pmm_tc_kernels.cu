@@ -99,6 +99,7 @@ struct TcKParams {
     int sync_tiles;
     int debug_skip;  // measurement only (TcArgs::debug_skip)
     int sync_slack;
+    int resume;      // lists already hold the candidates of earlier launches over other corpus rows
     int max_flush;   // row merges per warp at the end of a tile (rate limit; rows above URGENT_AT always go)
 };
 
@@ -555,7 +556,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
                 list_base = p.partial + (((slot * ESETS + eset) * GS + (crank4 & (uint32_t)(GS - 1))) * BM + row0) * KP;
-                for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
+                if (!p.resume) {
+                    for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
+                } else if (p.debug_skip != 3) {  // continue: the threshold is the list's k-th entry
+                    const uint64_t kth = list_base[(int64_t)lane * KP + (p.k - 1)];
+                    thr = kth;
+                    thr_f = kth == 0ull ? __uint_as_float(0x7fc00000u) : key_score(candidate_key(kth), true);
+                }
                 // q_aux is padded to the tile grid. cosine: 1 unless the query norm is ~0; euclidean: |q|^2
                 if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > 1e-6f ? 1.0f : 0.0f;
                 if (p.metric == METRIC_EUCLIDEAN) rowc = p.q_aux[qrow];
@@ -779,6 +786,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.round_sync = a.round_sync;
     p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
     p.debug_skip = a.debug_skip;
+    p.resume = a.resume;
     // merges that fit beside one tile's MMA time: a merge costs about as much as 8 k-blocks of one plane
     p.max_flush = a.max_flush > 0 ? a.max_flush : (p.num_kb * a.terms / 8 > 1 ? p.num_kb * a.terms / 8 : 1);
     p.sync_slack = a.sync_slack > 0 ? a.sync_slack : 0;
@@ -827,14 +835,17 @@ bool tc_supported() {
     return prop.major == 10 && get_encode_fn() != nullptr;
 }
 
-TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg) {
+TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg, int64_t layout_rows) {
     TcSchedule s;
     const int tile_m = BM * cg;   // query rows per scheduling unit; cg = CTAs per unit (1, 2, or 4 for a cluster of two pairs)
     s.m_tiles = (int)((q_rows + tile_m - 1) / tile_m);
     s.n_tiles = (int)((c_rows + BN - 1) / BN);
+    // the sharing factors (and with them the list layout) are capped by the corpus tiles of `layout_rows` rows:
+    // launches over different corpus chunks that carry their lists along pass the smallest chunk here
+    const int cap_tiles = layout_rows > 0 ? (int)((layout_rows + BN - 1) / BN) : s.n_tiles;
     int G = num_units > 0 ? num_units : 1;
     s.g = group < 1 ? 1 : group;
-    if (s.g > s.n_tiles) s.g = s.n_tiles;
+    if (s.g > cap_tiles) s.g = cap_tiles;
     if (s.g > G) s.g = G;
     s.mc = G / s.g;
     s.rounds = s.m_tiles / s.mc;
@@ -843,7 +854,7 @@ TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int g
     s.g_rem = 0;
     if (s.m_rem > 0) {
         s.g_rem = G / s.m_rem;
-        if (s.g_rem > s.n_tiles) s.g_rem = s.n_tiles;
+        if (s.g_rem > cap_tiles) s.g_rem = cap_tiles;
         if (s.g_rem < 1) s.g_rem = 1;
     }
     int used_full = s.rounds > 0 ? s.mc * s.g : 0;
