@@ -389,6 +389,44 @@ def test_host_chunked_upload_path(pmm, native, oracle):
     parity.check_topk(idx, sc, q, dense, 20, "dot", oracle, exact=True)
 
 
+def test_host_chunked_many_chunks_carry_lists(native, oracle):
+    """Eight equal corpus chunks: the candidate lists are carried from launch to launch (no per-chunk list warm-up,
+    no cross-chunk merge). Ties across chunk boundaries, f32 (one epilogue set) and f16 (two sets)."""
+    rng = np.random.default_rng(78)
+    native.set_option("host_chunk_first_div", 8)
+    native.set_option("host_chunk_ratio_pct", 100)
+    try:
+        q, c = _randn(rng, 150, 128), _randn(rng, 140_000, 128)     # 72 MB -> 8 chunks of 17408 rows (+ remainder)
+        c[[17_500, 60_000, 139_999]] = c[7]                          # exact ties in different chunks
+        q[3] = c[7]
+        for metric, k in (("cosine", 10), ("dot", 100), ("euclidean", 30)):
+            idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+            parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+        h, hc = _randn(rng, 150, 256).astype(np.float16), _randn(rng, 140_000, 256).astype(np.float16)   # 72 MB of f16
+        hc[[100, 70_000]] = hc[139_000]
+        idx, sc = native.topk(_hm(h), _hm(hc), 10, "cosine")
+        parity.check_topk(idx, sc, h.astype(np.float32), hc.astype(np.float32), 10, "cosine", oracle, exact=True)
+    finally:
+        native.set_option("host_chunk_first_div", 0)
+        native.set_option("host_chunk_ratio_pct", 0)
+
+
+def test_host_chunked_requery_runs_piecewise(native, oracle):
+    """Chunked upload + queries the first filter level cannot prove: the 3xTF32 level rebuilds the corpus planes
+    piece by piece (131072 rows at a time) and carries the lists; massive exact ties push some queries on to the
+    exact fallback. Result must still be the oracle's, tie order included."""
+    rng = np.random.default_rng(79)
+    base = _randn(rng, 40, 128)
+    c = base[rng.integers(0, 40, size=150_000)]                      # 150k rows, only 40 distinct vectors: 77 MB
+    c[::1000] += 1e-3 * _randn(rng, 150, 128)                        # and some near ties
+    q = _randn(rng, 64, 128)
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q), _hm(c), 10, "dot")
+    parity.check_topk(idx, sc, q, c, 10, "dot", oracle, exact=True)
+    assert native.get_stat("requeried_tf32x3") > 0
+    assert native.get_stat("fallback_queries") > 0
+
+
 # ---------------------------------------------------------------------------------------------- device entry points
 def test_device_level_shards_merge(native, oracle):
     """Two corpus shards on one GPU -> packed candidates with global indices -> merge == unsharded."""
