@@ -180,11 +180,28 @@ PMM_API int pmm_set_device(int32_t device);   /* device used by the calling thre
 PMM_API int64_t pmm_kernel_launch_count(void);
 PMM_API void pmm_reset_kernel_launch_count(void);
 
-/* Tuning / diagnostics. Known keys: "force_generic" (0/1: route f32 top-k through the SIMT
- * scores+select path), "profile" (0/1: bracket kernels with CUDA events on the launching stream
- * and accumulate per-kernel milliseconds, read back with pmm_get_stat), "tc_cg" (1|2: tcgen05
- * cta_group of the fused kernels, default 2), "tc_group" (CTA groups sharing a query tile, 0 = auto),
- * "generic_workspace_mb" (score slab of the SIMT path). */
+/* Tuning / diagnostics. Known keys:
+ *   "force_generic" (0/1)      route f32 top-k through the exact SIMT scores+select path
+ *   "profile" (0/1)            bracket kernels with CUDA events on the launching stream and accumulate per-kernel
+ *                              milliseconds, read back with pmm_get_stat("<kernel>_ms")
+ *   "verify" (0/1, default 1)  per-query losslessness proof of the tensor-core filter and its fallbacks
+ *   "tc_levels" (1|2)          2 (default): TF32 x1 first-level filter, 3xTF32 on demand; 1: 3xTF32 only
+ *   "tc_cg" (1|2)              tcgen05 cta_group of the fused kernels (default 2)
+ *   "tc_group"                 CTA groups sharing a query tile (0 = auto)
+ *   "tc_sync_tiles"            corpus tiles between the producers' pacing barriers (default 32, 0 = off)
+ *   "tc_sync_slack"            pacing: wait for the sync point this many points back (default 0)
+ *   "tc_max_flush"             list merges per epilogue warp and tile once thresholds settled (0 = auto)
+ *   "tc_clm", "tc_cluster4", "tc_max_units"   experimental cluster shapes, see profiles/sweep_r1.md (default off)
+ *   "tc_debug_skip"            measurement only, RESULTS ARE WRONG when set to 1..3: 1/2 epilogue without filter,
+ *                              3 filter without merges; 8: correct results + wait-cycle counters readable as
+ *                              pmm_get_stat("tc_dbg_wait0".."tc_dbg_wait51")
+ *   "host_chunked" (0/1)       overlapped chunked corpus upload of the host entry points (default 1)
+ *   "host_chunk_first_div", "host_chunk_ratio_pct"   first chunk = N / div (default 32); growth ratio in % (0 = auto)
+ *   "release_workspace"        return the calling thread's parked device blocks (>= 32 MB, kept between calls for
+ *                              reuse) to the CUDA memory pool
+ *   "f64_simt" (0/1)           f64 scores on FP64 FMA instead of DMMA
+ *   "generic_workspace_mb"     score slab of the SIMT path
+ * Unknown keys return PMM_ERR_INVALID. */
 PMM_API int pmm_set_option(const char *key, int64_t value);
 /* Accumulated statistics since the last pmm_reset_stats(): "<kernel>_ms", "<kernel>_launches",
  * "h2d_bytes", "d2h_bytes". Unknown name -> 0. */
