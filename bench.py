@@ -284,11 +284,11 @@ def main():
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = _native.kernel_launch_count()
-    kname = max(("tc_topk_tf32x1", "tc_topk_tf32x3"), key=lambda n: _native.get_stat(n + "_ms"))
+    kname = max(("tc_topk_f16r", "tc_topk_tf32x1", "tc_topk_tf32x3"), key=lambda n: _native.get_stat(n + "_ms"))
     k_ms = _native.get_stat(kname + "_ms")
     k_launches = _native.get_stat(kname + "_launches")
     stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps)
-             for n in ("prep", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge", "rescore", "gather", "scatter", "scores_f32", "select_f32")
+             for n in ("prep", "tc_topk_f16r", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge", "rescore", "gather", "scatter", "scores_f32", "select_f32")
              if _native.get_stat(n + "_ms") > 0}
     stats["requeried_tf32x3_per_step"] = _native.get_stat("requeried_tf32x3") / max(1, args.steps)
     stats["fallback_queries_per_step"] = _native.get_stat("fallback_queries") / max(1, args.steps)
@@ -327,8 +327,11 @@ def main():
         achieved = flops_per_launch / (k_avg_ms / 1000.0) / 1e12 if k_avg_ms > 0 else None
         # Tensor-pipe peak for ALGORITHMIC f32 flops: TF32 runs at half the bf16 rate; the first-level filter issues one
         # TF32 MMA per MAC (bf16 / 2), the 3xTF32 split three (bf16 / 6).
-        terms = 1 if kname.endswith("x1") else 3
-        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")) / (2.0 * terms)
+        # The default first level rounds the f32 operands to f16 (11 significant bits, like TF32) and issues one
+        # kind::f16 MMA per MAC: the bf16/f16 dense rate itself.
+        terms = 1 if kname.endswith("x1") or kname.endswith("f16r") else 3
+        rate_div = 1.0 if kname.endswith("f16r") else 2.0 * terms
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")) / rate_div
         tr = load_traffic(kname, f"{W['name']}:{Q}x{N}x{D}:k{k}")
         roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None,
@@ -336,8 +339,10 @@ def main():
                     "traffic_note": tr["source"] if tr else "no ncu capture committed for this workload",
                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms,
                     "kernel_share_of_step": (k_avg_ms / ms_step) if ms_step else None,
-                    "peak_note": f"{peak_src}: bf16_tflops_sustained / {2 * terms} (TF32 = 1/2 bf16 rate, {terms} TF32 MMA(s) per MAC "
-                                 f"in {kname}); raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}. "
+                    "peak_note": f"{peak_src}: bf16_tflops_sustained / {rate_div:g} ("
+                                 + ("one kind::f16 MMA per MAC on f16-rounded operands" if kname.endswith("f16r") else
+                                    f"TF32 = 1/2 bf16 rate, {terms} TF32 MMA(s) per MAC")
+                                 + f" in {kname}); raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}. "
                                  "The exact f32 result comes from the re-scoring kernel; queries whose filter is not provably "
                                  "lossless are re-run with 3xTF32 (requeried_tf32x3_per_step) or on the SIMT path",
                     "per_kernel_ms_per_step": stats}
@@ -353,8 +358,9 @@ def main():
                                    "candidates merged after one NCCL all-gather" if world > 1 else "single GPU",
                        "value_definition": "n_gpus * Q / step time: every rank scans its own shard for all Q queries",
                        "l2": "inputs (3.4 GB per rank) are far larger than the 126 MB L2; no explicit flush",
-                       "arithmetic": "tcgen05 kind::tf32 filter (x1 first level, 3xTF32 hi/lo split on demand), f32 accumulate in "
-                                     "TMEM; exact f32 re-scoring + per-query losslessness proof"},
+                       "arithmetic": "tcgen05 filter on f32 operands rounded to f16 (kind::f16, 11 significant bits; 3xTF32 hi/lo "
+                                     "split on demand), f32 accumulate in TMEM; exact f32 re-scoring + per-query losslessness "
+                                     "proof: results bit-identical to the f32 CPU oracle"},
             "tflops_effective": 2.0 * Q * n_total * D / (ms_step / 1000.0) / 1e12,
             "queries_per_sec_global_corpus": Q / (ms_step / 1000.0),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

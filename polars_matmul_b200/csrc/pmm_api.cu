@@ -41,7 +41,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{2}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -220,9 +220,17 @@ struct Prepared {
     unsigned int *max_sq_ptr = nullptr;  // own (max_sq) or shared across corpus chunks
 };
 
+// Norm range of a column, filled by the prep kernel: [0] largest squared norm (atomicMax on the float bits),
+// [1] smallest squared norm above 1e-12 (atomicMin; +inf while empty).
+cudaError_t init_norm_range(unsigned int *d, cudaStream_t s) {
+    static const unsigned int init[2] = {0u, 0x7f800000u};
+    return cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, s);
+}
+
 // Bytes of one operand plane prepare() allocates for `rows` x `dim` (tensor-core modes).
 size_t plane_bytes(int mode, int64_t rows, int64_t dim, int64_t row_tile) {
-    const int64_t kq = mode == PREP_F16 ? 64 : 32, es = mode == PREP_F16 ? 2 : 4;
+    const bool half_plane = mode == PREP_F16 || mode == PREP_F16R;
+    const int64_t kq = half_plane ? 64 : 32, es = half_plane ? 2 : 4;
     return (size_t)(round_up(rows, row_tile) * round_up(dim, kq) * es);
 }
 
@@ -239,8 +247,9 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
         out->ld = m.dim;
         CUDA_TRY(out->p0.alloc((size_t)(m.n_rows * m.dim * wsz), s));
     } else {
-        const int64_t kq = mode == PREP_F16 ? 64 : 32;
-        const int64_t es = mode == PREP_F16 ? 2 : 4;
+        const bool half_plane = mode == PREP_F16 || mode == PREP_F16R;
+        const int64_t kq = half_plane ? 64 : 32;
+        const int64_t es = half_plane ? 2 : 4;
         out->rows_pad = round_up(m.n_rows, row_tile);
         out->ld = round_up(m.dim, kq);
         CUDA_TRY(out->p0.alloc((size_t)(out->rows_pad * out->ld * es), s));
@@ -250,8 +259,8 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     if (want_sq) CUDA_TRY(out->sqnorm.alloc((size_t)(out->rows_pad * wsz), s));
     out->max_sq_ptr = shared_max;
     if (want_max && !shared_max) {
-        CUDA_TRY(out->max_sq.alloc(sizeof(unsigned int), s));
-        CUDA_TRY(cudaMemsetAsync(out->max_sq.p, 0, sizeof(unsigned int), s));
+        CUDA_TRY(out->max_sq.alloc(2 * sizeof(unsigned int), s));
+        CUDA_TRY(init_norm_range(out->max_sq.as<unsigned int>(), s));
         out->max_sq_ptr = out->max_sq.as<unsigned int>();
     }
     PrepArgs a;
@@ -415,7 +424,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.dim_pad = q.ld;
     a.nq = q.n_rows;
     a.n = c.n_rows;
-    a.f16 = q.mode == PREP_F16 ? 1 : 0;
+    a.f16 = (q.mode == PREP_F16 || q.mode == PREP_F16R) ? 1 : 0;
     a.terms = a.f16 ? 1 : terms;
     a.cg = (a.terms == 1 && !a.f16) ? 2 : g_tc_cg.load();
     a.clm = (a.cg == 2 && g_tc_clm.load() == 2) ? 2 : 1;
@@ -450,7 +459,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
         a.round_sync = rsync.as<unsigned int>();
     }
     a.partial = partial.as<uint64_t>();
-    cudaError_t e = launch_counted(a.f16 ? "tc_topk_f16" : a.terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3", s,
+    cudaError_t e = launch_counted(q.mode == PREP_F16R ? "tc_topk_f16r" : a.f16 ? "tc_topk_f16" : a.terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3", s,
                                    [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
@@ -468,9 +477,14 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
 //   operand rounding: TF32 has 11 significant bits, unit roundoff u = 2^-11 per operand (cvt.rna), so a TF32 x1
 //                     product is off by <= 2u + u^2 ~ 2^-10 and so is the sum (Cauchy-Schwarz);
 //                     3xTF32: each operand keeps a residue <= 2^-22 and the lo*lo term (<= 2^-22) is dropped:
-//                     <= 3 * 2^-22; f16 planes are exact;
+//                     <= 3 * 2^-22; f16 planes of f16 input are exact; f32 input rounded to f16 (PREP_F16R)
+//                     has the TF32 x1 bound (11 significant bits) plus an absolute subnormal term, see
+//                     f16r_abs_err();
 //   accumulation    : one f32 ulp of truncation per tcgen05 accumulate step (terms * D / 8 steps);
 //   the exact sum   : worst-case rounding of the sequential-FMA reference itself, D * 2^-24.
+// f32 -> f16 rounding below the normal range (|x| < 2^-14) is absolute, <= 2^-25 per element: <= sqrt(D) 2^-25 per row.
+float f16r_abs_err(int64_t dim) { return sqrtf((float)dim) * 2.98023224e-8f * 1.0001f; }
+
 float filter_eps(int64_t dim, int terms, bool f16) {
     const float split = f16 ? 0.0f : terms == 1 ? 9.8e-4f : 7.5e-7f;
     return split + (float)dim * (1.5e-8f * (float)terms + 6.0e-8f) + 1e-6f;
@@ -504,8 +518,8 @@ int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &r
 // after that (or for f16 planes) on the exact SIMT path (next_terms = 0). May synchronise the stream.
 int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, const float *q_sq,
                        const float *q_norm, const Prepared *c_planes, const float *c_norm, const float *c_sq,
-                       const unsigned int *c_max_sq, float eps, int next_terms, int metric, int64_t index_base, int64_t keff,
-                       TopkOut o, cudaStream_t s) {
+                       const unsigned int *c_max_sq, float eps, float abs_err, float max_norm, int next_terms, int metric,
+                       int64_t index_base, int64_t keff, TopkOut o, cudaStream_t s) {
     const int64_t Q = raw_q.n_rows;
     const float *q_aux = metric == PMM_METRIC_COSINE ? q_norm : metric == PMM_METRIC_EUCLIDEAN ? q_sq : nullptr;
     const float *c_aux = metric == PMM_METRIC_COSINE ? c_norm : metric == PMM_METRIC_EUCLIDEAN ? c_sq : nullptr;
@@ -521,6 +535,8 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
         chk.q_sq = q_sq;
         chk.c_max_sq = c_max_sq;
         chk.eps = eps;
+        chk.abs_err = abs_err;
+        chk.max_norm = max_norm;
         chk.flags = flags.as<unsigned char>();
         chk.flag_count = count.as<unsigned int>();
     }
@@ -611,7 +627,8 @@ int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &r
                      const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
                      int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s) {
     const int kp = tc_list_capacity(keff);
-    const bool f16 = q.mode == PREP_F16;
+    const bool f16 = q.mode == PREP_F16;     // exact f16 planes
+    const bool f16r = q.mode == PREP_F16R;   // f32 input rounded to f16: TF32-x1-like error, then 3xTF32 on demand
     DevBuf kept;
     const uint64_t *kept_ptr = kept_in;
     if (!kept_ptr) {
@@ -620,14 +637,16 @@ int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &r
         if (rc) return rc;
         kept_ptr = kept.as<uint64_t>();
     }
-    const int next_terms = (!f16 && terms == 1) ? 3 : 0;
-    return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), c, c_norm, c_sq, c_max_sq,
-                              filter_eps(raw_q.dim, terms, f16), next_terms, metric, index_base, keff, o, s);
+    const int next_terms = (f16r || (!f16 && terms == 1)) ? 3 : 0;
+    // f16r planes cannot serve the 3xTF32 level: it rebuilds TF32 planes piece by piece (c_planes = NULL)
+    return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), f16r ? nullptr : c, c_norm, c_sq,
+                              c_max_sq, filter_eps(raw_q.dim, f16r ? 1 : terms, f16), f16r ? f16r_abs_err(raw_q.dim) : 0.0f,
+                              f16r ? 65504.0f : 0.0f, next_terms, metric, index_base, keff, o, s);
 }
 
 // First filter level for f32 planes: TF32 x1 unless switched off ("tc_levels" = 1) or cta_group::1 was forced.
 int first_level_terms(const Prepared &q) {
-    return (q.mode == PREP_TF32 && g_tc_levels.load() >= 2 && g_tc_cg.load() == 2) ? 1 : 3;
+    return (q.mode == PREP_F16R || (q.mode == PREP_TF32 && g_tc_levels.load() >= 2 && g_tc_cg.load() == 2)) ? 1 : 3;
 }
 
 // Tensor-core path: filter -> exact re-scoring of the kept candidates -> verification (-> next level).
@@ -642,11 +661,13 @@ struct PathChoice {
     bool f64;
     int mode;  // prep mode for both operands
 };
-PathChoice choose_path(int q_dtype, int c_dtype, int64_t keff) {
+// for_topk: the f32 top-k starts with f16-rounded planes ("tc_levels" >= 3, the default); raw matmul needs 3xTF32.
+PathChoice choose_path(int q_dtype, int c_dtype, int64_t keff, bool for_topk = true) {
     PathChoice pc;
     pc.f64 = pmm_working_dtype(q_dtype, c_dtype) == PMM_DTYPE_F64;
     pc.tc = !pc.f64 && keff <= 128 && !g_force_generic.load() && dev_info().tc;
     pc.mode = !pc.tc ? PREP_DENSE : (q_dtype == PMM_DTYPE_F16 && c_dtype == PMM_DTYPE_F16) ? PREP_F16 : PREP_TF32;
+    if (pc.mode == PREP_TF32 && for_topk && g_tc_levels.load() >= 3 && g_tc_cg.load() == 2) pc.mode = PREP_F16R;
     return pc;
 }
 
@@ -683,7 +704,7 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
 }
 
 int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, cudaStream_t s) {
-    PathChoice pc = choose_path(dl->dtype, dr->dtype, 1);
+    PathChoice pc = choose_path(dl->dtype, dr->dtype, 1, false);
     DevBuf err;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
@@ -907,8 +928,8 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     Prepared q;
     if ((rc = prepare(uq.dm, pc.mode, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
     DevBuf c_max;
-    CUDA_TRY(c_max.alloc(sizeof(unsigned int), s));
-    CUDA_TRY(cudaMemsetAsync(c_max.p, 0, sizeof(unsigned int), s));
+    CUDA_TRY(c_max.alloc(2 * sizeof(unsigned int), s));
+    CUDA_TRY(init_norm_range(c_max.as<unsigned int>(), s));
     const int kp = tc_list_capacity(keff);
     const int terms0 = first_level_terms(q);
     TcCarry carry;
@@ -923,7 +944,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         int64_t max_rows = 0;
         for (int i = 0; i < n_chunks; ++i) max_rows = std::max<int64_t>(max_rows, cut[i + 1] - cut[i]);
         CUDA_TRY(c.p0.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));
-        if (pc.mode == PREP_TF32) CUDA_TRY(c.p1.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));
+        if (pc.mode == PREP_TF32) CUDA_TRY(c.p1.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));  // (f16 modes: one plane)
         if (want_norm) CUDA_TRY(c.norm.alloc((size_t)round_up(max_rows, TC_TILE_N) * 4, s));
         if (want_sq) CUDA_TRY(c.sqnorm.alloc((size_t)round_up(max_rows, TC_TILE_N) * 4, s));
     }
@@ -1029,7 +1050,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "tc_max_flush") g_tc_max_flush.store(value < 0 ? 0 : value);
     else if (k == "tc_debug_skip") g_tc_debug_skip.store(value);  // measurement only: results are wrong when set
     else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast
-    else if (k == "tc_levels") g_tc_levels.store(value >= 2 ? 2 : 1);  // 2: TF32 x1 first-level filter, 3xTF32 on demand
+    else if (k == "tc_levels") g_tc_levels.store(value >= 3 ? 3 : value == 2 ? 2 : 1);  // 3: f16-rounded first level, 2: TF32 x1, 1: 3xTF32 only
     else if (k == "verify") g_verify.store(value ? 1 : 0);  // 0: skip the filter-losslessness check (and its fallback)
     else if (k == "f64_simt") g_f64_simt.store(value ? 1 : 0);  // 1: bit-exact sequential-FMA f64 instead of DMMA
     else if (k == "host_chunked") g_host_chunked.store(value ? 1 : 0);

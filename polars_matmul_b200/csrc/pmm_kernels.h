@@ -22,7 +22,7 @@ struct PrepArgs {
     unsigned int *max_sq_out;     // f32 working type only: atomicMax of the squared norms' bit patterns, or NULL
     int *error_flag;              // set to 1 when a list row is longer than dim
 };
-enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2 };
+enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2, PREP_F16R = 3 };  // = MODE_* of pmm_prep.cu
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s);
 cudaError_t launch_norms(const PrepArgs &a, int src_dtype, cudaStream_t s);
 
@@ -64,8 +64,11 @@ struct RawMatrix {               // a device-resident column in Arrow layout (pm
 // Inputs of the "was the filter lossless for this query" check (all device pointers; flags == NULL: no check).
 struct RescoreCheck {
     const float *q_sq;             // [n_queries] squared query norms
-    const unsigned int *c_max_sq;  // bits of the largest squared corpus norm (float >= 0, compared as uint)
+    const unsigned int *c_max_sq;  // [0] bits of the largest squared corpus norm (float >= 0, compared as uint),
+                                   // [1] of the smallest one above 1e-12 (+inf bits if none)
     float eps;                     // relative error bound of the filter value vs the exact score, per |q||c|
+    float abs_err;                 // absolute rounding error bound of one operand ROW (f16 subnormals), 0 if none
+    float max_norm;                // operand rows with a larger norm may have overflowed the filter's format (0: no limit)
     unsigned char *flags;          // [n_queries] set to 1 when not provable
     unsigned int *flag_count;
 };

@@ -12,7 +12,11 @@
 //   MODE_DENSE : dense [n_rows x dim] copy in the working type (f32 or f64) for the SIMT path;
 //   MODE_TF32  : hi/lo TF32 planes [rows_pad x dim_pad] for the 3xTF32 split
 //                (hi = rna_tf32(x), lo = rna_tf32(x - hi); x = hi + lo to ~2^-24 relative);
-//   MODE_F16   : f16 plane [rows_pad x dim_pad] for f16-stored input (exact upcast, kind::f16 MMA).
+//   MODE_F16   : f16 plane [rows_pad x dim_pad] for f16-stored input (exact upcast, kind::f16 MMA);
+//   MODE_F16R  : f16 plane of f32 input ROUNDED to f16 (round to nearest even): 11 significant bits, the same
+//                unit roundoff 2^-11 as TF32, at twice the tensor rate and half the bytes - the first-level
+//                filter of the f32 top-k.  Values beyond the f16 range become inf and tiny ones subnormal;
+//                the losslessness check accounts for both (pmm_rescore.cu).
 // Padding rows/columns are written as zeros so TMA tiles never see garbage.
 //
 // Thread mapping: 8 lanes own one row (lane j of the group owns partial sum p_j), 4 rows per warp,
@@ -51,7 +55,7 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
     lo = __uint_as_float(tf32_rna(__fsub_rn(x, hi)));
 }
 
-enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2 };
+enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2, MODE_F16R = 3 };
 
 template <typename SRC, typename W, int MODE>
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
             hi[row * ld + i] = h;
             lo[row * ld + i] = l;
         } else {
-            hp[row * ld + i] = __float2half_rn((float)x);  // exact: x came from an f16
+            hp[row * ld + i] = __float2half_rn((float)x);  // MODE_F16: exact, x came from an f16; MODE_F16R: rounds
         }
     };
 
@@ -154,6 +158,10 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
         const unsigned am = __activemask();
         bits = __reduce_max_sync(am, bits);
         if (lane == __ffs(am) - 1 && bits) atomicMax(a.max_sq_out, bits);
+        // [1]: smallest squared norm among the rows cosine does not treat as zero (norm > 1e-6)
+        unsigned int lo_bits = (sub == 0 && row < a.n_rows && fs > 1e-12f) ? __float_as_uint(fs) : 0x7f800000u;
+        lo_bits = __reduce_min_sync(am, lo_bits);
+        if (lane == __ffs(am) - 1 && lo_bits != 0x7f800000u) atomicMin(a.max_sq_out + 1, lo_bits);
     }
 }
 
@@ -175,6 +183,11 @@ cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64
     }
     if (mode == MODE_F16) {
         if (src_dtype == 0) return launch_prep_t<__half, float, MODE_F16>(a, s);
+        return cudaErrorInvalidValue;
+    }
+    if (mode == MODE_F16R) {
+        if (src_dtype == 1) return launch_prep_t<float, float, MODE_F16R>(a, s);
+        if (src_dtype == 0) return launch_prep_t<__half, float, MODE_F16R>(a, s);
         return cudaErrorInvalidValue;
     }
     if (work_f64) {

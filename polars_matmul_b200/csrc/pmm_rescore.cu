@@ -45,6 +45,17 @@ __device__ __forceinline__ void raw_row(const RawMatrix &m, int64_t row, int64_t
     if (m.row_validity && !((m.row_validity[row >> 3] >> (row & 7)) & 1)) len = 0;
 }
 
+// Bound E on |filter value - its exact counterpart| for one query, in the units of the filter value
+// (dot: q.c; cosine: q.c / |c|; euclidean: squared distance).  eps = relative operand/accumulation error per |q||c|;
+// s = abs_err = absolute rounding error of one operand row (f32 rounded to f16 below the normal range):
+// |q'.c' - q.c| <= eps |q||c| + s (|q| + |c|) + s^2.  The small extra terms absorb the rounding of the metric pass.
+__device__ __forceinline__ float filter_error_bound(const RescoreCheck &chk, int metric, float qn, float cmax, float cmin) {
+    const float s = chk.abs_err;
+    if (metric == METRIC_DOT) return chk.eps * qn * cmax + s * (qn + cmax) + s * s;
+    if (metric == METRIC_COSINE) return (chk.eps + 1e-6f) * qn + (s > 0.0f ? s * qn / cmin + s + s * s / cmin : 0.0f);
+    return 2.0f * (chk.eps * qn * cmax + s * (qn + cmax) + s * s) + 1e-6f * (qn * qn + cmax * cmax);
+}
+
 template <typename CSRC, int NT>
 __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict__ cand, int kp_in, RawMatrix qm,
                                                      RawMatrix cm, const float *__restrict__ q_aux,
@@ -76,10 +87,8 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
         if (ck != 0ull) {
             const float f_k = key_score(candidate_key(ck), true), f_j = key_score(candidate_key(c_in), true);
             const float qn = sqrtf(chk.q_sq[q]);
-            const float cmax = sqrtf(__uint_as_float(*chk.c_max_sq));
-            const float e = metric == METRIC_DOT      ? chk.eps * qn * cmax
-                            : metric == METRIC_COSINE ? (chk.eps + 1e-6f) * qn
-                                                      : 2.0f * chk.eps * qn * cmax + 1e-6f * (qn * qn + cmax * cmax);
+            const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
+            const float e = filter_error_bound(chk, metric, qn, cmax, cmin);
             if (f_j < f_k - 2.0f * e - 1e-6f * fabsf(f_k)) c_in = 0ull;  // (NaN anywhere: keep)
         }
     }
@@ -206,15 +215,18 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             const float f_last = key_score(candidate_key(last), true);
             const float tk = key_score(candidate_key(sortbuf[k_out - 1]), higher);
             const float qn = sqrtf(chk.q_sq[q]);
-            const float cmax = sqrtf(__uint_as_float(*chk.c_max_sq));
+            const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
+            const float e = filter_error_bound(chk, metric, qn, cmax, cmin);
             if (metric == METRIC_DOT) {
-                ok = tk > f_last + chk.eps * qn * cmax;
+                ok = tk > f_last + e;
             } else if (metric == METRIC_COSINE) {
-                ok = qn > 1e-6f && tk > f_last / qn + chk.eps + 1e-6f;
+                ok = qn > 1e-6f && tk > (f_last + e) / qn;
             } else {  // filter value = -(squared distance)
-                const float sq_floor = -f_last - 2.0f * chk.eps * qn * cmax - 1e-6f * (qn * qn + cmax * cmax);
+                const float sq_floor = -f_last - e;
                 ok = sq_floor > 0.0f && tk < sqrtf(sq_floor) * (1.0f - 1e-6f);
             }
+            // operands beyond the filter format's range (f32 rounded to f16: 65504) made the filter value meaningless
+            if (chk.max_norm > 0.0f && !(qn <= chk.max_norm && cmax <= chk.max_norm)) ok = false;
             if (!(ok)) ok = false;  // NaN anywhere -> not provable
         }
         if (!ok) {

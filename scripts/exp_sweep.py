@@ -37,13 +37,13 @@ def run():
                      index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(), stream=st)
 res = []
 _native.set_option("verify", 0)
-configs = [(2, 0, 32, 2, 0, 8)]
+configs = [(2, 0, 32, 3, 0, 8), (2, 0, 32, 3, 0, 1), (2, 0, 32, 2, 0, 0)]
 for rowb, grp, rs, lv, clm, c4 in configs:
     _native.set_option("tc_cg", rowb); _native.set_option("tc_group", grp); _native.set_option("tc_sync_tiles", rs); _native.set_option("tc_levels", lv); _native.set_option("tc_max_flush", clm); _native.set_option("tc_debug_skip", c4)
     run(); torch.cuda.synchronize()
     _native.set_option("profile", 1); _native.reset_stats()
     run(); run(); torch.cuda.synchronize()
-    ms = (_native.get_stat("tc_topk_tf32x3_ms") + _native.get_stat("tc_topk_tf32x1_ms")) / 2
+    ms = (_native.get_stat("tc_topk_tf32x3_ms") + _native.get_stat("tc_topk_tf32x1_ms") + _native.get_stat("tc_topk_f16r_ms")) / 2
     rq = _native.get_stat("requeried_tf32x3") / 2
     _native.set_option("profile", 0)
     w = [_native.get_stat("tc_dbg_wait%d" % i) / 1e6 for i in range(52)]

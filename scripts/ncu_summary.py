@@ -24,6 +24,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 with open(out, "w") as f:
     f.write(f"# {title}\n\nSource: `{rep}` (`ncu --set full --clock-control none --import-source on`, one launch).\n\n")
@@ -31,8 +33,10 @@ with open(out, "w") as f:
         name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
         f.write(f"Kernel: `{name[:120]}`\n\n| metric | value | unit |\n|---|---|---|\n")
         for k in KEYS:
-            if k in hdr:
-                i = hdr.index(k)
-                f.write(f"| {k} | {r[i]} | {units[i]} |\n")
+            # some metrics carry a section prefix in the raw page (e.g. "TPC.TriageCompute.sm__pipe_tensor_...")
+            for i, h in enumerate(hdr):
+                if h == k or h.endswith("." + k):
+                    f.write(f"| {h} | {r[i]} | {units[i]} |\n")
+                    break
         f.write("\n")
 print(open(out).read())
