@@ -213,7 +213,7 @@ def test_tie_stress(native, oracle):
 
 
 def test_filter_levels_and_fallback_are_exercised(native, oracle):
-    """TF32 x1 filter -> 3xTF32 re-query -> exact SIMT fallback: craft inputs that need each level and check
+    """First-level filter (f16-rounded operands, 11 significant bits) -> 3xTF32 re-query -> exact SIMT fallback: craft inputs that need each level and check
     via the library's statistics that the level actually ran; the result must still equal the oracle."""
     rng = np.random.default_rng(123)
     d, n, k = 64, 4000, 10
@@ -242,14 +242,50 @@ def test_filter_levels_and_fallback_are_exercised(native, oracle):
     parity.check_topk(idx, sc, q2, c3, k, "cosine", oracle, exact=True)
     assert native.get_stat("fallback_queries") > 0
     assert (idx[:, 0] == 100).all()          # lowest index among the exact ties first
-    # (d) single level (3xTF32 first) gives the same answers
-    native.set_option("tc_levels", 1)
+    # (d) every choice of first level (3: f16-rounded operands [default], 2: TF32 x1, 1: 3xTF32) gives the same answers
+    results = []
     try:
-        i1, s1 = native.topk(_hm(q2), _hm(c2), k, "dot")
+        for levels in (1, 2, 3):
+            native.set_option("tc_levels", levels)
+            results.append(native.topk(_hm(q2), _hm(c2), k, "dot"))
     finally:
-        native.set_option("tc_levels", 2)
-    i2, s2 = native.topk(_hm(q2), _hm(c2), k, "dot")
-    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+        native.set_option("tc_levels", 3)
+    for i1, s1 in results[1:]:
+        assert np.array_equal(i1, results[0][0]) and np.array_equal(s1, results[0][1])
+
+
+def test_f16_rounded_level_handles_range(native, oracle):
+    """The default first level rounds f32 operands to f16: values beyond 65504 overflow there and values below 6e-5
+    become subnormal. The losslessness proof must notice both (norm limit, absolute error term) and hand the queries
+    to the 3xTF32 level; results stay the oracle's for every metric."""
+    rng = np.random.default_rng(321)
+    d, n, k = 96, 6000, 10
+    q, c = _randn(rng, 48, d), _randn(rng, n, d)
+    # (a) huge corpus values (f16 overflow): every query is re-run one level up
+    big = c.copy()
+    big[::7] *= 3.0e5
+    native.reset_stats()
+    for metric in ("dot", "cosine", "euclidean"):
+        idx, sc = native.topk(_hm(q), _hm(big), k, metric)
+        parity.check_topk(idx, sc, q, big, k, metric, oracle, exact=True)
+    assert native.get_stat("requeried_tf32x3") >= 3 * q.shape[0]
+    # (b) huge query rows only: only those queries are re-run
+    qb = q.copy()
+    qb[:5] *= 1.0e6
+    native.reset_stats()
+    idx, sc = native.topk(_hm(qb), _hm(c), k, "dot")
+    parity.check_topk(idx, sc, qb, c, k, "dot", oracle, exact=True)
+    assert 5 <= native.get_stat("requeried_tf32x3") < q.shape[0]
+    # (c) tiny magnitudes (f16 subnormals / flush): whole corpus scaled by 1e-6, and a mix of scales within one corpus
+    for corpus in (c * np.float32(1e-6), np.concatenate([c[:3000], c[3000:] * np.float32(1e-7)])):
+        for metric in ("cosine", "dot", "euclidean"):
+            idx, sc = native.topk(_hm(q), _hm(corpus), k, metric)
+            parity.check_topk(idx, sc, q, corpus, k, metric, oracle, exact=True)
+    # (d) tiny queries against a normal corpus
+    qs = q * np.float32(1e-7)
+    for metric in ("cosine", "dot"):
+        idx, sc = native.topk(_hm(qs), _hm(c), k, metric)
+        parity.check_topk(idx, sc, qs, c, k, metric, oracle, exact=True)
 
 
 def test_nan_and_inf_rank_last(native, oracle):
