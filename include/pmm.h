@@ -176,6 +176,14 @@ PMM_API const char *pmm_version(void);
 PMM_API int pmm_device_count(void);           /* 0 when no CUDA device is usable */
 PMM_API int pmm_set_device(int32_t device);   /* device used by the calling thread's subsequent calls */
 
+/* Page-locked host memory for result buffers. The reference returns freshly allocated Vecs (from_vec,
+ * src/matmul.rs:100-125, :497-518); a binding that hands this memory to pmm_topk / pmm_matmul as out_index /
+ * out_score / out gets the device->host copy at PCIe rate instead of through the driver's pageable staging
+ * (C3: 23 ms of a 165 ms call). cudaHostAlloc / cudaFreeHost underneath; allocation is slow (tens of ms per
+ * 100 MB), so bindings should pool the blocks (polars_matmul_b200/_native.py does). */
+PMM_API int pmm_host_alloc(int64_t bytes, void **out);
+PMM_API int pmm_host_free(void *p);
+
 /* Number of kernels this library has launched since load / since the last reset (process-wide). */
 PMM_API int64_t pmm_kernel_launch_count(void);
 PMM_API void pmm_reset_kernel_launch_count(void);

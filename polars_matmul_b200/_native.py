@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
         "pmm_set_option": (ctypes.c_int, [ctypes.c_char_p, i64]),
         "pmm_get_stat": (ctypes.c_double, [ctypes.c_char_p]),
         "pmm_reset_stats": (None, []),
+        "pmm_host_alloc": (ctypes.c_int, [i64, ctypes.POINTER(vp)]),
+        "pmm_host_free": (ctypes.c_int, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the .so does not export what include/pmm.h declares
@@ -102,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "pmm_corpus_create", "pmm_corpus_destroy", "pmm_corpus_rows", "pmm_topk_corpus", "pmm_dev_topk", "pmm_topk_shard",
     "pmm_dev_merge_candidates", "pmm_dev_matmul", "pmm_dev_norms", "pmm_last_error", "pmm_version",
     "pmm_device_count", "pmm_set_device", "pmm_kernel_launch_count", "pmm_reset_kernel_launch_count",
-    "pmm_set_option", "pmm_get_stat", "pmm_reset_stats",
+    "pmm_set_option", "pmm_get_stat", "pmm_reset_stats", "pmm_host_alloc", "pmm_host_free",
 ]
 
 
@@ -144,13 +146,85 @@ def working_dtype(left: HostMatrix, right: HostMatrix):
     return _CODE_TO_NP[lib().pmm_working_dtype(left.dtype_code, right.dtype_code)]
 
 
+class _PinnedBlock:
+    """One page-locked block; exposes itself to NumPy through the array interface, so arrays built on it keep it
+    alive and it goes back to the pool when the last of them is collected."""
+    __slots__ = ("ptr", "cap", "nbytes", "__weakref__")
+
+    def __init__(self, ptr: int, cap: int, nbytes: int):
+        self.ptr, self.cap, self.nbytes = ptr, cap, nbytes
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool.give(self.ptr, self.cap)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _PinnedPool:
+    """Result buffers in page-locked memory (pmm_host_alloc), recycled: cudaHostAlloc costs tens of ms per 100 MB,
+    a pooled block nothing. Blocks of at least 1 MB; at most MAX_FREE bytes are kept while unused."""
+    MIN_BYTES = 1 << 20
+    MAX_BYTES = 1 << 30   # larger results (raw matmul slabs) stay pageable: pinning GBs costs seconds
+    MAX_FREE = 4 << 30
+
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._free = {}      # capacity -> [ptr]
+        self._free_bytes = 0
+
+    def take(self, nbytes: int):
+        cap = (nbytes + self.MIN_BYTES - 1) // self.MIN_BYTES * self.MIN_BYTES
+        with self._lock:
+            lst = self._free.get(cap)
+            if lst:
+                self._free_bytes -= cap
+                return lst.pop(), cap
+        p = ctypes.c_void_p(None)
+        check(lib().pmm_host_alloc(cap, ctypes.byref(p)))
+        return p.value, cap
+
+    def give(self, ptr: int, cap: int) -> None:
+        with self._lock:
+            if self._free_bytes + cap <= self.MAX_FREE:
+                self._free.setdefault(cap, []).append(ptr)
+                self._free_bytes += cap
+                return
+        lib().pmm_host_free(ptr)
+
+    def clear(self) -> None:
+        with self._lock:
+            blocks, self._free, self._free_bytes = self._free, {}, 0
+        for lst in blocks.values():
+            for ptr in lst:
+                lib().pmm_host_free(ptr)
+
+
+_pinned_pool = _PinnedPool()
+
+
+def result_empty(shape, dtype) -> np.ndarray:
+    """np.empty for result buffers: page-locked (pooled) when large, so the device->host copy runs at PCIe rate."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes < _PinnedPool.MIN_BYTES or nbytes > _PinnedPool.MAX_BYTES:
+        return np.empty(shape, dtype)
+    ptr, cap = _pinned_pool.take(nbytes)
+    return np.asarray(_PinnedBlock(ptr, cap, nbytes)).view(dtype).reshape(shape)
+
+
 def topk(queries: HostMatrix, corpus: HostMatrix, k: int, metric: str):
     """pmm_topk. Returns (index uint32 [Q, k_eff], score float64 [Q, k_eff])."""
     if k < 0:
         raise OverflowError("can't convert negative int to unsigned")  # what PyO3 raises for usize
     keff = min(int(k), corpus.n_rows)
-    idx = np.empty((queries.n_rows, keff), np.uint32)
-    sc = np.empty((queries.n_rows, keff), np.float64)
+    idx = result_empty((queries.n_rows, keff), np.uint32)
+    sc = result_empty((queries.n_rows, keff), np.float64)
     ka = ctypes.c_int64(0)
     q, c = queries.c_struct(), corpus.c_struct()
     check(lib().pmm_topk(ctypes.byref(q), ctypes.byref(c), int(k), str(metric).encode(),
@@ -161,7 +235,7 @@ def topk(queries: HostMatrix, corpus: HostMatrix, k: int, metric: str):
 
 def matmul(left: HostMatrix, right: HostMatrix) -> np.ndarray:
     """pmm_matmul. Returns [Q, N] in the working dtype."""
-    out = np.empty((left.n_rows, right.n_rows), working_dtype(left, right))
+    out = result_empty((left.n_rows, right.n_rows), working_dtype(left, right))
     l, r = left.c_struct(), right.c_struct()
     check(lib().pmm_matmul(ctypes.byref(l), ctypes.byref(r), out.ctypes.data))
     return out
@@ -180,8 +254,8 @@ class ResidentCorpus:
         if k < 0:
             raise OverflowError("can't convert negative int to unsigned")
         keff = min(int(k), self.n_rows)
-        idx = np.empty((queries.n_rows, keff), np.uint32)
-        sc = np.empty((queries.n_rows, keff), np.float64)
+        idx = result_empty((queries.n_rows, keff), np.uint32)
+        sc = result_empty((queries.n_rows, keff), np.float64)
         ka = ctypes.c_int64(0)
         q = queries.c_struct()
         check(lib().pmm_topk_corpus(ctypes.byref(q), self._h, int(k), str(metric).encode(),

@@ -3,6 +3,7 @@
 // (matmul_impl / compute_topk_indices_scores / topk_impl) and src/lib.rs:15-55.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -842,6 +843,9 @@ cudaStream_t copy_stream() {
 // cores early; the rest of the upload hides behind it.
 // Outputs: host index/score buffers and/or exact packed candidates left on the device (d_cand, for the
 // multi-GPU exchange); corpus row j is reported as index_base + j.
+// Sustained algorithmic FLOP/s of the first filter level on f32 planes (TF32 x1 with two levels, else 3xTF32).
+double terms0_rate(int mode) { return (mode == PREP_TF32 && g_tc_levels.load() >= 2 && g_tc_cg.load() == 2) ? 7.5e14 : 2.6e14; }
+
 int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t keff, int metric, PathChoice pc,
                       int64_t index_base, uint32_t *out_index, double *out_score, uint64_t *d_cand) {
     cudaStream_t s = host_stream(), cs = copy_stream();
@@ -854,14 +858,19 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     // get equal chunks instead.
     std::vector<int64_t> cut{0};
     {
-        const double rate = corpus->dtype == PMM_DTYPE_F16 ? 1.2e15 : 7.0e14;   // sustained filter FLOP/s, measured
+        // sustained filter FLOP/s, measured: f16 planes (f16 input, or f32 rounded to f16) / TF32 x1 / 3xTF32
+        const double rate = (pc.mode == PREP_F16 || pc.mode == PREP_F16R) ? 1.25e15 : terms0_rate(pc.mode);
         double ratio = 0.8 * (2.0 * (double)Q / rate) / ((double)es / 4.0e10);  // 40 GB/s host -> device, 20 % margin
         if (g_host_chunk_ratio_pct.load() > 0) ratio = g_host_chunk_ratio_pct.load() / 100.0;
-        const int max_chunks = 8;
-        const int first_div = g_host_chunk_first_div.load() > 0 ? g_host_chunk_first_div.load() : 32;
-        int64_t size = (N / (ratio < 1.5 ? max_chunks : first_div)) / 256 * 256;
-        if (ratio < 1.5) ratio = 1.0;
+        if (ratio < 1.0) ratio = 1.0;
         if (ratio > 4.0) ratio = 4.0;
+        const int max_chunks = 8;
+        // first chunk of a geometric series of max_chunks terms that sums to N (equal chunks when ratio = 1) ...
+        double first = ratio > 1.001 ? (double)N * (ratio - 1.0) / (pow(ratio, max_chunks) - 1.0) : (double)N / max_chunks;
+        // ... but not below N / first_div: tiny first chunks buy nothing, the query upload comes first anyway
+        const int first_div = g_host_chunk_first_div.load() > 0 ? g_host_chunk_first_div.load() : 32;
+        if (first < (double)N / first_div) first = (double)N / first_div;
+        int64_t size = (int64_t)first / 256 * 256;
         if (size < 16384) size = 16384;
         int64_t at = 0;
         while (at + size < N && (int)cut.size() < max_chunks) {
@@ -1028,6 +1037,21 @@ int pmm_set_device(int32_t device) {
     int rc = ensure_device();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(device));
+    return PMM_OK;
+}
+
+int pmm_host_alloc(int64_t bytes, void **out) {
+    if (!out || bytes < 0) return fail(PMM_ERR_INVALID, "pmm_host_alloc: bad arguments");
+    *out = nullptr;
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaHostAlloc(out, bytes > 0 ? (size_t)bytes : 16, cudaHostAllocPortable));
+    return PMM_OK;
+}
+
+int pmm_host_free(void *p) {
+    if (!p) return PMM_OK;
+    CUDA_TRY(cudaFreeHost(p));
     return PMM_OK;
 }
 

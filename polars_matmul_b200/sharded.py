@@ -129,4 +129,9 @@ class ShardedTopk:
         sc = torch.empty((Q, k_eff), dtype=torch.float64, device=dev)
         _native.dev_merge_candidates(gathered.data_ptr(), gathered.shape[0], Q, k_eff, k_eff, m,
                                      idx.data_ptr(), sc.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
-        return idx.cpu().numpy().view(np.uint32), sc.cpu().numpy()
+        # results land in pooled page-locked buffers (device->host at PCIe rate, no pageable staging)
+        out_i = _native.result_empty((Q, k_eff), np.int32)
+        out_s = _native.result_empty((Q, k_eff), np.float64)
+        torch.from_numpy(out_i).copy_(idx)
+        torch.from_numpy(out_s).copy_(sc)
+        return out_i.view(np.uint32), out_s

@@ -21,11 +21,17 @@ def h2d_times(n):
         ts.append(round((time.perf_counter() - t0) * 1e3, 1))
     return ts
 print("pure H2D 3.07 GB ms:", h2d_times(12), flush=True)
-for div, ratio, verify in [(16, 0, 1), (32, 0, 1), (16, 350, 1), (8, 100, 1), (16, 0, 1)]:
-    _native.set_option("host_chunk_first_div", div); _native.set_option("host_chunk_ratio_pct", ratio); _native.set_option("verify", verify)
+import ctypes
+oi = torch.empty((Q, k), dtype=torch.int32).pin_memory(); osc = torch.empty((Q, k), dtype=torch.float64).pin_memory()
+ka = ctypes.c_int64(0)
+qs_, cs_ = hq.c_struct(), hc.c_struct()
+for label, ip, sp in (("numpy (pageable) outputs", None, None), ("pinned outputs", oi.data_ptr(), osc.data_ptr())):
     ts = []
-    for it in range(12):
+    for it in range(8):
         t0 = time.perf_counter()
-        idx, sc = _native.topk(hq, hc, k, "dot")
+        if ip is None:
+            idx, sc = _native.topk(hq, hc, k, "dot")
+        else:
+            _native.check(_native.lib().pmm_topk(ctypes.byref(qs_), ctypes.byref(cs_), k, b"dot", ip, sp, ctypes.byref(ka)))
         ts.append(round((time.perf_counter() - t0) * 1e3, 1))
-    print("first_div", div, "ratio_pct", ratio, "verify", verify, "wall ms", ts, flush=True)
+    print(label, ts, flush=True)

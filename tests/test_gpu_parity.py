@@ -380,6 +380,22 @@ def test_result_containers(pmm):
     assert len(pmm._topk(q, c, 0, "dot").to_pylist()[0]) == 0             # k = 0 -> empty lists
 
 
+def test_results_come_from_the_pinned_pool(native, oracle):
+    """Large result buffers are page-locked blocks from pmm_host_alloc, recycled once the arrays are dropped."""
+    rng = np.random.default_rng(5)
+    q, c = _randn(rng, 3000, 32), _randn(rng, 500, 32)
+    idx, sc = native.topk(_hm(q), _hm(c), 100, "dot")           # 1.2 MB + 2.4 MB of results
+    parity.check_topk(idx[:50], sc[:50], q[:50], c, 100, "dot", oracle, exact=True)
+    addr = sc.ctypes.data
+    keep = sc.copy()
+    del idx, sc
+    idx2, sc2 = native.topk(_hm(q), _hm(c), 100, "dot")
+    assert sc2.ctypes.data == addr                               # same block again
+    assert np.array_equal(sc2, keep)
+    small_i, small_s = native.topk(_hm(q[:4]), _hm(c), 5, "dot")  # tiny results stay ordinary arrays
+    assert small_s.base is None
+
+
 def test_resident_corpus_handle(native, oracle):
     rng = np.random.default_rng(12)
     q, c = _randn(rng, 50, 64), _randn(rng, 3000, 64)
