@@ -18,11 +18,11 @@ echo "exit $?" | tee -a gpurun_out/summary.txt
 echo "== ncu full capture (mid-size)" | tee -a gpurun_out/summary.txt
 CMD2="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --q 20000 --n 200000"
 timeout 300 $CMD2 > gpurun_out/plain_full.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:tc_kernel<1, 0" -s 1 -c 1 -f -o gpurun_out/tc_topk_$R $CMD2 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:tc_kernel<.bool.1" -s 1 -c 1 -f -o gpurun_out/tc_topk_$R $CMD2 > gpurun_out/ncu_full.log 2>&1
 echo "exit $?" | tee -a gpurun_out/summary.txt
 tail -n 3 gpurun_out/ncu_full.log | tee -a gpurun_out/summary.txt
 echo "== ncu DRAM traffic of the fused kernel at the bench size" | tee -a gpurun_out/summary.txt
 CMD3="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed --clock-control none --kernel-name-base demangled -k "regex:tc_kernel<1, 0" -s 1 -c 1 --csv --log-file gpurun_out/traffic_$R.csv $CMD3 > gpurun_out/ncu_traffic.log 2>&1
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed --clock-control none --kernel-name-base demangled -k "regex:tc_kernel<.bool.1" -s 1 -c 1 --csv --log-file gpurun_out/traffic_$R.csv $CMD3 > gpurun_out/ncu_traffic.log 2>&1
 echo "exit $?" | tee -a gpurun_out/summary.txt
 cat gpurun_out/traffic_$R.csv | tail -n 8 | tee -a gpurun_out/summary.txt
