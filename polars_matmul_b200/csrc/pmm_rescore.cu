@@ -45,6 +45,26 @@ __device__ __forceinline__ void raw_row(const RawMatrix &m, int64_t row, int64_t
     if (m.row_validity && !((m.row_validity[row >> 3] >> (row & 7)) & 1)) len = 0;
 }
 
+// One 32-element step of the gather: element `e` of candidate rows [0, n_act) of the warp, in batches of 8 rows
+// (a warp-uniform guard per batch, no branch per row: every batch is in flight before the first value is consumed).
+// PLAIN: no element validity bitmap (the usual case) -> one predicated load per row.
+template <typename CSRC, bool PLAIN>
+__device__ __forceinline__ void gather_step(float (&x)[32], const RawMatrix &cm, const int64_t *rowb, const int *rowl, int w0,
+                                            int n_act, int e) {
+#pragma unroll
+    for (int g = 0; g < 32; g += 8) {
+        if (g < n_act) {
+#pragma unroll
+            for (int i = g; i < g + 8; ++i) {
+                const int64_t cbi = rowb[w0 + i];
+                const int cli = rowl[w0 + i];
+                if (PLAIN) x[i] = e < cli ? RsLoad<CSRC>::get(cm.values, cbi + e) : 0.0f;
+                else x[i] = raw_fetch<CSRC>(cm, cbi, cli, e);
+            }
+        }
+    }
+}
+
 // Bound E on |filter value - its exact counterpart| for one query, in the units of the filter value
 // (dot: q.c; cosine: q.c / |c|; euclidean: squared distance).  eps = relative operand/accumulation error per |q||c|;
 // s = abs_err = absolute rounding error of one operand row (f32 rounded to f16 below the normal range):
@@ -63,8 +83,9 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
                                                      int64_t index_base, int k_out, uint32_t *out_idx,
                                                      double *out_score, uint64_t *out_cand, RescoreCheck chk) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    uint64_t *sortbuf = (uint64_t *)rs_smem;            // NT entries
-    float *qs = (float *)(rs_smem + NT * 8);            // dim floats, then one transpose tile per warp
+    uint64_t *sortbuf = (uint64_t *)rs_smem;            // NT entries; during the gather: the candidates' row offsets
+    int *rowl = (int *)(rs_smem + NT * 8);              // NT row lengths
+    float *qs = (float *)(rs_smem + NT * 12);           // dim floats, then one transpose tile per warp
     const int64_t q = blockIdx.x;
     const int t = threadIdx.x;
     const int dim = (int)qm.dim;
@@ -102,8 +123,14 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     // accumulates ITS candidate sequentially in d — the reference's order.  Candidates are sorted best first and
     // the skipped ones sit at the end, so the warp only fetches rows [0, n_act).
     const int n_act = 32 - __clz(__ballot_sync(0xffffffffu, c != 0ull));
+    // row offset / length of every candidate of the warp, read back as shared-memory broadcasts in the loops
+    int64_t *rowb = (int64_t *)sortbuf;
+    rowb[t] = cb;
+    rowl[t] = (int)cl;
+    __syncwarp();
+    const int w0 = wrp * 32;
     float acc = 0.0f;
-    unsigned char *tile_base = rs_smem + NT * 8 + (size_t)((dim + 3) & ~3) * 4;
+    unsigned char *tile_base = rs_smem + NT * 12 + (size_t)((dim + 3) & ~3) * 4;
     // f16 rows without nulls: 64 elements per step, one half2 per lane (128-byte requests per row)
     const bool wide16 = sizeof(CSRC) == 2 && !cm.offsets && !cm.validity && (dim & 1) == 0;
     if (wide16) {
@@ -118,7 +145,8 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
                 if (g < n_act) {
 #pragma unroll
                     for (int i = g; i < g + 8; ++i) {
-                        const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
+                        const int64_t cbi = rowb[w0 + i];
+                        const int cli = rowl[w0 + i];
                         const int e = d0 + 2 * lane;
                         x[i] = e < cli ? __half22float2(__ldg(vals + ((cbi + e) >> 1))) : make_float2(0.0f, 0.0f);
                     }
@@ -149,18 +177,11 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
         }
     } else {
         float (*tile)[RS_PITCH32] = (float (*)[RS_PITCH32])(tile_base + (size_t)wrp * 32 * RS_PITCH32 * 4);
+        const bool plain = !cm.validity;
         for (int d0 = 0; d0 < dim; d0 += 32) {
             float x[32];
-#pragma unroll
-            for (int g = 0; g < 32; g += 8) {  // up to 32 independent row reads in flight per lane before anything is consumed
-                if (g < n_act) {
-#pragma unroll
-                    for (int i = g; i < g + 8; ++i) {
-                        const int64_t cbi = __shfl_sync(0xffffffffu, cb, i), cli = __shfl_sync(0xffffffffu, cl, i);
-                        x[i] = raw_fetch<CSRC>(cm, cbi, cli, d0 + lane);
-                    }
-                }
-            }
+            if (plain) gather_step<CSRC, true>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
+            else gather_step<CSRC, false>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
                 if (g < n_act) {
@@ -185,6 +206,7 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             __syncwarp();
         }
     }
+    __syncwarp();  // the row offsets in sortbuf are dead from here on
     uint64_t packed = 0ull;
     if (c != 0ull) {
         float sc = acc;
@@ -251,7 +273,7 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
     const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
 #define PMM_RS(NT)                                                                                                  \
     {                                                                                                               \
-        size_t smem = NT * 8 + smem_q + (size_t)(NT / 32) * 32 * (sizeof(CSRC) == 2 ? RS_PITCH16 : RS_PITCH32) * 4;                                                                              \
+        size_t smem = NT * 12 + smem_q + (size_t)(NT / 32) * 32 * (sizeof(CSRC) == 2 ? RS_PITCH16 : RS_PITCH32) * 4;                                                                              \
         if (smem > 48 * 1024) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                         \
