@@ -193,7 +193,10 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *   "profile" (0/1)            bracket kernels with CUDA events on the launching stream and accumulate per-kernel
  *                              milliseconds, read back with pmm_get_stat("<kernel>_ms")
  *   "verify" (0/1, default 1)  per-query losslessness proof of the tensor-core filter and its fallbacks
- *   "tc_levels" (1|2)          2 (default): TF32 x1 first-level filter, 3xTF32 on demand; 1: 3xTF32 only
+ *   "tc_levels" (1|2|3)        3 (default): first level on f32 operands rounded to f16 (kind::f16), 3xTF32 on demand;
+ *                              2: TF32 x1 first level; 1: 3xTF32 only
+ *   "f16r_wide" (0/1, default 1)  queries the f16-rounded first level cannot prove are first re-run with 256-entry
+ *                              lists against the same planes, then with 3xTF32
  *   "tc_cg" (1|2)              tcgen05 cta_group of the fused kernels (default 2)
  *   "tc_group"                 CTA groups sharing a query tile (0 = auto)
  *   "tc_sync_tiles"            corpus tiles between the producers' pacing barriers (default 32, 0 = off)

@@ -42,7 +42,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0}, g_f16r_wide{1};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -493,7 +493,7 @@ float filter_eps(int64_t dim, int terms, bool f16) {
 
 int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
                      const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
-                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s);
+                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s, int kp_override = 0);
 
 // Rows [r0, r0 + rows) of a device-resident matrix as a matrix of its own. r0 must be a multiple of 256 (element
 // validity bitmaps are re-based by whole bytes).
@@ -509,10 +509,6 @@ pmm_matrix_t slice_rows(const pmm_matrix_t &m, int64_t r0, int64_t rows) {
     if (dm.row_validity) dm.row_validity += r0 / 8;
     return dm;
 }
-
-int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
-                     const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
-                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s);
 
 // Exact re-scoring of the kept candidates + the losslessness check. Queries the check cannot clear are
 // gathered and recomputed one level up: after the TF32 x1 filter by the 3xTF32 filter (next_terms = 3),
@@ -550,7 +546,7 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     CUDA_TRY(cudaMemcpyAsync(&n_flag, count.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (n_flag == 0) return PMM_OK;
-    stat_add(next_terms == 3 ? "requeried_tf32x3" : "fallback_queries", (double)n_flag);
+    stat_add(next_terms == 1 ? "requeried_f16_wide" : next_terms == 3 ? "requeried_tf32x3" : "fallback_queries", (double)n_flag);
     // ---- gather the flagged queries into a dense f32 matrix
     std::vector<unsigned char> hflags((size_t)Q);
     CUDA_TRY(cudaMemcpy(hflags.data(), flags.p, (size_t)Q, cudaMemcpyDeviceToHost));
@@ -578,7 +574,13 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     TopkOut t{t_idx.as<uint32_t>(), t_sc.as<double>(), t_cand.as<uint64_t>()};
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
     int rc;
-    if (next_terms == 3) {
+    if (next_terms == 1) {
+        // same f16-rounded filter against the planes at hand, 256 candidates per query
+        Prepared qf;
+        if ((rc = prepare(qd, PREP_F16R, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
+        if ((rc = tc_topk_verified(qf, c_planes, qd, raw_c, c_norm, c_sq, c_max_sq, 1, keff, metric, index_base, nullptr, t, s, 256)))
+            return rc;
+    } else if (next_terms == 3) {
         // one level up on the tensor cores: 3xTF32 planes of the flagged queries against the corpus planes
         Prepared qf, cf;
         if ((rc = prepare(qd, PREP_TF32, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
@@ -626,8 +628,8 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
 // c may be NULL only when kept_in is given. c_norm / c_sq / c_max_sq describe the whole corpus (index_base-relative).
 int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
                      const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
-                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s) {
-    const int kp = tc_list_capacity(keff);
+                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s, int kp_override) {
+    const int kp = kp_override ? kp_override : tc_list_capacity(keff);
     const bool f16 = q.mode == PREP_F16;     // exact f16 planes
     const bool f16r = q.mode == PREP_F16R;   // f32 input rounded to f16: TF32-x1-like error, then 3xTF32 on demand
     DevBuf kept;
@@ -638,9 +640,14 @@ int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &r
         if (rc) return rc;
         kept_ptr = kept.as<uint64_t>();
     }
-    const int next_terms = (f16r || (!f16 && terms == 1)) ? 3 : 0;
+    // Next level for the queries the proof rejects.  f16-rounded level with its planes at hand: first the SAME filter
+    // with 256-entry lists (next_terms = 1) - the proof needs the exact k-th score to clear the worst kept filter
+    // value by the error bound, and 128 more ranks of margin almost always do it, for one small launch instead of
+    // rebuilding TF32 planes of the whole corpus.  Then 3xTF32 (3), then the exact SIMT path (0).
+    const bool wide = f16r && c && !kept_in && kp < 256 && keff <= 248 && g_f16r_wide.load();
+    const int next_terms = wide ? 1 : (f16r || (!f16 && terms == 1)) ? 3 : 0;
     // f16r planes cannot serve the 3xTF32 level: it rebuilds TF32 planes piece by piece (c_planes = NULL)
-    return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), f16r ? nullptr : c, c_norm, c_sq,
+    return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), (f16r && !wide) ? nullptr : c, c_norm, c_sq,
                               c_max_sq, filter_eps(raw_q.dim, f16r ? 1 : terms, f16), f16r ? f16r_abs_err(raw_q.dim) : 0.0f,
                               f16r ? 65504.0f : 0.0f, next_terms, metric, index_base, keff, o, s);
 }
@@ -1071,6 +1078,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "release_workspace") g_block_cache.clear();  // this thread's parked device blocks go back to the pool
     else if (k == "host_chunk_ratio_pct") g_host_chunk_ratio_pct.store(value);  // 0 = auto
     else if (k == "host_chunk_first_div") g_host_chunk_first_div.store(value);  // first chunk = N / this (0 = 32)
+    else if (k == "f16r_wide") g_f16r_wide.store(value ? 1 : 0);  // 256-entry retry of the f16-rounded level before 3xTF32
     else if (k == "tc_max_flush") g_tc_max_flush.store(value < 0 ? 0 : value);
     else if (k == "tc_debug_skip") g_tc_debug_skip.store(value);  // measurement only: results are wrong when set
     else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast

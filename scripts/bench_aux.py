@@ -83,7 +83,7 @@ def topk_case(Q, N, D, k, metric, dt, label, iters=2):
     kern = max([k_ for k_ in s if k_.startswith(("tc_topk", "scores"))], key=lambda k_: s[k_])
     out[label] = {"step_ms": total_ms, "queries_per_s": Q / total_ms * 1e3, "kernel": kern[:-3], "kernel_ms": s[kern],
                   "kernel_TFLOPs": 2.0 * Q * N * D / s[kern] / 1e9, "per_kernel_ms": s,
-                  "requeried_tf32x3": _native.get_stat("requeried_tf32x3") / iters, "fallback_queries": _native.get_stat("fallback_queries") / iters}
+                  "requeried_f16_wide": _native.get_stat("requeried_f16_wide") / iters, "requeried_tf32x3": _native.get_stat("requeried_tf32x3") / iters, "fallback_queries": _native.get_stat("fallback_queries") / iters}
 topk_case(1000, 10000, 256, 10, "cosine", torch.float32, "topk_C1_1000x10000x256_cosine_k10", iters=20)
 topk_case(100_000, 1_000_000, 768, 100, "euclidean", torch.float32, "topk_C3_euclidean")
 topk_case(100_000, 1_000_000, 768, 100, "cosine", torch.float32, "topk_C3shape_cosine")

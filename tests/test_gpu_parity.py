@@ -233,10 +233,32 @@ def test_filter_levels_and_fallback_are_exercised(native, oracle):
     native.reset_stats()
     idx, sc = native.topk(_hm(q2), _hm(c2), k, "dot")
     parity.check_topk(idx, sc, q2, c2, k, "dot", oracle, exact=True)
-    assert native.get_stat("requeried_tf32x3") > 0
-    # (c) 60 exact duplicates at the top: no filter can prove anything about exact ties -> exact SIMT path
+    assert native.get_stat("requeried_f16_wide") > 0        # first retry: same filter, 256-entry lists (rank 256 is far enough)
+    assert native.get_stat("requeried_tf32x3") == 0
+    native.set_option("f16r_wide", 0)                        # without that retry the queries go straight to 3xTF32
+    try:
+        native.reset_stats()
+        i0, s0 = native.topk(_hm(q2), _hm(c2), k, "dot")
+        assert native.get_stat("requeried_tf32x3") > 0 and native.get_stat("requeried_f16_wide") == 0
+        assert np.array_equal(i0, idx) and np.array_equal(s0, sc)
+    finally:
+        native.set_option("f16r_wide", 1)
+    # (b2) 400 rows spaced 2e-6: even rank 256 is within the first level's bound -> wide retry fails too -> 3xTF32
+    c2b = c.copy()
+    c2b[:400] = base * (1.0 + 2e-6 * np.arange(400, dtype=np.float32)[:, None]) * 3.0
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q2), _hm(c2b), k, "dot")
+    parity.check_topk(idx, sc, q2, c2b, k, "dot", oracle, exact=True)
+    assert native.get_stat("requeried_f16_wide") > 0 and native.get_stat("requeried_tf32x3") > 0
+    # (c) 300 exact duplicates at the top (more than the longest candidate list): no filter can prove anything about
+    #     exact ties it did not keep -> exact SIMT path. (60 duplicates are settled by the 256-entry retry.)
     c3 = c.copy()
     c3[100:160] = base * 3.0
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q2), _hm(c3), k, "cosine")
+    parity.check_topk(idx, sc, q2, c3, k, "cosine", oracle, exact=True)
+    assert native.get_stat("requeried_f16_wide") > 0 and native.get_stat("fallback_queries") == 0
+    c3[100:400] = base * 3.0
     native.reset_stats()
     idx, sc = native.topk(_hm(q2), _hm(c3), k, "cosine")
     parity.check_topk(idx, sc, q2, c3, k, "cosine", oracle, exact=True)
