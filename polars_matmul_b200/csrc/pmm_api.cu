@@ -177,6 +177,7 @@ struct DevBuf {
     size_t cap = 0;
     cudaStream_t s = nullptr;
     int dev = 0;
+    bool owned = true;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -200,10 +201,19 @@ struct DevBuf {
         if (e != cudaSuccess) p = nullptr;
         return e;
     }
+    // A view of `bytes` bytes inside another buffer (never freed here); alloc() of up to that size keeps the view.
+    void borrow(void *ptr, size_t bytes, cudaStream_t stream) {
+        release();
+        p = ptr;
+        cap = bytes;
+        s = stream;
+        owned = false;
+    }
     void release() {
-        if (p && !g_block_cache.park(p, cap, s, dev)) cudaFreeAsync(p, s);
+        if (p && owned && !g_block_cache.park(p, cap, s, dev)) cudaFreeAsync(p, s);
         p = nullptr;
         cap = 0;
+        owned = true;
     }
     ~DevBuf() { release(); }
     template <typename T> T *as() const { return (T *)p; }
@@ -644,7 +654,7 @@ int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &r
     // with 256-entry lists (next_terms = 1) - the proof needs the exact k-th score to clear the worst kept filter
     // value by the error bound, and 128 more ranks of margin almost always do it, for one small launch instead of
     // rebuilding TF32 planes of the whole corpus.  Then 3xTF32 (3), then the exact SIMT path (0).
-    const bool wide = f16r && c && !kept_in && kp < 256 && keff <= 248 && g_f16r_wide.load();
+    const bool wide = f16r && c && kp < 256 && keff <= 248 && g_f16r_wide.load();
     const int next_terms = wide ? 1 : (f16r || (!f16 && terms == 1)) ? 3 : 0;
     // f16r planes cannot serve the 3xTF32 level: it rebuilds TF32 planes piece by piece (c_planes = NULL)
     return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), (f16r && !wide) ? nullptr : c, c_norm, c_sq,
@@ -953,37 +963,44 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     carry.layout_rows = N;
     for (int i = 0; i < n_chunks; ++i) carry.layout_rows = std::min<int64_t>(carry.layout_rows, cut[i + 1] - cut[i]);
     CUDA_TRY(kept.alloc((size_t)Q * kp * 8, s));
-    if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)N * 4, s));
-    // one set of plane buffers, sized for the largest chunk and reused by all of them
-    Prepared c;
-    {
-        int64_t max_rows = 0;
-        for (int i = 0; i < n_chunks; ++i) max_rows = std::max<int64_t>(max_rows, cut[i + 1] - cut[i]);
-        CUDA_TRY(c.p0.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));
-        if (pc.mode == PREP_TF32) CUDA_TRY(c.p1.alloc(plane_bytes(pc.mode, max_rows, D, TC_TILE_N), s));  // (f16 modes: one plane)
-        if (want_norm) CUDA_TRY(c.norm.alloc((size_t)round_up(max_rows, TC_TILE_N) * 4, s));
-        if (want_sq) CUDA_TRY(c.sqnorm.alloc((size_t)round_up(max_rows, TC_TILE_N) * 4, s));
-    }
+    if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)round_up(N, TC_TILE_N) * 4, s));  // chunks write their padded tails too
+    // Plane buffers for the WHOLE corpus; every chunk is prepared into its slice (chunk starts are multiples of the
+    // corpus tile), so that after the last chunk the planes of the full corpus are at hand for the re-query levels.
+    Prepared call;
+    call.mode = pc.mode;
+    call.n_rows = N;
+    call.dim = D;
+    call.rows_pad = round_up(N, TC_TILE_N);
+    const int64_t plane_es = (pc.mode == PREP_F16 || pc.mode == PREP_F16R) ? 2 : 4;
+    call.ld = round_up(D, plane_es == 2 ? 64 : 32);
+    CUDA_TRY(call.p0.alloc(plane_bytes(pc.mode, N, D, TC_TILE_N), s));
+    if (pc.mode == PREP_TF32) CUDA_TRY(call.p1.alloc(plane_bytes(pc.mode, N, D, TC_TILE_N), s));  // (f16 modes: one plane)
     for (int i = 0; i < n_chunks; ++i) {
         CUDA_TRY(cudaStreamWaitEvent(s, ev[i], 0));
         const int64_t r0 = cut[i], rows = cut[i + 1] - cut[i];
         const pmm_matrix_t dm = slice_rows(uc.dm, r0, rows);  // r0 is a multiple of 256
+        Prepared c;  // views into the whole-corpus buffers
+        const size_t off = (size_t)r0 * call.ld * plane_es, pb = plane_bytes(pc.mode, rows, D, TC_TILE_N);
+        c.p0.borrow((char *)call.p0.p + off, pb, s);
+        if (pc.mode == PREP_TF32) c.p1.borrow((char *)call.p1.p + off, pb, s);
+        if (want_norm) c.norm.borrow(c_aux_all.as<float>() + r0, (size_t)round_up(rows, TC_TILE_N) * 4, s);
+        if (want_sq) c.sqnorm.borrow(c_aux_all.as<float>() + r0, (size_t)round_up(rows, TC_TILE_N) * 4, s);
         if ((rc = prepare(dm, pc.mode, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
-        if (want_norm || want_sq)
-            CUDA_TRY(cudaMemcpyAsync(c_aux_all.as<float>() + r0, want_norm ? c.norm.p : c.sqnorm.p, (size_t)rows * 4,
-                                     cudaMemcpyDeviceToDevice, s));
         // the candidate lists are carried from chunk to chunk; the last launch merges them into `kept`
         if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept.as<uint64_t>(), s, terms0, &carry,
                             (i == 0 ? 1 : 0) | (i == n_chunks - 1 ? 2 : 0))))
             return rc;
     }
+    if (want_norm) call.norm.borrow(c_aux_all.p, (size_t)call.rows_pad * 4, s);
+    if (want_sq) call.sqnorm.borrow(c_aux_all.p, (size_t)call.rows_pad * 4, s);
+    call.max_sq_ptr = c_max.as<unsigned int>();
     const uint64_t *kept_ptr = kept.as<uint64_t>();
     const size_t cnt = (size_t)Q * keff;
     CUDA_TRY(d_idx.alloc(cnt * 4, s));
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), d_cand};
     // c_aux_all holds the corpus norms (cosine) or squared norms (euclidean) of the whole corpus
-    if ((rc = tc_topk_verified(q, nullptr, uq.dm, uc.dm, c_aux_all.as<float>(), c_aux_all.as<float>(), c_max.as<unsigned int>(),
+    if ((rc = tc_topk_verified(q, &call, uq.dm, uc.dm, c_aux_all.as<float>(), c_aux_all.as<float>(), c_max.as<unsigned int>(),
                                terms0, keff, metric, index_base, kept_ptr, o, s)))
         return rc;
     if (out_index) CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
