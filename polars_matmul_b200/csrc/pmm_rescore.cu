@@ -18,8 +18,7 @@ namespace pmm {
 
 // floats per candidate row of a warp's transpose tile: 16-byte aligned rows whose float4 reads (one row per lane)
 // and per-element writes (one column per lane) are both free of bank conflicts (pitch = 4 mod 32)
-constexpr int RS_PITCH32 = 36;  // 32 elements per step
-constexpr int RS_PITCH16 = 68;  // f16 rows: 64 elements per step
+constexpr int RS_PITCH32 = 36;  // words per row: 32 f32 elements per step, or 32 f16 pairs (64 elements) for f16 rows
 
 template <typename SRC> struct RsLoad;
 template <> struct RsLoad<float> { static __device__ __forceinline__ float get(const void *v, int64_t p) { return __ldg((const float *)v + p); } };
@@ -134,10 +133,12 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     // f16 rows without nulls: 64 elements per step, one half2 per lane (128-byte requests per row)
     const bool wide16 = sizeof(CSRC) == 2 && !cm.offsets && !cm.validity && (dim & 1) == 0;
     if (wide16) {
-        float (*tile2)[RS_PITCH16] = (float (*)[RS_PITCH16])(tile_base + (size_t)wrp * 32 * RS_PITCH16 * 4);
+        // the tile keeps the rows as f16 pairs (36-word pitch like the f32 tile: half the shared memory and registers
+        // of an upcast tile, so more blocks are resident); the upcast happens at the FMA
+        __half2 (*tileh)[RS_PITCH32] = (__half2 (*)[RS_PITCH32])(tile_base + (size_t)wrp * 32 * RS_PITCH32 * 4);
         const __half2 *vals = (const __half2 *)cm.values;
         for (int d0 = 0; d0 < dim; d0 += 64) {
-            float2 x[32];
+            __half2 x[32];
             // row reads are issued in batches of 8 candidates (a warp-uniform guard per batch, no branch per row):
             // every batch is in flight before the first value is consumed
 #pragma unroll
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
                         const int64_t cbi = rowb[w0 + i];
                         const int cli = rowl[w0 + i];
                         const int e = d0 + 2 * lane;
-                        x[i] = e < cli ? __half22float2(__ldg(vals + ((cbi + e) >> 1))) : make_float2(0.0f, 0.0f);
+                        x[i] = e < cli ? __ldg(vals + ((cbi + e) >> 1)) : __floats2half2_rn(0.0f, 0.0f);
                     }
                 }
             }
@@ -156,22 +157,30 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             for (int g = 0; g < 32; g += 8) {
                 if (g < n_act) {
 #pragma unroll
-                    for (int i = g; i < g + 8; ++i) *(float2 *)&tile2[i][2 * lane] = x[i];
+                    for (int i = g; i < g + 8; ++i) tileh[i][lane] = x[i];
                 }
             }
             __syncwarp();
             const int jn = dim - d0 < 64 ? dim - d0 : 64;
             if (jn == 64) {
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    const float4 qv = *(const float4 *)&qs[d0 + j], cv = *(const float4 *)&tile2[lane][j];
-                    acc = __fmaf_rn(qv.x, cv.x, acc);
-                    acc = __fmaf_rn(qv.y, cv.y, acc);
-                    acc = __fmaf_rn(qv.z, cv.z, acc);
-                    acc = __fmaf_rn(qv.w, cv.w, acc);
+                for (int j = 0; j < 64; j += 8) {
+                    const float4 q0 = *(const float4 *)&qs[d0 + j], q1 = *(const float4 *)&qs[d0 + j + 4];
+                    const uint4 raw = *(const uint4 *)&tileh[lane][j >> 1];   // 8 consecutive f16 of my candidate
+                    const float2 c0 = __half22float2(*(const __half2 *)&raw.x), c1 = __half22float2(*(const __half2 *)&raw.y);
+                    const float2 c2 = __half22float2(*(const __half2 *)&raw.z), c3 = __half22float2(*(const __half2 *)&raw.w);
+                    acc = __fmaf_rn(q0.x, c0.x, acc);
+                    acc = __fmaf_rn(q0.y, c0.y, acc);
+                    acc = __fmaf_rn(q0.z, c1.x, acc);
+                    acc = __fmaf_rn(q0.w, c1.y, acc);
+                    acc = __fmaf_rn(q1.x, c2.x, acc);
+                    acc = __fmaf_rn(q1.y, c2.y, acc);
+                    acc = __fmaf_rn(q1.z, c3.x, acc);
+                    acc = __fmaf_rn(q1.w, c3.y, acc);
                 }
             } else {
-                for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile2[lane][j], acc);
+                const __half *th = (const __half *)&tileh[lane][0];
+                for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], __half2float(th[j]), acc);
             }
             __syncwarp();
         }
@@ -273,7 +282,7 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
     const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
 #define PMM_RS(NT)                                                                                                  \
     {                                                                                                               \
-        size_t smem = NT * 12 + smem_q + (size_t)(NT / 32) * 32 * (sizeof(CSRC) == 2 ? RS_PITCH16 : RS_PITCH32) * 4;                                                                              \
+        size_t smem = NT * 12 + smem_q + (size_t)(NT / 32) * 32 * RS_PITCH32 * 4;                                                                              \
         if (smem > 48 * 1024) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                         \
