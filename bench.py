@@ -288,7 +288,7 @@ def main():
     k_ms = _native.get_stat(kname + "_ms")
     k_launches = _native.get_stat(kname + "_launches")
     stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps)
-             for n in ("prep", "tc_topk_f16r", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge", "rescore", "gather", "scatter", "scores_f32", "select_f32")
+             for n in ("prep", "tc_topk_f16r", "tc_topk_f16r_kp256", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge", "rescore", "gather", "scatter", "scores_f32", "select_f32")
              if _native.get_stat(n + "_ms") > 0}
     stats["requeried_f16_wide_per_step"] = _native.get_stat("requeried_f16_wide") / max(1, args.steps)
     stats["requeried_tf32x3_per_step"] = _native.get_stat("requeried_tf32x3") / max(1, args.steps)

@@ -470,7 +470,8 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
         a.round_sync = rsync.as<unsigned int>();
     }
     a.partial = partial.as<uint64_t>();
-    cudaError_t e = launch_counted(q.mode == PREP_F16R ? "tc_topk_f16r" : a.f16 ? "tc_topk_f16" : a.terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3", s,
+    // (256-entry lists: the retry level of the f16-rounded filter, or k > 120 - a kernel variant and a statistic of its own)
+    cudaError_t e = launch_counted(q.mode == PREP_F16R ? (kp == 256 ? "tc_topk_f16r_kp256" : "tc_topk_f16r") : a.f16 ? "tc_topk_f16" : a.terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3", s,
                                    [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());

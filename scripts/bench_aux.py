@@ -25,7 +25,7 @@ def timed(fn, name, iters=5, warm=2, flush=None):
         fn()
     ev[1].record(); torch.cuda.synchronize()
     stats = {}
-    for k in ("prep", "norms", "tc_topk_f16r", "tc_topk_tf32x1", "tc_topk_tf32x3", "tc_topk_f16", "tc_matmul_tf32x3", "tc_matmul_f16", "scores_f32", "scores_f64", "scores_f64_dmma",
+    for k in ("prep", "norms", "tc_topk_f16r", "tc_topk_f16r_kp256", "tc_topk_tf32x1", "tc_topk_tf32x3", "tc_topk_f16", "tc_matmul_tf32x3", "tc_matmul_f16", "scores_f32", "scores_f64", "scores_f64_dmma",
               "select_f32", "select_f64", "merge", "rescore"):
         v = _native.get_stat(k + "_ms")
         if v:
