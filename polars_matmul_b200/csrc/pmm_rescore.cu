@@ -109,7 +109,10 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             const float qn = sqrtf(chk.q_sq[q]);
             const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
             const float e = filter_error_bound(chk, metric, qn, cmax, cmin);
-            if (f_j < f_k - 2.0f * e - 1e-6f * fabsf(f_k)) c_in = 0ull;  // (NaN anywhere: keep)
+            // the bound only holds while no operand left the filter format's range (f16-rounded level: a row norm
+            // above 65504 may have become inf there, and the filter values are then meaningless)
+            const bool in_range = chk.max_norm <= 0.0f || (qn <= chk.max_norm && cmax <= chk.max_norm);
+            if (in_range && fabsf(f_k) <= 3.0e38f && f_j < f_k - 2.0f * e - 1e-6f * fabsf(f_k)) c_in = 0ull;  // (NaN anywhere: keep)
         }
     }
     const uint64_t c = c_in;

@@ -303,6 +303,14 @@ def test_f16_rounded_level_handles_range(native, oracle):
         for metric in ("cosine", "dot", "euclidean"):
             idx, sc = native.topk(_hm(q), _hm(corpus), k, metric)
             parity.check_topk(idx, sc, q, corpus, k, metric, oracle, exact=True)
+    # (e) regression (found by the property soak): fewer corpus rows than the candidate list holds, one of them beyond
+    #     the f16 range. Nothing is dropped by the filter, but the re-scoring must not skip candidates on the strength
+    #     of filter values that overflowed.
+    small = _randn(rng, 6, d)
+    small[2] *= 1.0e5
+    for metric in ("euclidean", "dot", "cosine"):
+        idx, sc = native.topk(_hm(q[:2]), _hm(small), 1, metric)
+        parity.check_topk(idx, sc, q[:2], small, 1, metric, oracle, exact=True)
     # (d) tiny queries against a normal corpus
     qs = q * np.float32(1e-7)
     for metric in ("cosine", "dot"):

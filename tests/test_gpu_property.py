@@ -3,6 +3,8 @@ Property tests on the GPU (hypothesis): random shapes, k, metrics, dtypes and co
 ABI against the oracle — the items the reference's own tests never pin (tie order, zero norms, nulls,
 ragged rows, k edge cases).  Top-k results must be bit-identical to the oracle.
 """
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -11,6 +13,7 @@ from tests import parity
 
 pytestmark = pytest.mark.gpu
 METRICS = ["cosine", "dot", "euclidean", "L2", "Cosine"]
+EXAMPLES = int(os.environ.get("PMM_PROPERTY_EXAMPLES", "40"))   # raise for a longer soak on the GPU box
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +37,7 @@ def problems(draw):
     k = draw(st.integers(0, 140))
     metric = draw(st.sampled_from(METRICS))
     seed = draw(st.integers(0, 2**31 - 1))
-    kind = draw(st.sampled_from(["gauss", "ints", "dups", "zeros"]))
+    kind = draw(st.sampled_from(["gauss", "ints", "dups", "zeros", "scaled", "tiny", "huge"]))
     return nq, n, d, k, metric, seed, kind
 
 
@@ -50,13 +53,24 @@ def _data(nq, n, d, seed, kind, dtype):
         src = rng.integers(0, n, size=n // 2)
         dst = rng.integers(0, n, size=n // 2)
         c[dst] = c[src]
+    # magnitudes outside the f16 range: the first filter level rounds f32 operands to f16 (subnormals below 6e-5,
+    # overflow above 65504); its losslessness proof must hand such rows to the next level
+    if kind == "scaled":             # every row at its own scale, 1e-8 .. 1e5
+        q *= (10.0 ** rng.uniform(-8, 5, size=(nq, 1))).astype(dtype)
+        c *= (10.0 ** rng.uniform(-8, 5, size=(n, 1))).astype(dtype)
+    if kind == "tiny":
+        q *= dtype(1e-6)
+        c *= dtype(3e-7)
+    if kind == "huge":
+        c[rng.integers(0, n, size=max(1, n // 20))] *= dtype(1e6)
+        q[rng.integers(0, nq, size=max(1, nq // 20))] *= dtype(2e5)
     if kind == "zeros":              # zero vectors: the cosine guards, euclidean cancellation
         c[rng.integers(0, n, size=max(1, n // 10))] = 0
         q[rng.integers(0, nq, size=max(1, nq // 10))] = 0
     return q, c
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=list(HealthCheck))
 @given(problems())
 def test_topk_f32_bit_exact_vs_oracle(native, oracle, p):
     nq, n, d, k, metric, seed, kind = p
