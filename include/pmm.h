@@ -208,6 +208,8 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *                              pmm_get_stat("tc_dbg_wait0".."tc_dbg_wait51")
  *   "host_chunked" (0/1)       overlapped chunked corpus upload of the host entry points (default 1)
  *   "host_chunk_first_div", "host_chunk_ratio_pct"   first chunk = N / div (default 32); growth ratio in % (0 = auto)
+ *   "host_chunk_min_rows", "host_chunk_min_mb"       smallest chunk (default 16384 rows) and smallest corpus (default
+ *                              64 MB) of the chunked upload; tests lower both to drive tiny corpora through it
  *   "release_workspace"        return the calling thread's parked device blocks (>= 32 MB, kept between calls for
  *                              reuse) to the CUDA memory pool
  *   "f64_simt" (0/1)           f64 scores on FP64 FMA instead of DMMA

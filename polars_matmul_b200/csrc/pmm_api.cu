@@ -42,7 +42,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0}, g_f16r_wide{1};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0}, g_f16r_wide{1}, g_host_chunk_min_rows{16384}, g_host_chunk_min_mb{64};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -889,7 +889,8 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         const int first_div = g_host_chunk_first_div.load() > 0 ? g_host_chunk_first_div.load() : 32;
         if (first < (double)N / first_div) first = (double)N / first_div;
         int64_t size = (int64_t)first / 256 * 256;
-        if (size < 16384) size = 16384;
+        const int64_t min_rows = (int64_t)g_host_chunk_min_rows.load() / 256 * 256 >= 256 ? (int64_t)g_host_chunk_min_rows.load() / 256 * 256 : 256;
+        if (size < min_rows) size = min_rows;
         int64_t at = 0;
         while (at + size < N && (int)cut.size() < max_chunks) {
             at += size;
@@ -1094,6 +1095,8 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "tc_cluster4") g_tc_cluster4.store(value ? 1 : 0);
     else if (k == "tc_sync_slack") g_tc_sync_slack.store(value < 0 ? 0 : value);
     else if (k == "release_workspace") g_block_cache.clear();  // this thread's parked device blocks go back to the pool
+    else if (k == "host_chunk_min_rows") g_host_chunk_min_rows.store(value);  // smallest chunk (rows, multiple of 256; default 16384)
+    else if (k == "host_chunk_min_mb") g_host_chunk_min_mb.store(value);      // corpora below this many MB are uploaded in one piece (default 64)
     else if (k == "host_chunk_ratio_pct") g_host_chunk_ratio_pct.store(value);  // 0 = auto
     else if (k == "host_chunk_first_div") g_host_chunk_first_div.store(value);  // first chunk = N / this (0 = 32)
     else if (k == "f16r_wide") g_f16r_wide.store(value ? 1 : 0);  // 256-entry retry of the f16-rounded level before 3xTF32
@@ -1207,7 +1210,7 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     cudaStream_t s = host_stream();
     {
         PathChoice pc = choose_path(queries->dtype, corpus->dtype, keff);
-        if (pc.tc && g_host_chunked.load() && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 64e6)
+        if (pc.tc && g_host_chunked.load() && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 1e6 * g_host_chunk_min_mb.load())
             return host_topk_chunked(queries, corpus, keff, m, pc, 0, out_index, out_score, nullptr);
     }
     Uploaded uq, uc;
@@ -1240,7 +1243,7 @@ int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard
     PathChoice pc = choose_path(queries->dtype, corpus_shard->dtype, keff);
     if (pc.f64) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
     if (pc.tc && g_host_chunked.load() &&
-        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 64e6)
+        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 1e6 * g_host_chunk_min_mb.load())
         return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
     cudaStream_t s = host_stream();
     Uploaded uq, uc;

@@ -80,6 +80,26 @@ def test_topk_f32_bit_exact_vs_oracle(native, oracle, p):
     parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
 
 
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=list(HealthCheck))
+@given(problems(), st.sampled_from([100, 150, 300]))
+def test_topk_chunked_host_path_bit_exact(native, oracle, p, ratio_pct):
+    """The chunked upload path on tiny corpora (256-row chunks, forced): candidate lists carried from launch to
+    launch, ties across chunk boundaries, re-query levels against the whole-corpus planes."""
+    nq, n, d, k, metric, seed, kind = p
+    n = 700 + n * 3                               # 700 .. 8200 rows -> 2 to 8 chunks
+    q, c = _data(nq, n, d, seed, kind, np.float32)
+    native.set_option("host_chunk_min_mb", 0)
+    native.set_option("host_chunk_min_rows", 256)
+    native.set_option("host_chunk_ratio_pct", ratio_pct)
+    try:
+        idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+    finally:
+        native.set_option("host_chunk_min_mb", 64)
+        native.set_option("host_chunk_min_rows", 16384)
+        native.set_option("host_chunk_ratio_pct", 0)
+    parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+
+
 @settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
 @given(problems())
 def test_topk_f64_vs_oracle(native, oracle, p):
