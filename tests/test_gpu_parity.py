@@ -161,6 +161,20 @@ def test_tc_topk_f32(native, oracle, metric, shape):
     parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
 
 
+def test_tc_topk_mid_size_long_scan(native, oracle):
+    """300k corpus rows (1172 corpus tiles per query tile): the per-row thresholds go through their whole life -
+    open lists, hard and soft merges, settled phase - on both epilogue warp sets; every query compared with the oracle."""
+    rng = np.random.default_rng(2024)
+    q, c = _randn(rng, 384, 64), _randn(rng, 300_000, 64)
+    c[rng.integers(0, 300_000, size=2000)] = c[rng.integers(0, 300_000, size=2000)]   # exact ties at arbitrary ranks
+    for metric, k in (("dot", 100), ("cosine", 10), ("euclidean", 33)):
+        idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+        parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+    h, hc = q.astype(np.float16), c[:200_000].astype(np.float16)
+    idx, sc = native.topk(_hm(h), _hm(hc), 100, "dot")
+    parity.check_topk(idx, sc, h.astype(np.float32), hc.astype(np.float32), 100, "dot", oracle, exact=True)
+
+
 def test_tc_readme_config_c1(native, oracle):
     # BASELINE.json configs[0]: 1000 x 10000, 256-d f32, cosine, k=10; same generator as
     # examples/benchmark_topk.py:69-71

@@ -100,6 +100,22 @@ def test_topk_chunked_host_path_bit_exact(native, oracle, p, ratio_pct):
     parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
 
 
+@settings(max_examples=max(15, EXAMPLES // 2), deadline=None, suppress_health_check=list(HealthCheck))
+@given(problems())
+def test_topk_f16_input_bit_exact(native, oracle, p):
+    """f16-stored inputs (README contract: upcast exactly to f32, then the f32 path): one kind::f16 MMA per K-step on
+    the exact planes, re-scoring and proof as for f32."""
+    nq, n, d, k, metric, seed, kind = p
+    if kind in ("scaled", "huge"):       # would not fit f16 storage itself
+        kind = "gauss"
+    q, c = _data(nq, n, d, seed, kind, np.float32)
+    if kind == "tiny":
+        q, c = q * np.float32(1e3), c * np.float32(1e3)      # f16 subnormal range, still non-zero
+    q16, c16 = q.astype(np.float16), c.astype(np.float16)
+    idx, sc = native.topk(_hm(q16), _hm(c16), k, metric)
+    parity.check_topk(idx, sc, q16.astype(np.float32), c16.astype(np.float32), k, metric, oracle, exact=True)
+
+
 @settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
 @given(problems())
 def test_topk_f64_vs_oracle(native, oracle, p):
