@@ -202,6 +202,7 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *   "tc_sync_tiles"            corpus tiles between the producers' pacing barriers (default 32, 0 = off)
  *   "tc_sync_slack"            pacing: wait for the sync point this many points back (default 0)
  *   "tc_max_flush"             list merges per epilogue warp and tile once thresholds settled (0 = auto)
+ *   "tc_soft_at"               staged candidates of a row that trigger its end-of-tile merge (0 = 48)
  *   "tc_clm", "tc_cluster4", "tc_max_units"   experimental cluster shapes, see profiles/sweep_r1.md (default off)
  *   "tc_debug_skip"            measurement only, RESULTS ARE WRONG when set to 1..3: 1/2 epilogue without filter,
  *                              3 filter without merges; 8: correct results + wait-cycle counters readable as

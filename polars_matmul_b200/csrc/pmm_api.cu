@@ -42,7 +42,7 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0}, g_f16r_wide{1}, g_host_chunk_min_rows{16384}, g_host_chunk_min_mb{64};
+std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0}, g_f16r_wide{1}, g_host_chunk_min_rows{16384}, g_host_chunk_min_mb{64}, g_tc_soft_at{0};
 std::atomic<int64_t> g_generic_ws_mb{1024};
 
 std::mutex g_stat_mu;
@@ -443,6 +443,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.debug_skip = g_tc_debug_skip.load();
     a.sync_slack = g_tc_sync_slack.load();
     a.max_flush = g_tc_max_flush.load();
+    a.soft_at = g_tc_soft_at.load();
     const int gs = a.cg * a.clm;   // CTAs per scheduling unit
     int units = di.num_sms / gs;
     if (g_tc_max_units.load() > 0 && units > g_tc_max_units.load()) units = g_tc_max_units.load();
@@ -1100,6 +1101,7 @@ int pmm_set_option(const char *key, int64_t value) {
     else if (k == "host_chunk_ratio_pct") g_host_chunk_ratio_pct.store(value);  // 0 = auto
     else if (k == "host_chunk_first_div") g_host_chunk_first_div.store(value);  // first chunk = N / this (0 = 32)
     else if (k == "f16r_wide") g_f16r_wide.store(value ? 1 : 0);  // 256-entry retry of the f16-rounded level before 3xTF32
+    else if (k == "tc_soft_at") g_tc_soft_at.store(value < 0 ? 0 : value > 88 ? 88 : value);  // staged candidates that trigger an end-of-tile merge (0 = 48)
     else if (k == "tc_max_flush") g_tc_max_flush.store(value < 0 ? 0 : value);
     else if (k == "tc_debug_skip") g_tc_debug_skip.store(value);  // measurement only: results are wrong when set
     else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast

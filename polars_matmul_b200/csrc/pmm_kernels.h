@@ -124,6 +124,7 @@ struct TcArgs {
     int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
     int cg;                        // tcgen05 cta_group: 1, or 2 (CTA pairs, UMMA M=256)
     int cluster4;                  // cg == 2, clm == 1: launch two independent pairs per cluster of 4
+    int soft_at;                   // end-of-tile merge threshold in staged candidates (0 = default 48)
     int resume;                    // 1: keep the lists in `partial` (same schedule layout) and continue from their thresholds
     int sync_slack;                // pacing: wait for the sync point this many points back (0 = strict lockstep)
     int max_flush;                 // list merges per epilogue warp and tile (0 = auto from the tile's MMA time)

@@ -99,6 +99,7 @@ struct TcKParams {
     int sync_tiles;
     int debug_skip;  // measurement only (TcArgs::debug_skip)
     int sync_slack;
+    int soft_at;     // end-of-tile merge threshold (SOFT_AT unless overridden for experiments)
     int resume;      // lists already hold the candidates of earlier launches over other corpus rows
     int max_flush;   // row merges per warp at the end of a tile (rate limit; rows above URGENT_AT always go)
 };
@@ -642,7 +643,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     // of 32 row merges takes several tiles' worth of MMA time and stalls the accumulator ring.
                     // Spread it: at most `max_flush` rows per tile (rows that are nearly full first), the rest
                     // keep staging (EMERGENCY_AT still bounds them).
-                    unsigned due = __ballot_sync(0xffffffffu, cnt > SOFT_AT);
+                    unsigned due = __ballot_sync(0xffffffffu, cnt > p.soft_at);
                     if (__popc(due) > max_flush && nt - n_start >= 32 * n_step) {  // (early tiles: thresholds move fast, merge all)
                         unsigned pick = __ballot_sync(0xffffffffu, cnt > URGENT_AT);
                         unsigned rest = due & ~pick;
@@ -787,6 +788,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
     p.debug_skip = a.debug_skip;
     p.resume = a.resume;
+    p.soft_at = a.soft_at > 0 ? a.soft_at : SOFT_AT;
     // merges that fit beside one tile's MMA time: a merge costs about as much as 8 k-blocks of one plane
     p.max_flush = a.max_flush > 0 ? a.max_flush : (p.num_kb * a.terms / 8 > 1 ? p.num_kb * a.terms / 8 : 1);
     p.sync_slack = a.sync_slack > 0 ? a.sync_slack : 0;
