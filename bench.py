@@ -205,9 +205,12 @@ def main():
     torch.cuda.set_device(local_rank)
     _native.lib()
     _native.set_device(local_rank)
+    numa = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if not os.environ.get("PMM_BENCH_NO_NUMA_BIND"):
+            numa = sharded.bind_near_gpu(local_rank)   # before the pinned host buffers are allocated
     dev = torch.device("cuda", local_rank)
 
     W = dict(WORKLOAD)
@@ -358,6 +361,7 @@ def main():
                        "sharding": f"corpus rows sharded over {world} rank(s), {N} rows each ({n_total} total); queries replicated; "
                                    "candidates merged after one NCCL all-gather" if world > 1 else "single GPU",
                        "value_definition": "n_gpus * Q / step time: every rank scans its own shard for all Q queries",
+                       "host_placement": numa or "not bound",
                        "l2": "inputs (3.4 GB per rank) are far larger than the 126 MB L2; no explicit flush",
                        "arithmetic": "tcgen05 filter on f32 operands rounded to f16 (kind::f16, 11 significant bits; 3xTF32 hi/lo "
                                      "split on demand), f32 accumulate in TMEM; exact f32 re-scoring + per-query losslessness "

@@ -65,6 +65,34 @@ def all_gather_candidates(cand, group=None):
     return out
 
 
+def bind_near_gpu(device_index: int):
+    """One process per GPU: restrict this process to the CPUs of the GPU's NUMA node, so that the page-locked host
+    buffers it allocates afterwards (and the threads that fill them) are local to the GPU's PCIe root. With 8 ranks
+    uploading their corpus shards at once the host side is the bottleneck and remote-socket pages cost bandwidth.
+    Best effort: returns a short description, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {device_index} ({bdf}) -> NUMA node {node}, {len(allowed)} cpus"
+    except Exception:
+        return None
+
+
 class ShardedTopk:
     """Top-k of replicated queries against a corpus sharded over the ranks of `group`."""
 
