@@ -65,6 +65,11 @@ extern "C" {
  * For the host entry points all pointers are host pointers; for the pmm_dev_* entry points all
  * pointers are device pointers.
  */
+/* pmm_matrix_t::reserved flag: all buffers of the descriptor are device pointers already (fixed-size rows, no
+ * bitmaps). Accepted for the QUERIES of pmm_topk_shard: a multi-GPU driver uploads the replicated query batch once
+ * and broadcasts it over NVLink instead of sending it through the host link of every rank. */
+#define PMM_MATRIX_ON_DEVICE 1
+
 typedef struct pmm_matrix {
     const void *values;
     const int64_t *offsets;
@@ -73,7 +78,7 @@ typedef struct pmm_matrix {
     int64_t n_rows;
     int64_t dim;
     int32_t dtype; /* PMM_DTYPE_* */
-    int32_t reserved;
+    int32_t reserved; /* flags: 0, or PMM_MATRIX_ON_DEVICE where an entry point says it accepts it */
 } pmm_matrix_t;
 
 /* ------------------------------------------------------------------ small helpers */

@@ -275,9 +275,13 @@ class ResidentCorpus:
 
 
 # ------------------------------------------------------------------------------------------ device level
-def dev_matrix(data_ptr: int, n_rows: int, dim: int, dtype_code: int, offsets_ptr: int = 0) -> PmmMatrix:
-    """Describes a device-resident matrix (e.g. a torch CUDA tensor's data_ptr())."""
-    return PmmMatrix(data_ptr or None, offsets_ptr or None, None, None, n_rows, dim, dtype_code, 0)
+PMM_MATRIX_ON_DEVICE = 1
+
+
+def dev_matrix(data_ptr: int, n_rows: int, dim: int, dtype_code: int, offsets_ptr: int = 0, flags: int = 0) -> PmmMatrix:
+    """Describes a device-resident matrix (e.g. a torch CUDA tensor's data_ptr()). flags: PMM_MATRIX_ON_DEVICE for
+    the entry points that take host descriptors by default (pmm_topk_shard's queries)."""
+    return PmmMatrix(data_ptr or None, offsets_ptr or None, None, None, n_rows, dim, dtype_code, flags)
 
 
 def dev_topk(dq: PmmMatrix, dc: PmmMatrix, k: int, metric: int, index_base: int = 0, index_ptr: int = 0,
@@ -286,9 +290,11 @@ def dev_topk(dq: PmmMatrix, dc: PmmMatrix, k: int, metric: int, index_base: int 
                              score_ptr or None, cand_ptr or None, stream or None))
 
 
-def topk_shard(queries: HostMatrix, corpus_shard: HostMatrix, k: int, metric: int, index_base: int, cand_ptr: int) -> None:
-    """pmm_topk_shard: host buffers in, exact packed candidates left on the device at cand_ptr."""
-    q, c = queries.c_struct(), corpus_shard.c_struct()
+def topk_shard(queries, corpus_shard: HostMatrix, k: int, metric: int, index_base: int, cand_ptr: int) -> None:
+    """pmm_topk_shard: host buffers in (queries: a HostMatrix, or a PmmMatrix flagged PMM_MATRIX_ON_DEVICE), exact
+    packed candidates left on the device at cand_ptr."""
+    q = queries if isinstance(queries, PmmMatrix) else queries.c_struct()
+    c = corpus_shard.c_struct()
     check(lib().pmm_topk_shard(ctypes.byref(q), ctypes.byref(c), int(k), int(metric), int(index_base), cand_ptr))
 
 

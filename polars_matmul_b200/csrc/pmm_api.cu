@@ -905,8 +905,13 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     const int n_chunks = (int)cut.size() - 1;
 
     Uploaded uq;
-    int rc = upload(queries, s, &uq);
-    if (rc) return rc;
+    int rc = PMM_OK;
+    if (queries->reserved & PMM_MATRIX_ON_DEVICE) {  // pmm_topk_shard: the driver broadcast the queries over NVLink
+        uq.dm = *queries;
+        uq.dm.reserved = 0;
+    } else if ((rc = upload(queries, s, &uq))) {
+        return rc;
+    }
     // corpus metadata now, values chunk by chunk
     Uploaded uc;
     uc.dm = *corpus;
@@ -1238,7 +1243,10 @@ int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard
     if (queries->n_rows == 0) return PMM_OK;
     if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
     if ((rc = check_pair(queries, corpus_shard))) return rc;
-    if ((rc = list_dim_check(queries, "queries")) || (rc = list_dim_check(corpus_shard, "corpus"))) return rc;
+    const bool q_on_device = (queries->reserved & PMM_MATRIX_ON_DEVICE) != 0;
+    if (q_on_device && (queries->offsets || queries->validity || queries->row_validity))
+        return fail(PMM_ERR_UNSUPPORTED, "device-resident queries must be fixed-size rows without bitmaps");
+    if ((!q_on_device && (rc = list_dim_check(queries, "queries"))) || (rc = list_dim_check(corpus_shard, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
     const int64_t keff = k < corpus_shard->n_rows ? k : corpus_shard->n_rows;
     if (keff == 0) return PMM_OK;
@@ -1249,7 +1257,13 @@ int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard
         return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
     cudaStream_t s = host_stream();
     Uploaded uq, uc;
-    if ((rc = upload(queries, s, &uq)) || (rc = upload(corpus_shard, s, &uc))) return rc;
+    if (q_on_device) {
+        uq.dm = *queries;
+        uq.dm.reserved = 0;
+    } else if ((rc = upload(queries, s, &uq))) {
+        return rc;
+    }
+    if ((rc = upload(corpus_shard, s, &uc))) return rc;
     TopkOut o{nullptr, nullptr, d_candidates};
     if ((rc = dev_topk_impl(&uq.dm, &uc.dm, nullptr, corpus_shard->dtype, k, metric, index_base, o, s))) return rc;
     CUDA_TRY(cudaStreamSynchronize(s));

@@ -136,6 +136,7 @@ class ShardedTopk:
         staging), host arrays out. The shard upload overlaps the fused kernel inside libpmm_b200
         (pmm_topk_shard); only the Q x k candidates cross NVLink."""
         import torch
+        import torch.distributed as dist
         from .arrow import to_host_matrix
         m = _native.metric_from_str(metric)
         q, c = to_host_matrix(queries), to_host_matrix(corpus_shard)
@@ -148,8 +149,18 @@ class ShardedTopk:
         cand = torch.zeros((Q, k_eff), dtype=torch.int64, device=dev)
         if k_local > 0:
             local = cand if k_local == k_eff else torch.empty((Q, k_local), dtype=torch.int64, device=dev)
-            torch.cuda.current_stream().synchronize()          # cand is zeroed before the library writes it
-            _native.topk_shard(q, c, k_local, m, index_base, local.data_ptr())
+            q_arg = q
+            if self.world > 1 and q.offsets is None and q.validity is None and q.row_validity is None and q.values.size:
+                # the query batch is the same on every rank: one rank sends it through its host link, the others get
+                # it over NVLink (8 ranks: 2.5 GB less through the host per C3 step)
+                tq = torch.empty((Q, q.dim), dtype=torch.from_numpy(q.values[:1]).dtype, device=dev)
+                src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                if self.rank == 0:
+                    tq.copy_(torch.from_numpy(q.values).view(Q, q.dim), non_blocking=True)
+                dist.broadcast(tq, src=src, group=self.group)
+                q_arg = _native.dev_matrix(tq.data_ptr(), Q, q.dim, q.dtype_code, flags=_native.PMM_MATRIX_ON_DEVICE)
+            torch.cuda.current_stream().synchronize()          # cand is zeroed (and the queries have arrived) before the library runs
+            _native.topk_shard(q_arg, c, k_local, m, index_base, local.data_ptr())
             if local is not cand:
                 cand[:, :k_local] = local
         gathered = all_gather_candidates(cand, self.group) if self.world > 1 else cand.unsqueeze(0)
