@@ -320,8 +320,11 @@ def main():
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1000 / n_e2e)
         barrier()
         e2e = {"value": world * Q / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int((Q + N) * D * 4), "d2h_bytes_per_step": int(Q * k * 12),
-               "note": "pmm_topk C ABI with pinned host buffers; corpus re-uploaded every step as the reference re-marshals it (src/matmul.rs:430-431)"}
+               # whole job: every rank uploads its corpus shard; the replicated queries cross ONE host link and are
+               # broadcast over NVLink (world > 1); every rank reads the merged result back
+               "h2d_bytes_per_step": int((Q + world * N) * D * 4), "d2h_bytes_per_step": int(world * Q * k * 12),
+               "note": "pmm_topk C ABI with pinned host buffers; corpus re-uploaded every step as the reference re-marshals it "
+                       "(src/matmul.rs:430-431)" + ("; bytes are whole-job totals over all ranks" if world > 1 else "")}
 
     # ---- sanity: sampled oracle check of the timed result (rank 0, N=1) ---------------------------
     if rank == 0:
