@@ -868,6 +868,25 @@ double terms0_rate(int mode) { return (mode == PREP_TF32 && g_tc_levels.load() >
 int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t keff, int metric, PathChoice pc,
                       int64_t index_base, uint32_t *out_index, double *out_score, uint64_t *d_cand) {
     cudaStream_t s = host_stream(), cs = copy_stream();
+    // Everything that owns device memory is declared first and the guard last, so that on EVERY way out (errors
+    // included) both streams are drained before a buffer is released: the copy stream may still be writing into the
+    // corpus buffer, and the caller's host buffers must not be in use by a DMA after we return.
+    Uploaded uq, uc;
+    DevBuf err, kept, c_aux_all, d_idx, d_sc, c_max;
+    Prepared q, call;
+    TcCarry carry;
+    struct Drain {
+        cudaStream_t s, cs;
+        cudaEvent_t ready = nullptr;
+        std::vector<cudaEvent_t> ev;
+        ~Drain() {
+            cudaStreamSynchronize(cs);
+            cudaStreamSynchronize(s);
+            if (ready) cudaEventDestroy(ready);
+            for (cudaEvent_t e : ev)
+                if (e) cudaEventDestroy(e);
+        }
+    } drain{s, cs};
     const int64_t Q = queries->n_rows, N = corpus->n_rows, D = corpus->dim;
     const int es = esize(corpus->dtype);
     // Chunk boundaries in rows (multiples of 256 so bitmaps can be re-based by whole bytes).  The filter of chunk i
@@ -904,7 +923,6 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     }
     const int n_chunks = (int)cut.size() - 1;
 
-    Uploaded uq;
     int rc = PMM_OK;
     if (queries->reserved & PMM_MATRIX_ON_DEVICE) {  // pmm_topk_shard: the driver broadcast the queries over NVLink
         uq.dm = *queries;
@@ -913,7 +931,6 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         return rc;
     }
     // corpus metadata now, values chunk by chunk
-    Uploaded uc;
     uc.dm = *corpus;
     int64_t pos0 = 0, pos1 = N * D;
     if (corpus->offsets) {
@@ -939,11 +956,11 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         CUDA_TRY(cudaMemcpyAsync(uc.row_validity.p, corpus->row_validity, nb, cudaMemcpyHostToDevice, s));
         uc.dm.row_validity = uc.row_validity.as<uint8_t>();
     }
-    cudaEvent_t ready;
-    CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(ready, s));
-    CUDA_TRY(cudaStreamWaitEvent(cs, ready, 0));  // the copy stream may touch the buffers once they exist
-    std::vector<cudaEvent_t> ev(n_chunks);
+    CUDA_TRY(cudaEventCreateWithFlags(&drain.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(drain.ready, s));
+    CUDA_TRY(cudaStreamWaitEvent(cs, drain.ready, 0));  // the copy stream may touch the buffers once they exist
+    std::vector<cudaEvent_t> &ev = drain.ev;
+    ev.assign(n_chunks, nullptr);
     for (int i = 0; i < n_chunks; ++i) {
         const int64_t a = corpus->offsets ? corpus->offsets[cut[i]] : cut[i] * D;
         const int64_t b = corpus->offsets ? corpus->offsets[cut[i + 1]] : cut[i + 1] * D;
@@ -956,17 +973,13 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     }
 
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
-    DevBuf err, kept_all, kept, c_aux_all, d_idx, d_sc;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
-    Prepared q;
     if ((rc = prepare(uq.dm, pc.mode, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
-    DevBuf c_max;
     CUDA_TRY(c_max.alloc(2 * sizeof(unsigned int), s));
     CUDA_TRY(init_norm_range(c_max.as<unsigned int>(), s));
     const int kp = tc_list_capacity(keff);
     const int terms0 = first_level_terms(q);
-    TcCarry carry;
     carry.corpus_rows_total = N;
     carry.layout_rows = N;
     for (int i = 0; i < n_chunks; ++i) carry.layout_rows = std::min<int64_t>(carry.layout_rows, cut[i + 1] - cut[i]);
@@ -974,7 +987,6 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)round_up(N, TC_TILE_N) * 4, s));  // chunks write their padded tails too
     // Plane buffers for the WHOLE corpus; every chunk is prepared into its slice (chunk starts are multiples of the
     // corpus tile), so that after the last chunk the planes of the full corpus are at hand for the re-query levels.
-    Prepared call;
     call.mode = pc.mode;
     call.n_rows = N;
     call.dim = D;
@@ -1017,8 +1029,6 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     if (queries->offsets || corpus->offsets) rc = finish_error_flag(err.as<int>(), s);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(cs));
-    cudaEventDestroy(ready);
-    for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }
 

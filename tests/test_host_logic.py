@@ -149,3 +149,40 @@ def test_shard_bounds():
     assert shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
     b = shard_bounds(10_000_000, 8)
     assert b[0] == (0, 1_250_000) and b[-1] == (8_750_000, 10_000_000)
+
+
+def test_small_results_are_plain_arrays_and_device_flag_is_declared():
+    """result_empty only takes page-locked pool blocks for results of at least 1 MB (no GPU needed below that);
+    the PMM_MATRIX_ON_DEVICE flag of the shim equals the header's."""
+    from polars_matmul_b200 import _native
+    a = _native.result_empty((10, 7), np.float64)
+    assert a.shape == (10, 7) and a.dtype == np.float64 and a.base is None
+    header = open(os.path.join(ROOT, "include", "pmm.h")).read()
+    m = re.search(r"#define\s+PMM_MATRIX_ON_DEVICE\s+(\d+)", header)
+    assert m and int(m.group(1)) == _native.PMM_MATRIX_ON_DEVICE
+    dm = _native.dev_matrix(0x1000, 5, 8, _native.DTYPE_F32, flags=_native.PMM_MATRIX_ON_DEVICE)
+    assert dm.reserved == 1 and dm.n_rows == 5 and dm.dim == 8
+
+
+def test_bind_near_gpu_is_best_effort_without_a_device():
+    from polars_matmul_b200 import sharded
+    before = os.sched_getaffinity(0)
+    assert sharded.bind_near_gpu(0) is None          # no GPU / no topology here: nothing may change
+    assert os.sched_getaffinity(0) == before
+
+
+def test_every_documented_option_is_accepted_and_unknown_ones_are_not():
+    """include/pmm.h lists the runtime options; each must be known to pmm_set_option (setting an option needs no GPU)."""
+    from polars_matmul_b200 import _native
+    header = open(os.path.join(ROOT, "include", "pmm.h")).read()
+    block = header[header.index("Tuning / diagnostics"):header.index("PMM_API int pmm_set_option")]
+    names = set(re.findall(r'"([a-z0-9_]+)"', block)) - {"kernel"}
+    assert {"tc_levels", "f16r_wide", "host_chunked", "verify", "profile"} <= names
+    defaults = {"tc_levels": 3, "tc_cg": 2, "tc_sync_tiles": 32, "host_chunked": 1, "verify": 1, "f16r_wide": 1, "tc_clm": 1,
+                "host_chunk_min_rows": 16384, "host_chunk_min_mb": 64, "generic_workspace_mb": 0}
+    for n in sorted(names):
+        if n in ("release_workspace", "generic_workspace_mb") or n.startswith("tc_dbg"):
+            continue
+        _native.set_option(n, defaults.get(n, 0))      # restores the default as it goes
+    with pytest.raises(_native.PmmError):
+        _native.set_option("no_such_option", 1)
