@@ -200,6 +200,37 @@ cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64
     return cudaErrorInvalidValue;
 }
 
+// f16 rows, fixed size, no bitmaps, even dim: each lane loads one f16 PAIR per 16 elements (4-byte requests, a full
+// 32-byte sector per row and step like the f32 path) and the 8 lanes of the row hand each other the elements of
+// their own residue class mod 8 by shuffles, so every partial sum p_j still adds its elements in index order.
+// Consumes whole 16-element steps from *t on; returns the partial sum of this lane.
+template <typename W>
+__device__ __forceinline__ W norms_f16_pairs(const void *values, int64_t base, bool row_live, int64_t d8, int64_t *t, int sub,
+                                             int gbase, unsigned gmask, W p) {
+    const __half2 *v2 = (const __half2 *)values;
+    int64_t i = *t;
+    for (; i + 64 <= d8; i += 64) {  // 4 sectors in flight per row
+        unsigned bits[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            __half2 h = row_live ? __ldg(v2 + ((base + i + 16 * u + 2 * sub) >> 1)) : __floats2half2_rn(0.0f, 0.0f);
+            bits[u] = *(unsigned *)&h;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            unsigned lo = __shfl_sync(gmask, bits[u], gbase + (sub >> 1));      // holds element i+16u+sub
+            unsigned hi = __shfl_sync(gmask, bits[u], gbase + 4 + (sub >> 1));  // holds element i+16u+8+sub
+            const __half2 a2 = *(__half2 *)&lo, b2 = *(__half2 *)&hi;
+            const W x0 = (W)((sub & 1) ? __high2float(a2) : __low2float(a2));
+            const W x1 = (W)((sub & 1) ? __high2float(b2) : __low2float(b2));
+            p = add_rn(p, mul_rn(x0, x0));
+            p = add_rn(p, mul_rn(x1, x1));
+        }
+    }
+    *t = i;
+    return p;
+}
+
 // Norms only (pmm_dev_norms): same reduction, no planes written.
 template <typename SRC, typename W>
 __global__ void __launch_bounds__(256) norms_kernel(PrepArgs a) {
@@ -224,6 +255,8 @@ __global__ void __launch_bounds__(256) norms_kernel(PrepArgs a) {
     const int64_t d8 = dim & ~(int64_t)7;
     W p = (W)0;
     int64_t t = 0;
+    if (sizeof(SRC) == 2 && !a.offsets && !a.validity && (dim & 1) == 0)
+        p = norms_f16_pairs<W>(a.values, base, len > 0, d8, &t, sub, lane & 24, gmask, p);
     for (; t + 64 <= d8; t += 64) {  // 8 sectors in flight per row
         W x[8];
 #pragma unroll

@@ -589,6 +589,17 @@ def test_device_norms_bit_exact(native, oracle):
                              stream=torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             assert np.array_equal(out.cpu().numpy(), oracle.norms(x, squared=squared))
+    # f16 storage (working type f32): even dims take the paired-load path (whole 64-element steps, then the scalar tail),
+    # an odd dim the element-wise one; both must reproduce ndarray's summation order on the upcast values
+    for dim in (64, 200, 1024, 203):
+        h = _randn(rng, 515, dim).astype(np.float16)
+        dh = torch.from_numpy(h).cuda()
+        out = torch.empty(515, dtype=torch.float32, device="cuda")
+        for squared in (False, True):
+            native.dev_norms(native.dev_matrix(dh.data_ptr(), 515, dim, 0), squared, out.data_ptr(),
+                             stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), oracle.norms(h.astype(np.float32), squared=squared)), dim
 
 
 def test_full_size_c3_properties(native, oracle):
