@@ -206,8 +206,8 @@ __device__ __forceinline__ float filter_value(float acc, float aux, float rowc) 
 // One 32-column chunk of the accumulator tile for this thread's row.
 // Common case: no score of the chunk beats any row's threshold. It costs the filter values, a max tree
 // (one FMNMX per score; fmaxf drops NaN, and NaN can only matter while a list is not full, when thr_f is NaN
-// and every test below is true) and ONE warp vote. Otherwise the warp descends group by group (8 scores),
-// again behind a vote, and only then tests single scores.
+// and every test below is true) and ONE warp vote. Otherwise every lane collects the bit mask of its own hits and
+// the lanes append their hits side by side (see below).
 template <int METRIC, int R>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t aux_s /* shared address: 32 floats */,
                                              uint32_t look_s /* shared address: the warp's 32 x LOOK_PITCH floats */, float rowc,
