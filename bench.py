@@ -344,6 +344,7 @@ def main():
                     "frac": (achieved / peak) if achieved else None,
                     "traffic": tr["dram_bytes_per_launch"] if tr else None,
                     "traffic_note": tr["source"] if tr else "no ncu capture committed for this workload",
+                    "ncu_tensor_pipe_active_pct": tr.get("tensor_pipe_active_pct_of_elapsed") if tr else None,
                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms,
                     "kernel_share_of_step": (k_avg_ms / ms_step) if ms_step else None,
                     "peak_note": f"{peak_src}: bf16_tflops_sustained / {rate_div:g} ("
