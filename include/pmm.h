@@ -150,6 +150,9 @@ PMM_API int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *cor
  *                       (ordered score key << 32) | ~index ; larger = better under the total order
  *                       (score best-first, lower index first), so shards merge by plain u64 max.
  *                       f32 working precision only.
+ * Path: k_eff <= 248 runs the fused tcgen05 filter (operands rounded to f16 / TF32 planes) + exact re-scoring in the
+ * working precision (f32 or f64; sequential FMA like the reference) + a per-query losslessness proof; larger k takes
+ * the SIMT score-slab path.  Either way scores and indices equal the reference arithmetic's.
  */
 PMM_API int pmm_dev_topk(const pmm_matrix_t *d_queries, const pmm_matrix_t *d_corpus, int64_t k, int32_t metric,
                  int64_t index_base, uint32_t *d_index, double *d_score, uint64_t *d_candidates,
@@ -163,7 +166,7 @@ PMM_API int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corp
 
 /* K-way merge of `n_lists` candidate lists laid out [n_lists][n_queries][k_in] (each sorted best
  * first, as pmm_dev_topk writes them; e.g. the all-gathered shards) into the final
- * [n_queries * k_out] index/score buffers.  k_out <= k_in <= 128. */
+ * [n_queries * k_out] index/score buffers.  k_out <= k_in <= 256. */
 PMM_API int pmm_dev_merge_candidates(const uint64_t *d_lists, int64_t n_lists, int64_t n_queries, int64_t k_in,
                              int64_t k_out, int32_t metric, uint32_t *d_index, double *d_score,
                              void *stream);
@@ -174,6 +177,22 @@ PMM_API int pmm_dev_matmul(const pmm_matrix_t *d_left, const pmm_matrix_t *d_rig
 /* Row norms (squared != 0: squared norms) in the storage-derived working dtype (f16 -> f32),
  * compute_norms_* / compute_squared_norms_*, src/metrics.rs:367-393. d_out [n_rows]. */
 PMM_API int pmm_dev_norms(const pmm_matrix_t *d_x, int32_t squared, void *d_out, void *stream);
+
+/* ------------------------------------------------------------------ diagnostics of the tensor-core filter
+ * The top-k path selects candidates with a reduced-precision tensor-core FILTER and proves per query that nothing
+ * relevant was dropped; that proof rests on an error bound.  These two entry points let a test measure the filter's
+ * real error against the very bound the proof uses (tests/test_gpu_bound.py).
+ *   level 0: the default first level (operands rounded to f16, kind::f16; exact planes when both inputs are f16),
+ *         1: one TF32 MMA per K-step, 3: the 3xTF32 split.
+ * pmm_dev_filter_candidates: d_kept [Q * kp] packed candidates whose key is the FILTER value (a float in "filter
+ * units": dot q.c; cosine q.c/|c|; euclidean -|q-c|^2), sorted best first; kp in {32,64,128,256}; device pointers.
+ * pmm_filter_error_bound: the bound E on |filter value - exact value| in the same units for a query of norm q_norm
+ * against a corpus whose row norms lie in [c_norm_min, c_norm_max]; *max_norm (may be NULL) receives the operand
+ * norm above which the level's proof refuses to trust the filter at all (0 = no limit). */
+PMM_API int pmm_dev_filter_candidates(const pmm_matrix_t *d_queries, const pmm_matrix_t *d_corpus, int32_t metric, int32_t level,
+                                      int32_t kp, int64_t index_base, uint64_t *d_kept, void *stream);
+PMM_API int pmm_filter_error_bound(int32_t level, int32_t q_dtype, int32_t c_dtype, int64_t dim, int32_t metric, float q_norm,
+                                   float c_norm_max, float c_norm_min, float *bound, float *max_norm);
 
 /* ------------------------------------------------------------------ runtime */
 PMM_API const char *pmm_last_error(void);     /* thread-local, never NULL */
@@ -193,15 +212,20 @@ PMM_API int pmm_host_free(void *p);
 PMM_API int64_t pmm_kernel_launch_count(void);
 PMM_API void pmm_reset_kernel_launch_count(void);
 
-/* Tuning / diagnostics. Known keys:
- *   "force_generic" (0/1)      route f32 top-k through the exact SIMT scores+select path
+/* Tuning / diagnostics.  pmm_set_option changes the process-wide DEFAULTS; pmm_set_thread_option overrides a key for
+ * the calling thread only (key == NULL drops the thread's overrides).  Every compute call takes one consistent snapshot
+ * (defaults + the calling thread's overrides) when it starts, so options never change under a running call and
+ * concurrent callers may use different settings.  Known keys:
+ *   "force_generic" (0/1)      route top-k through the exact SIMT scores+select path (a Q x N slab in chunks)
  *   "profile" (0/1)            bracket kernels with CUDA events on the launching stream and accumulate per-kernel
  *                              milliseconds, read back with pmm_get_stat("<kernel>_ms")
  *   "verify" (0/1, default 1)  per-query losslessness proof of the tensor-core filter and its fallbacks
- *   "tc_levels" (1|2|3)        3 (default): first level on f32 operands rounded to f16 (kind::f16), 3xTF32 on demand;
+ *   "tc_levels" (1|2|3)        3 (default): first level on operands rounded to f16 (kind::f16), 3xTF32 on demand;
  *                              2: TF32 x1 first level; 1: 3xTF32 only
- *   "f16r_wide" (0/1, default 1)  queries the f16-rounded first level cannot prove are first re-run with 256-entry
- *                              lists against the same planes, then with 3xTF32
+ *   "f16r_wide" (0/1, default 1)  queries the f16-rounded first level cannot prove are first re-run against the same
+ *                              planes with 256-entry lists, then with 3xTF32
+ *   "seed_retry" (0/1, default 1) re-query levels start from thresholds seeded by the exact k-th scores at hand
+ *   "f64_tc" (0/1, default 1)  f64 top-k: tensor-core filter + exact f64 re-scoring; 0: DMMA score slab + select
  *   "tc_cg" (1|2)              tcgen05 cta_group of the fused kernels (default 2)
  *   "tc_group"                 CTA groups sharing a query tile (0 = auto)
  *   "tc_sync_tiles"            corpus tiles between the producers' pacing barriers (default 32, 0 = off)
@@ -209,21 +233,30 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *   "tc_max_flush"             list merges per epilogue warp and tile once thresholds settled (0 = auto)
  *   "tc_soft_at"               staged candidates of a row that trigger its end-of-tile merge (0 = 48)
  *   "tc_clm", "tc_cluster4", "tc_max_units"   experimental cluster shapes, see profiles/sweep_r1.md (default off)
- *   "tc_debug_skip"            measurement only, RESULTS ARE WRONG when set to 1..3: 1/2 epilogue without filter,
- *                              3 filter without merges; 8: correct results + wait-cycle counters readable as
- *                              pmm_get_stat("tc_dbg_wait0".."tc_dbg_wait51")
+ *   "tc_debug_skip"            8: correct results + wait-cycle counters readable as pmm_get_stat("tc_dbg_wait<i>"), i = 0..51.
+ *                              1..3 (kernel timing experiments that return WRONG results) exist only in builds made
+ *                              with -DPMM_DIAG; the default build answers PMM_ERR_UNSUPPORTED
  *   "host_chunked" (0/1)       overlapped chunked corpus upload of the host entry points (default 1)
  *   "host_chunk_first_div", "host_chunk_ratio_pct"   first chunk = N / div (default 32); growth ratio in % (0 = auto)
  *   "host_chunk_min_rows", "host_chunk_min_mb"       smallest chunk (default 16384 rows) and smallest corpus (default
  *                              64 MB) of the chunked upload; tests lower both to drive tiny corpora through it
- *   "release_workspace"        return the calling thread's parked device blocks (>= 32 MB, kept between calls for
- *                              reuse) to the CUDA memory pool
- *   "f64_simt" (0/1)           f64 scores on FP64 FMA instead of DMMA
+ *   "f64_simt" (0/1)           f64 contraction (raw matmul, slab path) on FP64 FMA instead of DMMA
  *   "generic_workspace_mb"     score slab of the SIMT path
+ *   "multi_gpu" (0/1, default 1), "multi_gpu_min_gflop" (default 4000)   pmm_topk / pmm_matmul spread one call over all
+ *                              visible GPUs when the call has at least that many GFLOP of contraction work
+ * Acting immediately, process-wide (not part of the snapshot):
+ *   "stage" (0/1, default 1)   pageable host buffers go through the library's page-locked staging ring (pmm_stage.h);
+ *                              0: plain cudaMemcpyAsync, staged by the driver
+ *   "stage_threads"            host threads per staged copy (0 = auto: half the cores, at most 8)
+ *   "stage_slot_mb", "stage_slots"   ring geometry (default 4 slots of 32 MB per calling thread)
+ *   "workspace_cache_mb"       device blocks (>= 32 MB) a thread keeps parked between calls for reuse (default 24576)
+ *   "release_workspace"        return the calling thread's parked device blocks and its staging ring
  * Unknown keys return PMM_ERR_INVALID. */
 PMM_API int pmm_set_option(const char *key, int64_t value);
+PMM_API int pmm_set_thread_option(const char *key, int64_t value);
 /* Accumulated statistics since the last pmm_reset_stats(): "<kernel>_ms", "<kernel>_launches",
- * "h2d_bytes", "d2h_bytes". Unknown name -> 0. */
+ * "h2d_bytes", "d2h_bytes", "staged_h2d_bytes", "staged_d2h_bytes" (the part that went through the staging ring),
+ * "requeried_f16_wide", "requeried_tf32x3", "fallback_queries". Unknown name -> 0. */
 PMM_API double pmm_get_stat(const char *name);
 PMM_API void pmm_reset_stats(void);
 

@@ -86,6 +86,10 @@ def lib() -> ctypes.CDLL:
         "pmm_kernel_launch_count": (i64, []),
         "pmm_reset_kernel_launch_count": (None, []),
         "pmm_set_option": (ctypes.c_int, [ctypes.c_char_p, i64]),
+        "pmm_set_thread_option": (ctypes.c_int, [ctypes.c_char_p, i64]),
+        "pmm_dev_filter_candidates": (ctypes.c_int, [P, P, i32, i32, i32, i64, vp, vp]),
+        "pmm_filter_error_bound": (ctypes.c_int, [i32, i32, i32, i64, i32, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "pmm_get_stat": (ctypes.c_double, [ctypes.c_char_p]),
         "pmm_reset_stats": (None, []),
         "pmm_host_alloc": (ctypes.c_int, [i64, ctypes.POINTER(vp)]),
@@ -104,7 +108,8 @@ EXPORTED_SYMBOLS = [
     "pmm_corpus_create", "pmm_corpus_destroy", "pmm_corpus_rows", "pmm_topk_corpus", "pmm_dev_topk", "pmm_topk_shard",
     "pmm_dev_merge_candidates", "pmm_dev_matmul", "pmm_dev_norms", "pmm_last_error", "pmm_version",
     "pmm_device_count", "pmm_set_device", "pmm_kernel_launch_count", "pmm_reset_kernel_launch_count",
-    "pmm_set_option", "pmm_get_stat", "pmm_reset_stats", "pmm_host_alloc", "pmm_host_free",
+    "pmm_set_option", "pmm_set_thread_option", "pmm_get_stat", "pmm_reset_stats", "pmm_host_alloc", "pmm_host_free",
+    "pmm_dev_filter_candidates", "pmm_filter_error_bound",
 ]
 
 
@@ -174,7 +179,7 @@ class _PinnedPool:
 
     def __init__(self):
         import threading
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()   # give() runs from __del__, possibly during a GC triggered under the lock
         self._free = {}      # capacity -> [ptr]
         self._free_bytes = 0
 
@@ -186,7 +191,10 @@ class _PinnedPool:
                 self._free_bytes -= cap
                 return lst.pop(), cap
         p = ctypes.c_void_p(None)
-        check(lib().pmm_host_alloc(cap, ctypes.byref(p)))
+        if lib().pmm_host_alloc(cap, ctypes.byref(p)) != PMM_OK:
+            # page-locked memory exhausted: give back what the pool holds and let the caller use pageable memory
+            self.clear()
+            return None, cap
         return p.value, cap
 
     def give(self, ptr: int, cap: int) -> None:
@@ -215,6 +223,8 @@ def result_empty(shape, dtype) -> np.ndarray:
     if nbytes < _PinnedPool.MIN_BYTES or nbytes > _PinnedPool.MAX_BYTES:
         return np.empty(shape, dtype)
     ptr, cap = _pinned_pool.take(nbytes)
+    if ptr is None:
+        return np.empty(shape, dtype)
     return np.asarray(_PinnedBlock(ptr, cap, nbytes)).view(dtype).reshape(shape)
 
 
@@ -314,6 +324,27 @@ def dev_norms(dx: PmmMatrix, squared: bool, out_ptr: int, stream: int = 0) -> No
 
 def set_option(key: str, value: int) -> None:
     check(lib().pmm_set_option(key.encode(), int(value)))
+
+
+def set_thread_option(key, value: int = 0) -> None:
+    """Per-thread override of an option (key=None drops the calling thread's overrides)."""
+    check(lib().pmm_set_thread_option(None if key is None else key.encode(), int(value)))
+
+
+def dev_filter_candidates(dq: PmmMatrix, dc: PmmMatrix, metric: int, level: int, kp: int, kept_ptr: int,
+                          index_base: int = 0, stream: int = 0) -> None:
+    """Diagnostics: the raw output of one tensor-core filter level (packed candidates keyed by FILTER value)."""
+    check(lib().pmm_dev_filter_candidates(ctypes.byref(dq), ctypes.byref(dc), metric, level, kp, index_base, kept_ptr,
+                                          stream or None))
+
+
+def filter_error_bound(level: int, q_dtype: int, c_dtype: int, dim: int, metric: int, q_norm: float, c_norm_max: float,
+                       c_norm_min: float):
+    """(E, max_norm): the bound the losslessness proof uses for |filter value - exact value| (filter units)."""
+    e, mx = ctypes.c_float(0), ctypes.c_float(0)
+    check(lib().pmm_filter_error_bound(level, q_dtype, c_dtype, dim, metric, q_norm, c_norm_max, c_norm_min,
+                                       ctypes.byref(e), ctypes.byref(mx)))
+    return e.value, mx.value
 
 
 def get_stat(name: str) -> float:

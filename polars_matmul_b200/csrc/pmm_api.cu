@@ -16,6 +16,7 @@
 
 #include "../../include/pmm.h"
 #include "pmm_kernels.h"
+#include "pmm_stage.h"
 
 using namespace pmm;
 
@@ -42,8 +43,63 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ options / stats
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_profile{0}, g_tc_group{0}, g_tc_cg{2}, g_tc_sync_tiles{32}, g_host_chunked{1}, g_f64_simt{0}, g_verify{1}, g_tc_levels{3}, g_tc_clm{1}, g_tc_cluster4{0}, g_tc_max_units{0}, g_tc_debug_skip{0}, g_tc_sync_slack{0}, g_tc_max_flush{0}, g_host_chunk_ratio_pct{0}, g_host_chunk_first_div{0}, g_f16r_wide{1}, g_host_chunk_min_rows{16384}, g_host_chunk_min_mb{64}, g_tc_soft_at{0};
-std::atomic<int64_t> g_generic_ws_mb{1024};
+
+// Tuning / diagnostic options (include/pmm.h).  pmm_set_option changes the process-wide defaults; every compute
+// entry point takes ONE consistent snapshot of them when it starts (plus the calling thread's own overrides,
+// pmm_set_thread_option), so a call never sees an option change half way through and concurrent callers
+// (src/lib.rs:25,45 releases the GIL: the reference is re-entrant) can run with different settings.
+struct Options {
+    int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
+        tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
+        host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1;
+    int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000;
+};
+Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
+std::mutex g_opt_mu;
+thread_local Options t_opt;    // the snapshot the current call runs with
+thread_local std::vector<std::pair<std::string, int64_t>> t_overrides;
+
+// Returns false for an unknown key.
+bool apply_option(Options &o, const std::string &k, int64_t value) {
+    if (k == "force_generic") o.force_generic = (int)value;
+    else if (k == "profile") o.profile = (int)value;
+    else if (k == "tc_group") o.tc_group = value < 0 ? 0 : (int)value;  // 0 = automatic
+    else if (k == "tc_cg") o.tc_cg = value == 2 ? 2 : 1;
+    else if (k == "tc_max_units") o.tc_max_units = (int)value;
+    else if (k == "tc_cluster4") o.tc_cluster4 = value ? 1 : 0;
+    else if (k == "tc_sync_slack") o.tc_sync_slack = value < 0 ? 0 : (int)value;
+    else if (k == "host_chunk_min_rows") o.host_chunk_min_rows = (int)value;   // smallest chunk (rows, multiple of 256; default 16384)
+    else if (k == "host_chunk_min_mb") o.host_chunk_min_mb = (int)value;       // corpora below this many MB are uploaded in one piece (default 64)
+    else if (k == "host_chunk_ratio_pct") o.host_chunk_ratio_pct = (int)value; // 0 = auto
+    else if (k == "host_chunk_first_div") o.host_chunk_first_div = (int)value; // first chunk = N / this (0 = 32)
+    else if (k == "f16r_wide") o.f16r_wide = value ? 1 : 0;                     // retry of the f16-rounded level before 3xTF32
+    else if (k == "seed_retry") o.seed_retry = value ? 1 : 0;                   // that retry starts from thresholds seeded by the exact k-th scores
+    else if (k == "tc_soft_at") o.tc_soft_at = value < 0 ? 0 : value > 88 ? 88 : (int)value;  // staged candidates that trigger an end-of-tile merge (0 = 48)
+    else if (k == "tc_max_flush") o.tc_max_flush = value < 0 ? 0 : (int)value;
+    else if (k == "tc_debug_skip") o.tc_debug_skip = (int)value;               // 1..3 need a -DPMM_DIAG build (checked by pmm_set_option)
+    else if (k == "tc_clm") o.tc_clm = value == 2 ? 2 : 1;                      // 2: clusters of two CTA pairs, corpus tile multicast
+    else if (k == "tc_levels") o.tc_levels = value >= 3 ? 3 : value == 2 ? 2 : 1;  // 3: f16-rounded first level, 2: TF32 x1, 1: 3xTF32 only
+    else if (k == "verify") o.verify = value ? 1 : 0;                           // 0: skip the filter-losslessness check (and its fallback)
+    else if (k == "f64_simt") o.f64_simt = value ? 1 : 0;                       // 1: bit-exact sequential-FMA f64 contraction instead of DMMA
+    else if (k == "f64_tc") o.f64_tc = value ? 1 : 0;                           // f64 top-k: tensor-core filter + exact f64 re-scoring (default) or the slab path
+    else if (k == "host_chunked") o.host_chunked = value ? 1 : 0;
+    else if (k == "tc_sync_tiles") o.tc_sync_tiles = value < 0 ? 0 : (int)value;  // 0 = no pacing barriers
+    else if (k == "generic_workspace_mb") o.generic_ws_mb = value < 1 ? 1 : value;
+    else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
+    else if (k == "multi_gpu_min_gflop") o.multi_gpu_min_gflop = value < 0 ? 0 : value;
+    else return false;
+    return true;
+}
+
+// Every compute entry point starts with this: one consistent option snapshot for the whole call.
+void begin_call() {
+    {
+        std::lock_guard<std::mutex> lk(g_opt_mu);
+        t_opt = g_opt;
+    }
+    for (const auto &kv : t_overrides) apply_option(t_opt, kv.first, kv.second);
+}
 
 std::mutex g_stat_mu;
 std::map<std::string, double> g_stats;
@@ -74,7 +130,7 @@ void resolve_pending_locked() {
 template <typename F>
 cudaError_t launch_counted(const char *name, cudaStream_t s, F &&f) {
     g_launches.fetch_add(1);
-    if (!g_profile.load()) return f();
+    if (!t_opt.profile) return f();
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -102,14 +158,53 @@ DevInfo &dev_info() {
         cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev);
         d.tc = tc_supported();
         d.init = true;
-        // keep freed stream-ordered allocations in the pool instead of returning them to the OS
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
     }
     return d;
+}
+
+// The library's own stream-ordered memory pool per device (freed blocks stay in it instead of going back to the OS).
+// A private pool: the device's default pool, which other libraries in the process (torch, cuDF) may use, is left
+// untouched.  NULL when the pool cannot be created: allocations then come from the default pool.
+cudaMemPool_t device_pool() {
+    static std::mutex mu;
+    static cudaMemPool_t pools[16] = {nullptr};
+    static bool tried[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    const int i = dev & 15;
+    if (!tried[i]) {
+        tried[i] = true;
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[i], &props) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pools[i], cudaMemPoolAttrReleaseThreshold, &thr);
+        } else {
+            cudaGetLastError();
+            pools[i] = nullptr;
+        }
+    }
+    return pools[i];
+}
+
+cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t s) {
+    cudaMemPool_t pool = device_pool();
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, s) : cudaMallocAsync(p, bytes, s);
+}
+
+// One host call at a time per device: every call saturates the GPU anyway, and the fused kernel is a persistent grid
+// whose pacing barriers assume its CTAs are co-resident.  Concurrent callers (the reference releases the GIL and is
+// re-entrant, tests/test_polars_matmul.py:551-572) are therefore serialised here, per device, not rejected.
+std::mutex &device_mutex() {
+    static std::mutex mus[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return mus[dev & 15];
 }
 
 int ensure_device() {
@@ -129,6 +224,9 @@ int ensure_device() {
 // bytes but not as one range and re-maps physical memory to serve the request, which showed up as 0.3-1.5 s stalls
 // in 1 of 5 end-to-end calls.  Reuse on the SAME stream keeps stream order (like cudaFreeAsync + cudaMallocAsync).
 // pmm_set_option("release_workspace", 1) returns the parked blocks to the pool.
+std::atomic<int64_t> g_block_cache_cap_mb{24576};  // option "workspace_cache_mb": parked bytes per thread
+std::atomic<int64_t> g_stage_slot_mb{32};
+std::atomic<int> g_stage_slots{4};
 struct BlockCache {
     struct Entry {
         void *p;
@@ -138,7 +236,7 @@ struct BlockCache {
     };
     std::vector<Entry> free_blocks;
     size_t bytes = 0;
-    static constexpr size_t kMinBlock = (size_t)32 << 20, kMaxBytes = (size_t)48 << 30;
+    static constexpr size_t kMinBlock = (size_t)32 << 20;
     void *take(size_t want, cudaStream_t s, int dev, size_t *cap) {
         int best = -1;
         for (int i = 0; i < (int)free_blocks.size(); ++i) {
@@ -155,7 +253,7 @@ struct BlockCache {
         return p;
     }
     bool park(void *p, size_t cap, cudaStream_t s, int dev) {
-        if (cap < kMinBlock || bytes + cap > kMaxBytes) return false;
+        if (cap < kMinBlock || bytes + cap > ((size_t)g_block_cache_cap_mb.load() << 20)) return false;
         free_blocks.push_back(Entry{p, cap, s, dev});
         bytes += cap;
         return true;
@@ -191,11 +289,11 @@ struct DevBuf {
             bytes = (bytes + BlockCache::kMinBlock - 1) / BlockCache::kMinBlock * BlockCache::kMinBlock;
             if ((p = g_block_cache.take(bytes, stream, dev, &cap))) return cudaSuccess;
         }
-        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        cudaError_t e = pool_alloc(&p, bytes, stream);
         if (e != cudaSuccess && g_block_cache.bytes) {  // out of memory with blocks parked: give them back and retry
             cudaGetLastError();
             g_block_cache.clear();
-            e = cudaMallocAsync(&p, bytes, stream);
+            e = pool_alloc(&p, bytes, stream);
         }
         cap = e == cudaSuccess ? bytes : 0;
         if (e != cudaSuccess) p = nullptr;
@@ -225,10 +323,14 @@ int esize(int dtype) { return dtype == PMM_DTYPE_F16 ? 2 : dtype == PMM_DTYPE_F3
 // ------------------------------------------------------------------------------------------------ prepared operands
 struct Prepared {
     int mode = PREP_DENSE;   // PREP_*
-    bool f64 = false;
+    bool f64 = false;        // working precision of norm / sqnorm (and of the DENSE copy)
     int64_t n_rows = 0, dim = 0, rows_pad = 0, ld = 0;
-    DevBuf p0, p1, norm, sqnorm, max_sq;
+    DevBuf p0, p1, norm, sqnorm, norm32, sqnorm32, max_sq;
     unsigned int *max_sq_ptr = nullptr;  // own (max_sq) or shared across corpus chunks
+    // f32 views of the norms for the tensor-core filter and its proof: the working-type buffers themselves for f32
+    // working precision, rounded copies written by the same prep pass for f64
+    const float *norm_f32() const { return f64 ? norm32.as<float>() : norm.as<float>(); }
+    const float *sq_f32() const { return f64 ? sqnorm32.as<float>() : sqnorm.as<float>(); }
 };
 
 // Norm range of a column, filled by the prep kernel: [0] largest squared norm (atomicMax on the float bits),
@@ -268,6 +370,9 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     }
     if (want_norm) CUDA_TRY(out->norm.alloc((size_t)(out->rows_pad * wsz), s));
     if (want_sq) CUDA_TRY(out->sqnorm.alloc((size_t)(out->rows_pad * wsz), s));
+    const bool want32 = f64 && mode != PREP_DENSE;
+    if (want32 && want_norm) CUDA_TRY(out->norm32.alloc((size_t)(out->rows_pad * 4), s));
+    if (want32 && want_sq) CUDA_TRY(out->sqnorm32.alloc((size_t)(out->rows_pad * 4), s));
     out->max_sq_ptr = shared_max;
     if (want_max && !shared_max) {
         CUDA_TRY(out->max_sq.alloc(2 * sizeof(unsigned int), s));
@@ -287,6 +392,9 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     a.out1 = out->p1.p;
     a.norm_out = out->norm.p;
     a.sqnorm_out = out->sqnorm.p;
+    a.norm32_out = want32 ? out->norm32.as<float>() : nullptr;
+    a.sqnorm32_out = want32 ? out->sqnorm32.as<float>() : nullptr;
+    a.zero_guard_sq = f64 ? 1e-20f : 1e-12f;   // square of the cosine zero-norm guard (1e-10 f64 / 1e-6 f32)
     a.max_sq_out = out->max_sq_ptr;
     a.error_flag = d_err;
     CUDA_TRY(launch_counted("prep", s, [&] { return launch_prep(a, m.dtype, mode, f64 ? 1 : 0, s); }));
@@ -336,7 +444,7 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
     if (f64 && o.cand) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
     const int64_t Q = q.n_rows, N = c.n_rows, D = q.dim;
     const int64_t wsz = f64 ? 8 : 4;
-    int64_t chunk = (g_generic_ws_mb.load() << 20) / (N * wsz);
+    int64_t chunk = (t_opt.generic_ws_mb << 20) / (N * wsz);
     chunk = chunk / 64 * 64;
     if (chunk < 64) chunk = 64;
     if (chunk > 1 << 20) chunk = 1 << 20;
@@ -354,7 +462,7 @@ int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric,
         double *os = o.score ? o.score + q0 * keff : nullptr;
         uint64_t *oc = o.cand ? o.cand + q0 * keff : nullptr;
         if (f64) {
-            const bool simt = g_f64_simt.load() != 0;
+            const bool simt = t_opt.f64_simt != 0;
             CUDA_TRY(launch_counted(simt ? "scores_f64" : "scores_f64_dmma", s, [&] {
                 return (simt ? launch_scores_f64 : launch_scores_f64_dmma)(
                     q.p0.as<double>() + q0 * D, c.p0.as<double>(), qa ? (const double *)qa + q0 : nullptr, (const double *)ca, nq,
@@ -394,7 +502,7 @@ RawMatrix raw_of(const pmm_matrix_t &m) {
 // pacing barriers on, profiles/sweep_r1.md): the smallest g in {1,2,4} that keeps the in-flight query
 // planes under 64 MB, as long as every sharer still sweeps >= 64 corpus tiles.
 int tc_group_for(int64_t corpus_rows, int64_t dim_pad, bool f16, int units, int cg) {
-    int g = g_tc_group.load();
+    int g = t_opt.tc_group;
     if (g > 0) return g;
     const int64_t n_tiles = (corpus_rows + TC_TILE_N - 1) / TC_TILE_N;
     const int64_t tile_bytes = (int64_t)TC_TILE_M * cg * dim_pad * (f16 ? 2 : 8);  // hi+lo planes for f32
@@ -404,7 +512,8 @@ int tc_group_for(int64_t corpus_rows, int64_t dim_pad, bool f16, int units, int 
 }
 
 // List capacity of the tensor-core filter: at least 8 more candidates than requested are kept, so the
-// exact re-scoring can reorder near-ties across the k-th position.
+// exact re-scoring can reorder near-ties across the k-th position.  k <= 248.
+constexpr int64_t TC_MAX_K = 248;
 int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : keff <= 120 ? 128 : 256; }
 
 // Tensor-core filter on prepared PLANES: fused kernel -> merge of the corpus pieces of every query tile.
@@ -415,14 +524,21 @@ int tc_list_capacity(int64_t keff) { return keff <= 24 ? 32 : keff <= 56 ? 64 : 
 // chunks never have to be merged.  All launches of one carry use the schedule group of the WHOLE corpus
 // (`corpus_rows_total`), which fixes the list layout.  phase bit 0: first launch (fresh lists), bit 1: last launch
 // (merge the pieces of every query tile into `kept`).
+// seed: per query row (padded like the planes) an initial threshold in filter units, or NULL (see make_seeds_kernel).
 struct TcCarry {
     DevBuf partial;
     int64_t corpus_rows_total = 0;
     int64_t layout_rows = 0;  // rows of the smallest chunk (caps the sharing factors of every launch alike)
 };
 
+const char *tc_kernel_stat_name(const Prepared &q, int terms, int kp, bool seeded) {
+    if (q.mode == PREP_F16R) return seeded ? "tc_topk_f16r_seeded" : kp == 256 ? "tc_topk_f16r_kp256" : "tc_topk_f16r";
+    if (q.mode == PREP_F16) return "tc_topk_f16";
+    return terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3";
+}
+
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
-              cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3) {
+              cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3, const float *seed = nullptr) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -437,21 +553,26 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.n = c.n_rows;
     a.f16 = (q.mode == PREP_F16 || q.mode == PREP_F16R) ? 1 : 0;
     a.terms = a.f16 ? 1 : terms;
-    a.cg = (a.terms == 1 && !a.f16) ? 2 : g_tc_cg.load();
-    a.clm = (a.cg == 2 && g_tc_clm.load() == 2) ? 2 : 1;
-    a.cluster4 = g_tc_cluster4.load();
-    a.debug_skip = g_tc_debug_skip.load();
-    a.sync_slack = g_tc_sync_slack.load();
-    a.max_flush = g_tc_max_flush.load();
-    a.soft_at = g_tc_soft_at.load();
+    a.cg = (a.terms == 1 && !a.f16) ? 2 : t_opt.tc_cg;
+    a.clm = (a.cg == 2 && t_opt.tc_clm == 2) ? 2 : 1;
+    a.cluster4 = t_opt.tc_cluster4;
+    a.debug_skip = t_opt.tc_debug_skip;
+    a.sync_slack = t_opt.tc_sync_slack;
+    a.max_flush = t_opt.tc_max_flush;
+    a.soft_at = t_opt.tc_soft_at;
     const int gs = a.cg * a.clm;   // CTAs per scheduling unit
     int units = di.num_sms / gs;
-    if (g_tc_max_units.load() > 0 && units > g_tc_max_units.load()) units = g_tc_max_units.load();
+    if (t_opt.tc_max_units > 0 && units > t_opt.tc_max_units) units = t_opt.tc_max_units;
     const int64_t group_rows = carry ? carry->corpus_rows_total : c.n_rows;
     a.sched = make_tc_schedule(q.n_rows, c.n_rows, units, tc_group_for(group_rows, q.ld, a.f16 != 0 || a.terms == 1, units, gs), gs,
                                carry ? carry->layout_rows : 0);
-    a.q_aux = metric == PMM_METRIC_COSINE ? q.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.as<float>() : nullptr;
-    a.c_aux = metric == PMM_METRIC_COSINE ? c.norm.as<float>() : metric == PMM_METRIC_EUCLIDEAN ? c.sqnorm.as<float>() : nullptr;
+    // the filter runs on f32 copies of the norms (f64 working precision keeps the exact ones for the re-scoring)
+    a.q_aux = metric == PMM_METRIC_COSINE ? q.norm_f32() : metric == PMM_METRIC_EUCLIDEAN ? q.sq_f32() : nullptr;
+    a.c_aux = metric == PMM_METRIC_COSINE ? c.norm_f32() : metric == PMM_METRIC_EUCLIDEAN ? c.sq_f32() : nullptr;
+    // f64: the reference's guard is 1e-10 (src/metrics.rs:275); a shade lower on the rounded norm, so that a row the
+    // exact pass treats as non-zero is never zeroed by the filter (the other way round only costs a list slot)
+    a.norm_guard = q.f64 ? 0.999999e-10f : 0.0f;
+    a.seed_thr = seed;
     a.index_base = index_base;
     a.metric = metric;
     a.kp = kp;
@@ -463,17 +584,16 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.resume = (carry && !(phase & 1)) ? 1 : 0;
     CUDA_TRY(staged.alloc((size_t)tc_staged_bytes(a.sched.num_ctas * gs, esets), s));
     a.staged = staged.as<uint64_t>();
-    if (g_tc_sync_tiles.load() > 0) {
-        a.sync_tiles = g_tc_sync_tiles.load();
+    if (t_opt.tc_sync_tiles > 0) {
+        a.sync_tiles = t_opt.tc_sync_tiles;
         const size_t nb = (size_t)tc_sync_counters(a.sched, a.sync_tiles) * sizeof(unsigned int);
         CUDA_TRY(rsync.alloc(nb, s));
         CUDA_TRY(cudaMemsetAsync(rsync.p, 0, nb, s));
         a.round_sync = rsync.as<unsigned int>();
     }
     a.partial = partial.as<uint64_t>();
-    // (256-entry lists: the retry level of the f16-rounded filter, or k > 120 - a kernel variant and a statistic of its own)
-    cudaError_t e = launch_counted(q.mode == PREP_F16R ? (kp == 256 ? "tc_topk_f16r_kp256" : "tc_topk_f16r") : a.f16 ? "tc_topk_f16" : a.terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3", s,
-                                   [&] { return launch_tc_topk(a, s); });
+    // (256-entry lists and seeded launches are the retry levels: statistics of their own)
+    cudaError_t e = launch_counted(tc_kernel_stat_name(q, a.terms, kp, seed != nullptr), s, [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
     if (phase & 2)
@@ -483,29 +603,33 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     return PMM_OK;
 }
 
-int topk_generic(const Prepared &q, const Prepared &c, int64_t keff, int metric, int64_t index_base, TopkOut o,
-                 cudaStream_t s);
-
-// Relative error bound (per |q||c|) of the tensor-core filter value against the exact f32 score:
-//   operand rounding: TF32 has 11 significant bits, unit roundoff u = 2^-11 per operand (cvt.rna), so a TF32 x1
-//                     product is off by <= 2u + u^2 ~ 2^-10 and so is the sum (Cauchy-Schwarz);
-//                     3xTF32: each operand keeps a residue <= 2^-22 and the lo*lo term (<= 2^-22) is dropped:
-//                     <= 3 * 2^-22; f16 planes of f16 input are exact; f32 input rounded to f16 (PREP_F16R)
-//                     has the TF32 x1 bound (11 significant bits) plus an absolute subnormal term, see
-//                     f16r_abs_err();
-//   accumulation    : one f32 ulp of truncation per tcgen05 accumulate step (terms * D / 8 steps);
-//   the exact sum   : worst-case rounding of the sequential-FMA reference itself, D * 2^-24.
-// f32 -> f16 rounding below the normal range (|x| < 2^-14) is absolute, <= 2^-25 per element: <= sqrt(D) 2^-25 per row.
-float f16r_abs_err(int64_t dim) { return sqrtf((float)dim) * 2.98023224e-8f * 1.0001f; }
-
-float filter_eps(int64_t dim, int terms, bool f16) {
-    const float split = f16 ? 0.0f : terms == 1 ? 9.8e-4f : 7.5e-7f;
-    return split + (float)dim * (1.5e-8f * (float)terms + 6.0e-8f) + 1e-6f;
+// Error model of one filter level (formulas and their derivation: pmm_kernels.h).
+struct LevelErr {
+    float eps, abs_err, max_norm;
+};
+LevelErr level_err(int mode, int terms, bool f64_source, int64_t dim) {
+    if (mode == PREP_F16) return LevelErr{filter_eps(dim, 1, true), 0.0f, 0.0f};   // exact planes of f16 input
+    if (mode == PREP_F16R)                                                        // rounded to f16: 11 bits + range terms
+        return LevelErr{filter_eps(dim, 1, false) + (f64_source ? 2.0e-7f : 0.0f), f16r_abs_err(dim), 65504.0f};
+    // TF32 planes. From f64 sources the value is first rounded to f32 (2^-24 per operand) and may leave the f32 range.
+    return LevelErr{filter_eps(dim, terms, false) + (f64_source ? 1.3e-7f : 0.0f), f64_source ? f32_flush_abs_err(dim) : 0.0f,
+                    f64_source ? 1.0e38f : 0.0f};
 }
 
-int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
-                     const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
-                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s, int kp_override = 0);
+// What all levels of one top-k call share: the raw corpus on the device (the exact re-scoring gathers candidate rows
+// from it), the corpus norms in the working type (exact metric pass) and as f32 (proof), and the call's parameters.
+struct VerifyCtx {
+    pmm_matrix_t raw_c;
+    bool f64 = false;
+    const void *c_norm = nullptr, *c_sq = nullptr;   // working type, whole corpus
+    const unsigned int *c_range = nullptr;           // norm range from the prep pass (f32 bits)
+    int metric = 0;
+    int64_t index_base = 0, keff = 0;
+    cudaStream_t s = nullptr;
+};
+
+int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared *c, int terms,
+                     const uint64_t *kept_in, TopkOut o, int kp_override = 0, const float *seed = nullptr);
 
 // Rows [r0, r0 + rows) of a device-resident matrix as a matrix of its own. r0 must be a multiple of 256 (element
 // validity bitmaps are re-based by whole bytes).
@@ -522,44 +646,58 @@ pmm_matrix_t slice_rows(const pmm_matrix_t &m, int64_t r0, int64_t rows) {
     return dm;
 }
 
-// Exact re-scoring of the kept candidates + the losslessness check. Queries the check cannot clear are
-// gathered and recomputed one level up: after the TF32 x1 filter by the 3xTF32 filter (next_terms = 3),
-// after that (or for f16 planes) on the exact SIMT path (next_terms = 0). May synchronise the stream.
-int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, const float *q_sq,
-                       const float *q_norm, const Prepared *c_planes, const float *c_norm, const float *c_sq,
-                       const unsigned int *c_max_sq, float eps, float abs_err, float max_norm, int next_terms, int metric,
-                       int64_t index_base, int64_t keff, TopkOut o, cudaStream_t s) {
-    const int64_t Q = raw_q.n_rows;
-    const float *q_aux = metric == PMM_METRIC_COSINE ? q_norm : metric == PMM_METRIC_EUCLIDEAN ? q_sq : nullptr;
-    const float *c_aux = metric == PMM_METRIC_COSINE ? c_norm : metric == PMM_METRIC_EUCLIDEAN ? c_sq : nullptr;
-    DevBuf flags, count;
+// Exact re-scoring of the kept candidates + the losslessness check.  Queries the check cannot clear are gathered and
+// recomputed one level up: next_terms = 1: the same f16-rounded filter again, 256 candidates per query; 3: the 3xTF32
+// filter; 0: the exact SIMT path.  Re-query levels on the tensor cores start from SEEDED thresholds (option
+// "seed_retry"): the flagged query's exact k-th score among the candidates at hand bounds what can still matter.
+// May synchronise the stream.
+int rescore_and_verify(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const uint64_t *kept, int kp,
+                       const Prepared *c_planes, LevelErr le, int next_terms, const float *seed, TopkOut o) {
+    cudaStream_t s = vc.s;
+    const int metric = vc.metric;
+    const int64_t Q = raw_q.n_rows, keff = vc.keff;
+    const void *q_aux = metric == PMM_METRIC_COSINE ? q.norm.p : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.p : nullptr;
+    const void *c_aux = metric == PMM_METRIC_COSINE ? vc.c_norm : metric == PMM_METRIC_EUCLIDEAN ? vc.c_sq : nullptr;
+    DevBuf flags, count, kth;
     RescoreCheck chk;
     memset(&chk, 0, sizeof(chk));
-    const bool verify = g_verify.load() && q_sq && c_max_sq;
+    const float *q_sq32 = q.sq_f32();
+    const bool verify = t_opt.verify && q_sq32 && vc.c_range;
     if (verify) {
         CUDA_TRY(flags.alloc((size_t)Q, s));
         CUDA_TRY(count.alloc(sizeof(unsigned int), s));
+        CUDA_TRY(kth.alloc((size_t)Q * 4, s));
         CUDA_TRY(cudaMemsetAsync(flags.p, 0, (size_t)Q, s));
         CUDA_TRY(cudaMemsetAsync(count.p, 0, sizeof(unsigned int), s));
-        chk.q_sq = q_sq;
-        chk.c_max_sq = c_max_sq;
-        chk.eps = eps;
-        chk.abs_err = abs_err;
-        chk.max_norm = max_norm;
+        chk.q_sq = q_sq32;
+        chk.c_max_sq = vc.c_range;
+        chk.eps = le.eps;
+        chk.abs_err = le.abs_err;
+        chk.max_norm = le.max_norm;
+        chk.seed = seed;
         chk.flags = flags.as<unsigned char>();
         chk.flag_count = count.as<unsigned int>();
+        chk.kth_units = kth.as<float>();
     }
-    CUDA_TRY(launch_counted("rescore", s, [&] {
-        return launch_rescore(kept, kp, raw_of(raw_q), raw_of(raw_c), q_aux, c_aux, metric, index_base, (int)keff, o.index,
-                              o.score, o.cand, chk, s);
-    }));
+    if (vc.f64) {
+        if (o.cand) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
+        CUDA_TRY(launch_counted("rescore_f64", s, [&] {
+            return launch_rescore_f64(kept, kp, raw_of(raw_q), raw_of(vc.raw_c), (const double *)q_aux, (const double *)c_aux, metric,
+                                      vc.index_base, (int)keff, o.index, o.score, chk, s);
+        }));
+    } else {
+        CUDA_TRY(launch_counted("rescore", s, [&] {
+            return launch_rescore(kept, kp, raw_of(raw_q), raw_of(vc.raw_c), (const float *)q_aux, (const float *)c_aux, metric,
+                                  vc.index_base, (int)keff, o.index, o.score, o.cand, chk, s);
+        }));
+    }
     if (!verify) return PMM_OK;
     unsigned int n_flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_flag, count.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (n_flag == 0) return PMM_OK;
     stat_add(next_terms == 1 ? "requeried_f16_wide" : next_terms == 3 ? "requeried_tf32x3" : "fallback_queries", (double)n_flag);
-    // ---- gather the flagged queries into a dense f32 matrix
+    // ---- gather the flagged queries into a dense matrix of the working type
     std::vector<unsigned char> hflags((size_t)Q);
     CUDA_TRY(cudaMemcpy(hflags.data(), flags.p, (size_t)Q, cudaMemcpyDeviceToHost));
     std::vector<int64_t> ids;
@@ -567,44 +705,58 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
     for (int64_t i = 0; i < Q; ++i)
         if (hflags[(size_t)i]) ids.push_back(i);
     const int64_t F = (int64_t)ids.size();
-    DevBuf d_ids, dense_q, t_idx, t_sc, t_cand, err;
+    const int64_t wsz = vc.f64 ? 8 : 4;
+    DevBuf d_ids, dense_q, t_idx, t_sc, t_cand, err, seeds;
     CUDA_TRY(d_ids.alloc((size_t)F * 8, s));
     CUDA_TRY(cudaMemcpyAsync(d_ids.p, ids.data(), (size_t)F * 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(dense_q.alloc((size_t)F * raw_q.dim * 4, s));
-    CUDA_TRY(launch_counted("gather", s, [&] { return launch_gather_rows(raw_of(raw_q), d_ids.as<int64_t>(), F, dense_q.as<float>(), s); }));
+    CUDA_TRY(dense_q.alloc((size_t)F * raw_q.dim * wsz, s));
+    CUDA_TRY(launch_counted("gather", s, [&] { return launch_gather_rows(raw_of(raw_q), d_ids.as<int64_t>(), F, dense_q.p, vc.f64 ? 1 : 0, s); }));
     pmm_matrix_t qd;
     memset(&qd, 0, sizeof(qd));
     qd.values = dense_q.p;
     qd.n_rows = F;
     qd.dim = raw_q.dim;
-    qd.dtype = PMM_DTYPE_F32;
+    qd.dtype = vc.f64 ? PMM_DTYPE_F64 : PMM_DTYPE_F32;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     CUDA_TRY(t_idx.alloc((size_t)F * keff * 4, s));
     CUDA_TRY(t_sc.alloc((size_t)F * keff * 8, s));
-    CUDA_TRY(t_cand.alloc((size_t)F * keff * 8, s));
-    TopkOut t{t_idx.as<uint32_t>(), t_sc.as<double>(), t_cand.as<uint64_t>()};
+    if (o.cand) CUDA_TRY(t_cand.alloc((size_t)F * keff * 8, s));
+    TopkOut t{t_idx.as<uint32_t>(), t_sc.as<double>(), o.cand ? t_cand.as<uint64_t>() : nullptr};
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
+    const int64_t q_tile = 4 * TC_TILE_M;
+    const float *seed_next = nullptr;
+    if (next_terms != 0 && t_opt.seed_retry) {
+        const int64_t n_pad = round_up(F, q_tile);
+        CUDA_TRY(seeds.alloc((size_t)n_pad * 4, s));
+        const LevelErr ne = level_err(next_terms == 1 ? PREP_F16R : PREP_TF32, next_terms, vc.f64, raw_q.dim);
+        RescoreCheck nx = chk;
+        nx.eps = ne.eps;
+        nx.abs_err = ne.abs_err;
+        nx.max_norm = ne.max_norm;
+        CUDA_TRY(launch_counted("seeds", s, [&] {
+            return launch_make_seeds(d_ids.as<int64_t>(), F, n_pad, kth.as<float>(), nx, metric, seeds.as<float>(), s);
+        }));
+        seed_next = seeds.as<float>();
+    }
     int rc;
     if (next_terms == 1) {
         // same f16-rounded filter against the planes at hand, 256 candidates per query
         Prepared qf;
-        if ((rc = prepare(qd, PREP_F16R, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
-        if ((rc = tc_topk_verified(qf, c_planes, qd, raw_c, c_norm, c_sq, c_max_sq, 1, keff, metric, index_base, nullptr, t, s, 256)))
-            return rc;
+        if ((rc = prepare(qd, PREP_F16R, vc.f64, q_tile, want_norm, true, err.as<int>(), s, &qf))) return rc;
+        if ((rc = tc_topk_verified(vc, qf, qd, c_planes, 1, nullptr, t, 256, seed_next))) return rc;
     } else if (next_terms == 3) {
         // one level up on the tensor cores: 3xTF32 planes of the flagged queries against the corpus planes
-        Prepared qf, cf;
-        if ((rc = prepare(qd, PREP_TF32, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &qf))) return rc;
+        Prepared qf;
+        if ((rc = prepare(qd, PREP_TF32, vc.f64, q_tile, want_norm, true, err.as<int>(), s, &qf))) return rc;
         if (c_planes) {
-            if ((rc = tc_topk_verified(qf, c_planes, qd, raw_c, c_norm, c_sq, c_max_sq, 3, keff, metric, index_base, nullptr, t, s)))
-                return rc;
+            if ((rc = tc_topk_verified(vc, qf, qd, c_planes, 3, nullptr, t, 0, seed_next))) return rc;
         } else {
-            // Chunked upload: the per-chunk planes are gone. Rebuild them from the resident raw corpus piece by piece
-            // (planes of at most 128k rows: bounded, equally sized scratch that the memory pool hands back without
-            // mapping new memory — a 2 x corpus-size request after the chunk-sized frees stalled for 0.3-1.5 s),
+            // The corpus planes at hand are f16 planes: rebuild TF32 planes from the resident raw corpus piece by piece
+            // (at most 128k rows at a time: bounded, equally sized scratch that the memory pool hands back without
+            // mapping new memory - a 2 x corpus-size request after the chunk-sized frees stalled for 0.3-1.5 s),
             // carrying the candidate lists from piece to piece.
-            const int64_t N = raw_c.n_rows, step = 131072;
+            const int64_t N = vc.raw_c.n_rows, step = 131072;
             const int kp1 = tc_list_capacity(keff);
             DevBuf kept1;
             CUDA_TRY(kept1.alloc((size_t)F * kp1 * 8, s));
@@ -614,20 +766,19 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
             Prepared cpiece;  // plane buffers of the first (largest) piece are reused by the others
             for (int64_t r0 = 0; r0 < N; r0 += step) {
                 const int64_t rows = N - r0 < step ? N - r0 : step;
-                if ((rc = prepare(slice_rows(raw_c, r0, rows), PREP_TF32, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &cpiece)))
+                if ((rc = prepare(slice_rows(vc.raw_c, r0, rows), PREP_TF32, vc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &cpiece)))
                     return rc;
-                if ((rc = tc_filter(qf, cpiece, kp1, metric, index_base + r0, kept1.as<uint64_t>(), s, 3, &carry,
-                                    (r0 == 0 ? 1 : 0) | (r0 + rows >= N ? 2 : 0))))
+                if ((rc = tc_filter(qf, cpiece, kp1, metric, vc.index_base + r0, kept1.as<uint64_t>(), s, 3, &carry,
+                                    (r0 == 0 ? 1 : 0) | (r0 + rows >= N ? 2 : 0), seed_next)))
                     return rc;
             }
-            if ((rc = tc_topk_verified(qf, nullptr, qd, raw_c, c_norm, c_sq, c_max_sq, 3, keff, metric, index_base, kept1.as<uint64_t>(), t, s)))
-                return rc;
+            if ((rc = tc_topk_verified(vc, qf, qd, nullptr, 3, kept1.as<uint64_t>(), t, 0, seed_next))) return rc;
         }
     } else {
         Prepared qf, cf;
-        if ((rc = prepare(qd, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &qf))) return rc;
-        if ((rc = prepare(raw_c, PREP_DENSE, false, 1, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
-        if ((rc = topk_generic(qf, cf, keff, metric, index_base, t, s))) return rc;
+        if ((rc = prepare(qd, PREP_DENSE, vc.f64, 1, want_norm, want_sq, err.as<int>(), s, &qf))) return rc;
+        if ((rc = prepare(vc.raw_c, PREP_DENSE, vc.f64, 1, want_norm, want_sq, err.as<int>(), s, &cf))) return rc;
+        if ((rc = topk_generic(qf, cf, keff, metric, vc.index_base, t, s))) return rc;
     }
     CUDA_TRY(launch_counted("scatter", s, [&] {
         return launch_scatter_results(d_ids.as<int64_t>(), F, (int)keff, t.index, t.score, t.cand, o.index, o.score, o.cand, s);
@@ -637,43 +788,55 @@ int rescore_and_verify(const uint64_t *kept, int kp, const pmm_matrix_t &raw_q, 
 }
 
 // Filter at `terms` (unless the kept lists are supplied) -> exact re-scoring -> verification -> next level.
-// c may be NULL only when kept_in is given. c_norm / c_sq / c_max_sq describe the whole corpus (index_base-relative).
-int tc_topk_verified(const Prepared &q, const Prepared *c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c,
-                     const float *c_norm, const float *c_sq, const unsigned int *c_max_sq, int terms, int64_t keff, int metric,
-                     int64_t index_base, const uint64_t *kept_in, TopkOut o, cudaStream_t s, int kp_override) {
-    const int kp = kp_override ? kp_override : tc_list_capacity(keff);
+// c may be NULL only when kept_in is given.
+int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared *c, int terms,
+                     const uint64_t *kept_in, TopkOut o, int kp_override, const float *seed) {
+    const int kp = kp_override ? kp_override : tc_list_capacity(vc.keff);
     const bool f16 = q.mode == PREP_F16;     // exact f16 planes
-    const bool f16r = q.mode == PREP_F16R;   // f32 input rounded to f16: TF32-x1-like error, then 3xTF32 on demand
+    const bool f16r = q.mode == PREP_F16R;   // input rounded to f16: TF32-x1-like error, then 3xTF32 on demand
     DevBuf kept;
     const uint64_t *kept_ptr = kept_in;
     if (!kept_ptr) {
-        CUDA_TRY(kept.alloc((size_t)q.n_rows * kp * 8, s));
-        int rc = tc_filter(q, *c, kp, metric, index_base, kept.as<uint64_t>(), s, terms);
+        CUDA_TRY(kept.alloc((size_t)q.n_rows * kp * 8, vc.s));
+        int rc = tc_filter(q, *c, kp, vc.metric, vc.index_base, kept.as<uint64_t>(), vc.s, terms, nullptr, 3, seed);
         if (rc) return rc;
         kept_ptr = kept.as<uint64_t>();
     }
     // Next level for the queries the proof rejects.  f16-rounded level with its planes at hand: first the SAME filter
     // with 256-entry lists (next_terms = 1) - the proof needs the exact k-th score to clear the worst kept filter
-    // value by the error bound, and 128 more ranks of margin almost always do it, for one small launch instead of
-    // rebuilding TF32 planes of the whole corpus.  Then 3xTF32 (3), then the exact SIMT path (0).
-    const bool wide = f16r && c && kp < 256 && keff <= 248 && g_f16r_wide.load();
+    // value by the error bound; seeded thresholds (or, without them, 128 more ranks of margin) almost always do it,
+    // for one small launch instead of rebuilding TF32 planes of the whole corpus.  Then 3xTF32 (3), then the exact
+    // SIMT path (0).
+    const bool wide = f16r && c && kp < 256 && !seed && t_opt.f16r_wide;
     const int next_terms = wide ? 1 : (f16r || (!f16 && terms == 1)) ? 3 : 0;
-    // f16r planes cannot serve the 3xTF32 level: it rebuilds TF32 planes piece by piece (c_planes = NULL)
-    return rescore_and_verify(kept_ptr, kp, raw_q, raw_c, q.sqnorm.as<float>(), q.norm.as<float>(), (f16r && !wide) ? nullptr : c, c_norm, c_sq,
-                              c_max_sq, filter_eps(raw_q.dim, f16r ? 1 : terms, f16), f16r ? f16r_abs_err(raw_q.dim) : 0.0f,
-                              f16r ? 65504.0f : 0.0f, next_terms, metric, index_base, keff, o, s);
+    // f16 planes cannot serve the 3xTF32 level: it rebuilds TF32 planes piece by piece (c_planes = NULL)
+    return rescore_and_verify(vc, q, raw_q, kept_ptr, kp, (f16r && !wide) ? nullptr : c, level_err(q.mode, f16r ? 1 : terms, vc.f64, raw_q.dim),
+                              next_terms, seed, o);
 }
 
 // First filter level for f32 planes: TF32 x1 unless switched off ("tc_levels" = 1) or cta_group::1 was forced.
 int first_level_terms(const Prepared &q) {
-    return (q.mode == PREP_F16R || (q.mode == PREP_TF32 && g_tc_levels.load() >= 2 && g_tc_cg.load() == 2)) ? 1 : 3;
+    return (q.mode == PREP_F16R || (q.mode == PREP_TF32 && t_opt.tc_levels >= 2 && t_opt.tc_cg == 2)) ? 1 : 3;
+}
+
+VerifyCtx verify_ctx(const Prepared &c, const pmm_matrix_t &raw_c, int64_t keff, int metric, int64_t index_base, cudaStream_t s) {
+    VerifyCtx vc;
+    vc.raw_c = raw_c;
+    vc.f64 = c.f64;
+    vc.c_norm = c.norm.p;
+    vc.c_sq = c.sqnorm.p;
+    vc.c_range = c.max_sq_ptr;
+    vc.metric = metric;
+    vc.index_base = index_base;
+    vc.keff = keff;
+    vc.s = s;
+    return vc;
 }
 
 // Tensor-core path: filter -> exact re-scoring of the kept candidates -> verification (-> next level).
 int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
             int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
-    return tc_topk_verified(q, &c, raw_q, raw_c, c.norm.as<float>(), c.sqnorm.as<float>(), c.max_sq_ptr, first_level_terms(q),
-                            keff, metric, index_base, nullptr, o, s);
+    return tc_topk_verified(verify_ctx(c, raw_c, keff, metric, index_base, s), q, raw_q, &c, first_level_terms(q), nullptr, o);
 }
 
 struct PathChoice {
@@ -681,13 +844,15 @@ struct PathChoice {
     bool f64;
     int mode;  // prep mode for both operands
 };
-// for_topk: the f32 top-k starts with f16-rounded planes ("tc_levels" >= 3, the default); raw matmul needs 3xTF32.
+// for_topk: the top-k starts with f16-rounded planes ("tc_levels" >= 3, the default) whatever the working precision -
+// the filter only selects, the exact scores come from the re-scoring in f32 or f64; raw matmul needs 3xTF32 (f32) or
+// DMMA (f64) because its result IS the output.
 PathChoice choose_path(int q_dtype, int c_dtype, int64_t keff, bool for_topk = true) {
     PathChoice pc;
     pc.f64 = pmm_working_dtype(q_dtype, c_dtype) == PMM_DTYPE_F64;
-    pc.tc = !pc.f64 && keff <= 128 && !g_force_generic.load() && dev_info().tc;
+    pc.tc = keff <= TC_MAX_K && !t_opt.force_generic && dev_info().tc && (!pc.f64 || (for_topk && t_opt.f64_tc));
     pc.mode = !pc.tc ? PREP_DENSE : (q_dtype == PMM_DTYPE_F16 && c_dtype == PMM_DTYPE_F16) ? PREP_F16 : PREP_TF32;
-    if (pc.mode == PREP_TF32 && for_topk && g_tc_levels.load() >= 3 && g_tc_cg.load() == 2) pc.mode = PREP_F16R;
+    if (pc.mode == PREP_TF32 && for_topk && t_opt.tc_levels >= 3 && t_opt.tc_cg == 2) pc.mode = PREP_F16R;
     return pc;
 }
 
@@ -700,9 +865,9 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
     const int64_t keff = k < N ? k : N;
     if (keff == 0) return PMM_OK;
     PathChoice pc = choose_path(dq->dtype, corpus_dtype, keff);
-    if (pc_corpus && (pc_corpus->mode != pc.mode || pc_corpus->f64 != pc.f64))
-        return fail(PMM_ERR_UNSUPPORTED,
-                    "resident corpus was prepared for a different path (query dtype or k > 128 changed); recreate the handle");
+    // a resident corpus prepared for another path (query dtype, k > 248 or an option changed): prepare afresh from
+    // the raw column, which the handle keeps on the device as well
+    if (pc_corpus && (pc_corpus->mode != pc.mode || pc_corpus->f64 != pc.f64)) pc_corpus = nullptr;
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
     DevBuf err;
     CUDA_TRY(err.alloc(sizeof(int), s));
@@ -748,7 +913,7 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         a.nq = Q;
         a.n = N;
         a.f16 = pc.mode == PREP_F16 ? 1 : 0;
-        a.cg = g_tc_cg.load();
+        a.cg = t_opt.tc_cg;
         a.sched = make_tc_schedule(Q, N, di.num_sms / a.cg, 1, a.cg);
         a.metric = PMM_METRIC_DOT;
         a.k = 1;
@@ -760,7 +925,7 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
     } else if (pc.f64) {
         for (int64_t q0 = 0; q0 < Q; q0 += (1 << 20)) {
             int64_t nq = Q - q0 < (1 << 20) ? Q - q0 : (1 << 20);
-            const bool simt = g_f64_simt.load() != 0;
+            const bool simt = t_opt.f64_simt != 0;
             CUDA_TRY(launch_counted(simt ? "scores_f64" : "scores_f64_dmma", s, [&] {
                 return (simt ? launch_scores_f64 : launch_scores_f64_dmma)(l.p0.as<double>() + q0 * D, r.p0.as<double>(), nullptr,
                                                                            nullptr, nq, N, D, PMM_METRIC_DOT,
@@ -808,28 +973,28 @@ int upload(const pmm_matrix_t *m, cudaStream_t s, Uploaded *u) {
         last = m->offsets[m->n_rows];
         if (last < first) return fail(PMM_ERR_INVALID, "list offsets are not monotonic");
         CUDA_TRY(u->offsets.alloc((size_t)(m->n_rows + 1) * 8, s));
-        CUDA_TRY(cudaMemcpyAsync(u->offsets.p, m->offsets, (size_t)(m->n_rows + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(u->offsets.p, m->offsets, (size_t)(m->n_rows + 1) * 8, s));
         u->dm.offsets = u->offsets.as<int64_t>();
         stat_add("h2d_bytes", (double)(m->n_rows + 1) * 8);
     }
     const size_t vbytes = (size_t)(last - first) * es;
     CUDA_TRY(u->values.alloc(vbytes, s));
     if (vbytes)
-        CUDA_TRY(cudaMemcpyAsync(u->values.p, (const char *)m->values + (size_t)first * es, vbytes, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(u->values.p, (const char *)m->values + (size_t)first * es, vbytes, s));
     stat_add("h2d_bytes", (double)vbytes);
     // kernels index child values by absolute position: rebase so that position `first` is byte 0 of the buffer
     u->dm.values = (const char *)u->values.p - (size_t)first * es;
     if (m->validity) {
         const size_t nb = (size_t)((last + 7) / 8);
         CUDA_TRY(u->validity.alloc(nb, s));
-        CUDA_TRY(cudaMemcpyAsync(u->validity.p, m->validity, nb, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(u->validity.p, m->validity, nb, s));
         u->dm.validity = u->validity.as<uint8_t>();
         stat_add("h2d_bytes", (double)nb);
     }
     if (m->row_validity) {
         const size_t nb = (size_t)((m->n_rows + 7) / 8);
         CUDA_TRY(u->row_validity.alloc(nb, s));
-        CUDA_TRY(cudaMemcpyAsync(u->row_validity.p, m->row_validity, nb, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(u->row_validity.p, m->row_validity, nb, s));
         u->dm.row_validity = u->row_validity.as<uint8_t>();
         stat_add("h2d_bytes", (double)nb);
     }
@@ -863,7 +1028,7 @@ cudaStream_t copy_stream() {
 // Outputs: host index/score buffers and/or exact packed candidates left on the device (d_cand, for the
 // multi-GPU exchange); corpus row j is reported as index_base + j.
 // Sustained algorithmic FLOP/s of the first filter level on f32 planes (TF32 x1 with two levels, else 3xTF32).
-double terms0_rate(int mode) { return (mode == PREP_TF32 && g_tc_levels.load() >= 2 && g_tc_cg.load() == 2) ? 7.5e14 : 2.6e14; }
+double terms0_rate(int mode) { return (mode == PREP_TF32 && t_opt.tc_levels >= 2 && t_opt.tc_cg == 2) ? 7.5e14 : 2.6e14; }
 
 int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t keff, int metric, PathChoice pc,
                       int64_t index_base, uint32_t *out_index, double *out_score, uint64_t *d_cand) {
@@ -894,22 +1059,25 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     // by the ratio of filter time to copy time per row (2 Q / tensor rate vs element size / PCIe rate, about 3.5 at
     // Q = 100k f32), so that each copy finishes just before the filter wants it.  Copy-bound shapes (few queries)
     // get equal chunks instead.
+    const bool copy_up_front = !stage_enabled() || host_ptr_is_pinned(corpus->values);
     std::vector<int64_t> cut{0};
     {
         // sustained filter FLOP/s, measured: f16 planes (f16 input, or f32 rounded to f16) / TF32 x1 / 3xTF32
         const double rate = (pc.mode == PREP_F16 || pc.mode == PREP_F16R) ? 1.25e15 : terms0_rate(pc.mode);
-        double ratio = 0.8 * (2.0 * (double)Q / rate) / ((double)es / 4.0e10);  // 40 GB/s host -> device, 20 % margin
-        if (g_host_chunk_ratio_pct.load() > 0) ratio = g_host_chunk_ratio_pct.load() / 100.0;
+        // host -> device: ~40 GB/s from page-locked memory, ~22 GB/s through the staging ring (pageable source); 20 % margin
+        const double bw = copy_up_front ? 4.0e10 : 2.2e10;
+        double ratio = 0.8 * (2.0 * (double)Q / rate) / ((double)es / bw);
+        if (t_opt.host_chunk_ratio_pct > 0) ratio = t_opt.host_chunk_ratio_pct / 100.0;
         if (ratio < 1.0) ratio = 1.0;
         if (ratio > 4.0) ratio = 4.0;
         const int max_chunks = 8;
         // first chunk of a geometric series of max_chunks terms that sums to N (equal chunks when ratio = 1) ...
         double first = ratio > 1.001 ? (double)N * (ratio - 1.0) / (pow(ratio, max_chunks) - 1.0) : (double)N / max_chunks;
         // ... but not below N / first_div: tiny first chunks buy nothing, the query upload comes first anyway
-        const int first_div = g_host_chunk_first_div.load() > 0 ? g_host_chunk_first_div.load() : 32;
+        const int first_div = t_opt.host_chunk_first_div > 0 ? t_opt.host_chunk_first_div : 32;
         if (first < (double)N / first_div) first = (double)N / first_div;
         int64_t size = (int64_t)first / 256 * 256;
-        const int64_t min_rows = (int64_t)g_host_chunk_min_rows.load() / 256 * 256 >= 256 ? (int64_t)g_host_chunk_min_rows.load() / 256 * 256 : 256;
+        const int64_t min_rows = (int64_t)t_opt.host_chunk_min_rows / 256 * 256 >= 256 ? (int64_t)t_opt.host_chunk_min_rows / 256 * 256 : 256;
         if (size < min_rows) size = min_rows;
         int64_t at = 0;
         while (at + size < N && (int)cut.size() < max_chunks) {
@@ -938,7 +1106,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         pos1 = corpus->offsets[N];
         if (pos1 < pos0) return fail(PMM_ERR_INVALID, "list offsets are not monotonic");
         CUDA_TRY(uc.offsets.alloc((size_t)(N + 1) * 8, s));
-        CUDA_TRY(cudaMemcpyAsync(uc.offsets.p, corpus->offsets, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(uc.offsets.p, corpus->offsets, (size_t)(N + 1) * 8, s));
         uc.dm.offsets = uc.offsets.as<int64_t>();
         stat_add("h2d_bytes", (double)(N + 1) * 8);
     }
@@ -947,13 +1115,13 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     if (corpus->validity) {
         const size_t nb = (size_t)((pos1 + 7) / 8);
         CUDA_TRY(uc.validity.alloc(nb, s));
-        CUDA_TRY(cudaMemcpyAsync(uc.validity.p, corpus->validity, nb, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(uc.validity.p, corpus->validity, nb, s));
         uc.dm.validity = uc.validity.as<uint8_t>();
     }
     if (corpus->row_validity) {
         const size_t nb = (size_t)((N + 7) / 8);
         CUDA_TRY(uc.row_validity.alloc(nb, s));
-        CUDA_TRY(cudaMemcpyAsync(uc.row_validity.p, corpus->row_validity, nb, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(stage_h2d(uc.row_validity.p, corpus->row_validity, nb, s));
         uc.dm.row_validity = uc.row_validity.as<uint8_t>();
     }
     CUDA_TRY(cudaEventCreateWithFlags(&drain.ready, cudaEventDisableTiming));
@@ -961,16 +1129,25 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(cudaStreamWaitEvent(cs, drain.ready, 0));  // the copy stream may touch the buffers once they exist
     std::vector<cudaEvent_t> &ev = drain.ev;
     ev.assign(n_chunks, nullptr);
-    for (int i = 0; i < n_chunks; ++i) {
+    // Chunk i of the corpus values -> its place in the device buffer, on the copy stream; ev[i] fires when it has landed.
+    // Page-locked source: plain DMA, all chunks are queued up front.  Pageable source (what Polars hands over): the
+    // bytes go through the page-locked staging ring (pmm_stage.h), which keeps this thread busy for the duration of
+    // the host-side copy - so chunk i+1 is staged AFTER the kernels of chunk i have been enqueued and the host copy
+    // overlaps the GPU's work on the previous chunk.
+    auto copy_chunk = [&](int i) -> int {
         const int64_t a = corpus->offsets ? corpus->offsets[cut[i]] : cut[i] * D;
         const int64_t b = corpus->offsets ? corpus->offsets[cut[i + 1]] : cut[i + 1] * D;
         if (b > a)
-            CUDA_TRY(cudaMemcpyAsync((char *)uc.values.p + (size_t)(a - pos0) * es, (const char *)corpus->values + (size_t)a * es,
-                                     (size_t)(b - a) * es, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(stage_h2d((char *)uc.values.p + (size_t)(a - pos0) * es, (const char *)corpus->values + (size_t)a * es,
+                               (size_t)(b - a) * es, cs));
         stat_add("h2d_bytes", (double)(b - a) * es);
         CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(ev[i], cs));
-    }
+        return PMM_OK;
+    };
+    if (copy_up_front)
+        for (int i = 0; i < n_chunks; ++i)
+            if ((rc = copy_chunk(i))) return rc;
 
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
     CUDA_TRY(err.alloc(sizeof(int), s));
@@ -996,6 +1173,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(call.p0.alloc(plane_bytes(pc.mode, N, D, TC_TILE_N), s));
     if (pc.mode == PREP_TF32) CUDA_TRY(call.p1.alloc(plane_bytes(pc.mode, N, D, TC_TILE_N), s));  // (f16 modes: one plane)
     for (int i = 0; i < n_chunks; ++i) {
+        if (!copy_up_front && (rc = copy_chunk(i))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(s, ev[i], 0));
         const int64_t r0 = cut[i], rows = cut[i + 1] - cut[i];
         const pmm_matrix_t dm = slice_rows(uc.dm, r0, rows);  // r0 is a multiple of 256
@@ -1020,11 +1198,10 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), d_cand};
     // c_aux_all holds the corpus norms (cosine) or squared norms (euclidean) of the whole corpus
-    if ((rc = tc_topk_verified(q, &call, uq.dm, uc.dm, c_aux_all.as<float>(), c_aux_all.as<float>(), c_max.as<unsigned int>(),
-                               terms0, keff, metric, index_base, kept_ptr, o, s)))
-        return rc;
-    if (out_index) CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
-    if (out_score) CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    VerifyCtx vc = verify_ctx(call, uc.dm, keff, metric, index_base, s);
+    if ((rc = tc_topk_verified(vc, q, uq.dm, &call, terms0, kept_ptr, o))) return rc;
+    if (out_index) CUDA_TRY(stage_d2h(out_index, d_idx.p, cnt * 4, s));
+    if (out_score) CUDA_TRY(stage_d2h(out_score, d_sc.p, cnt * 8, s));
     if (out_index || out_score) stat_add("d2h_bytes", (double)cnt * 12);
     if (queries->offsets || corpus->offsets) rc = finish_error_flag(err.as<int>(), s);
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1047,7 +1224,7 @@ struct pmm_corpus {
 extern "C" {
 
 const char *pmm_last_error(void) { return g_err.c_str(); }
-const char *pmm_version(void) { return "0.1.4+b200.r1"; }
+const char *pmm_version(void) { return "0.1.4+b200.r2"; }
 
 int pmm_metric_from_str(const char *name, int32_t *metric) {
     if (!name || !metric) return fail(PMM_ERR_INVALID, "Unknown metric: ''. Supported: cosine, dot, euclidean");
@@ -1100,33 +1277,60 @@ int pmm_host_free(void *p) {
 int64_t pmm_kernel_launch_count(void) { return g_launches.load(); }
 void pmm_reset_kernel_launch_count(void) { g_launches.store(0); }
 
+// Options that act immediately instead of being part of the per-call snapshot. Returns 1 when handled.
+static int immediate_option(const std::string &k, int64_t value) {
+    if (k == "release_workspace") {  // this thread's parked device blocks and staging ring go back to the system
+        g_block_cache.clear();
+        stage_release_thread_ring();
+        return 1;
+    }
+    if (k == "workspace_cache_mb") { g_block_cache_cap_mb.store(value < 0 ? 0 : value); return 1; }
+    if (k == "stage") { stage_set_enabled(value != 0); return 1; }
+    if (k == "stage_threads") { stage_set_threads((int)value); return 1; }
+    if (k == "stage_slot_mb") { stage_set_ring((size_t)(value < 1 ? 1 : value) << 20, g_stage_slots.load()); g_stage_slot_mb.store(value < 1 ? 1 : value); return 1; }
+    if (k == "stage_slots") { g_stage_slots.store((int)value); stage_set_ring((size_t)g_stage_slot_mb.load() << 20, (int)value); return 1; }
+    return 0;
+}
+
+static int check_diag_option(const std::string &k, int64_t value) {
+#ifndef PMM_DIAG
+    if (k == "tc_debug_skip" && value >= 1 && value <= 3)
+        return fail(PMM_ERR_UNSUPPORTED,
+                    "tc_debug_skip=%lld returns wrong results by design (kernel timing experiments) and is compiled out of this "
+                    "build; rebuild with -DPMM_DIAG", (long long)value);
+#endif
+    (void)k;
+    (void)value;
+    return PMM_OK;
+}
+
 int pmm_set_option(const char *key, int64_t value) {
     if (!key) return fail(PMM_ERR_INVALID, "null option key");
-    std::string k(key);
-    if (k == "force_generic") g_force_generic.store((int)value);
-    else if (k == "profile") g_profile.store((int)value);
-    else if (k == "tc_group") g_tc_group.store(value < 0 ? 0 : (int)value);  // 0 = automatic
-    else if (k == "tc_cg") g_tc_cg.store(value == 2 ? 2 : 1);
-    else if (k == "tc_max_units") g_tc_max_units.store((int)value);
-    else if (k == "tc_cluster4") g_tc_cluster4.store(value ? 1 : 0);
-    else if (k == "tc_sync_slack") g_tc_sync_slack.store(value < 0 ? 0 : value);
-    else if (k == "release_workspace") g_block_cache.clear();  // this thread's parked device blocks go back to the pool
-    else if (k == "host_chunk_min_rows") g_host_chunk_min_rows.store(value);  // smallest chunk (rows, multiple of 256; default 16384)
-    else if (k == "host_chunk_min_mb") g_host_chunk_min_mb.store(value);      // corpora below this many MB are uploaded in one piece (default 64)
-    else if (k == "host_chunk_ratio_pct") g_host_chunk_ratio_pct.store(value);  // 0 = auto
-    else if (k == "host_chunk_first_div") g_host_chunk_first_div.store(value);  // first chunk = N / this (0 = 32)
-    else if (k == "f16r_wide") g_f16r_wide.store(value ? 1 : 0);  // 256-entry retry of the f16-rounded level before 3xTF32
-    else if (k == "tc_soft_at") g_tc_soft_at.store(value < 0 ? 0 : value > 88 ? 88 : value);  // staged candidates that trigger an end-of-tile merge (0 = 48)
-    else if (k == "tc_max_flush") g_tc_max_flush.store(value < 0 ? 0 : value);
-    else if (k == "tc_debug_skip") g_tc_debug_skip.store(value);  // measurement only: results are wrong when set
-    else if (k == "tc_clm") g_tc_clm.store(value == 2 ? 2 : 1);  // 2: clusters of two CTA pairs, corpus tile multicast
-    else if (k == "tc_levels") g_tc_levels.store(value >= 3 ? 3 : value == 2 ? 2 : 1);  // 3: f16-rounded first level, 2: TF32 x1, 1: 3xTF32 only
-    else if (k == "verify") g_verify.store(value ? 1 : 0);  // 0: skip the filter-losslessness check (and its fallback)
-    else if (k == "f64_simt") g_f64_simt.store(value ? 1 : 0);  // 1: bit-exact sequential-FMA f64 instead of DMMA
-    else if (k == "host_chunked") g_host_chunked.store(value ? 1 : 0);
-    else if (k == "tc_sync_tiles") g_tc_sync_tiles.store(value < 0 ? 0 : (int)value);  // 0 = no pacing barriers
-    else if (k == "generic_workspace_mb") g_generic_ws_mb.store(value < 1 ? 1 : value);
-    else return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
+    const std::string k(key);
+    if (immediate_option(k, value)) return PMM_OK;
+    int rc = check_diag_option(k, value);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    if (!apply_option(g_opt, k, value)) return fail(PMM_ERR_INVALID, "unknown option '%s'", key);
+    return PMM_OK;
+}
+
+int pmm_set_thread_option(const char *key, int64_t value) {
+    if (!key) {  // NULL key: drop all overrides of the calling thread
+        t_overrides.clear();
+        return PMM_OK;
+    }
+    const std::string k(key);
+    int rc = check_diag_option(k, value);
+    if (rc) return rc;
+    Options probe;
+    if (!apply_option(probe, k, value)) return fail(PMM_ERR_INVALID, "unknown per-thread option '%s'", key);
+    for (auto &kv : t_overrides)
+        if (kv.first == k) {
+            kv.second = value;
+            return PMM_OK;
+        }
+    t_overrides.emplace_back(k, value);
     return PMM_OK;
 }
 
@@ -1140,6 +1344,12 @@ double pmm_get_stat(const char *name) {
     }
     std::lock_guard<std::mutex> lk(g_stat_mu);
     resolve_pending_locked();
+    {
+        double h2d = 0, d2h = 0;
+        stage_take_counters(&h2d, &d2h);
+        g_stats["staged_h2d_bytes"] += h2d;
+        g_stats["staged_d2h_bytes"] += d2h;
+    }
     auto it = g_stats.find(name);
     return it == g_stats.end() ? 0.0 : it->second;
 }
@@ -1147,6 +1357,7 @@ double pmm_get_stat(const char *name) {
 void pmm_reset_stats(void) {
     std::lock_guard<std::mutex> lk(g_stat_mu);
     resolve_pending_locked();
+    stage_take_counters(nullptr, nullptr);
     g_stats.clear();
 }
 
@@ -1155,6 +1366,8 @@ int pmm_dev_topk(const pmm_matrix_t *dq, const pmm_matrix_t *dc, int64_t k, int3
                  uint32_t *d_index, double *d_score, uint64_t *d_candidates, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     if ((rc = check_matrix(dq, "queries")) || (rc = check_matrix(dc, "corpus"))) return rc;
     if (dq->n_rows == 0) return PMM_OK;
     if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
@@ -1168,8 +1381,10 @@ int pmm_dev_merge_candidates(const uint64_t *d_lists, int64_t n_lists, int64_t n
                              int32_t metric, uint32_t *d_index, double *d_score, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
-    if (n_lists < 1 || k_in < 1 || k_in > 128 || k_out < 0 || k_out > k_in)
-        return fail(PMM_ERR_INVALID, "merge: need 1 <= k_out <= k_in <= 128 and at least one list");
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
+    if (n_lists < 1 || k_in < 1 || k_in > 256 || k_out < 0 || k_out > k_in)
+        return fail(PMM_ERR_INVALID, "merge: need 1 <= k_out <= k_in <= 256 and at least one list");
     if (n_queries == 0 || k_out == 0) return PMM_OK;
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(launch_counted("merge", s, [&] {
@@ -1182,6 +1397,8 @@ int pmm_dev_merge_candidates(const uint64_t *d_lists, int64_t n_lists, int64_t n
 int pmm_dev_matmul(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     if ((rc = check_matrix(dl, "left")) || (rc = check_matrix(dr, "right"))) return rc;
     if (dl->n_rows == 0) return PMM_OK;
     if ((rc = check_pair(dl, dr))) return rc;
@@ -1191,6 +1408,8 @@ int pmm_dev_matmul(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, 
 int pmm_dev_norms(const pmm_matrix_t *dx, int32_t squared, void *d_out, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     if ((rc = check_matrix(dx, "matrix"))) return rc;
     if (dx->n_rows == 0) return PMM_OK;
     PrepArgs a;
@@ -1209,6 +1428,58 @@ int pmm_dev_norms(const pmm_matrix_t *dx, int32_t squared, void *d_out, void *st
     return PMM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- diagnostics
+// Mode and MMA terms of a filter level for the given storage dtypes: level 0 = the default first level, 1 = TF32 x1,
+// 3 = 3xTF32.
+static void filter_level_mode(int level, int q_dtype, int c_dtype, int *mode, int *terms) {
+    const bool both_f16 = q_dtype == PMM_DTYPE_F16 && c_dtype == PMM_DTYPE_F16;
+    if (level == 0) {
+        *mode = both_f16 ? PREP_F16 : PREP_F16R;
+        *terms = 1;
+    } else {
+        *mode = PREP_TF32;
+        *terms = level == 1 ? 1 : 3;
+    }
+}
+
+int pmm_dev_filter_candidates(const pmm_matrix_t *dq, const pmm_matrix_t *dc, int32_t metric, int32_t level, int32_t kp,
+                              int64_t index_base, uint64_t *d_kept, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
+    if ((rc = check_matrix(dq, "queries")) || (rc = check_matrix(dc, "corpus"))) return rc;
+    if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
+    if ((rc = check_pair(dq, dc))) return rc;
+    if (!(kp == 32 || kp == 64 || kp == 128 || kp == 256)) return fail(PMM_ERR_INVALID, "kp must be 32, 64, 128 or 256");
+    if (!(level == 0 || level == 1 || level == 3)) return fail(PMM_ERR_INVALID, "level must be 0, 1 or 3");
+    if (!dev_info().tc) return fail(PMM_ERR_UNSUPPORTED, "the tensor-core filter needs an sm_100 device");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool f64 = pmm_working_dtype(dq->dtype, dc->dtype) == PMM_DTYPE_F64;
+    int mode, terms;
+    filter_level_mode(level, dq->dtype, dc->dtype, &mode, &terms);
+    DevBuf err;
+    CUDA_TRY(err.alloc(sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    Prepared q, c;
+    if ((rc = prepare(*dq, mode, f64, 4 * TC_TILE_M, true, true, err.as<int>(), s, &q))) return rc;
+    if ((rc = prepare(*dc, mode, f64, TC_TILE_N, true, true, err.as<int>(), s, &c, true))) return rc;
+    if ((rc = tc_filter(q, c, kp, metric, index_base, d_kept, s, terms))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+int pmm_filter_error_bound(int32_t level, int32_t q_dtype, int32_t c_dtype, int64_t dim, int32_t metric, float q_norm, float c_norm_max,
+                           float c_norm_min, float *bound, float *max_norm) {
+    if (!bound) return fail(PMM_ERR_INVALID, "null output");
+    int mode, terms;
+    filter_level_mode(level, q_dtype, c_dtype, &mode, &terms);
+    const LevelErr le = level_err(mode, terms, pmm_working_dtype(q_dtype, c_dtype) == PMM_DTYPE_F64, dim);
+    *bound = filter_error_bound(le.eps, le.abs_err, metric, q_norm, c_norm_max, c_norm_min);
+    if (max_norm) *max_norm = le.max_norm;
+    return PMM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- host entry points
 int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k, const char *metric, uint32_t *out_index,
              double *out_score, int64_t *k_actual) {
@@ -1223,11 +1494,13 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     if ((rc = check_pair(queries, corpus))) return rc;
     if ((rc = list_dim_check(queries, "queries")) || (rc = list_dim_check(corpus, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     if (keff == 0) return PMM_OK;
     cudaStream_t s = host_stream();
     {
         PathChoice pc = choose_path(queries->dtype, corpus->dtype, keff);
-        if (pc.tc && g_host_chunked.load() && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 1e6 * g_host_chunk_min_mb.load())
+        if (pc.tc && !pc.f64 && t_opt.host_chunked && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
             return host_topk_chunked(queries, corpus, keff, m, pc, 0, out_index, out_score, nullptr);
     }
     Uploaded uq, uc;
@@ -1238,8 +1511,8 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
     if ((rc = dev_topk_impl(&uq.dm, &uc.dm, nullptr, corpus->dtype, k, m, 0, o, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(stage_d2h(out_index, d_idx.p, cnt * 4, s));
+    CUDA_TRY(stage_d2h(out_score, d_sc.p, cnt * 8, s));
     stat_add("d2h_bytes", (double)cnt * 12);
     CUDA_TRY(cudaStreamSynchronize(s));
     return PMM_OK;
@@ -1258,12 +1531,14 @@ int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard
         return fail(PMM_ERR_UNSUPPORTED, "device-resident queries must be fixed-size rows without bitmaps");
     if ((!q_on_device && (rc = list_dim_check(queries, "queries"))) || (rc = list_dim_check(corpus_shard, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     const int64_t keff = k < corpus_shard->n_rows ? k : corpus_shard->n_rows;
     if (keff == 0) return PMM_OK;
     PathChoice pc = choose_path(queries->dtype, corpus_shard->dtype, keff);
     if (pc.f64) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
-    if (pc.tc && g_host_chunked.load() &&
-        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 1e6 * g_host_chunk_min_mb.load())
+    if (pc.tc && t_opt.host_chunked &&
+        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
         return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
     cudaStream_t s = host_stream();
     Uploaded uq, uc;
@@ -1287,6 +1562,8 @@ int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
     if ((rc = check_pair(left, right))) return rc;
     if ((rc = list_dim_check(left, "left")) || (rc = list_dim_check(right, "right"))) return rc;
     if ((rc = ensure_device())) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     cudaStream_t s = host_stream();
     Uploaded ul, ur;
     if ((rc = upload(left, s, &ul)) || (rc = upload(right, s, &ur))) return rc;
@@ -1295,7 +1572,7 @@ int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
     DevBuf d_out;
     CUDA_TRY(d_out.alloc(bytes, s));
     if ((rc = dev_matmul_impl(&ul.dm, &ur.dm, d_out.p, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(stage_d2h(out, d_out.p, bytes, s));
     stat_add("d2h_bytes", (double)bytes);
     CUDA_TRY(cudaStreamSynchronize(s));
     return PMM_OK;
@@ -1311,6 +1588,8 @@ int pmm_corpus_create(const pmm_matrix_t *corpus, int32_t query_dtype, pmm_corpu
     if (corpus->dim == 0) return fail(PMM_ERR_INVALID, "Zero-dimensional vectors");
     if ((rc = list_dim_check(corpus, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     cudaStream_t s = host_stream();
     pmm_corpus *h = new pmm_corpus();
     Uploaded &uc = h->raw;
@@ -1367,6 +1646,8 @@ int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *corpus, int
                     (long long)queries->dim, (long long)corpus->prep.dim);
     if ((rc = list_dim_check(queries, "queries"))) return rc;
     if ((rc = ensure_device())) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     if (keff == 0) return PMM_OK;
     cudaStream_t s = host_stream();
     Uploaded uq;
@@ -1377,8 +1658,8 @@ int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *corpus, int
     CUDA_TRY(d_sc.alloc(cnt * 8, s));
     TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), nullptr};
     if ((rc = dev_topk_impl(&uq.dm, &corpus->raw.dm, &corpus->prep, corpus->storage_dtype, k, m, 0, o, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_index, d_idx.p, cnt * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_score, d_sc.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(stage_d2h(out_index, d_idx.p, cnt * 4, s));
+    CUDA_TRY(stage_d2h(out_score, d_sc.p, cnt * 8, s));
     stat_add("d2h_bytes", (double)cnt * 12);
     CUDA_TRY(cudaStreamSynchronize(s));
     return PMM_OK;

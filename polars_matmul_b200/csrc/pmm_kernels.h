@@ -1,6 +1,7 @@
 // pmm_kernels.h — internal launcher interface between the kernel translation units and pmm_api.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace pmm {
@@ -19,6 +20,9 @@ struct PrepArgs {
     void *out1;                   // lo plane (MODE_TF32) or NULL
     void *norm_out;               // [rows_out] working type or NULL
     void *sqnorm_out;             // [rows_out] working type or NULL
+    float *norm32_out;            // [rows_out] f32 copy of the norms (f64 working precision + planes) or NULL
+    float *sqnorm32_out;          // [rows_out] f32 copy of the squared norms or NULL
+    float zero_guard_sq;          // rows with a squared norm at or below this do not enter the "smallest norm" statistic
     unsigned int *max_sq_out;     // f32 working type only: atomicMax of the squared norms' bit patterns, or NULL
     int *error_flag;              // set to 1 when a list row is longer than dim
 };
@@ -59,25 +63,67 @@ struct RawMatrix {               // a device-resident column in Arrow layout (pm
     const uint8_t *validity;
     const uint8_t *row_validity;
     int64_t n_rows, dim;
-    int dtype;                   // 0 f16, 1 f32
+    int dtype;                   // 0 f16, 1 f32, 2 f64
 };
+// ---- error model of the tensor-core filter (shared by the re-scoring kernel, the host driver and the diagnostic
+// entry points, so that tests measure the SAME bound the proof uses) -------------------------------------------------
+// Relative error bound (per |q||c|) of a filter value against the exact working-precision score:
+//   operand rounding: an 11-bit significand (TF32 via cvt.rna, or f32/f64 rounded to f16 inside the f16 normal range)
+//                     has unit roundoff u = 2^-11 per operand, so one product is off by <= 2u + u^2 ~ 2^-10 and so is the
+//                     sum (Cauchy-Schwarz): 9.8e-4.  3xTF32: each operand keeps a residue <= 2^-22 and the lo*lo term
+//                     (<= 2^-22) is dropped: <= 3 * 2^-22 = 7.5e-7.  f16 planes of f16 input are exact: 0.
+//   accumulation    : <= one f32 ulp (2^-23, truncation) of the running sum per tcgen05 accumulate step; a step
+//                     covers 8 (TF32) or 16 (f16) elements of K and there are `terms` MMAs per step:
+//                     D * 1.5e-8 * terms covers D/8 * 2^-23 per term (measured against adversarial inputs by
+//                     tests/test_gpu_bound.py up to D = 8192);
+//   the exact sum   : worst-case rounding of the sequential-FMA reference itself, D * 2^-24 = D * 6e-8.
+inline float filter_eps(int64_t dim, int terms, bool exact_operands) {
+    const float split = exact_operands ? 0.0f : terms == 1 ? 9.8e-4f : 7.5e-7f;
+    return split + (float)dim * (1.5e-8f * (float)terms + 6.0e-8f) + 1e-6f;
+}
+// Rounding to f16 below the f16 normal range (|x| < 2^-14) is absolute, <= 2^-25 per element: <= sqrt(D) 2^-25 per row.
+inline float f16r_abs_err(int64_t dim) { return sqrtf((float)dim) * 2.98023224e-8f * 1.0001f; }
+// f64 sources at the TF32 level: elements below the f32 normal range (2^-126) may be flushed: <= sqrt(D) 2^-126 per row.
+inline float f32_flush_abs_err(int64_t dim) { return sqrtf((float)dim) * 1.1754944e-38f * 1.0001f; }
+
+// Bound E on |filter value - its exact counterpart| for one query, in the units of the filter value
+// (dot: q.c; cosine: q.c / |c|; euclidean: squared distance).  eps = relative operand/accumulation error per |q||c|;
+// s = absolute rounding error of one operand row: |q'.c' - q.c| <= eps |q||c| + s (|q| + |c|) + s^2.
+// The small extra terms absorb the rounding of the metric pass.
+__host__ __device__ inline float filter_error_bound(float eps, float s, int metric, float qn, float cmax, float cmin) {
+    if (metric == 1 /* dot */) return eps * qn * cmax + s * (qn + cmax) + s * s;
+    if (metric == 0 /* cosine */) return (eps + 1e-6f) * qn + (s > 0.0f ? s * qn / cmin + s + s * s / cmin : 0.0f);
+    return 2.0f * (eps * qn * cmax + s * (qn + cmax) + s * s) + 1e-6f * (qn * qn + cmax * cmax);
+}
+
 // Inputs of the "was the filter lossless for this query" check (all device pointers; flags == NULL: no check).
 struct RescoreCheck {
-    const float *q_sq;             // [n_queries] squared query norms
+    const float *q_sq;             // [n_queries] squared query norms (f32; from f64 sources: rounded, inf when too large)
     const unsigned int *c_max_sq;  // [0] bits of the largest squared corpus norm (float >= 0, compared as uint),
                                    // [1] of the smallest one above 1e-12 (+inf bits if none)
     float eps;                     // relative error bound of the filter value vs the exact score, per |q||c|
     float abs_err;                 // absolute rounding error bound of one operand ROW (f16 subnormals), 0 if none
     float max_norm;                // operand rows with a larger norm may have overflowed the filter's format (0: no limit)
+    const float *seed;             // [n_queries] seed thresholds the filter launch started from (filter units, NaN = none)
+                                   // or NULL: everything at or below a row's seed was dropped, full list or not
     unsigned char *flags;          // [n_queries] set to 1 when not provable
     unsigned int *flag_count;
+    float *kth_units;              // [n_queries] out (flagged queries): the exact k-th score in filter units, or NULL
 };
 // cand [n_queries][kp_in] packed candidates (approximate keys, global indices) -> exact top-k_out.
 cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
                            const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
                            uint32_t *out_idx, double *out_score, uint64_t *out_cand, const RescoreCheck &chk,
                            cudaStream_t s);
-cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, float *out, cudaStream_t s);
+// Seeds for a re-query level: out[r] = kth_units[ids[r]] - E_next(query) - margin for r < n_ids, NaN for the padding
+// rows [n_ids, n_pad).  `next` carries the NEXT level's eps / abs_err / max_norm and the norm inputs.
+cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, const float *kth_units,
+                              const RescoreCheck &next, int metric, float *out, cudaStream_t s);
+// f64 working precision: exact f64 scores of the kept candidates (raw columns may be f16 / f32 / f64).
+cudaError_t launch_rescore_f64(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm, const double *q_aux,
+                               const double *c_aux, int metric, int64_t index_base, int k_out, uint32_t *out_idx,
+                               double *out_score, const RescoreCheck &chk, cudaStream_t s);
+cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, void *out, int out_f64, cudaStream_t s);
 cudaError_t launch_scatter_results(const int64_t *ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,
                                    const uint64_t *sc, uint32_t *di, double *ds, uint64_t *dc, cudaStream_t s);
 
@@ -139,6 +185,10 @@ struct TcArgs {
     int k;                         // candidates kept per query and piece: the list position that sets the threshold (<= kp)
     int kp;                        // list capacity: 32, 64, 128 or 256
     uint64_t *partial;             // [sched.total_slots()][tc_epilogue_sets()][cg][128][kp]
+    float norm_guard;              // cosine zero-norm guard of the filter (0 = 1e-6, the f32 reference constant)
+    const float *seed_thr;         // top-k: [q_rows_pad] initial per-query thresholds in filter units (NaN = none) or NULL.
+                                   // Everything with a filter value <= the seed is dropped from the start: the caller
+                                   // must know that nothing at or below it can matter (re-query levels, pmm_api.cu)
     uint64_t *staged;              // top-k: scratch of tc_staged_bytes(grid CTAs) bytes (unsorted candidates per CTA and row)
     // matmul mode
     float *out;                    // [nq x n] row-major

@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
             tf32_split((float)x, h, l);
             hi[row * ld + i] = h;
             lo[row * ld + i] = l;
+        } else if (sizeof(W) == 8) {
+            hp[row * ld + i] = __double2half((double)x);   // f64 source: one rounding, straight to f16
         } else {
             hp[row * ld + i] = __float2half_rn((float)x);  // MODE_F16: exact, x came from an f16; MODE_F16R: rounds
         }
@@ -151,15 +153,18 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     if (sub == 0) {
         if (a.sqnorm_out) ((W *)a.sqnorm_out)[row] = sum;
         if (a.norm_out) ((W *)a.norm_out)[row] = sqrt_rn(sum);
+        // f64 working precision on the tensor-core path: f32 copies for the filter kernel and its proof
+        if (a.sqnorm32_out) a.sqnorm32_out[row] = (float)sum;
+        if (a.norm32_out) a.norm32_out[row] = (float)sqrt_rn(sum);
     }
-    if (sizeof(W) == 4 && a.max_sq_out) {  // largest squared norm of the column: one atomic per warp
+    if (a.max_sq_out) {  // norm range of the column (f32; an f64 norm beyond the f32 range becomes inf): one atomic per warp
         const float fs = (float)sum;
         unsigned int bits = (sub == 0 && row < a.n_rows && fs == fs) ? __float_as_uint(fs) : 0u;  // >= 0: orders like uint
         const unsigned am = __activemask();
         bits = __reduce_max_sync(am, bits);
         if (lane == __ffs(am) - 1 && bits) atomicMax(a.max_sq_out, bits);
         // [1]: smallest squared norm among the rows cosine does not treat as zero (norm > 1e-6)
-        unsigned int lo_bits = (sub == 0 && row < a.n_rows && fs > 1e-12f) ? __float_as_uint(fs) : 0x7f800000u;
+        unsigned int lo_bits = (sub == 0 && row < a.n_rows && fs > a.zero_guard_sq) ? __float_as_uint(fs) : 0x7f800000u;
         lo_bits = __reduce_min_sync(am, lo_bits);
         if (lane == __ffs(am) - 1 && lo_bits != 0x7f800000u) atomicMin(a.max_sq_out + 1, lo_bits);
     }
@@ -173,9 +178,20 @@ static cudaError_t launch_prep_t(const PrepArgs &a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// src_dtype: PMM_DTYPE_* of `values`; mode selects the product; working type: MODE_DENSE uses
-// `work_f64` (0: f32, 1: f64), the plane modes are f32 by construction.
+// src_dtype: PMM_DTYPE_* of `values`; mode selects the product; `work_f64` (0: f32, 1: f64) is the type the norms
+// are computed and written in (and of the DENSE copy).  Plane modes with f64 working precision: the planes are the
+// tensor-core FILTER's operands (rounded to f16 / split to TF32 from the f64 value), the norms stay exact f64.
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s) {
+    if (work_f64 && (mode == MODE_F16R || mode == MODE_TF32)) {
+        if (mode == MODE_F16R) {
+            if (src_dtype == 0) return launch_prep_t<__half, double, MODE_F16R>(a, s);
+            if (src_dtype == 1) return launch_prep_t<float, double, MODE_F16R>(a, s);
+            return launch_prep_t<double, double, MODE_F16R>(a, s);
+        }
+        if (src_dtype == 0) return launch_prep_t<__half, double, MODE_TF32>(a, s);
+        if (src_dtype == 1) return launch_prep_t<float, double, MODE_TF32>(a, s);
+        return launch_prep_t<double, double, MODE_TF32>(a, s);
+    }
     if (mode == MODE_TF32) {
         if (src_dtype == 1) return launch_prep_t<float, float, MODE_TF32>(a, s);
         if (src_dtype == 0) return launch_prep_t<__half, float, MODE_TF32>(a, s);

@@ -64,17 +64,6 @@ __device__ __forceinline__ void gather_step(float (&x)[32], const RawMatrix &cm,
     }
 }
 
-// Bound E on |filter value - its exact counterpart| for one query, in the units of the filter value
-// (dot: q.c; cosine: q.c / |c|; euclidean: squared distance).  eps = relative operand/accumulation error per |q||c|;
-// s = abs_err = absolute rounding error of one operand row (f32 rounded to f16 below the normal range):
-// |q'.c' - q.c| <= eps |q||c| + s (|q| + |c|) + s^2.  The small extra terms absorb the rounding of the metric pass.
-__device__ __forceinline__ float filter_error_bound(const RescoreCheck &chk, int metric, float qn, float cmax, float cmin) {
-    const float s = chk.abs_err;
-    if (metric == METRIC_DOT) return chk.eps * qn * cmax + s * (qn + cmax) + s * s;
-    if (metric == METRIC_COSINE) return (chk.eps + 1e-6f) * qn + (s > 0.0f ? s * qn / cmin + s + s * s / cmin : 0.0f);
-    return 2.0f * (chk.eps * qn * cmax + s * (qn + cmax) + s * s) + 1e-6f * (qn * qn + cmax * cmax);
-}
-
 template <typename CSRC, int NT>
 __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict__ cand, int kp_in, RawMatrix qm,
                                                      RawMatrix cm, const float *__restrict__ q_aux,
@@ -108,7 +97,7 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             const float f_k = key_score(candidate_key(ck), true), f_j = key_score(candidate_key(c_in), true);
             const float qn = sqrtf(chk.q_sq[q]);
             const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
-            const float e = filter_error_bound(chk, metric, qn, cmax, cmin);
+            const float e = filter_error_bound(chk.eps, chk.abs_err, metric, qn, cmax, cmin);
             // the bound only holds while no operand left the filter format's range (f16-rounded level: a row norm
             // above 65504 may have become inf there, and the filter values are then meaningless)
             const bool in_range = chk.max_norm <= 0.0f || (qn <= chk.max_norm && cmax <= chk.max_norm);
@@ -243,14 +232,24 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     // filter's error bound; if the exact k-th score is not strictly better than that, a dropped candidate
     // might belong to (or tie into) the top-k: flag the query, the host recomputes it on the exact path.
     if (t == 0 && chk.flags) {
-        const uint64_t last = cand[q * kp_in + kp_in - 1];   // 0: fewer than kp_in candidates exist -> nothing dropped
+        // worst filter value that was kept = upper bound of everything dropped.  A list that is not full dropped
+        // nothing - unless the launch started from a seed threshold, then everything at or below the seed is gone.
+        const uint64_t last = cand[q * kp_in + kp_in - 1];
+        float f_last = 0.0f;
+        bool dropped = false;
+        if (last != 0ull) {
+            f_last = key_score(candidate_key(last), true);
+            dropped = true;
+        } else if (chk.seed && chk.seed[q] == chk.seed[q]) {
+            f_last = chk.seed[q];
+            dropped = true;
+        }
         bool ok = true;
-        if (last != 0ull && k_out > 0) {
-            const float f_last = key_score(candidate_key(last), true);
-            const float tk = key_score(candidate_key(sortbuf[k_out - 1]), higher);
-            const float qn = sqrtf(chk.q_sq[q]);
+        const float tk = k_out > 0 ? key_score(candidate_key(sortbuf[k_out - 1]), higher) : 0.0f;
+        const float qn = sqrtf(chk.q_sq[q]);
+        if (dropped && k_out > 0) {
             const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
-            const float e = filter_error_bound(chk, metric, qn, cmax, cmin);
+            const float e = filter_error_bound(chk.eps, chk.abs_err, metric, qn, cmax, cmin);
             if (metric == METRIC_DOT) {
                 ok = tk > f_last + e;
             } else if (metric == METRIC_COSINE) {
@@ -263,6 +262,8 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
             if (chk.max_norm > 0.0f && !(qn <= chk.max_norm && cmax <= chk.max_norm)) ok = false;
             if (!(ok)) ok = false;  // NaN anywhere -> not provable
         }
+        if (!ok && chk.kth_units)   // what a re-query level may seed its thresholds from (filter units)
+            chk.kth_units[q] = metric == METRIC_DOT ? tk : metric == METRIC_COSINE ? tk * qn : -(tk * tk);
         if (!ok) {
             chk.flags[q] = 1;
             atomicAdd(chk.flag_count, 1u);
@@ -313,19 +314,232 @@ cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm,
 }
 
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// f64 working precision (what Polars hands the reference by default: every list-of-floats column is Float64).
+// Same scheme: the tensor-core filter (operands rounded to f16 / TF32) only SELECTS; this kernel recomputes each kept
+// candidate with the reference's f64 arithmetic - one FMA per element, sequential in the vector dimension
+// (src/metrics.rs:40-97 as restated by the oracle), the metric pass of src/metrics.rs:267-308 with exact f64 norms,
+// best-first order of src/topk.rs:6-39 under (score, lower index) - so f64 top-k results are bit-identical to the
+// oracle's, and no Q x N score slab is ever written.  The raw columns may be f16 / f32 / f64 (mixed dtypes are
+// widened exactly, src/matmul.rs:308).
+__device__ __forceinline__ double raw_fetch_f64(const RawMatrix &m, int64_t base, int64_t len, int64_t i) {
+    if (i >= len) return 0.0;
+    const int64_t p = base + i;
+    if (m.validity && !((m.validity[p >> 3] >> (p & 7)) & 1)) return 0.0;
+    if (m.dtype == 2) return __ldg((const double *)m.values + p);
+    if (m.dtype == 1) return (double)__ldg((const float *)m.values + p);
+    return (double)__half2float(__ldg((const __half *)m.values + p));
+}
+
+constexpr int RS_PITCH64 = 33;  // doubles per candidate row of a warp's transpose tile
+
+template <int NT>
+__global__ void __launch_bounds__(NT) rescore_f64_kernel(const uint64_t *__restrict__ cand, int kp_in, RawMatrix qm, RawMatrix cm,
+                                                         const double *__restrict__ q_aux, const double *__restrict__ c_aux,
+                                                         int metric, int64_t index_base, int k_out, uint32_t *out_idx,
+                                                         double *out_score, RescoreCheck chk) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t *skey = (uint64_t *)rs_smem;                    // NT exact score keys; during the gather: row offsets
+    uint32_t *sidx = (uint32_t *)(rs_smem + NT * 8);         // NT corpus indices;   during the gather: row lengths
+    double *qs = (double *)(rs_smem + NT * 12 + ((NT * 12) % 8 ? 4 : 0));
+    const int64_t q = blockIdx.x;
+    const int t = threadIdx.x;
+    const int dim = (int)qm.dim;
+    {
+        int64_t qb, ql;
+        raw_row(qm, q, qb, ql);
+        for (int i = t; i < dim; i += NT) qs[i] = raw_fetch_f64(qm, qb, ql, i);
+    }
+    __syncthreads();
+    const bool higher = higher_is_better(metric);
+    const int lane = t & 31, wrp = t >> 5;
+    uint64_t c_in = (t < kp_in) ? cand[q * kp_in + t] : 0ull;
+    // skip rule: as in rescore_kernel (the filter values and their bound are f32 quantities in both cases)
+    if (chk.q_sq && chk.c_max_sq && k_out > 0 && t >= k_out && k_out <= kp_in && c_in != 0ull) {
+        const uint64_t ck = cand[q * kp_in + k_out - 1];
+        if (ck != 0ull) {
+            const float f_k = key_score(candidate_key(ck), true), f_j = key_score(candidate_key(c_in), true);
+            const float qn = sqrtf(chk.q_sq[q]);
+            const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
+            const float e = filter_error_bound(chk.eps, chk.abs_err, metric, qn, cmax, cmin);
+            const bool in_range = chk.max_norm <= 0.0f || (qn <= chk.max_norm && cmax <= chk.max_norm);
+            if (in_range && fabsf(f_k) <= 3.0e38f && f_j < f_k - 2.0f * e - 1e-6f * fabsf(f_k)) c_in = 0ull;
+        }
+    }
+    const uint64_t c = c_in;
+    const uint32_t gidx = candidate_index(c);
+    const int64_t row = (int64_t)gidx - index_base;
+    int64_t cb = 0, cl = 0;
+    if (c != 0ull) raw_row(cm, row, cb, cl);
+    const int n_act = 32 - __clz(__ballot_sync(0xffffffffu, c != 0ull));
+    int64_t *rowb = (int64_t *)skey;
+    int *rowl = (int *)sidx;
+    rowb[t] = cb;
+    rowl[t] = (int)cl;
+    __syncwarp();
+    const int w0 = wrp * 32;
+    double acc = 0.0;
+    double (*tile)[RS_PITCH64] = (double (*)[RS_PITCH64])((unsigned char *)(qs + ((dim + 1) & ~1)) + (size_t)wrp * 32 * RS_PITCH64 * 8);
+    for (int d0 = 0; d0 < dim; d0 += 32) {
+        // coalesced row reads (lane = element), 8 candidate rows in flight per batch, transposed through shared
+        // memory; every thread then accumulates ITS candidate sequentially in d - the reference's order
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+            if (g < n_act) {
+                double x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = raw_fetch_f64(cm, rowb[w0 + g + i], rowl[w0 + g + i], d0 + lane);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tile[g + i][lane] = x[i];
+            }
+        }
+        __syncwarp();
+        const int jn = dim - d0 < 32 ? dim - d0 : 32;
+        if (lane < n_act)
+            for (int j = 0; j < jn; ++j) acc = __fma_rn(qs[d0 + j], tile[lane][j], acc);
+        __syncwarp();
+    }
+    __syncwarp();  // row offsets / lengths are dead from here on
+    uint64_t key = 0ull;
+    uint32_t idx = 0xffffffffu;
+    if (c != 0ull) {
+        double sc = acc;
+        if (metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN) sc = metric_finish(acc, metric, q_aux[q], c_aux[row]);
+        key = score_key(sc, higher);
+        idx = gidx;
+    }
+    __syncthreads();
+    // an empty slot must rank after every real candidate, NaN scores (key 0) included: real ones get bit 0 of a
+    // side flag through the index order (empty: index 2^32-1, and candidates never carry that index)
+    skey[t] = key;
+    sidx[t] = idx;
+    __syncthreads();
+    for (int size = 2; size <= NT; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int p = t ^ stride;
+            if (p > t) {
+                const bool desc = (t & size) == 0;
+                const uint64_t ka = skey[t], kb = skey[p];
+                const uint32_t ia = sidx[t], ib = sidx[p];
+                const bool a_first = ka > kb || (ka == kb && ia < ib);
+                if (a_first != desc) { skey[t] = kb; skey[p] = ka; sidx[t] = ib; sidx[p] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    if (t == 0 && chk.flags) {
+        const uint64_t last = cand[q * kp_in + kp_in - 1];
+        float f_last = 0.0f;
+        bool dropped = false;
+        if (last != 0ull) {
+            f_last = key_score(candidate_key(last), true);
+            dropped = true;
+        } else if (chk.seed && chk.seed[q] == chk.seed[q]) {
+            f_last = chk.seed[q];
+            dropped = true;
+        }
+        bool ok = true;
+        const double tk = k_out > 0 ? key_score(skey[k_out - 1], higher) : 0.0;
+        const float qn = sqrtf(chk.q_sq[q]);
+        if (dropped && k_out > 0) {
+            const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
+            const double e = (double)filter_error_bound(chk.eps, chk.abs_err, metric, qn, cmax, cmin);
+            if (metric == METRIC_DOT) {
+                ok = tk > (double)f_last + e;
+            } else if (metric == METRIC_COSINE) {
+                const double th = ((double)f_last + e) / (double)qn;
+                ok = qn > 1e-6f && tk > th + 1e-6 * fabs(th);
+            } else {
+                const double sq_floor = -(double)f_last - e;
+                ok = sq_floor > 0.0 && tk < sqrt(sq_floor) * (1.0 - 1e-6);
+            }
+            if (chk.max_norm > 0.0f && !(qn <= chk.max_norm && cmax <= chk.max_norm)) ok = false;
+            if (!(ok)) ok = false;
+        }
+        if (!ok && chk.kth_units)
+            chk.kth_units[q] = (float)(metric == METRIC_DOT ? tk : metric == METRIC_COSINE ? tk * (double)qn : -(tk * tk));
+        if (!ok) {
+            chk.flags[q] = 1;
+            atomicAdd(chk.flag_count, 1u);
+        }
+    }
+    if (t < k_out) {
+        if (out_idx) out_idx[q * k_out + t] = sidx[t];
+        if (out_score) out_score[q * k_out + t] = key_score(skey[t], higher);
+    }
+}
+
+cudaError_t launch_rescore_f64(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm, const double *q_aux,
+                               const double *c_aux, int metric, int64_t index_base, int k_out, uint32_t *out_idx,
+                               double *out_score, const RescoreCheck &chk, cudaStream_t s) {
+    if (qm.n_rows <= 0 || k_out <= 0) return cudaSuccess;
+    if (qm.dim * 8 > 128 * 1024) return cudaErrorInvalidValue;  // query row must fit shared memory
+    const unsigned grid = (unsigned)qm.n_rows;
+    const size_t smem_q = (size_t)((qm.dim + 1) & ~(int64_t)1) * 8;
+#define PMM_RS64(NT)                                                                                                       \
+    {                                                                                                                      \
+        size_t smem = NT * 12 + 8 + smem_q + (size_t)(NT / 32) * 32 * RS_PITCH64 * 8;                                     \
+        if (smem > 48 * 1024) {                                                                                            \
+            cudaError_t e = cudaFuncSetAttribute(rescore_f64_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                                \
+        }                                                                                                                  \
+        rescore_f64_kernel<NT><<<grid, NT, smem, s>>>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, out_idx, \
+                                                      out_score, chk);                                                     \
+    }
+    if (kp_in <= 32) PMM_RS64(32)
+    else if (kp_in <= 64) PMM_RS64(64)
+    else if (kp_in <= 128) PMM_RS64(128)
+    else if (kp_in <= 256) PMM_RS64(256)
+    else return cudaErrorInvalidValue;
+#undef PMM_RS64
+    return cudaGetLastError();
+}
+
+// ---- seeds of a re-query level --------------------------------------------------------------------------------
+// A flagged query's exact k-th score t (from the candidates the previous level kept) is a LOWER bound of its true
+// k-th score, so a candidate that belongs to the top k (or ties into it) has an exact score >= t and therefore a
+// filter value >= t - E at the next level (E = that level's error bound).  The next level starts each row's
+// threshold just below that: no list warm-up, and usually fewer candidates than the list holds, so nothing at all is
+// dropped above the seed.  Margins: 8e-6 relative covers the float rounding of the checks in rescore_kernel.
+__global__ void make_seeds_kernel(const int64_t *__restrict__ ids, int64_t n_ids, int64_t n_pad,
+                                  const float *__restrict__ kth_units, RescoreCheck next, int metric, float *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    float seed = __uint_as_float(0x7fc00000u);
+    if (r < n_ids) {
+        const int64_t q = ids[r];
+        const float v = kth_units[q];
+        const float qn = sqrtf(next.q_sq[q]);
+        const float cmax = sqrtf(__uint_as_float(next.c_max_sq[0])), cmin = sqrtf(__uint_as_float(next.c_max_sq[1]));
+        const float e = filter_error_bound(next.eps, next.abs_err, metric, qn, cmax, cmin);
+        const bool in_range = next.max_norm <= 0.0f || (qn <= next.max_norm && cmax <= next.max_norm);
+        const float sd = (v - e) - 8e-6f * fabsf(v) - 1e-30f;
+        if (in_range && sd == sd && fabsf(sd) <= 3.0e38f) seed = sd;
+    }
+    out[r] = seed;
+}
+cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, const float *kth_units,
+                              const RescoreCheck &next, int metric, float *out, cudaStream_t s) {
+    if (n_pad <= 0) return cudaSuccess;
+    make_seeds_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(ids, n_ids, n_pad, kth_units, next, metric, out);
+    return cudaGetLastError();
+}
+
 // ---- fallback plumbing: gather flagged query rows into a dense f32 matrix, scatter their results back ----
-template <typename SRC>
-__global__ void gather_rows_kernel(RawMatrix qm, const int64_t *__restrict__ ids, int64_t n_ids, float *__restrict__ out) {
+template <typename OUT>
+__global__ void gather_rows_kernel(RawMatrix qm, const int64_t *__restrict__ ids, int64_t n_ids, OUT *__restrict__ out) {
     const int64_t r = blockIdx.x;
     if (r >= n_ids) return;
     int64_t b, l;
     raw_row(qm, ids[r], b, l);
-    for (int64_t i = threadIdx.x; i < qm.dim; i += blockDim.x) out[r * qm.dim + i] = raw_fetch<SRC>(qm, b, l, i);
+    for (int64_t i = threadIdx.x; i < qm.dim; i += blockDim.x) out[r * qm.dim + i] = (OUT)raw_fetch_f64(qm, b, l, i);  // widening, then exact back
 }
-cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, float *out, cudaStream_t s) {
+// out: [n_ids x dim] dense rows in f32 (out_f64 = 0; the source is f16 or f32 then) or f64.
+cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, void *out, int out_f64, cudaStream_t s) {
     if (n_ids <= 0) return cudaSuccess;
-    if (qm.dtype == 0) gather_rows_kernel<__half><<<(unsigned)n_ids, 128, 0, s>>>(qm, ids, n_ids, out);
-    else gather_rows_kernel<float><<<(unsigned)n_ids, 128, 0, s>>>(qm, ids, n_ids, out);
+    if (out_f64) gather_rows_kernel<double><<<(unsigned)n_ids, 128, 0, s>>>(qm, ids, n_ids, (double *)out);
+    else gather_rows_kernel<float><<<(unsigned)n_ids, 128, 0, s>>>(qm, ids, n_ids, (float *)out);
     return cudaGetLastError();
 }
 __global__ void scatter_results_kernel(const int64_t *__restrict__ ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,

@@ -10,18 +10,25 @@
 //              only candidates that beat the row's current k-th best.
 //   * matmul : replaces matmul_slice_f32 (src/metrics.rs:160-202): 128-bit stores of the tile rows.
 //
-// Precision: f32 inputs use the 3xTF32 split (hi*hi + hi*lo + lo*hi with hi/lo planes from
-// pmm_prep.cu; f32 accumulation in TMEM); f16-stored inputs use kind::f16 directly (products of two
-// f16 values are exact in f32, so only the summation order differs from the reference's upcast path).
+// Precision: the top-k epilogue is a FILTER - final scores come from the exact re-scoring kernel (pmm_rescore.cu)
+// and every query carries a proof that the filter dropped nothing relevant - so the operand format is an internal
+// choice per level: f32 (or f64) inputs rounded to one f16 plane + ONE kind::f16 MMA per K-step (default first
+// level, 11 significant bits at the full f16 rate), one TF32 plane (TERMS = 1), or the 3xTF32 split
+// hi*hi + hi*lo + lo*hi on hi/lo planes from pmm_prep.cu (re-query level; also the raw matmul, whose result IS the
+// output and must stay within 1e-5).  f16-stored inputs use kind::f16 on exact planes (products of two f16 values
+// are exact in f32, so only the summation order differs from the reference's upcast path).  f32 accumulation in TMEM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
-// (one lane), warps 2..5 = epilogue (TMEM lane group = warp % 4).  Two accumulator buffers of 256
-// TMEM columns let the epilogue of tile i overlap the MMAs of tile i+1.
+// Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM lane group = warp % 4); the single-plane top-k kernels run a second set of four
+// epilogue warps (6..9), each set owning half of the columns of every tile.  Two accumulator buffers of 256 TMEM
+// columns let the epilogue of tile i overlap the MMAs of tile i+1.
 //
-// Running top-k: per row a threshold (the k-th best packed candidate so far) and a 16-slot staging
-// buffer in shared memory; the sorted list of KP = 32/64/128 candidates lives in global memory
-// (L2-resident).  When a row's staging buffer fills, its warp sorts the staged candidates with
-// shuffles, bitonic-merges them into the list (KP/32 registers per lane) and refreshes the threshold.
+// Running top-k: per row a threshold (the k-th best packed candidate so far).  Scores that beat it are appended to a
+// 128-slot per-row staging area in global memory (L2-resident, one per CTA and row); the row's sorted list of
+// KP = 32/64/128/256 candidates lives in global memory too (KP/32 registers per lane when it is merged).  Staged
+// candidates are merged in batches - at the end of a tile, after the TMEM buffer went back to the MMA warp - by a
+// shuffle-based bitonic sort of the batch plus one bitonic merge with the list, which also refreshes the threshold.
+// A launch may start from per-row SEED thresholds (TcArgs::seed_thr: "collect everything above this value").
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
@@ -102,9 +109,19 @@ struct TcKParams {
     int soft_at;     // end-of-tile merge threshold (SOFT_AT unless overridden for experiments)
     int resume;      // lists already hold the candidates of earlier launches over other corpus rows
     int max_flush;   // row merges per warp at the end of a tile (rate limit; rows above URGENT_AT always go)
+    float norm_guard;       // cosine: norms at or below this count as zero (1e-6 f32; just under 1e-10 for f64 sources)
+    const float *seed_thr;  // per query row (padded like q_aux): initial threshold in filter units, NaN = none; or NULL
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
+
+// Timing experiments that return WRONG results (debug_skip 1..3: epilogue without filter / without merges) exist only
+// in -DPMM_DIAG builds; debug_skip == 8 (correct results + wait-cycle counters) is always available.
+#ifdef PMM_DIAG
+#define PMM_DSKIP(p, x) ((p).debug_skip == (x))
+#else
+#define PMM_DSKIP(p, x) false
+#endif
 
 // Diagnostics (option tc_debug_skip = 8): cycles the MMA warps spent waiting for [0] a free accumulator buffer,
 // [1] a filled operand stage, [2] in total; [3] cycles epilogue warp 2 of the leader CTAs spent in list flushes.
@@ -137,7 +154,7 @@ __device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int 
 template <int R>
 __device__ __forceinline__ void flush_rows(unsigned rows, const uint64_t *stg /* the warp's 32 staging rows */,
                                            uint64_t *list_base /* lane group's 32 lists */, int lane, int k, uint64_t &thr,
-                                           float &thr_f, int &cnt) {
+                                           float &thr_f, int &cnt, uint64_t seed_c /* this lane's seed threshold, 0 = none */) {
     constexpr int KP = 32 * R;
     __syncwarp();
     if (k < 0) {  // measurement only (debug_skip == 3): drop the staged candidates
@@ -183,8 +200,8 @@ __device__ __forceinline__ void flush_rows(unsigned rows, const uint64_t *stg /*
             if (r == ((k - 1) >> 5)) kreg = L[r];
         const uint64_t kth = __shfl_sync(0xffffffffu, kreg, (k - 1) & 31);
         if (lane == src) {
-            thr = kth;
-            thr_f = kth == 0ull ? __uint_as_float(0x7fc00000u) : key_score(candidate_key(kth), true);
+            thr = kth > seed_c ? kth : seed_c;   // a seeded row never opens up again below its seed
+            thr_f = thr == 0ull ? __uint_as_float(0x7fc00000u) : key_score(candidate_key(thr), true);
             cnt = 0;
         }
     }
@@ -212,7 +229,8 @@ template <int METRIC, int R>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t aux_s /* shared address: 32 floats */,
                                              uint32_t look_s /* shared address: the warp's 32 x LOOK_PITCH floats */, float rowc,
                                              int64_t col0, int64_t n, int64_t index_base, uint64_t *stg /* warp's staging rows */,
-                                             uint64_t *list_base, int lane, int k, uint64_t &thr, float &thr_f, int &cnt) {
+                                             uint64_t *list_base, int lane, int k, uint64_t &thr, float &thr_f, int &cnt,
+                                             uint64_t seed_c) {
     float f[32];
 #pragma unroll
     for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -263,7 +281,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t a
         } while (m);
     }
     const unsigned over = __ballot_sync(0xffffffffu, cnt > HARD_AT);  // room for the next chunk's (at most) 32
-    if (over) flush_rows<R>(over, stg, list_base, lane, k, thr, thr_f, cnt);
+    if (over) flush_rows<R>(over, stg, list_base, lane, k, thr, thr_f, cnt, seed_c);
 }
 
 template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM>
@@ -334,6 +352,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         int stage = 0;
         uint32_t phase = 0;
         const int n_sync_full = p.round_sync ? ((S.n_tiles + S.g - 1) / S.g + p.sync_tiles - 1) / p.sync_tiles : 0;
+        bool pace = true;  // cleared by the first timeout: this CTA keeps arriving but no longer waits (the grid is
+                           // evidently not co-resident, e.g. another kernel holds SMs; waiting again would cost 4 ms a time)
         for (int it = 0; it < total_rounds; ++it) {
             // Pacing. All CTAs are co-resident (persistent grid <= #SMs), so their producers can meet: every
             // `sync_tiles` corpus tiles of a round all producers wait for each other, which keeps the groups
@@ -362,13 +382,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         // wait until every producer has reached the sync point `sync_slack` points back (0: this one):
                         // CTAs may drift apart by sync_slack + 1 segments, which absorbs epilogue jitter
                         unsigned int *wctr = ctr - p.sync_slack;
-                        if (wctr >= p.round_sync) {
+                        if (pace && wctr >= p.round_sync) {
                             const long long t0 = clock64();
                             // best-effort, never a correctness dependency: give up after ~4 ms (e.g. when another
                             // kernel holds some SMs and part of this grid is not resident yet)
                             while (ld_acquire_u32(wctr) < gridDim.x) {
                                 __nanosleep(100);
-                                if (clock64() - t0 > 8000000ll) break;
+                                if (clock64() - t0 > 8000000ll) {
+                                    pace = false;
+                                    break;
+                                }
                             }
                         }
                     }
@@ -546,26 +569,35 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
             const int64_t qrow = (((int64_t)m_tile * CLM + pairc) * CG + crank) * BM + row;
             uint64_t thr = 0ull;
-            float thr_f = p.debug_skip == 3 ? 103.0f : __uint_as_float(0x7fc00000u);  // DEBUGSKIP3
-            if (p.debug_skip == 3) thr = 1ull;
-            const int kk = p.debug_skip == 3 ? -1 : p.k;
+            float thr_f = PMM_DSKIP(p, 3) ? 103.0f : __uint_as_float(0x7fc00000u);
+            if (PMM_DSKIP(p, 3)) thr = 1ull;
+            const int kk = PMM_DSKIP(p, 3) ? -1 : p.k;
             int cnt = 0;
             unsigned rot = 0;
             const int max_flush = p.max_flush;
             float rowc = 0.0f;
+            uint64_t seed_c = 0ull;
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
                 list_base = p.partial + (((slot * ESETS + eset) * GS + (crank4 & (uint32_t)(GS - 1))) * BM + row0) * KP;
                 if (!p.resume) {
                     for (int i = lane; i < 32 * KP; i += 32) list_base[i] = 0ull;  // this warp's 32 empty lists
-                } else if (p.debug_skip != 3) {  // continue: the threshold is the list's k-th entry
+                } else if (!PMM_DSKIP(p, 3)) {  // continue: the threshold is the list's k-th entry
                     const uint64_t kth = list_base[(int64_t)lane * KP + (p.k - 1)];
                     thr = kth;
                     thr_f = kth == 0ull ? __uint_as_float(0x7fc00000u) : key_score(candidate_key(kth), true);
                 }
+                if (p.seed_thr) {  // "collect everything above this filter value" (NaN: no seed for this row)
+                    const float sf = p.seed_thr[qrow];   // padded to the tile grid like q_aux
+                    if (sf == sf) seed_c = pack_candidate(score_key(sf, true), 0xffffffffu);
+                    if (seed_c > thr) {
+                        thr = seed_c;
+                        thr_f = key_score(candidate_key(seed_c), true);
+                    }
+                }
                 // q_aux is padded to the tile grid. cosine: 1 unless the query norm is ~0; euclidean: |q|^2
-                if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > 1e-6f ? 1.0f : 0.0f;
+                if (p.metric == METRIC_COSINE) rowc = p.q_aux[qrow] > p.norm_guard ? 1.0f : 0.0f;
                 if (p.metric == METRIC_EUCLIDEAN) rowc = p.q_aux[qrow];
                 __syncwarp();
             }
@@ -576,7 +608,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
 #pragma unroll
                     for (int i = 0; i < CPS; ++i) {
                         const float a = __ldg(p.c_aux + col_tile + (ch0 + i) * 32 + lane);  // c_aux is padded to the tile grid
-                        aux_s[i * 32 + lane] = p.metric == METRIC_COSINE ? (a > 1e-6f ? __frcp_rn(a) : 0.0f) : a;
+                        aux_s[i * 32 + lane] = p.metric == METRIC_COSINE ? (a > p.norm_guard ? __frcp_rn(a) : 0.0f) : a;
                     }
                     __syncwarp();
                 }
@@ -587,7 +619,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
 #pragma unroll 1
                 for (int ch = ch0; ch < ch0 + CPS; ++ch) {
                     uint32_t v[32];
-                    if (EPI == EPI_TOPK && p.debug_skip == 2 && ch != ch0 + CPS - 1) continue;
+                    if (EPI == EPI_TOPK && PMM_DSKIP(p, 2) && ch != ch0 + CPS - 1) continue;
                     tmem_ld_32x32(tmem_base + ((uint32_t)row0 << 16) + (uint32_t)(abuf * BN + ch * 32), v);
                     tmem_ld_wait();
                     if (ch == ch0 + CPS - 1) {  // this warp's TMEM reads of the buffer are done: hand it back
@@ -598,7 +630,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         }
                     }
                     const int64_t col0 = col_tile + ch * 32;
-                    if (EPI == EPI_TOPK && (p.debug_skip == 1 || p.debug_skip == 2)) continue;
+                    if (EPI == EPI_TOPK && (PMM_DSKIP(p, 1) || PMM_DSKIP(p, 2))) continue;
                     if (EPI == EPI_MATMUL) {
                         if (p.out_tma) {
                             // registers -> swizzled 32x32 smem tile -> one TMA store per warp and chunk: full 128-byte
@@ -627,13 +659,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         }
                     } else if (p.metric == METRIC_DOT) {
                         filter_chunk<METRIC_DOT, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane, kk,
-                                                    thr, thr_f, cnt);
+                                                    thr, thr_f, cnt, seed_c);
                     } else if (p.metric == METRIC_COSINE) {
                         filter_chunk<METRIC_COSINE, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane,
-                                                       kk, thr, thr_f, cnt);
+                                                       kk, thr, thr_f, cnt, seed_c);
                     } else {
                         filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base,
-                                                          lane, kk, thr, thr_f, cnt);
+                                                          lane, kk, thr, thr_f, cnt, seed_c);
                     }
                 }
                 if (edbg && lane == 0)
@@ -660,7 +692,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     }
                     if (due) {
                         const long long f0 = p.debug_skip == 8 ? clock64() : 0ll;
-                        flush_rows<R>(due, stg, list_base, lane, kk, thr, thr_f, cnt);
+                        flush_rows<R>(due, stg, list_base, lane, kk, thr, thr_f, cnt, seed_c);
                         if (edbg && lane == 0) {
                             atomicAdd(&g_tc_wait[3], (unsigned long long)(clock64() - f0));
                             atomicAdd(&g_tc_wait[36 + (31 - __clz((nt - n_start) / n_step + 1))], (unsigned long long)(clock64() - f0));
@@ -672,7 +704,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             }
             if (EPI == EPI_TOPK) {
                 const unsigned pending = __ballot_sync(0xffffffffu, cnt > 0);
-                if (pending) flush_rows<R>(pending, stg, list_base, lane, kk, thr, thr_f, cnt);
+                if (pending) flush_rows<R>(pending, stg, list_base, lane, kk, thr, thr_f, cnt, seed_c);
             }
         }
     }
@@ -788,6 +820,8 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.sync_tiles = a.sync_tiles > 0 ? a.sync_tiles : 1;
     p.debug_skip = a.debug_skip;
     p.resume = a.resume;
+    p.seed_thr = a.seed_thr;
+    p.norm_guard = a.norm_guard > 0.0f ? a.norm_guard : 1e-6f;
     p.soft_at = a.soft_at > 0 ? a.soft_at : SOFT_AT;
     // merges that fit beside one tile's MMA time: a merge costs about as much as 8 k-blocks of one plane
     p.max_flush = a.max_flush > 0 ? a.max_flush : (p.num_kb * a.terms / 8 > 1 ? p.num_kb * a.terms / 8 : 1);

@@ -179,10 +179,25 @@ def test_every_documented_option_is_accepted_and_unknown_ones_are_not():
     names = set(re.findall(r'"([a-z0-9_]+)"', block)) - {"kernel"}
     assert {"tc_levels", "f16r_wide", "host_chunked", "verify", "profile"} <= names
     defaults = {"tc_levels": 3, "tc_cg": 2, "tc_sync_tiles": 32, "host_chunked": 1, "verify": 1, "f16r_wide": 1, "tc_clm": 1,
-                "host_chunk_min_rows": 16384, "host_chunk_min_mb": 64, "generic_workspace_mb": 0}
+                "host_chunk_min_rows": 16384, "host_chunk_min_mb": 64, "generic_workspace_mb": 0, "seed_retry": 1, "f64_tc": 1,
+                "multi_gpu": 1, "multi_gpu_min_gflop": 4000, "stage": 1, "stage_slot_mb": 32, "stage_slots": 4,
+                "workspace_cache_mb": 24576}
     for n in sorted(names):
         if n in ("release_workspace", "generic_workspace_mb") or n.startswith("tc_dbg"):
             continue
         _native.set_option(n, defaults.get(n, 0))      # restores the default as it goes
     with pytest.raises(_native.PmmError):
         _native.set_option("no_such_option", 1)
+    # the wrong-result timing modes are compiled out of the default build
+    for v in (1, 2, 3):
+        with pytest.raises(_native.PmmError, match="PMM_DIAG"):
+            _native.set_option("tc_debug_skip", v)
+    _native.set_option("tc_debug_skip", 8)
+    _native.set_option("tc_debug_skip", 0)
+    # per-thread overrides: same key space (minus the immediate, process-wide ones), dropped with key=None
+    _native.set_thread_option("tc_levels", 2)
+    with pytest.raises(_native.PmmError):
+        _native.set_thread_option("stage_threads", 2)
+    with pytest.raises(_native.PmmError):
+        _native.set_thread_option("no_such_option", 1)
+    _native.set_thread_option(None)
