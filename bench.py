@@ -5,19 +5,25 @@ bench.py — headline benchmark of the pmm.topk hot path on B200.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[2], the largest single-GPU configuration): 100k queries x 1M corpus
-rows, 768-d f32, metric=dot, k=100, synthetic Gaussian data.  With N > 1 ranks the corpus is sharded
-by rows, 1M rows per rank (weak scaling; N=8 is configs[3]'s shape at 8M rows): every rank scans its
-shard for all queries with the fused kernel, the ranks exchange Q x k packed candidates with one NCCL
-all-gather and every rank merges them.
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): 100k queries x 1M corpus rows, 768-d f32,
+metric=dot, k=100, synthetic Gaussian data.  With N > 1 ranks the corpus is sharded by rows, 1M rows per rank (weak
+scaling; N=8 is configs[3]'s shape at 8M rows): every rank scans its shard for all queries with the fused kernel, the
+ranks exchange packed candidates over NCCL (all-to-all inside libpmm_b200: each rank merges 1/N of the queries) and
+the merged slices are broadcast so that every rank holds the full result.
 
-One "step" = one full pass of the hot path (norm/split precompute, fused GEMM+top-k, merge) over the
-batch.  `value` has the inputs resident in HBM when the timed region starts; `e2e` goes through the
-host C ABI (pmm_topk) with host buffers in pinned memory, H2D and D2H copies inside the timed region.
+One "step" = one full pass of the hot path (norm/plane precompute, fused GEMM+top-k, merge, exact re-scoring) over the
+batch.  `value` has the inputs resident in HBM when the timed region starts.  `e2e` is the call a user makes:
+`polars_matmul_b200._topk(queries, corpus, k, metric)` with ordinary PAGEABLE NumPy buffers — the library stages them
+through its page-locked ring, H2D / D2H copies and the Arrow result assembly are inside the timed region
+(`e2e.pinned_inputs` repeats it with page-locked inputs for comparison).
 
-`--impl reference`: the reference's CPU implementation cannot be built here (Rust + un-vendored faer,
-no cargo in the image), so this arm times the oracle port (oracle/pmm_oracle.c, OpenMP, all host
-threads) on a bounded query sample of the same workload.
+Self-check: after the timed loops, 16 sampled queries are recomputed by the CPU oracle against the GLOBAL corpus (each
+rank scans its own shard with the oracle, rank 0 merges) and compared bit for bit with the result of the timed resident
+step -> `selfcheck` in the JSON line.  Outside every timed region.
+
+`--impl reference`: the reference's CPU implementation cannot be built here (Rust + un-vendored faer, no cargo in the
+image), so this arm times the oracle port (oracle/pmm_oracle.c, OpenMP, all host threads — it sets its own thread
+count, torchrun's OMP_NUM_THREADS=1 notwithstanding) on a bounded query sample of the same workload.
 """
 from __future__ import annotations
 
@@ -38,6 +44,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(name="C3", Q=100_000, N=1_000_000, D=768, k=100, metric="dot")
 METRIC_NAME = "topk_queries_per_sec"
 UNIT = "queries/s"
+SELFCHECK_QUERIES = 16
 
 
 def load_traffic(kernel: str, workload: str):
@@ -105,10 +112,20 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_sample(q_host: np.ndarray, c_host: np.ndarray, k: int, metric: str, target_s: float = 12.0):
-    """Times the oracle port on a bounded query sample against the full corpus shard."""
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline_sample(q_host: np.ndarray, c_host: np.ndarray, k: int, metric: str, target_s: float = 10.0):
+    """CPU data points on the box's host cores, on a bounded query sample against the full corpus shard:
+    the oracle port (measured), the reference's own NumPy comparator (measured; cosine-normalised BLAS matmul +
+    argpartition, examples/benchmark_topk.py:14-33) and the labelled faer estimate BASELINE.md §3 describes."""
     from oracle import pmm_oracle as oracle
     oracle.build()
+    oracle.set_num_threads(host_threads())
     n_cal = 8 * max(1, oracle.num_threads())      # the oracle parallelises over blocks of 8 queries
     t0 = time.perf_counter()
     oracle.topk(q_host[:n_cal], c_host, k, metric)
@@ -118,23 +135,46 @@ def cpu_baseline_sample(q_host: np.ndarray, c_host: np.ndarray, k: int, metric: 
     t0 = time.perf_counter()
     oracle.topk(q_host[:n], c_host, k, metric)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-            "sample": f"{n} of {q_host.shape[0]} queries x full {c_host.shape[0]}-row corpus, {dt:.1f} s, "
-                      f"oracle/pmm_oracle.c (OpenMP, -O3 -mavx2 -mfma); the reference (Rust/faer) cannot be built in this image"}
+    out = {"value": n / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+           "sample": f"{n} of {q_host.shape[0]} queries x full {c_host.shape[0]}-row corpus, {dt:.1f} s, "
+                     f"oracle/pmm_oracle.c (OpenMP, -O3 -mavx2 -mfma); the reference (Rust/faer) cannot be built in this image"}
+    # the reference's own comparator: NumPy (OpenBLAS sgemm + argpartition), chunked over the queries so that the
+    # score matrix stays bounded (256 x N f32 = 1 GB at N = 1M); timed at the benchmark's metric via its cosine recipe
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        blas_threads = None
+    nq_np, chunk = 512, 256
+    t0 = time.perf_counter()
+    for lo in range(0, nq_np, chunk):
+        oracle.numpy_topk_cosine(q_host[lo:lo + chunk], c_host, k)
+    dt_np = time.perf_counter() - t0
+    np_rate = nq_np / dt_np
+    out["numpy"] = {"value": np_rate, "unit": UNIT, "blas_threads": blas_threads,
+                    "sample": f"{nq_np} queries x full corpus in chunks of {chunk}, {dt_np:.1f} s; the reference's own comparator "
+                              "numpy_topk_cosine (examples/benchmark_topk.py:14-33; cosine recipe, the corpus normalisation is "
+                              "re-done per chunk as the script does per call)"}
+    out["faer_estimate"] = {"value": np_rate / 0.64, "unit": UNIT,
+                            "note": "ESTIMATE, not measured: NumPy rate / 0.64 (README.md:166: polars-matmul 45 ms vs NumPy 73-75 ms "
+                                    "on its own 1000x10000x256 benchmark, hardware unstated); the Rust/faer reference cannot be built here"}
+    return out
 
 
 def run_reference(args, emit):
-    """--impl reference: oracle port on host cores (rank 0 only)."""
+    """--impl reference: oracle port on host cores (rank 0 only; the other ranks exit without work)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     from oracle import pmm_oracle as oracle
     oracle.build()
+    oracle.set_num_threads(host_threads())          # torchrun exports OMP_NUM_THREADS=1: this arm uses every host core
     W = dict(WORKLOAD)
     if args.small:
         W.update(Q=2000, N=50_000)
     rng = np.random.default_rng(42)
-    # bounded sample: the oracle scans the FULL corpus for a subset of the queries
+    # bounded sample: the oracle scans a FULL 1M-row shard for a subset of the queries
     n_probe = 8 * max(1, oracle.num_threads())    # the oracle parallelises over blocks of 8 queries
     c = rng.standard_normal((W["N"], W["D"]), dtype=np.float32)
     q = rng.standard_normal((4096, W["D"]), dtype=np.float32)
@@ -152,19 +192,106 @@ def run_reference(args, emit):
             times.append(dt)
     ms = 1000 * sum(times) / len(times)
     val = n / (ms / 1000)
-    sample = (f"{n} of {W['Q']} queries x full {W['N']}-row corpus per step; oracle port "
-              f"(oracle/pmm_oracle.c, OpenMP {oracle.num_threads()} threads); the Rust/faer reference cannot be built here")
+    sample = (f"{n} of {W['Q']} queries x one full {W['N']}-row shard per step; oracle port "
+              f"(oracle/pmm_oracle.c, OpenMP {oracle.num_threads()} threads, set by this arm itself); the Rust/faer reference cannot be built here")
+    scaling_note = ("value counts query x 1M-row-shard scans per second, the same unit as the GPU arm's n_gpus * Q / step: a CPU "
+                    f"scanning the global {world}M-row corpus needs {world}x as long per query, i.e. the same number of shard scans per "
+                    "second, so this figure does not depend on n_gpus (linear in N; stated, not re-measured on the larger corpus)")
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W['name']}: {W['Q']} queries x {W['N']} corpus rows, {W['D']}d f32, metric={W['metric']}, k={W['k']}",
-                   "timed": sample},
+        "config": {"workload": f"{W['name']}: {W['Q']} queries x {W['N']} corpus rows per GPU, {W['D']}d f32, metric={W['metric']}, k={W['k']}",
+                   "timed": sample, "value_definition": scaling_note},
+        "queries_per_sec_global_corpus": val / max(1, world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def hbm_extras(_native, torch, peaks):
+    """The second half of BASELINE.json's metric inside the driver-run line: raw matmul and norms as HBM GB/s (and
+    TFLOP/s, with the roofline that binds each shape - SURVEY §8d ridge analysis).  Kernel-only, CUDA events recorded by
+    the library on the launching stream, inputs resident, a 256 MB buffer is rewritten between launches (L2 flush)."""
+    st = torch.cuda.current_stream().cuda_stream
+    code = {torch.float16: 0, torch.float32: 1, torch.float64: 2}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    out = {"hbm_peak_gbs": hbm, "matmul": {}, "norms": {}}
+
+    def run(fn, names, iters=5):
+        fn()
+        torch.cuda.synchronize()
+        _native.set_option("profile", 1)
+        _native.reset_stats()
+        for _ in range(iters):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        r = {n: _native.get_stat(n + "_ms") / iters for n in names if _native.get_stat(n + "_ms") > 0}
+        _native.set_option("profile", 0)
+        return r
+
+    for (Q, N, D, dt, label) in ((1000, 10000, 256, torch.float32, "C2_f32_1000x10000x256"),
+                                 (1000, 10000, 256, torch.float64, "C2_f64_1000x10000x256"),
+                                 (16384, 65536, 32, torch.float32, "f32_16384x65536x32"),
+                                 (16384, 65536, 256, torch.float32, "f32_16384x65536x256"),
+                                 (16384, 65536, 256, torch.float16, "f16_16384x65536x256")):
+        a = torch.randn((Q, D), generator=g, device="cuda", dtype=torch.float32).to(dt)
+        b = torch.randn((N, D), generator=g, device="cuda", dtype=torch.float32).to(dt)
+        o = torch.empty((Q, N), dtype=torch.float64 if dt == torch.float64 else torch.float32, device="cuda")
+        r = run(lambda: _native.dev_matmul(_native.dev_matrix(a.data_ptr(), Q, D, code[dt]), _native.dev_matrix(b.data_ptr(), N, D, code[dt]),
+                                           o.data_ptr(), st), ("tc_matmul_tf32x3", "tc_matmul_f16", "scores_f64_dmma", "scores_f32", "prep"))
+        kern = [k for k in r if k != "prep"][0]
+        gb = (Q * N * o.element_size() + (Q + N) * D * a.element_size()) / 1e9
+        tf = 2.0 * Q * N * D / r[kern] / 1e9
+        # which roofline binds the shape: HBM (write-bound) when the contraction is cheaper than the writes
+        tensor_peak = {"tc_matmul_tf32x3": peaks.get("bf16_tflops_sustained", 1400.0) / 6.0, "tc_matmul_f16": peaks.get("bf16_tflops_sustained", 1400.0)}.get(kern)
+        t_hbm = gb / hbm * 1e3
+        t_tc = (2.0 * Q * N * D / 1e12 / tensor_peak * 1e3) if tensor_peak else None
+        out["matmul"][label] = {"kernel": kern, "kernel_ms": r[kern], "prep_ms": r.get("prep"), "algorithmic_GB": gb,
+                                "GBps": gb / r[kern] * 1e3, "frac_hbm": gb / r[kern] * 1e3 / hbm, "TFLOPs": tf,
+                                "binding_roofline": ("dmma (fp64 tensor path, peak not in MEASURED_PEAKS)" if kern == "scores_f64_dmma" else
+                                                     "hbm" if (t_tc is None or t_hbm >= t_tc) else "tensor"),
+                                "frac_tensor": (tf / tensor_peak) if tensor_peak else None}
+        del a, b, o
+    for (N, D, dt) in ((1_000_000, 768, torch.float32), (4_000_000, 256, torch.float32), (1_000_000, 1024, torch.float16)):
+        x = torch.randn((N, D), generator=g, device="cuda", dtype=torch.float32).to(dt)
+        o = torch.empty(N, dtype=torch.float32, device="cuda")
+        r = run(lambda: _native.dev_norms(_native.dev_matrix(x.data_ptr(), N, D, code[dt]), False, o.data_ptr(), st), ("norms",))
+        gb = N * D * x.element_size() / 1e9
+        out["norms"][f"{N}x{D}_{str(dt)[6:]}"] = {"kernel_ms": r["norms"], "algorithmic_GB": gb, "GBps": gb / r["norms"] * 1e3,
+                                                  "frac_hbm": gb / r["norms"] * 1e3 / hbm}
+        del x, o
+    return out
+
+
+def c1_e2e(pmm):
+    """BASELINE.json configs[0] end to end through the plugin's native call, the only config with a published reference
+    figure (README.md:16: 45 ms, hardware unstated): 1000 x 10000 x 256 f32 cosine k=10, generator and protocol of
+    examples/benchmark_topk.py (2 warm-ups, median of 5), pl.List-like (LargeList) and pl.Array-like (FixedSizeList) input."""
+    import pyarrow as pa
+    np.random.seed(42)
+    q = np.random.randn(1000, 256).astype(np.float32)
+    c = np.random.randn(10000, 256).astype(np.float32)
+    res = {}
+    for label, conv in (("list", lambda a: pa.LargeListArray.from_arrays(pa.array(np.arange(a.shape[0] + 1, dtype=np.int64) * a.shape[1]), pa.array(a.reshape(-1)))),
+                        ("array", lambda a: pa.FixedSizeListArray.from_arrays(pa.array(a.reshape(-1)), a.shape[1]))):
+        qa, ca = conv(q), conv(c)
+        for _ in range(2):
+            pmm._topk(qa, ca, 10, "cosine")
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            pmm._topk(qa, ca, 10, "cosine")
+            ts.append((time.perf_counter() - t0) * 1e3)
+        res[label + "_ms_median"] = statistics.median(ts)
+    res["reference_readme_ms"] = 45.0
+    res["note"] = "polars_matmul_b200._topk(Arrow in, Arrow out), pageable inputs, H2D + D2H + result assembly inside; README figure: hardware unstated"
+    return res
 
 
 def main():
@@ -186,6 +313,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny shapes for a functional check (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the raw-matmul / norms / C1 / C4-strong extras")
     ap.add_argument("--q", type=int, default=None, help="override the query count (profiling runs only)")
     ap.add_argument("--n", type=int, default=None, help="override the corpus rows per GPU (profiling runs only)")
     ap.add_argument("--metric", default=None)
@@ -196,8 +324,9 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import polars_matmul_b200 as pmm
     from polars_matmul_b200 import _native, sharded
-    from polars_matmul_b200.arrow import from_numpy
+    from polars_matmul_b200.arrow import from_numpy, topk_to_arrow
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,12 +334,19 @@ def main():
     torch.cuda.set_device(local_rank)
     _native.lib()
     _native.set_device(local_rank)
+    _native.set_option("multi_gpu", 0)     # one process per GPU here: the library must not spread a call over the box itself
     numa = None
+    group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         if not os.environ.get("PMM_BENCH_NO_NUMA_BIND"):
-            numa = sharded.bind_near_gpu(local_rank)   # before the pinned host buffers are allocated
+            numa = sharded.bind_near_gpu(local_rank)   # before the staging ring is allocated
+        # the ranks share one host: split its cores between their staging threads
+        _native.set_option("stage_threads", max(1, min(8, host_threads() // world)))
+        uid = [sharded.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)          # torch.distributed only carries the 128-byte id and the timing barriers
+        group = sharded.RankGroup(uid[0], rank, world)
     dev = torch.device("cuda", local_rank)
 
     W = dict(WORKLOAD)
@@ -228,21 +364,18 @@ def main():
     mcode = _native.metric_from_str(metric)
     n_total = N * world
 
-    # synthetic data, generated on the host so that the e2e leg has real host buffers (pinned)
+    # synthetic data in ordinary (pageable) host memory - what a Polars / Arrow buffer is
     rng_q = np.random.default_rng(42)
-    q_pin = torch.empty((Q, D), dtype=torch.float32).pin_memory()
-    q_pin.numpy()[...] = rng_q.standard_normal((Q, D), dtype=np.float32)
-    c_pin = torch.empty((N, D), dtype=torch.float32).pin_memory()
+    q_host = rng_q.standard_normal((Q, D), dtype=np.float32)
+    c_host = np.empty((N, D), np.float32)
     rng_c = np.random.default_rng(1000 + rank)
-    cn = c_pin.numpy()
     for lo in range(0, N, 65536):
         hi = min(N, lo + 65536)
-        cn[lo:hi] = rng_c.standard_normal((hi - lo, D), dtype=np.float32)
-    dq = q_pin.to(dev)
-    dc = c_pin.to(dev)
+        c_host[lo:hi] = rng_c.standard_normal((hi - lo, D), dtype=np.float32)
+    dq = torch.from_numpy(q_host).to(dev)
+    dc = torch.from_numpy(c_host).to(dev)
     torch.cuda.synchronize()
 
-    driver = sharded.ShardedTopk() if world > 1 else None
     idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
     sc = torch.empty((Q, k), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -252,20 +385,25 @@ def main():
             _native.dev_topk(_native.dev_matrix(dq.data_ptr(), Q, D, _native.DTYPE_F32),
                              _native.dev_matrix(dc.data_ptr(), N, D, _native.DTYPE_F32), k, mcode,
                              index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(), stream=stream)
-            return idx, sc
-        return driver.topk_device(dq, dc, rank * N, n_total, k, metric)
+        else:   # collective inside libpmm_b200; synchronous; every rank receives the full result
+            group.topk_device(dq.data_ptr(), Q, D, _native.DTYPE_F32, dc.data_ptr(), N, _native.DTYPE_F32, rank * N, n_total,
+                              k, metric, idx.data_ptr(), sc.data_ptr(), full=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
+    def reduce_ranks(ms: float):
+        """(max, min) over ranks."""
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            return ms, ms
+        t = torch.tensor([ms, -ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return float(t[0].item()), -float(t[1].item())
+
+    # The group path runs on the library's own stream of this thread: record the timing events there.
+    tstream = torch.cuda.ExternalStream(_native.thread_stream(), device=dev) if world > 1 else torch.cuda.current_stream()
 
     # ---- kernel/device-resident measurement -------------------------------------------------------
     for _ in range(args.warmup):
@@ -279,63 +417,189 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
+    ev0.record(tstream)
     for _ in range(args.steps):
         step_resident()
-    ev1.record()
+    ev1.record(tstream)
     barrier()
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_step, ms_step_min = reduce_ranks(ev0.elapsed_time(ev1) / args.steps)
     launches = _native.kernel_launch_count()
     kname = max(("tc_topk_f16r", "tc_topk_tf32x1", "tc_topk_tf32x3"), key=lambda n: _native.get_stat(n + "_ms"))
     k_ms = _native.get_stat(kname + "_ms")
     k_launches = _native.get_stat(kname + "_launches")
-    stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps)
-             for n in ("prep", "tc_topk_f16r", "tc_topk_f16r_kp256", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge", "rescore", "gather", "scatter", "scores_f32", "select_f32")
-             if _native.get_stat(n + "_ms") > 0}
+    stat_names = ("prep", "tc_topk_f16r", "tc_topk_f16r_seeded", "tc_topk_f16r_kp256", "tc_topk_tf32x1", "tc_topk_tf32x3", "merge",
+                  "rescore", "seeds", "gather", "scatter", "scores_f32", "select_f32", "group_broadcast", "group_exchange",
+                  "group_merge", "group_gather")
+    stats = {n: _native.get_stat(n + "_ms") / max(1, args.steps) for n in stat_names if _native.get_stat(n + "_ms") > 0}
     stats["requeried_f16_wide_per_step"] = _native.get_stat("requeried_f16_wide") / max(1, args.steps)
     stats["requeried_tf32x3_per_step"] = _native.get_stat("requeried_tf32x3") / max(1, args.steps)
     stats["fallback_queries_per_step"] = _native.get_stat("fallback_queries") / max(1, args.steps)
+    if world > 1:
+        stats["rank_skew_ms"] = ms_step - ms_step_min          # slowest minus fastest rank, per step
+        stats["note"] = "rank 0's kernels; the collectives (group_*) are bracketed with CUDA events like the kernels"
     _native.set_option("profile", 0)
     value = world * Q / (ms_step / 1000.0)
 
-    # ---- end-to-end through the host C ABI ---------------------------------------------------------
+    # ---- self-check of the timed result: oracle on a query sample against the GLOBAL corpus ------------------------
+    def selfcheck(index_dev, score_dev, c_shard_host, base, label_metric, kk):
+        """Every rank scans ITS shard with the CPU oracle for the sampled queries; rank 0 merges the per-shard lists
+        under (score best first, lower index first) and compares with the product's merged result: bit-identical
+        scores and indices, or exact=false."""
+        from oracle import pmm_oracle as oracle
+        oracle.build()
+        oracle.set_num_threads(max(1, host_threads() // world))
+        sample = np.arange(0, Q, max(1, Q // SELFCHECK_QUERIES))[:SELFCHECK_QUERIES]
+        ts = torch.from_numpy(sample).to(dev)
+        qs = dq[ts].cpu().numpy()
+        li, ls = oracle.topk(qs, c_shard_host, min(kk, c_shard_host.shape[0]), label_metric)
+        li = li.astype(np.int64) + base
+        if world > 1:
+            gi = [None] * world
+            gs = [None] * world
+            dist.all_gather_object(gi, li)
+            dist.all_gather_object(gs, ls)
+            li, ls = np.concatenate(gi, axis=1), np.concatenate(gs, axis=1)
+        if rank != 0:
+            return None
+        higher = label_metric != "euclidean"
+        key = -ls if higher else ls
+        order = np.lexsort((li, key), axis=1)[:, :kk]            # primary: score (best first), secondary: lower index
+        rows = np.arange(li.shape[0])[:, None]
+        oi, osc = li[rows, order], ls[rows, order]
+        mi = (index_dev[ts].cpu().numpy().view(np.uint32)).astype(np.int64)
+        msc = score_dev[ts].cpu().numpy()
+        exact = bool(np.array_equal(mi, oi) and np.array_equal(msc, osc))
+        return {"queries": int(len(sample)), "exact": exact, "index_match_frac": float((mi == oi).mean()),
+                "max_abs_score_diff": float(np.abs(msc - osc).max()), "corpus_rows": int(n_total if c_shard_host is c_host else c_shard_host.shape[0] * world),
+                "how": "CPU oracle (oracle/pmm_oracle.c) per shard on every rank, merged on rank 0 under (score, lower index); compared "
+                       "bit for bit with the result of the last timed resident step"}
+
+    check = selfcheck(idx, sc, c_host, rank * N, metric, k)
+
+    # ---- end-to-end through the plugin's native call -----------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        hq, hc = from_numpy(q_pin.numpy()), from_numpy(c_pin.numpy())
+        def measure_e2e(qh, ch, n_warm, n_timed):
+            hq, hc = from_numpy(qh), from_numpy(ch)
 
-        def step_e2e():
-            if world == 1:
-                return _native.topk(hq, hc, k, metric)
-            return driver.topk_host(hq, hc, rank * N, n_total, k, metric)
+            def step_e2e():
+                if world == 1:
+                    return pmm._topk(qh, ch, k, metric)                 # NumPy in, Arrow List[Struct{index,score}] out
+                i_, s_ = group.topk_host(hq, hc, rank * N, n_total, k, metric, full=False)
+                q0, q1 = group.query_slice(Q)
+                return topk_to_arrow(i_[q0:q1], s_[q0:q1])              # this rank's slice of the whole-job result
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
+            for _ in range(n_warm):
+                step_e2e()
+            barrier()
+            _native.reset_stats()
+            t0 = time.perf_counter()
+            for _ in range(n_timed):
+                step_e2e()
+            torch.cuda.synchronize()
+            ms_max, _ = reduce_ranks((time.perf_counter() - t0) * 1000 / n_timed)
+            staged = _native.get_stat("staged_h2d_bytes") / n_timed
+            h2d = _native.get_stat("h2d_bytes") / n_timed
+            d2h = _native.get_stat("d2h_bytes") / n_timed
+            barrier()
+            return ms_max, staged, h2d, d2h
+
         n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            step_e2e()
-        torch.cuda.synchronize()
-        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1000 / n_e2e)
-        barrier()
+        ms_e2e, staged, h2d, d2h = measure_e2e(q_host, c_host, max(1, min(args.warmup, 2)), n_e2e)
+        bytes_note = ""
+        if world > 1:
+            t = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            h2d, d2h = float(t[0].item()), float(t[1].item())
+            bytes_note = "; bytes are whole-job totals over all ranks (the replicated queries cross ONE host link and are broadcast over NVLink; every rank reads back only its query slice)"
         e2e = {"value": world * Q / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
-               # whole job: every rank uploads its corpus shard; the replicated queries cross ONE host link and are
-               # broadcast over NVLink (world > 1); every rank reads the merged result back
-               "h2d_bytes_per_step": int((Q + world * N) * D * 4), "d2h_bytes_per_step": int(world * Q * k * 12),
-               "note": "pmm_topk C ABI with pinned host buffers; corpus re-uploaded every step as the reference re-marshals it "
-                       "(src/matmul.rs:430-431)" + ("; bytes are whole-job totals over all ranks" if world > 1 else "")}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "inputs": "pageable",
+               "staged_h2d_bytes_per_step_rank0": int(staged),
+               "note": ("polars_matmul_b200._topk(NumPy, NumPy, k, metric) -> Arrow List[Struct{index,score}]" if world == 1 else
+                        "RankGroup.topk_host per rank -> Arrow slice per rank")
+                       + ": ordinary pageable host buffers, staged through the library's page-locked ring; the corpus is re-uploaded every "
+                         "step as the reference re-marshals it (src/matmul.rs:430-431); byte counts from the library's own copy counters" + bytes_note}
+        # the same with page-locked inputs (what round 1 measured): the staging copy drops out
+        qp = _native.result_empty(q_host.shape, np.float32)
+        cp = np.empty((0,), np.float32)
+        try:
+            qp[...] = q_host
+            ptr = _native.ctypes.c_void_p(None)
+            _native.check(_native.lib().pmm_host_alloc(c_host.nbytes, _native.ctypes.byref(ptr)))
+            cp = np.ctypeslib.as_array(_native.ctypes.cast(ptr, _native.ctypes.POINTER(_native.ctypes.c_float)), shape=c_host.shape)
+            cp[...] = c_host
+            ms_pin, _, _, _ = measure_e2e(qp, cp, 1, n_e2e)
+            e2e["pinned_inputs"] = {"value": world * Q / (ms_pin / 1000.0), "ms_per_step": ms_pin, "inputs": "page-locked (pmm_host_alloc)"}
+            del cp
+            _native.lib().pmm_host_free(ptr)
+        except Exception as ex:  # page-locked memory exhausted: report, do not fail the bench
+            e2e["pinned_inputs"] = {"error": repr(ex)}
 
-    # ---- sanity: sampled oracle check of the timed result (rank 0, N=1) ---------------------------
+    # ---- extras inside the same clock-sampled window -------------------------------------------------------------------
+    extra = {}
+    peaks, peak_src = load_peaks()
+    if not args.no_extras and not args.small:
+        if world == 1:
+            try:
+                extra.update(hbm_extras(_native, torch, peaks))
+                extra["c1_e2e"] = c1_e2e(pmm)
+            except Exception as ex:
+                extra["error"] = repr(ex)
+        else:
+            # BASELINE.json configs[3] as stated: ONE corpus of 10M x 768 f32 rows, cosine, k=100, sharded over the ranks
+            # (strong scaling: 10M / n_gpus rows per rank), Gaussian data generated on the devices, resident timing.
+            try:
+                del dc
+                torch.cuda.empty_cache()
+                n4 = 10_000_000 // world
+                g4 = torch.Generator(device=dev).manual_seed(4000 + rank)
+                dc4 = torch.empty((n4, D), dtype=torch.float32, device=dev)
+                for lo in range(0, n4, 1 << 20):
+                    hi = min(n4, lo + (1 << 20))
+                    dc4[lo:hi] = torch.randn((hi - lo, D), generator=g4, device=dev, dtype=torch.float32)
+                i4 = torch.empty((Q, k), dtype=torch.int32, device=dev)
+                s4 = torch.empty((Q, k), dtype=torch.float64, device=dev)
+
+                def step4():
+                    group.topk_device(dq.data_ptr(), Q, D, _native.DTYPE_F32, dc4.data_ptr(), n4, _native.DTYPE_F32, rank * n4,
+                                      n4 * world, k, "cosine", i4.data_ptr(), s4.data_ptr(), full=True)
+                step4()
+                barrier()
+                _native.set_option("profile", 1)
+                _native.reset_stats()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n4_steps = 2
+                e0.record(tstream)
+                for _ in range(n4_steps):
+                    step4()
+                e1.record(tstream)
+                barrier()
+                ms4, _ = reduce_ranks(e0.elapsed_time(e1) / n4_steps)
+                k4 = _native.get_stat("tc_topk_f16r_ms") / max(1.0, _native.get_stat("tc_topk_f16r_launches"))
+                _native.set_option("profile", 0)
+                c4_host = dc4.cpu().numpy()
+                chk4 = selfcheck(i4, s4, c4_host, rank * n4, "cosine", k)
+                tf_gpu = 2.0 * Q * n4 * D / (k4 / 1e3) / 1e12 if k4 > 0 else None
+                extra["c4_strong"] = {
+                    "workload": f"C4: {Q} queries x 10M corpus rows ({n4} per rank), {D}d f32, cosine, k={k}, {world} GPUs",
+                    "ms_per_step": ms4, "queries_per_sec": Q / (ms4 / 1e3), "tflops_effective_whole_job": 2.0 * Q * n4 * world * D / (ms4 / 1e3) / 1e12,
+                    "filter_kernel_ms_rank0": k4, "filter_tflops_per_gpu": tf_gpu,
+                    "frac_of_bf16_sustained_per_gpu": (tf_gpu / peaks.get("bf16_tflops_sustained", 1400.0)) if tf_gpu else None,
+                    "frac_of_bf16_burst_per_gpu": (tf_gpu / peaks.get("bf16_tflops", 1660.0)) if tf_gpu else None,
+                    "steps": n4_steps, "selfcheck": chk4,
+                    "note": "north_star target: >= 60 % of tensor-pipe peak (kernel-only) with reference-matching indices"}
+                del dc4, c4_host
+            except Exception as ex:
+                extra["c4_strong"] = {"error": repr(ex)}
+    clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0:
-        peaks, peak_src = load_peaks()
         flops_per_launch = 2.0 * Q * N * D
         k_avg_ms = k_ms / max(1.0, k_launches)
         achieved = flops_per_launch / (k_avg_ms / 1000.0) / 1e12 if k_avg_ms > 0 else None
-        # Tensor-pipe peak for ALGORITHMIC f32 flops: TF32 runs at half the bf16 rate; the first-level filter issues one
-        # TF32 MMA per MAC (bf16 / 2), the 3xTF32 split three (bf16 / 6).
-        # The default first level rounds the f32 operands to f16 (11 significant bits, like TF32) and issues one
-        # kind::f16 MMA per MAC: the bf16/f16 dense rate itself.
+        # Tensor-pipe peak for ALGORITHMIC flops: the default first level rounds the operands to f16 (11 significant bits,
+        # like TF32) and issues one kind::f16 MMA per MAC: the bf16/f16 dense rate itself.  TF32 runs at half that rate:
+        # one TF32 MMA per MAC (bf16 / 2) or, for the 3xTF32 split, three (bf16 / 6).
         terms = 1 if kname.endswith("x1") or kname.endswith("f16r") else 3
         rate_div = 1.0 if kname.endswith("f16r") else 2.0 * terms
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")) / rate_div
@@ -352,18 +616,19 @@ def main():
                                     f"TF32 = 1/2 bf16 rate, {terms} TF32 MMA(s) per MAC")
                                  + f" in {kname}); raw bf16 sustained {peaks.get('bf16_tflops_sustained')} burst {peaks.get('bf16_tflops')}. "
                                  "The exact f32 result comes from the re-scoring kernel; queries whose filter is not provably "
-                                 "lossless are re-run with 256-entry lists (requeried_f16_wide_per_step), then 3xTF32 (requeried_tf32x3_per_step), then on the SIMT path",
+                                 "lossless are re-run from seeded thresholds (requeried_f16_wide_per_step), then 3xTF32 (requeried_tf32x3_per_step), then on the SIMT path",
                     "per_kernel_ms_per_step": stats}
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_baseline_sample(q_pin.numpy(), c_pin.numpy(), k, metric)
+            cpu_base = cpu_baseline_sample(q_host, c_host, k, metric)
         line = {
             "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{W['name']}: {Q} queries x {N} corpus rows per GPU, {D}d f32, metric={metric}, k={k}",
-                       "sharding": f"corpus rows sharded over {world} rank(s), {N} rows each ({n_total} total); queries replicated; "
-                                   "candidates merged after one NCCL all-gather" if world > 1 else "single GPU",
+                       "sharding": (f"corpus rows sharded over {world} rank(s), {N} rows each ({n_total} total); queries replicated; "
+                                    "packed candidates exchanged all-to-all over NCCL inside libpmm_b200 (rank g merges 1/N of the queries), "
+                                    "merged slices broadcast so every rank holds the full result") if world > 1 else "single GPU",
                        "value_definition": "n_gpus * Q / step time: every rank scans its own shard for all Q queries",
                        "host_placement": numa or "not bound",
                        "l2": "inputs (3.4 GB per rank) are far larger than the 126 MB L2; no explicit flush",
@@ -372,9 +637,13 @@ def main():
                                      "proof: results bit-identical to the f32 CPU oracle"},
             "tflops_effective": 2.0 * Q * n_total * D / (ms_step / 1000.0) / 1e12,
             "queries_per_sec_global_corpus": Q / (ms_step / 1000.0),
+            "selfcheck": check,
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "extra": extra,
         }
         emit(line)
+    if group is not None:
+        group.close()
     if world > 1:
         dist.destroy_process_group()
 

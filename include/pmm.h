@@ -69,6 +69,20 @@ extern "C" {
  * bitmaps). Accepted for the QUERIES of pmm_topk_shard: a multi-GPU driver uploads the replicated query batch once
  * and broadcasts it over NVLink instead of sending it through the host link of every rank. */
 #define PMM_MATRIX_ON_DEVICE 1
+/* pmm_matrix_t::reserved flag: the column's rows live in SEVERAL host buffers (a multi-chunk Polars Series; the
+ * reference's zero-copy path gives up there, `cont_slice` at src/matmul.rs:53, and concatenates on the host).
+ * `values` then points to a pmm_chunks_t; fixed-size rows only (offsets / validity / row_validity NULL); n_rows = total.
+ * Accepted by pmm_topk, pmm_matmul, pmm_corpus_create and pmm_topk_corpus (queries): the chunks are uploaded one after
+ * the other into one device buffer. */
+#define PMM_MATRIX_CHUNKED 2
+typedef struct pmm_chunk {
+    const void *values; /* n_rows * dim elements of the column's dtype */
+    int64_t n_rows;
+} pmm_chunk_t;
+typedef struct pmm_chunks {
+    int64_t n_chunks;
+    const pmm_chunk_t *chunks;
+} pmm_chunks_t;
 
 typedef struct pmm_matrix {
     const void *values;
@@ -178,6 +192,49 @@ PMM_API int pmm_dev_matmul(const pmm_matrix_t *d_left, const pmm_matrix_t *d_rig
  * compute_norms_* / compute_squared_norms_*, src/metrics.rs:367-393. d_out [n_rows]. */
 PMM_API int pmm_dev_norms(const pmm_matrix_t *d_x, int32_t squared, void *d_out, void *stream);
 
+/* ------------------------------------------------------------------ groups of GPUs (north_star item 6)
+ * The corpus partitions by rows: every GPU of a group scans its shard for ALL queries with the fused kernel and emits
+ * its exact local top-k as packed candidates with global row numbers; the GPUs exchange candidates with NCCL over
+ * NVLink (an all-to-all: GPU g receives only the rows of the queries it merges, [g Q/G, (g+1) Q/G)) and merge by
+ * u64 max.  The total order of packed candidates makes the result independent of the number of shards.
+ * libnccl is opened at run time (dlopen); without it every group function returns PMM_ERR_UNSUPPORTED.
+ *
+ * Two process models:
+ *   single process  pmm_group_init_local: ncclCommInitAll over the first n visible devices (0 = all), one persistent
+ *                   host thread per GPU.  pmm_topk / pmm_matmul use such a group on their own for large calls (options
+ *                   "multi_gpu", "multi_gpu_min_gflop"); pmm_group_topk runs one call on a given group.
+ *   process per GPU pmm_group_unique_id on one rank, distributed by the host application (MPI, torch.distributed, a
+ *                   file ...), then pmm_group_init_rank on every rank with its device current; pmm_group_topk_shard is
+ *                   collective: every rank passes ITS corpus shard and the same queries, k and metric.
+ * f32 working precision, k <= 248. */
+typedef struct pmm_group pmm_group_t;
+#define PMM_GROUP_ID_BYTES 128
+PMM_API int pmm_group_unique_id(void *id /* PMM_GROUP_ID_BYTES */);
+PMM_API int pmm_group_init_rank(const void *id, int32_t rank, int32_t world, pmm_group_t **out);
+PMM_API int pmm_group_init_local(int32_t n_devices, pmm_group_t **out);
+PMM_API int pmm_group_destroy(pmm_group_t *group);
+PMM_API int pmm_group_size(const pmm_group_t *group);
+
+/* Same contract as pmm_topk (host buffers in and out), the corpus rows sharded over the GPUs of a single-process group;
+ * the query batch crosses one host link and is broadcast over NVLink; every GPU writes its slice of the result. */
+PMM_API int pmm_group_topk(pmm_group_t *group, const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
+                           const char *metric, uint32_t *out_index, double *out_score, int64_t *k_actual);
+
+/* flags of pmm_group_topk_shard: one output mode ... */
+#define PMM_GROUP_OUT_HOST_SLICE 1   /* out_* = host buffers [Q x k_eff]; this rank fills only the rows of ITS query slice */
+#define PMM_GROUP_OUT_DEVICE_FULL 2  /* out_* = device buffers [Q x k_eff]; every rank receives the full result */
+#define PMM_GROUP_OUT_DEVICE_SLICE 3 /* out_* = device buffers [Q x k_eff]; this rank fills only its query slice */
+#define PMM_GROUP_OUT_HOST_FULL 4    /* out_* = host buffers [Q x k_eff]; every rank reads the full result back */
+/* ... optionally OR-ed with: */
+#define PMM_GROUP_QUERIES_FROM_ROOT 256 /* host queries (dense rows): only rank 0 uploads them, NCCL broadcast to the rest */
+/* Query slice of rank r: rows [min(Q, r * ceil(Q/G)), min(Q, (r+1) * ceil(Q/G))).
+ * queries / corpus_shard: host descriptors, or device-resident ones (reserved = PMM_MATRIX_ON_DEVICE, fixed-size rows).
+ * corpus_shard may have zero rows (more ranks than rows); index_base = global row number of the shard's row 0;
+ * n_total = rows of the whole corpus; k_eff = min(k, n_total). Collective and synchronous. */
+PMM_API int pmm_group_topk_shard(pmm_group_t *group, const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard,
+                                 int64_t index_base, int64_t n_total, int64_t k, int32_t metric, int32_t flags,
+                                 uint32_t *out_index, double *out_score);
+
 /* ------------------------------------------------------------------ diagnostics of the tensor-core filter
  * The top-k path selects candidates with a reduced-precision tensor-core FILTER and proves per query that nothing
  * relevant was dropped; that proof rests on an error bound.  These two entry points let a test measure the filter's
@@ -199,6 +256,10 @@ PMM_API const char *pmm_last_error(void);     /* thread-local, never NULL */
 PMM_API const char *pmm_version(void);
 PMM_API int pmm_device_count(void);           /* 0 when no CUDA device is usable */
 PMM_API int pmm_set_device(int32_t device);   /* device used by the calling thread's subsequent calls */
+
+/* The CUDA stream (cudaStream_t) the host entry points and the group calls of the CALLING THREAD enqueue their work on,
+ * for the thread's current device - e.g. to record timing events around synchronous calls. NULL without a device. */
+PMM_API void *pmm_thread_stream(void);
 
 /* Page-locked host memory for result buffers. The reference returns freshly allocated Vecs (from_vec,
  * src/matmul.rs:100-125, :497-518); a binding that hands this memory to pmm_topk / pmm_matmul as out_index /

@@ -74,6 +74,15 @@ int pmm_oracle_num_threads(void) {
 #endif
 }
 
+/* The benchmark's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: it sets its thread count itself. */
+void pmm_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---------------------------------------------------------------- norms (src/metrics.rs:367-393) */
 #define DEF_UNROLLED_DOT(NAME, T)                                                         \
     static T NAME(const T *x, const T *y, int64_t n) {                                    \

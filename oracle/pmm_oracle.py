@@ -47,6 +47,8 @@ def lib() -> ctypes.CDLL:
         L.pmm_oracle_higher_is_better.argtypes = [ctypes.c_int]
         L.pmm_oracle_higher_is_better.restype = ctypes.c_int
         L.pmm_oracle_num_threads.restype = ctypes.c_int
+        L.pmm_oracle_set_num_threads.argtypes = [ctypes.c_int]
+        L.pmm_oracle_set_num_threads.restype = None
         for t in ("f32", "f64"):
             getattr(L, f"pmm_oracle_norms_{t}").argtypes = [p, i64, i64, p]
             getattr(L, f"pmm_oracle_sqnorms_{t}").argtypes = [p, i64, i64, p]
@@ -88,6 +90,11 @@ def higher_is_better(metric: int) -> bool:
 
 def num_threads() -> int:
     return int(lib().pmm_oracle_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP thread count of the oracle (torchrun exports OMP_NUM_THREADS=1; the CPU arms set their own)."""
+    lib().pmm_oracle_set_num_threads(int(n))
 
 
 def working_dtype(q_dtype, c_dtype):

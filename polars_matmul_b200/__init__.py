@@ -50,6 +50,102 @@ def matmul_array(left: Any, right: Any) -> np.ndarray:
     return _native.matmul(l, r)
 
 
+class _CorpusCache:
+    """Device-resident corpora for repeated plugin calls.
+
+    `map_batches(is_elementwise=True)` lets Polars call the UDF once per batch, and the reference re-marshals the whole
+    corpus each time (python/polars_matmul/__init__.py:115-119, src/matmul.rs:430-431); on a GPU that would be a repeated
+    multi-GB upload.  Keyed on the identity of the corpus buffers (addresses, shape, dtype, bitmap addresses) and the
+    query dtype.  Only IMMUTABLE sources are cached - Arrow-backed columns (Polars Series, pyarrow arrays) and read-only
+    NumPy arrays - and the cache holds a reference to the source, so the addresses cannot be recycled while an entry
+    lives.  A corpus is made resident the SECOND time it is seen (a one-shot call keeps the overlapped streaming upload
+    and holds no device memory afterwards); least recently used entries go when the byte cap is exceeded."""
+
+    def __init__(self):
+        import threading
+        self.lock = threading.RLock()
+        self.enabled = True
+        self.max_bytes = 32 << 30
+        self.entries = {}       # key -> [ResidentCorpus | None, source HostMatrix, bytes, last use]
+        self.tick = 0
+        self.hits = 0
+
+    def configure(self, enabled=None, max_bytes=None):
+        with self.lock:
+            if enabled is not None:
+                self.enabled = bool(enabled)
+            if max_bytes is not None:
+                self.max_bytes = int(max_bytes)
+            if not self.enabled:
+                self.clear()
+            self._evict()
+
+    def clear(self):
+        with self.lock:
+            for e in self.entries.values():
+                if e[0] is not None:
+                    e[0].close()
+            self.entries.clear()
+
+    def _evict(self):
+        while sum(e[2] for e in self.entries.values() if e[0] is not None) > self.max_bytes:
+            key = min((k for k, e in self.entries.items() if e[0] is not None), key=lambda k: self.entries[k][3])
+            self.entries.pop(key)[0].close()
+        if len(self.entries) > 64:          # sightings without a resident copy are cheap, but not free
+            for key in sorted(self.entries, key=lambda k: self.entries[k][3])[: len(self.entries) - 64]:
+                e = self.entries.pop(key)
+                if e[0] is not None:
+                    e[0].close()
+
+    @staticmethod
+    def cacheable(source: Any, hm) -> bool:
+        if isinstance(source, np.ndarray):
+            return not source.flags.writeable
+        if isinstance(source, (list, tuple)) or hm.n_rows == 0:
+            return False
+        return True                          # Polars Series / pyarrow arrays: Arrow buffers are immutable
+
+    def lookup(self, source: Any, hm, query_dtype_code: int):
+        """The resident handle for this corpus, or None (not cacheable, first sighting, or creation failed)."""
+        if not self.enabled or not self.cacheable(source, hm):
+            return None
+        key = (hm.cache_key(), query_dtype_code)
+        with self.lock:
+            self.tick += 1
+            e = self.entries.get(key)
+            if e is None:
+                self.entries[key] = [None, hm, 0, self.tick]     # first sighting: remember, stream as usual
+                self._evict()
+                return None
+            e[3] = self.tick
+            if e[0] is None:
+                try:
+                    e[0] = _native.ResidentCorpus(hm, query_dtype_code)
+                except _native.PmmError:
+                    return None
+                nbytes = sum(c.nbytes for c in hm.chunks) if hm.chunks is not None else hm.values.nbytes
+                e[2] = int(nbytes * 1.6)                          # raw column + operand planes + norms
+                self._evict()
+                if key not in self.entries:
+                    return None
+            else:
+                self.hits += 1
+            return e[0]
+
+
+_corpus_cache = _CorpusCache()
+
+
+def corpus_cache_configure(enabled: bool = None, max_bytes: int = None) -> None:
+    """Switch the resident-corpus cache of `_topk` on/off or change its byte cap (default 32 GB of device memory)."""
+    _corpus_cache.configure(enabled, max_bytes)
+
+
+def corpus_cache_clear() -> None:
+    """Drop every resident corpus (explicit invalidation)."""
+    _corpus_cache.clear()
+
+
 def _topk(left: Any, right: Any, k: int, metric: str):
     """Mirror of `_topk` (src/lib.rs:33-55): Series in, Series `topk` of List[Struct{index,score}] out.
     With pyarrow / NumPy inputs a pyarrow LargeListArray is returned instead of a Polars Series."""
@@ -58,21 +154,31 @@ def _topk(left: Any, right: Any, k: int, metric: str):
         out = _arrow.empty_topk_arrow()
     else:
         c = _arrow.to_host_matrix(right)
-        idx, sc = _native.topk(q, c, int(k), metric)
+        handle = _corpus_cache.lookup(right, c, q.dtype_code) if c.n_rows > 0 and c.dim > 0 else None
+        if handle is not None:
+            idx, sc = handle.topk(q, int(k), metric)
+        else:
+            idx, sc = _native.topk(q, c, int(k), metric)
         out = _arrow.topk_to_arrow(idx, sc)
     if _is_polars_series(left):
         return pl.Series("topk", out)
     return out
 
 
-def _matmul(left: Any, right: Any):
-    """Mirror of `_matmul` (src/lib.rs:15-30): Series in, Series `matmul` of Array[T, N] out."""
+def _matmul(left: Any, right: Any, flatten: bool = False):
+    """Mirror of `_matmul` (src/lib.rs:15-30): Series in, Series `matmul` of Array[T, N] out.  flatten=True returns the
+    flat row-major column the reference obtains with `.explode()` (python/polars_matmul/__init__.py:173-187) directly
+    over the result buffer."""
     l = _arrow.to_host_matrix(left)
     r = _arrow.to_host_matrix(right)
     if l.n_rows == 0:
         out = _arrow.empty_matmul_arrow(_native.working_dtype(l, r))
+        if flatten:
+            import pyarrow as pa
+            out = pa.array([], type=pa.from_numpy_dtype(_native.working_dtype(l, r)))
     else:
-        out = _arrow.matmul_to_arrow(_native.matmul(l, r))
+        res = _native.matmul(l, r)
+        out = _arrow.matmul_flat_to_arrow(res) if flatten else _arrow.matmul_to_arrow(res)
     if _is_polars_series(left):
         return pl.Series("matmul", out)
     return out
@@ -103,14 +209,16 @@ class PmmNamespace:
                 "corpus must be a Polars Series, not an Expression. "
                 "Use corpus['column_name'] or corpus.get_column('column_name').")
         n_corpus = len(corpus)
-        try:  # the declared dtype follows the CORPUS only (python/polars_matmul/__init__.py:166-171)
-            is_f32 = corpus.dtype.inner == pl.Float32
+        try:  # the declared dtype follows the CORPUS only (python/polars_matmul/__init__.py:166-171); Float16 storage is
+            # upcast exactly and computed in f32 (pmm_working_dtype: the README's "cast f16 to f32" contract), so an f16
+            # corpus declares Float32 like an f32 one - the dtype _matmul then actually returns
+            is_f32 = corpus.dtype.inner in (pl.Float32, getattr(pl, "Float16", pl.Float32))
         except Exception:
             is_f32 = False
         inner = pl.Float32 if is_f32 else pl.Float64
         if flatten:
             return self._expr.map_batches(
-                lambda s: _matmul(s, corpus).explode(),
+                lambda s: _matmul(s, corpus, flatten=True),   # the flat buffer itself: no Array wrapper + explode() round trip
                 is_elementwise=False,
                 return_dtype=inner,
             )

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmm_b200.so")
 
 PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_UNSUPPORTED = 0, 1, 2, 3
+PMM_MATRIX_ON_DEVICE, PMM_MATRIX_CHUNKED = 1, 2
 DTYPE_F16, DTYPE_F32, DTYPE_F64 = 0, 1, 2
 METRIC_COSINE, METRIC_DOT, METRIC_EUCLIDEAN = 0, 1, 2
 
@@ -38,6 +39,16 @@ class PmmMatrix(ctypes.Structure):
         ("dtype", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
     ]
+
+
+class PmmChunk(ctypes.Structure):
+    """struct pmm_chunk (include/pmm.h)."""
+    _fields_ = [("values", ctypes.c_void_p), ("n_rows", ctypes.c_int64)]
+
+
+class PmmChunks(ctypes.Structure):
+    """struct pmm_chunks (include/pmm.h)."""
+    _fields_ = [("n_chunks", ctypes.c_int64), ("chunks", ctypes.POINTER(PmmChunk))]
 
 
 class PmmError(RuntimeError):
@@ -88,10 +99,18 @@ def lib() -> ctypes.CDLL:
         "pmm_set_option": (ctypes.c_int, [ctypes.c_char_p, i64]),
         "pmm_set_thread_option": (ctypes.c_int, [ctypes.c_char_p, i64]),
         "pmm_dev_filter_candidates": (ctypes.c_int, [P, P, i32, i32, i32, i64, vp, vp]),
+        "pmm_group_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+        "pmm_group_init_rank": (ctypes.c_int, [ctypes.c_char_p, i32, i32, ctypes.POINTER(vp)]),
+        "pmm_group_init_local": (ctypes.c_int, [i32, ctypes.POINTER(vp)]),
+        "pmm_group_destroy": (ctypes.c_int, [vp]),
+        "pmm_group_size": (ctypes.c_int, [vp]),
+        "pmm_group_topk": (ctypes.c_int, [vp, P, P, i64, ctypes.c_char_p, vp, vp, ctypes.POINTER(i64)]),
+        "pmm_group_topk_shard": (ctypes.c_int, [vp, P, P, i64, i64, i64, i32, i32, vp, vp]),
         "pmm_filter_error_bound": (ctypes.c_int, [i32, i32, i32, i64, i32, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                                   ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "pmm_get_stat": (ctypes.c_double, [ctypes.c_char_p]),
         "pmm_reset_stats": (None, []),
+        "pmm_thread_stream": (vp, []),
         "pmm_host_alloc": (ctypes.c_int, [i64, ctypes.POINTER(vp)]),
         "pmm_host_free": (ctypes.c_int, [vp]),
     }
@@ -109,7 +128,8 @@ EXPORTED_SYMBOLS = [
     "pmm_dev_merge_candidates", "pmm_dev_matmul", "pmm_dev_norms", "pmm_last_error", "pmm_version",
     "pmm_device_count", "pmm_set_device", "pmm_kernel_launch_count", "pmm_reset_kernel_launch_count",
     "pmm_set_option", "pmm_set_thread_option", "pmm_get_stat", "pmm_reset_stats", "pmm_host_alloc", "pmm_host_free",
-    "pmm_dev_filter_candidates", "pmm_filter_error_bound",
+    "pmm_thread_stream", "pmm_dev_filter_candidates", "pmm_filter_error_bound", "pmm_group_unique_id", "pmm_group_init_rank",
+    "pmm_group_init_local", "pmm_group_destroy", "pmm_group_size", "pmm_group_topk", "pmm_group_topk_shard",
 ]
 
 
@@ -128,6 +148,9 @@ class HostMatrix:
     offsets: Optional[np.ndarray] = None     # int64 [n_rows+1] or None (fixed-size rows)
     validity: Optional[np.ndarray] = None    # uint8 Arrow bitmap over child values
     row_validity: Optional[np.ndarray] = None
+    chunks: Optional[list] = None            # multi-chunk column: list of 1-D value views (fixed-size rows, no nulls);
+                                             # `values` is then an empty array that only carries the dtype
+    owner: object = None                     # whatever keeps the viewed buffers alive (an Arrow array, a Series)
 
     @property
     def dtype_code(self) -> int:
@@ -137,8 +160,22 @@ class HostMatrix:
         def ptr(a):
             return None if a is None else a.ctypes.data
 
+        if self.chunks is not None:   # PMM_MATRIX_CHUNKED: values -> pmm_chunks_t; the ctypes objects live on the struct
+            arr = (PmmChunk * len(self.chunks))(*[PmmChunk(c.ctypes.data if c.size else None, c.size // max(1, self.dim))
+                                                  for c in self.chunks])
+            desc = PmmChunks(len(self.chunks), arr)
+            m = PmmMatrix(ctypes.addressof(desc), None, None, None, self.n_rows, self.dim, self.dtype_code, PMM_MATRIX_CHUNKED)
+            m._keep = (arr, desc)
+            return m
         return PmmMatrix(ptr(self.values) if self.values.size else None, ptr(self.offsets), ptr(self.validity),
                          ptr(self.row_validity), self.n_rows, self.dim, self.dtype_code, 0)
+
+    def cache_key(self):
+        """Identity of the underlying buffers (addresses, shape, dtype) - what the resident-corpus cache keys on."""
+        def addr(a):
+            return 0 if a is None else a.ctypes.data
+        vals = tuple((c.ctypes.data, c.size) for c in self.chunks) if self.chunks is not None else ((addr(self.values), self.values.size),)
+        return (vals, self.n_rows, self.dim, self.dtype_code, addr(self.offsets), addr(self.validity), addr(self.row_validity))
 
 
 def metric_from_str(name: str) -> int:
@@ -285,8 +322,6 @@ class ResidentCorpus:
 
 
 # ------------------------------------------------------------------------------------------ device level
-PMM_MATRIX_ON_DEVICE = 1
-
 
 def dev_matrix(data_ptr: int, n_rows: int, dim: int, dtype_code: int, offsets_ptr: int = 0, flags: int = 0) -> PmmMatrix:
     """Describes a device-resident matrix (e.g. a torch CUDA tensor's data_ptr()). flags: PMM_MATRIX_ON_DEVICE for
@@ -361,6 +396,11 @@ def kernel_launch_count() -> int:
 
 def reset_kernel_launch_count() -> None:
     lib().pmm_reset_kernel_launch_count()
+
+
+def thread_stream() -> int:
+    """cudaStream_t of the calling thread's host entry points / group calls (0 without a device)."""
+    return int(lib().pmm_thread_stream() or 0)
 
 
 def device_count() -> int:

@@ -59,9 +59,40 @@ def _bitmap(arr: "pa.Array") -> Optional[np.ndarray]:
     return np.packbits(mask, bitorder="little")
 
 
+def _chunked_fixed(arr: "pa.ChunkedArray") -> Optional[HostMatrix]:
+    """A multi-chunk Array (fixed-size list) column of floats without nulls -> one HostMatrix over the chunks' buffers
+    (PMM_MATRIX_CHUNKED: uploaded chunk by chunk, no host-side concatenation; the reference's zero-copy path gives up
+    here, src/matmul.rs:53).  None when the column does not qualify (the caller then concatenates)."""
+    t = arr.type
+    if not pa.types.is_fixed_size_list(t) or arr.null_count:
+        return None
+    vt = t.value_type
+    if not (pa.types.is_float16(vt) or pa.types.is_float32(vt) or pa.types.is_float64(vt)):
+        return None
+    dim = t.list_size
+    views = []
+    for ch in arr.chunks:
+        if len(ch) == 0:
+            continue
+        child = ch.values.slice(ch.offset * dim, len(ch) * dim)
+        if child.null_count:
+            return None
+        vals, _, off = _child_to_numpy(child)
+        views.append(vals[off: off + len(ch) * dim])
+    if len(views) < 2:
+        return None
+    return HostMatrix(np.empty(0, views[0].dtype), len(arr), dim, chunks=views, owner=arr)
+
+
 def from_arrow(arr: Any) -> HostMatrix:
     if isinstance(arr, pa.ChunkedArray):
+        if arr.num_chunks > 1:
+            hm = _chunked_fixed(arr)
+            if hm is not None:
+                return hm
         arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+        if isinstance(arr, pa.ChunkedArray):   # combine_chunks of some pyarrow versions still returns a ChunkedArray
+            arr = arr.chunk(0) if arr.num_chunks == 1 else pa.concat_arrays(arr.chunks)
     t = arr.type
     n_rows = len(arr)
     if pa.types.is_fixed_size_list(t):
@@ -73,7 +104,7 @@ def from_arrow(arr: Any) -> HostMatrix:
         if validity is not None:  # re-base the child bitmap to the sliced values
             bits = np.unpackbits(validity, bitorder="little")[child_off: child_off + n_rows * dim]
             validity = np.packbits(bits, bitorder="little")
-        return HostMatrix(np.ascontiguousarray(vals), n_rows, dim, None, validity, _bitmap(arr))
+        return HostMatrix(np.ascontiguousarray(vals), n_rows, dim, None, validity, _bitmap(arr), owner=arr)
     if pa.types.is_list(t) or pa.types.is_large_list(t):
         odt = np.int64 if pa.types.is_large_list(t) else np.int32
         obuf = arr.buffers()[1]
@@ -89,7 +120,7 @@ def from_arrow(arr: Any) -> HostMatrix:
             if row_valid is not None and not (row_valid[0] & 1):
                 raise RuntimeError("First element is null")  # src/matmul.rs:238
             dim = int(offsets[1] - offsets[0])               # row 0 defines the dimension
-        return HostMatrix(vals, n_rows, dim, np.ascontiguousarray(offsets), validity, row_valid)
+        return HostMatrix(vals, n_rows, dim, np.ascontiguousarray(offsets), validity, row_valid, owner=arr)
     raise RuntimeError(f"expected a List or Array (fixed-size list) column of numbers, got {t}")
 
 
@@ -130,6 +161,12 @@ def topk_to_arrow(index: np.ndarray, score: np.ndarray) -> "pa.Array":
         names=["index", "score"])
     offsets = pa.array(np.arange(q + 1, dtype=np.int64) * k, type=pa.int64())
     return pa.LargeListArray.from_arrays(offsets, st)
+
+
+def matmul_flat_to_arrow(out: np.ndarray) -> "pa.Array":
+    """[Q,N] -> the flat row-major column of flatten=True (python/polars_matmul/__init__.py:173-187), over the result
+    buffer itself: no Array[T, N] wrapper and no explode() round trip."""
+    return pa.array(out.reshape(-1))
 
 
 def matmul_to_arrow(out: np.ndarray) -> "pa.Array":

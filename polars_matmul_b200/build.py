@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libpmm_b200.so")
-SOURCES = ["pmm_prep.cu", "pmm_generic.cu", "pmm_merge.cu", "pmm_rescore.cu", "pmm_tc_kernels.cu", "pmm_stage.cu", "pmm_api.cu"]
-HEADERS = ["pmm_common.cuh", "pmm_kernels.h", "pmm_tc.cuh", "pmm_stage.h", os.path.join("..", "..", "include", "pmm.h")]
+SOURCES = ["pmm_prep.cu", "pmm_generic.cu", "pmm_merge.cu", "pmm_rescore.cu", "pmm_tc_kernels.cu", "pmm_stage.cu", "pmm_nccl.cu", "pmm_api.cu"]
+HEADERS = ["pmm_common.cuh", "pmm_kernels.h", "pmm_tc.cuh", "pmm_stage.h", "pmm_nccl.h", os.path.join("..", "..", "include", "pmm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++",
-               "-gencode", "arch=compute_100a,code=sm_100a"] + objs
+               "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

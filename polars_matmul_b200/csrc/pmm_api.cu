@@ -8,14 +8,20 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pmm.h"
 #include "pmm_kernels.h"
+#include "pmm_nccl.h"
 #include "pmm_stage.h"
 
 using namespace pmm;
@@ -964,9 +970,66 @@ struct Uploaded {
     pmm_matrix_t dm;
 };
 
+// ---- multi-chunk host columns (PMM_MATRIX_CHUNKED): a Polars Series with several chunks keeps its rows in several
+// buffers; the reference's zero-copy path gives up there (`cont_slice`, src/matmul.rs:53) and copies.  Here the chunks
+// are uploaded one after the other into ONE device buffer - no host-side concatenation.
+bool is_chunked(const pmm_matrix_t *m) { return (m->reserved & PMM_MATRIX_CHUNKED) != 0; }
+const pmm_chunks_t *chunks_of(const pmm_matrix_t *m) { return (const pmm_chunks_t *)m->values; }
+
+int check_chunked(const pmm_matrix_t *m, const char *what) {
+    if (!is_chunked(m)) return PMM_OK;
+    if (m->offsets || m->validity || m->row_validity || (m->reserved & PMM_MATRIX_ON_DEVICE))
+        return fail(PMM_ERR_UNSUPPORTED, "%s: a chunked column must be fixed-size rows in host memory without bitmaps", what);
+    const pmm_chunks_t *ch = chunks_of(m);
+    if (!ch || ch->n_chunks < 0 || (ch->n_chunks > 0 && !ch->chunks)) return fail(PMM_ERR_INVALID, "%s: bad chunk list", what);
+    int64_t rows = 0;
+    for (int64_t i = 0; i < ch->n_chunks; ++i) {
+        if (ch->chunks[i].n_rows < 0 || (ch->chunks[i].n_rows > 0 && !ch->chunks[i].values)) return fail(PMM_ERR_INVALID, "%s: bad chunk %lld", what, (long long)i);
+        rows += ch->chunks[i].n_rows;
+    }
+    if (rows != m->n_rows) return fail(PMM_ERR_INVALID, "%s: the chunks hold %lld rows, the column says %lld", what, (long long)rows, (long long)m->n_rows);
+    return PMM_OK;
+}
+
+// Rows [r0, r1) of a fixed-size-row host column -> dst (device), on stream s; walks the chunk list when there is one.
+cudaError_t copy_host_rows(const pmm_matrix_t *m, int64_t r0, int64_t r1, void *dst, cudaStream_t s) {
+    const size_t row_bytes = (size_t)m->dim * esize(m->dtype);
+    if (r1 <= r0) return cudaSuccess;
+    if (!is_chunked(m)) return stage_h2d(dst, (const char *)m->values + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes, s);
+    const pmm_chunks_t *ch = chunks_of(m);
+    int64_t base = 0;
+    for (int64_t i = 0; i < ch->n_chunks && base < r1; ++i) {
+        const int64_t n = ch->chunks[i].n_rows, lo = std::max(r0, base), hi = std::min(r1, base + n);
+        if (hi > lo) {
+            cudaError_t e = stage_h2d((char *)dst + (size_t)(lo - r0) * row_bytes, (const char *)ch->chunks[i].values + (size_t)(lo - base) * row_bytes,
+                                      (size_t)(hi - lo) * row_bytes, s);
+            if (e != cudaSuccess) return e;
+        }
+        base += n;
+    }
+    return cudaSuccess;
+}
+
+const void *first_host_values(const pmm_matrix_t *m) {
+    if (!is_chunked(m)) return m->values;
+    const pmm_chunks_t *ch = chunks_of(m);
+    for (int64_t i = 0; i < ch->n_chunks; ++i)
+        if (ch->chunks[i].n_rows > 0) return ch->chunks[i].values;
+    return nullptr;
+}
+
 int upload(const pmm_matrix_t *m, cudaStream_t s, Uploaded *u) {
     u->dm = *m;
     const int es = esize(m->dtype);
+    if (is_chunked(m)) {
+        const size_t vbytes = (size_t)m->n_rows * m->dim * es;
+        CUDA_TRY(u->values.alloc(vbytes, s));
+        CUDA_TRY(copy_host_rows(m, 0, m->n_rows, u->values.p, s));
+        stat_add("h2d_bytes", (double)vbytes);
+        u->dm.values = u->values.p;
+        u->dm.reserved = 0;
+        return PMM_OK;
+    }
     int64_t first = 0, last = m->n_rows * m->dim;
     if (m->offsets) {
         first = m->offsets[0];
@@ -1059,7 +1122,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     // by the ratio of filter time to copy time per row (2 Q / tensor rate vs element size / PCIe rate, about 3.5 at
     // Q = 100k f32), so that each copy finishes just before the filter wants it.  Copy-bound shapes (few queries)
     // get equal chunks instead.
-    const bool copy_up_front = !stage_enabled() || host_ptr_is_pinned(corpus->values);
+    const bool copy_up_front = !stage_enabled() || host_ptr_is_pinned(first_host_values(corpus));
     std::vector<int64_t> cut{0};
     {
         // sustained filter FLOP/s, measured: f16 planes (f16 input, or f32 rounded to f16) / TF32 x1 / 3xTF32
@@ -1100,6 +1163,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     }
     // corpus metadata now, values chunk by chunk
     uc.dm = *corpus;
+    uc.dm.reserved = 0;
     int64_t pos0 = 0, pos1 = N * D;
     if (corpus->offsets) {
         pos0 = corpus->offsets[0];
@@ -1137,9 +1201,13 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     auto copy_chunk = [&](int i) -> int {
         const int64_t a = corpus->offsets ? corpus->offsets[cut[i]] : cut[i] * D;
         const int64_t b = corpus->offsets ? corpus->offsets[cut[i + 1]] : cut[i + 1] * D;
-        if (b > a)
-            CUDA_TRY(stage_h2d((char *)uc.values.p + (size_t)(a - pos0) * es, (const char *)corpus->values + (size_t)a * es,
-                               (size_t)(b - a) * es, cs));
+        if (b > a) {
+            if (corpus->offsets)
+                CUDA_TRY(stage_h2d((char *)uc.values.p + (size_t)(a - pos0) * es, (const char *)corpus->values + (size_t)a * es,
+                                   (size_t)(b - a) * es, cs));
+            else   // fixed-size rows: one buffer, or the chunk list of a multi-chunk column
+                CUDA_TRY(copy_host_rows(corpus, cut[i], cut[i + 1], (char *)uc.values.p + (size_t)a * es, cs));
+        }
         stat_add("h2d_bytes", (double)(b - a) * es);
         CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(ev[i], cs));
@@ -1209,6 +1277,523 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------------ shard -> candidates
+int check_shard_args(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard, int64_t k, int32_t metric) {
+    int rc;
+    if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus_shard, "corpus"))) return rc;
+    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative");
+    if (queries->n_rows == 0) return PMM_OK;
+    if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
+    if ((rc = check_pair(queries, corpus_shard))) return rc;
+    const bool q_on_device = (queries->reserved & PMM_MATRIX_ON_DEVICE) != 0;
+    if (q_on_device && (queries->offsets || queries->validity || queries->row_validity))
+        return fail(PMM_ERR_UNSUPPORTED, "device-resident queries must be fixed-size rows without bitmaps");
+    if ((!q_on_device && (rc = list_dim_check(queries, "queries"))) || (rc = list_dim_check(corpus_shard, "corpus"))) return rc;
+    if ((rc = check_chunked(queries, "queries")) || (rc = check_chunked(corpus_shard, "corpus"))) return rc;
+    return PMM_OK;
+}
+
+// Host shard (+ host or device-resident queries) -> this GPU's exact local top-k as packed candidates
+// [Q * min(k, shard rows)] in device memory.  Synchronous.  Arguments already validated.
+int shard_candidates(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard, int64_t k, int32_t metric,
+                     int64_t index_base, uint64_t *d_candidates) {
+    int rc;
+    const int64_t keff = k < corpus_shard->n_rows ? k : corpus_shard->n_rows;
+    if (keff == 0) return PMM_OK;
+    PathChoice pc = choose_path(queries->dtype, corpus_shard->dtype, keff);
+    if (pc.f64) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
+    if (pc.tc && t_opt.host_chunked &&
+        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
+        return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
+    cudaStream_t s = host_stream();
+    Uploaded uq, uc;
+    if (queries->reserved & PMM_MATRIX_ON_DEVICE) {
+        uq.dm = *queries;
+        uq.dm.reserved = 0;
+    } else if ((rc = upload(queries, s, &uq))) {
+        return rc;
+    }
+    if ((rc = upload(corpus_shard, s, &uc))) return rc;
+    TopkOut o{nullptr, nullptr, d_candidates};
+    if ((rc = dev_topk_impl(&uq.dm, &uc.dm, nullptr, corpus_shard->dtype, k, metric, index_base, o, s))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU groups
+// SURVEY §8e / north_star item 6: the corpus partitions by rows, every GPU scans its shard for ALL queries with the
+// fused kernel and emits its exact local top-k as packed candidates with GLOBAL row numbers; the GPUs then exchange
+// candidates with NCCL over NVLink and merge with the same u64-max merge the single-GPU path uses between corpus
+// pieces.  The exchange is an ALL-TO-ALL, not an all-gather: GPU g receives, from every GPU, only the rows of the
+// queries it merges ([g Q/G, (g+1) Q/G)), so each GPU moves and merges 1/G of the candidates; the merged slices are
+// either left where they are (each rank returns its query slice), written to one shared host buffer (single
+// process) or broadcast back so every rank holds the full result.
+//
+// Two process models, one code path:
+//   * single process (the plugin call, pmm_topk): ncclCommInitAll, one persistent host thread per GPU;
+//   * one process per GPU (torchrun, MPI, ...): ncclCommInitRank from a unique id the host application distributes.
+#define NCCL_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        ncclResult_t r__ = (expr);                                                                            \
+        if (r__ != ncclSuccess) return fail(PMM_ERR_CUDA, "NCCL error: %s (%s)", nccl->GetErrorString(r__), #expr); \
+    } while (0)
+
+// A persistent host thread bound to one device.
+class DeviceWorker {
+  public:
+    explicit DeviceWorker(int device) : device_(device), th_([this] { loop(); }) {}
+    ~DeviceWorker() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    void post(std::function<void()> job) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = std::move(job);
+            has_job_ = true;
+            done_ = false;
+        }
+        cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return done_; });
+    }
+
+  private:
+    void loop() {
+        cudaSetDevice(device_);
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return has_job_ || quit_; });
+                if (quit_) return;
+                job = std::move(job_);
+                has_job_ = false;
+            }
+            job();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                done_ = true;
+            }
+            cv_.notify_all();
+        }
+    }
+    int device_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::function<void()> job_;
+    bool has_job_ = false, done_ = true, quit_ = false;
+    std::thread th_;   // last member: starts after everything above is initialised
+};
+
+}  // namespace
+
+struct pmm_group {
+    int world = 1;                        // ranks in the group
+    struct Member {
+        int device = 0, rank = 0;
+        ncclComm_t comm = nullptr;
+        std::unique_ptr<DeviceWorker> worker;   // single-process groups only
+    };
+    std::vector<Member> members;          // the ranks THIS process drives: all of them, or exactly one
+    bool local = false;                   // single-process group (ncclCommInitAll)
+    std::mutex mu;                        // one collective at a time
+    // Rendezvous of the member threads of a single-process group, carrying an error status.  Besides agreeing on
+    // errors it keeps CUDA calls that may synchronise the whole process (first cudaHostAlloc of a staging ring, pool
+    // growth) out of the window in which another GPU already spins inside an NCCL kernel waiting for this one.
+    struct HostBarrier {
+        std::mutex mu;
+        std::condition_variable cv;
+        int count = 0, gen = 0, acc = 0, last = 0;
+        int arrive(int n, int status) {
+            std::unique_lock<std::mutex> lk(mu);
+            acc |= status;
+            const int my_gen = gen;
+            if (++count == n) {
+                count = 0;
+                last = acc;
+                acc = 0;
+                ++gen;
+                cv.notify_all();
+                return last;
+            }
+            cv.wait(lk, [&] { return gen != my_gen; });
+            return last;
+        }
+    } barrier;
+};
+
+namespace {
+
+// Contiguous split of n rows over `parts`, boundaries rounded up to `align` rows (bitmaps slice by whole bytes).
+void split_rows(int64_t n, int parts, int64_t align, std::vector<int64_t> *cut) {
+    int64_t per = parts > 0 ? (n + parts - 1) / parts : n;
+    per = (per + align - 1) / align * align;
+    if (per < align) per = align;
+    cut->assign(parts + 1, 0);
+    for (int g = 0; g <= parts; ++g) (*cut)[g] = std::min<int64_t>(n, (int64_t)g * per);
+}
+
+constexpr int GROUP_OUT_HOST_SLICE = 1;    // out_* are host buffers of the FULL result; this rank writes only its query slice
+constexpr int GROUP_OUT_DEVICE_FULL = 2;   // out_* are device buffers [Q x k]; every rank receives the full result
+constexpr int GROUP_OUT_DEVICE_SLICE = 3;  // out_* are device buffers [Q x k]; this rank writes only its query slice
+constexpr int GROUP_OUT_HOST_FULL = 4;     // out_* are host buffers; every rank reads the full result back
+
+struct GroupTopkArgs {
+    const pmm_matrix_t *queries = nullptr;   // host descriptor (replicated), or device-resident (PMM_MATRIX_ON_DEVICE)
+    const pmm_matrix_t *shard = nullptr;     // this rank's corpus rows: host descriptor, or device-resident (reserved flag)
+    bool queries_from_root = false;          // host queries: only rank 0 uploads, the others receive them over NVLink
+    int64_t index_base = 0, n_total = 0, k = 0;
+    int metric = 0;
+    int out_mode = GROUP_OUT_HOST_SLICE;
+    uint32_t *out_index = nullptr;
+    double *out_score = nullptr;
+};
+
+// One rank's part of a sharded top-k.  Collective: every rank of the group runs it with the same Q, k, metric.
+// Runs on the thread that owns the rank's device (current device = member.device), options already in t_opt.
+// Structure: phases that may fail on their own (CUDA_TRY inside a lambda) separated by rendezvous points that every
+// rank reaches whatever happened before, so that no rank is ever left alone inside a collective.
+int group_rank_topk(pmm_group *g, pmm_group::Member &m, const GroupTopkArgs &a) {
+    const NcclApi *nccl = nccl_api();
+    const int G = g->world, me = m.rank;
+    if (!nccl && G > 1) return fail(PMM_ERR_UNSUPPORTED, "%s", nccl_load_error());
+    std::lock_guard<std::mutex> device_lock(device_mutex());
+    cudaStream_t s = host_stream();
+    const int64_t Q = a.queries->n_rows, D = a.queries->dim;
+    const int64_t keff = a.k < a.n_total ? a.k : a.n_total;
+    if (Q == 0 || keff == 0) return PMM_OK;
+    const int64_t n_local = a.shard->n_rows;
+    const int64_t k_local = keff < n_local ? keff : n_local;
+    const bool profile = t_opt.profile != 0;
+    // CUDA-event bracket around a collective (statistics "<name>_ms"), like launch_counted for kernels
+    struct Bracket {
+        const char *name;
+        cudaStream_t s;
+        bool on;
+        cudaEvent_t a = nullptr, b = nullptr;
+        Bracket(const char *n, cudaStream_t st, bool enabled) : name(n), s(st), on(enabled) {
+            if (on) {
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                cudaEventRecord(a, s);
+            }
+        }
+        ~Bracket() {
+            if (!on) return;
+            cudaEventRecord(b, s);
+            std::lock_guard<std::mutex> lk(g_stat_mu);
+            g_pending.push_back({name, a, b});
+            g_stats[std::string(name) + "_launches"] += 1;
+        }
+    };
+    // rendezvous with error agreement: host barrier inside one process, a 4-byte all-reduce between processes
+    DevBuf st;
+    auto agree = [&](int rc_mine, const char *what) -> int {
+        int any = rc_mine ? 1 : 0;
+        if (g->local) {
+            any = g->barrier.arrive(G, any);
+        } else if (st.p) {
+            int h = any;
+            CUDA_TRY(cudaMemcpyAsync(st.p, &h, sizeof(int), cudaMemcpyHostToDevice, s));
+            NCCL_TRY(nccl->AllReduce(st.p, st.p, 1, ncclInt32, ncclMax, m.comm, s));
+            CUDA_TRY(cudaMemcpyAsync(&h, st.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            any = h;
+        }
+        if (rc_mine) return rc_mine;
+        if (any) return fail(PMM_ERR_CUDA, "another GPU of the group failed (%s)", what);
+        return PMM_OK;
+    };
+    if (G > 1 && !g->local) CUDA_TRY(st.alloc(sizeof(int), s));   // (nothing collective has started yet: a plain return is safe)
+
+    // ---- phase 1: the replicated queries.  Dense host queries cross ONE host link (rank 0) and reach the other GPUs
+    //      over NVLink; anything else (lists, bitmaps, already on the device) is taken as it is by every rank.
+    DevBuf d_q;
+    pmm_matrix_t q_desc = *a.queries;
+    const bool bcast = G > 1 && a.queries_from_root && !(a.queries->reserved & PMM_MATRIX_ON_DEVICE) && !a.queries->offsets &&
+                       !a.queries->validity && !a.queries->row_validity;
+    int rc = PMM_OK;
+    if (bcast) {
+        const size_t qbytes = (size_t)Q * D * esize(a.queries->dtype);
+        rc = [&]() -> int {
+            CUDA_TRY(d_q.alloc(qbytes, s));
+            if (me == 0) {
+                CUDA_TRY(stage_h2d(d_q.p, a.queries->values, qbytes, s));
+                stat_add("h2d_bytes", (double)qbytes);
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+            return PMM_OK;
+        }();
+        if ((rc = agree(rc, "query upload"))) return rc;
+        {
+            Bracket br("group_broadcast", s, profile);
+            NCCL_TRY(nccl->Broadcast(d_q.p, d_q.p, qbytes, ncclUint8, 0, m.comm, s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        q_desc.values = d_q.p;
+        q_desc.reserved = PMM_MATRIX_ON_DEVICE;
+    }
+
+    // ---- phase 2: local exact top-k of the shard -> packed candidates [Q x keff] (zero = empty slot), and the
+    //      buffers of the exchange (allocated before the rendezvous: see HostBarrier)
+    std::vector<int64_t> qcut;
+    split_rows(Q, G, 1, &qcut);
+    const int64_t q0 = qcut[me], qn = qcut[me + 1] - qcut[me];
+    const bool full_dev = a.out_mode == GROUP_OUT_DEVICE_FULL, full_host = a.out_mode == GROUP_OUT_HOST_FULL;
+    const bool to_host = a.out_mode == GROUP_OUT_HOST_SLICE || full_host;
+    DevBuf cand, cand_local, recv, oi, os, full_i, full_s;
+    uint32_t *mi = nullptr;   // where this rank's merged slice goes (device)
+    double *ms = nullptr;
+    uint32_t *fi = nullptr;   // the full [Q x keff] result on the device, when one is assembled
+    double *fs = nullptr;
+    rc = [&]() -> int {
+        CUDA_TRY(cand.alloc((size_t)Q * keff * 8, s));
+        uint64_t *local_ptr = cand.as<uint64_t>();
+        if (k_local < keff) {
+            CUDA_TRY(cudaMemsetAsync(cand.p, 0, (size_t)Q * keff * 8, s));
+            if (k_local > 0) {
+                CUDA_TRY(cand_local.alloc((size_t)Q * k_local * 8, s));
+                local_ptr = cand_local.as<uint64_t>();
+            }
+        }
+        if (k_local > 0) {
+            int r2;
+            if (a.shard->reserved & PMM_MATRIX_ON_DEVICE) {
+                if (!(q_desc.reserved & PMM_MATRIX_ON_DEVICE)) return fail(PMM_ERR_INVALID, "a device-resident shard needs device-resident queries");
+                pmm_matrix_t dq = q_desc, dc = *a.shard;
+                dq.reserved = 0;
+                dc.reserved = 0;
+                TopkOut o{nullptr, nullptr, local_ptr};
+                if ((r2 = dev_topk_impl(&dq, &dc, nullptr, dc.dtype, k_local, a.metric, a.index_base, o, s))) return r2;
+            } else {
+                CUDA_TRY(cudaStreamSynchronize(s));   // cand is zeroed before the shard path (its own stream syncs) fills it
+                if ((r2 = shard_candidates(&q_desc, a.shard, k_local, a.metric, a.index_base, local_ptr))) return r2;
+            }
+            if (local_ptr != cand.as<uint64_t>())
+                CUDA_TRY(cudaMemcpy2DAsync(cand.p, (size_t)keff * 8, local_ptr, (size_t)k_local * 8, (size_t)k_local * 8, (size_t)Q,
+                                           cudaMemcpyDeviceToDevice, s));
+        }
+        const int64_t qn1 = qn > 0 ? qn : 1;
+        if (G > 1) CUDA_TRY(recv.alloc((size_t)G * qn1 * keff * 8, s));
+        if (full_dev) {
+            fi = a.out_index;
+            fs = a.out_score;
+        } else if (full_host && G > 1) {
+            CUDA_TRY(full_i.alloc((size_t)Q * keff * 4, s));
+            CUDA_TRY(full_s.alloc((size_t)Q * keff * 8, s));
+            fi = full_i.as<uint32_t>();
+            fs = full_s.as<double>();
+        }
+        if (fi) {
+            mi = fi + q0 * keff;
+            ms = fs + q0 * keff;
+        } else if (a.out_mode == GROUP_OUT_DEVICE_SLICE) {
+            mi = a.out_index + q0 * keff;
+            ms = a.out_score + q0 * keff;
+        } else {
+            CUDA_TRY(oi.alloc((size_t)qn1 * keff * 4, s));
+            CUDA_TRY(os.alloc((size_t)qn1 * keff * 8, s));
+            mi = oi.as<uint32_t>();
+            ms = os.as<double>();
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return PMM_OK;
+    }();
+    if (G > 1 && (rc = agree(rc, "local top-k"))) return rc;
+    if (rc) return rc;
+
+    // ---- phase 3: all-to-all of candidates (rank r merges the queries [qcut[r], qcut[r+1])), merge of my slice
+    const uint64_t *lists = cand.as<uint64_t>() + q0 * keff;
+    int64_t list_stride = 0;
+    if (G > 1) {
+        Bracket br("group_exchange", s, profile);
+        NCCL_TRY(nccl->GroupStart());
+        for (int r = 0; r < G; ++r) {
+            const int64_t rn = qcut[r + 1] - qcut[r];
+            if (rn > 0) NCCL_TRY(nccl->Send(cand.as<uint64_t>() + qcut[r] * keff, (size_t)rn * keff, ncclUint64, r, m.comm, s));
+            if (qn > 0) NCCL_TRY(nccl->Recv(recv.as<uint64_t>() + (int64_t)r * qn * keff, (size_t)qn * keff, ncclUint64, r, m.comm, s));
+        }
+        NCCL_TRY(nccl->GroupEnd());
+        lists = recv.as<uint64_t>();
+        list_stride = qn * keff;
+    }
+    if (qn > 0)
+        CUDA_TRY(launch_counted("group_merge", s, [&] {
+            return launch_merge_regular(lists, G, list_stride, keff, qn, (int)keff, (int)keff, a.metric != PMM_METRIC_EUCLIDEAN, mi, ms,
+                                        nullptr, s);
+        }));
+
+    // ---- phase 4: results
+    if (fi && G > 1) {  // every rank ends up with the whole [Q x keff] result: one broadcast per slice
+        Bracket br("group_gather", s, profile);
+        NCCL_TRY(nccl->GroupStart());
+        for (int r = 0; r < G; ++r) {
+            const int64_t rn = qcut[r + 1] - qcut[r];
+            if (rn <= 0) continue;
+            NCCL_TRY(nccl->Broadcast(fi + qcut[r] * keff, fi + qcut[r] * keff, (size_t)rn * keff, ncclUint32, r, m.comm, s));
+            NCCL_TRY(nccl->Broadcast(fs + qcut[r] * keff, fs + qcut[r] * keff, (size_t)rn * keff, ncclFloat64, r, m.comm, s));
+        }
+        NCCL_TRY(nccl->GroupEnd());
+    }
+    if (to_host) {
+        const bool whole = full_host;   // G == 1: q0 = 0 and qn = Q, so the "slice" is everything
+        const int64_t r0 = whole ? 0 : q0, rn = whole ? Q : qn;
+        const uint32_t *src_i = whole && fi ? fi : mi;
+        const double *src_s = whole && fs ? fs : ms;
+        if (rn > 0) {
+            CUDA_TRY(stage_d2h(a.out_index + r0 * keff, src_i, (size_t)rn * keff * 4, s));
+            CUDA_TRY(stage_d2h(a.out_score + r0 * keff, src_s, (size_t)rn * keff * 8, s));
+            stat_add("d2h_bytes", (double)rn * keff * 12);
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PMM_OK;
+}
+
+// ---- the process-wide single-process group behind pmm_topk / pmm_matmul -----------------------------------------------
+std::mutex g_local_group_mu;
+pmm_group *g_local_group = nullptr;
+bool g_local_group_failed = false;
+
+int create_local_group(int n_devices, pmm_group **out) {
+    const NcclApi *nccl = nccl_api();
+    if (!nccl) return fail(PMM_ERR_UNSUPPORTED, "%s", nccl_load_error());
+    int have = 0;
+    CUDA_TRY(cudaGetDeviceCount(&have));
+    if (n_devices <= 0 || n_devices > have) n_devices = have;
+    if (n_devices > 16) n_devices = 16;
+    std::unique_ptr<pmm_group> g(new pmm_group());
+    g->world = n_devices;
+    g->local = true;
+    std::vector<int> devs(n_devices);
+    std::vector<ncclComm_t> comms(n_devices, nullptr);
+    for (int i = 0; i < n_devices; ++i) devs[i] = i;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    NCCL_TRY(nccl->CommInitAll(comms.data(), n_devices, devs.data()));
+    cudaSetDevice(cur);
+    g->members.resize(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        g->members[i].device = i;
+        g->members[i].rank = i;
+        g->members[i].comm = comms[i];
+        g->members[i].worker.reset(new DeviceWorker(i));
+    }
+    *out = g.release();
+    return PMM_OK;
+}
+
+// NULL when the box has one GPU, NCCL is missing or the communicator could not be created (the caller then stays on
+// one GPU; the reason is in pmm_get_stat-independent g_err of the creating thread only, which is fine: it is a fallback
+// to the path every call used to take, not to a CPU).
+pmm_group *local_group() {
+    std::lock_guard<std::mutex> lk(g_local_group_mu);
+    if (g_local_group || g_local_group_failed) return g_local_group;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 2) {
+        cudaGetLastError();
+        g_local_group_failed = true;
+        return nullptr;
+    }
+    if (create_local_group(n, &g_local_group) != PMM_OK) {
+        g_local_group = nullptr;
+        g_local_group_failed = true;
+    }
+    return g_local_group;
+}
+
+// Runs fn(member index) on every member's worker thread with the caller's option snapshot; returns the first error.
+int run_on_members(pmm_group *g, const std::function<int(int)> &fn) {
+    const Options opt = t_opt;
+    const int n = (int)g->members.size();
+    std::vector<int> rcs(n, PMM_OK);
+    std::vector<std::string> errs(n);
+    for (int i = 0; i < n; ++i)
+        g->members[i].worker->post([&, i] {
+            t_opt = opt;
+            rcs[i] = fn(i);
+            if (rcs[i]) errs[i] = g_err;
+        });
+    for (int i = 0; i < n; ++i) g->members[i].worker->wait();
+    for (int i = 0; i < n; ++i)
+        if (rcs[i]) {
+            g_err = errs[i];
+            return rcs[i];
+        }
+    return PMM_OK;
+}
+
+// Whole-corpus host call spread over the GPUs of a single-process group: corpus rows sharded (boundaries multiples of
+// 256 rows), queries uploaded once and broadcast, every GPU writes its slice of the result into the caller's buffers.
+int group_host_topk(pmm_group *g, const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k, int metric, uint32_t *out_index,
+                    double *out_score) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    std::vector<int64_t> cut;
+    split_rows(corpus->n_rows, g->world, 256, &cut);
+    std::vector<pmm_matrix_t> shards(g->world);
+    for (int r = 0; r < g->world; ++r) shards[r] = slice_rows(*corpus, cut[r], cut[r + 1] - cut[r]);
+    return run_on_members(g, [&](int i) {
+        GroupTopkArgs a;
+        a.queries = queries;
+        a.shard = &shards[i];
+        a.queries_from_root = true;
+        a.index_base = cut[i];
+        a.n_total = corpus->n_rows;
+        a.k = k;
+        a.metric = metric;
+        a.out_mode = GROUP_OUT_HOST_SLICE;
+        a.out_index = out_index;
+        a.out_score = out_score;
+        return group_rank_topk(g, g->members[i], a);
+    });
+}
+
+// Raw matmul over a single-process group: output ROWS (left rows) are sharded, no collective is needed:
+// every GPU uploads its slice of `left` and the whole of `right`, and writes its slab of the result through its own
+// host link - the device->host copy of the result, which dominates this path, runs on all links at once.
+int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, cudaStream_t s);
+int group_host_matmul(pmm_group *g, const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    std::vector<int64_t> cut;
+    split_rows(left->n_rows, g->world, 256, &cut);
+    const int wd = pmm_working_dtype(left->dtype, right->dtype);
+    const size_t osz = wd == PMM_DTYPE_F64 ? 8 : 4;
+    return run_on_members(g, [&](int i) -> int {
+        const int64_t rows = cut[i + 1] - cut[i];
+        if (rows <= 0) return PMM_OK;
+        std::lock_guard<std::mutex> device_lock(device_mutex());
+        cudaStream_t s = host_stream();
+        const pmm_matrix_t part = slice_rows(*left, cut[i], rows);
+        Uploaded ul, ur;
+        int rc;
+        if ((rc = upload(&part, s, &ul)) || (rc = upload(right, s, &ur))) return rc;
+        DevBuf d_out;
+        const size_t bytes = (size_t)rows * right->n_rows * osz;
+        CUDA_TRY(d_out.alloc(bytes, s));
+        if ((rc = dev_matmul_impl(&ul.dm, &ur.dm, d_out.p, s))) return rc;
+        CUDA_TRY(stage_d2h((char *)out + (size_t)cut[i] * right->n_rows * osz, d_out.p, bytes, s));
+        stat_add("d2h_bytes", (double)bytes);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return PMM_OK;
+    });
+}
+
+// Is this call worth spreading over the box?  (GFLOP of contraction work; the multi-GPU path costs ~1 ms of
+// dispatch, broadcast and exchange.)
+bool wants_multi_gpu(double q_rows, double c_rows, double dim, double out_bytes) {
+    if (!t_opt.multi_gpu) return false;
+    const double gflop = 2.0 * q_rows * c_rows * dim / 1e9;
+    return gflop >= (double)t_opt.multi_gpu_min_gflop || out_bytes >= 1.0e9;
+}
+
 }  // namespace
 
 struct pmm_corpus {
@@ -1272,6 +1857,11 @@ int pmm_host_free(void *p) {
     if (!p) return PMM_OK;
     CUDA_TRY(cudaFreeHost(p));
     return PMM_OK;
+}
+
+void *pmm_thread_stream(void) {
+    if (ensure_device()) return nullptr;
+    return (void *)host_stream();
 }
 
 int64_t pmm_kernel_launch_count(void) { return g_launches.load(); }
@@ -1493,10 +2083,19 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     if ((rc = pmm_metric_from_str(metric, &m))) return rc;
     if ((rc = check_pair(queries, corpus))) return rc;
     if ((rc = list_dim_check(queries, "queries")) || (rc = list_dim_check(corpus, "corpus"))) return rc;
+    if ((rc = check_chunked(queries, "queries")) || (rc = check_chunked(corpus, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
     begin_call();
-    std::lock_guard<std::mutex> device_lock(device_mutex());
     if (keff == 0) return PMM_OK;
+    // One call, the whole box (north_star item 6): above a size threshold the corpus rows are sharded over all visible
+    // GPUs by a single-process group (one host thread per GPU, NCCL candidate exchange).  f32 working precision,
+    // fused path only; everything else stays on the calling thread's device.
+    if (wants_multi_gpu((double)queries->n_rows, (double)corpus->n_rows, (double)corpus->dim, 0.0) &&
+        pmm_working_dtype(queries->dtype, corpus->dtype) == PMM_DTYPE_F32 && keff <= TC_MAX_K && !t_opt.force_generic && dev_info().tc) {
+        pmm_group *g = (is_chunked(queries) || is_chunked(corpus)) ? nullptr : local_group();
+        if (g && corpus->n_rows >= (int64_t)4096 * g->world) return group_host_topk(g, queries, corpus, k, m, out_index, out_score);
+    }
+    std::lock_guard<std::mutex> device_lock(device_mutex());
     cudaStream_t s = host_stream();
     {
         PathChoice pc = choose_path(queries->dtype, corpus->dtype, keff);
@@ -1521,38 +2120,12 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
 int pmm_topk_shard(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard, int64_t k, int32_t metric,
                    int64_t index_base, uint64_t *d_candidates) {
     int rc;
-    if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus_shard, "corpus"))) return rc;
-    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative");
+    if ((rc = check_shard_args(queries, corpus_shard, k, metric))) return rc;
     if (queries->n_rows == 0) return PMM_OK;
-    if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
-    if ((rc = check_pair(queries, corpus_shard))) return rc;
-    const bool q_on_device = (queries->reserved & PMM_MATRIX_ON_DEVICE) != 0;
-    if (q_on_device && (queries->offsets || queries->validity || queries->row_validity))
-        return fail(PMM_ERR_UNSUPPORTED, "device-resident queries must be fixed-size rows without bitmaps");
-    if ((!q_on_device && (rc = list_dim_check(queries, "queries"))) || (rc = list_dim_check(corpus_shard, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
     begin_call();
     std::lock_guard<std::mutex> device_lock(device_mutex());
-    const int64_t keff = k < corpus_shard->n_rows ? k : corpus_shard->n_rows;
-    if (keff == 0) return PMM_OK;
-    PathChoice pc = choose_path(queries->dtype, corpus_shard->dtype, keff);
-    if (pc.f64) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
-    if (pc.tc && t_opt.host_chunked &&
-        (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
-        return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
-    cudaStream_t s = host_stream();
-    Uploaded uq, uc;
-    if (q_on_device) {
-        uq.dm = *queries;
-        uq.dm.reserved = 0;
-    } else if ((rc = upload(queries, s, &uq))) {
-        return rc;
-    }
-    if ((rc = upload(corpus_shard, s, &uc))) return rc;
-    TopkOut o{nullptr, nullptr, d_candidates};
-    if ((rc = dev_topk_impl(&uq.dm, &uc.dm, nullptr, corpus_shard->dtype, k, metric, index_base, o, s))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return PMM_OK;
+    return shard_candidates(queries, corpus_shard, k, metric, index_base, d_candidates);
 }
 
 int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
@@ -1561,14 +2134,19 @@ int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
     if (left->n_rows == 0) return PMM_OK;  // src/matmul.rs:297-305
     if ((rc = check_pair(left, right))) return rc;
     if ((rc = list_dim_check(left, "left")) || (rc = list_dim_check(right, "right"))) return rc;
+    if ((rc = check_chunked(left, "left")) || (rc = check_chunked(right, "right"))) return rc;
     if ((rc = ensure_device())) return rc;
     begin_call();
+    const int wd = pmm_working_dtype(left->dtype, right->dtype);
+    const size_t bytes = (size_t)left->n_rows * right->n_rows * (wd == PMM_DTYPE_F64 ? 8 : 4);
+    if (wants_multi_gpu((double)left->n_rows, (double)right->n_rows, (double)left->dim, (double)bytes)) {
+        pmm_group *g = (is_chunked(left) || is_chunked(right)) ? nullptr : local_group();   // output rows sharded over the GPUs, no collective
+        if (g && left->n_rows >= (int64_t)512 * g->world) return group_host_matmul(g, left, right, out);
+    }
     std::lock_guard<std::mutex> device_lock(device_mutex());
     cudaStream_t s = host_stream();
     Uploaded ul, ur;
     if ((rc = upload(left, s, &ul)) || (rc = upload(right, s, &ur))) return rc;
-    const int wd = pmm_working_dtype(left->dtype, right->dtype);
-    const size_t bytes = (size_t)left->n_rows * right->n_rows * (wd == PMM_DTYPE_F64 ? 8 : 4);
     DevBuf d_out;
     CUDA_TRY(d_out.alloc(bytes, s));
     if ((rc = dev_matmul_impl(&ul.dm, &ur.dm, d_out.p, s))) return rc;
@@ -1576,6 +2154,120 @@ int pmm_matmul(const pmm_matrix_t *left, const pmm_matrix_t *right, void *out) {
     stat_add("d2h_bytes", (double)bytes);
     CUDA_TRY(cudaStreamSynchronize(s));
     return PMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- groups of GPUs
+int pmm_group_unique_id(void *id) {
+    if (!id) return fail(PMM_ERR_INVALID, "null id buffer");
+    const NcclApi *nccl = nccl_api();
+    if (!nccl) return fail(PMM_ERR_UNSUPPORTED, "%s", nccl_load_error());
+    ncclUniqueId u;
+    NCCL_TRY(nccl->GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return PMM_OK;
+}
+
+int pmm_group_init_rank(const void *id, int32_t rank, int32_t world, pmm_group_t **out) {
+    if (!out || !id) return fail(PMM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(PMM_ERR_INVALID, "need 0 <= rank < world");
+    int rc = ensure_device();
+    if (rc) return rc;
+    std::unique_ptr<pmm_group> g(new pmm_group());
+    g->world = world;
+    g->local = false;
+    g->members.resize(1);
+    cudaGetDevice(&g->members[0].device);
+    g->members[0].rank = rank;
+    if (world > 1) {
+        const NcclApi *nccl = nccl_api();
+        if (!nccl) return fail(PMM_ERR_UNSUPPORTED, "%s", nccl_load_error());
+        ncclUniqueId u;
+        memcpy(&u, id, sizeof(u));
+        NCCL_TRY(nccl->CommInitRank(&g->members[0].comm, world, u, rank));
+    }
+    *out = g.release();
+    return PMM_OK;
+}
+
+int pmm_group_init_local(int32_t n_devices, pmm_group_t **out) {
+    if (!out) return fail(PMM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = ensure_device();
+    if (rc) return rc;
+    return create_local_group(n_devices, out);
+}
+
+int pmm_group_destroy(pmm_group_t *g) {
+    if (!g) return PMM_OK;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        const NcclApi *nccl = nccl_api();
+        for (auto &m : g->members) {
+            m.worker.reset();
+            if (m.comm && nccl) nccl->CommDestroy(m.comm);
+            m.comm = nullptr;
+        }
+    }
+    delete g;
+    return PMM_OK;
+}
+
+int pmm_group_size(const pmm_group_t *g) { return g ? g->world : 0; }
+
+int pmm_group_topk(pmm_group_t *g, const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k, const char *metric,
+                   uint32_t *out_index, double *out_score, int64_t *k_actual) {
+    int rc;
+    if (!g || !g->local) return fail(PMM_ERR_INVALID, "pmm_group_topk needs a single-process group (pmm_group_init_local)");
+    if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus, "corpus"))) return rc;
+    if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative (can't convert negative int to unsigned)");
+    const int64_t keff = k < corpus->n_rows ? k : corpus->n_rows;
+    if (k_actual) *k_actual = keff;
+    if (queries->n_rows == 0) return PMM_OK;
+    int32_t m;
+    if ((rc = pmm_metric_from_str(metric, &m))) return rc;
+    if ((rc = check_pair(queries, corpus))) return rc;
+    if ((rc = list_dim_check(queries, "queries")) || (rc = list_dim_check(corpus, "corpus"))) return rc;
+    if (keff == 0) return PMM_OK;
+    if (pmm_working_dtype(queries->dtype, corpus->dtype) != PMM_DTYPE_F32 || keff > TC_MAX_K)
+        return fail(PMM_ERR_UNSUPPORTED, "sharded top-k covers f32 working precision and k <= 248 (packed 8-byte candidates)");
+    begin_call();
+    return group_host_topk(g, queries, corpus, k, m, out_index, out_score);
+}
+
+int pmm_group_topk_shard(pmm_group_t *g, const pmm_matrix_t *queries, const pmm_matrix_t *corpus_shard, int64_t index_base,
+                         int64_t n_total, int64_t k, int32_t metric, int32_t flags, uint32_t *out_index, double *out_score) {
+    int rc;
+    if (!g || g->local || g->members.size() != 1)
+        return fail(PMM_ERR_INVALID, "pmm_group_topk_shard needs a one-rank-per-process group (pmm_group_init_rank)");
+    if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus_shard, "corpus"))) return rc;
+    if (k < 0 || n_total < corpus_shard->n_rows || index_base < 0) return fail(PMM_ERR_INVALID, "bad k / n_total / index_base");
+    if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
+    if (queries->n_rows == 0) return PMM_OK;
+    if (n_total == 0) return fail(PMM_ERR_INVALID, "Empty series");
+    if (corpus_shard->n_rows > 0) {
+        if ((rc = check_pair(queries, corpus_shard))) return rc;
+        if ((rc = list_dim_check(corpus_shard, "corpus"))) return rc;
+    }
+    if (pmm_working_dtype(queries->dtype, corpus_shard->dtype) != PMM_DTYPE_F32 || (k < n_total ? k : n_total) > TC_MAX_K)
+        return fail(PMM_ERR_UNSUPPORTED, "sharded top-k covers f32 working precision and k <= 248 (packed 8-byte candidates)");
+    const int out_mode = flags & 7;
+    if (out_mode < GROUP_OUT_HOST_SLICE || out_mode > GROUP_OUT_HOST_FULL) return fail(PMM_ERR_INVALID, "bad output mode in flags");
+    if ((rc = ensure_device())) return rc;
+    begin_call();
+    std::lock_guard<std::mutex> lk(g->mu);
+    GroupTopkArgs a;
+    a.queries = queries;
+    a.shard = corpus_shard;
+    a.queries_from_root = (flags & PMM_GROUP_QUERIES_FROM_ROOT) != 0;
+    a.index_base = index_base;
+    a.n_total = n_total;
+    a.k = k;
+    a.metric = metric;
+    a.out_mode = out_mode;
+    a.out_index = out_index;
+    a.out_score = out_score;
+    return group_rank_topk(g, g->members[0], a);
 }
 
 // ---------------------------------------------------------------------------------------------- resident corpus
@@ -1586,7 +2278,7 @@ int pmm_corpus_create(const pmm_matrix_t *corpus, int32_t query_dtype, pmm_corpu
     if ((rc = check_matrix(corpus, "corpus"))) return rc;
     if (corpus->n_rows == 0) return fail(PMM_ERR_INVALID, "Empty series");
     if (corpus->dim == 0) return fail(PMM_ERR_INVALID, "Zero-dimensional vectors");
-    if ((rc = list_dim_check(corpus, "corpus"))) return rc;
+    if ((rc = list_dim_check(corpus, "corpus")) || (rc = check_chunked(corpus, "corpus"))) return rc;
     if ((rc = ensure_device())) return rc;
     begin_call();
     std::lock_guard<std::mutex> device_lock(device_mutex());
@@ -1644,7 +2336,7 @@ int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *corpus, int
     if (queries->dim != corpus->prep.dim)
         return fail(PMM_ERR_INVALID, "Dimension mismatch: left has %lld dimensional vectors, right has %lld dimensional vectors",
                     (long long)queries->dim, (long long)corpus->prep.dim);
-    if ((rc = list_dim_check(queries, "queries"))) return rc;
+    if ((rc = list_dim_check(queries, "queries")) || (rc = check_chunked(queries, "queries"))) return rc;
     if ((rc = ensure_device())) return rc;
     begin_call();
     std::lock_guard<std::mutex> device_lock(device_mutex());

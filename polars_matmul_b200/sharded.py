@@ -1,28 +1,39 @@
 """
-Multi-GPU driver for the top-k path: one process per GPU, corpus rows sharded contiguously, queries
-replicated (BASELINE.json north_star item 6).
+Multi-GPU top-k: corpus rows sharded over the GPUs of one box, queries replicated (BASELINE.json
+north_star item 6).  The reference has no distributed code at all; the corpus partitions naturally.
 
-The reference has no distributed code at all; the corpus partitions naturally, so every rank runs the
-fused kernel on its shard with global row numbers (index_base), the ranks exchange only Q x k packed
-candidates (8 bytes each) with one NCCL all-gather over NVLink, and every rank merges the gathered lists
-with the same merge kernel the single-GPU path uses between corpus pieces.  Because the packed order
-(score key, then lower index) is a total order, the result does not depend on the number of shards.
+All of the multi-GPU work lives behind the C ABI (include/pmm.h, "groups of GPUs"): every GPU runs the fused kernel on
+its shard with global row numbers, the GPUs exchange Q x k packed candidates (8 bytes each) with NCCL over NVLink — an
+all-to-all, so each GPU receives and merges only its slice of the queries — and merge by u64 max.  Because the packed
+order (score key, then lower index) is a total order, the result does not depend on the number of shards.
 
-torch / torch.distributed are plumbing here (device buffers, the NCCL communicator, streams); the
-compute is libpmm_b200.so.
+Two process models (both thin ctypes wrappers, no torch, no NCCL binding of their own):
+
+  * `LocalGroup`  one process drives all GPUs (one host thread per GPU inside the library).  This is what the plugin
+                  call uses on its own: `pmm_topk` / `pmm_matmul` spread large calls over the box.
+  * `RankGroup`   one process per GPU (torchrun, MPI ...).  The host application only has to hand the 128-byte id
+                  that `unique_id()` returns on one rank to every other rank.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Tuple
 
 import numpy as np
 
 from . import _native
 
+OUT_HOST_SLICE, OUT_DEVICE_FULL, OUT_DEVICE_SLICE, OUT_HOST_FULL = 1, 2, 3, 4
+QUERIES_FROM_ROOT = 256
+MAX_K = 248
 
-def shard_bounds(n_rows: int, world_size: int) -> List[Tuple[int, int]]:
-    """Contiguous row ranges: rank g owns [g*ceil(N/G), min(N, (g+1)*ceil(N/G)))."""
+
+def shard_bounds(n_rows: int, world_size: int, align: int = 1) -> List[Tuple[int, int]]:
+    """Contiguous row ranges: rank g owns [g*per, min(N, (g+1)*per)), per = ceil(N/G) rounded up to `align`.
+    align=1 is the library's split of the QUERY rows (who merges what); the single-process driver shards CORPUS rows
+    with align=256 so that validity bitmaps slice by whole bytes."""
     per = -(-n_rows // world_size) if world_size > 0 else n_rows
+    per = max(align, -(-per // align) * align)
     return [(min(n_rows, g * per), min(n_rows, (g + 1) * per)) for g in range(world_size)]
 
 
@@ -50,31 +61,26 @@ def unpack_candidates(cand: np.ndarray, higher_is_better: bool):
     return index, score
 
 
-def all_gather_candidates(cand, group=None):
-    """[Q, k] int64 tensor per rank -> [G, Q, k] on every rank (NCCL on GPU tensors, gloo on CPU)."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(cand.shape), dtype=cand.dtype, device=cand.device)
-    if cand.is_cuda:
-        dist.all_gather_into_tensor(out, cand.contiguous(), group=group)
-    else:  # gloo has no all_gather_into_tensor for every build: use the list form
-        parts = [torch.empty_like(cand) for _ in range(world)]
-        dist.all_gather(parts, cand.contiguous(), group=group)
-        out = torch.stack(parts, 0)
-    return out
+def unique_id() -> bytes:
+    """pmm_group_unique_id: call on ONE rank and distribute the bytes to the others."""
+    buf = ctypes.create_string_buffer(128)
+    _native.check(_native.lib().pmm_group_unique_id(buf))
+    return buf.raw
 
 
 def bind_near_gpu(device_index: int):
-    """One process per GPU: restrict this process to the CPUs of the GPU's NUMA node, so that the page-locked host
-    buffers it allocates afterwards (and the threads that fill them) are local to the GPU's PCIe root. With 8 ranks
-    uploading their corpus shards at once the host side is the bottleneck and remote-socket pages cost bandwidth.
-    Best effort: returns a short description, or None when the topology cannot be read (nothing is changed then)."""
+    """One process per GPU: restrict this process to the CPUs of the GPU's NUMA node, so that the staging buffers it
+    allocates afterwards (and the threads that fill them) are local to the GPU's PCIe root. Best effort: returns a
+    short description, or None when the topology cannot be read (nothing is changed then)."""
     import os
     try:
-        import torch
-        props = torch.cuda.get_device_properties(device_index)
-        bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        import subprocess
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bdf:
+            return None
+        if len(bdf.split(":")[0]) == 8:      # 00000000:1B:00.0 -> 0000:1b:00.0
+            bdf = bdf[4:]
         with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
@@ -93,84 +99,88 @@ def bind_near_gpu(device_index: int):
         return None
 
 
-class ShardedTopk:
-    """Top-k of replicated queries against a corpus sharded over the ranks of `group`."""
+class _Group:
+    def __init__(self):
+        self._h = ctypes.c_void_p(None)
 
-    def __init__(self, group=None):
-        import torch.distributed as dist
-        self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+    @property
+    def size(self) -> int:
+        return int(_native.lib().pmm_group_size(self._h))
 
-    def topk_device(self, d_queries, d_corpus_shard, index_base: int, n_total: int, k: int, metric: str):
-        """d_queries [Q, D], d_corpus_shard [n_local, D]: CUDA tensors (f32 or f16) on this rank's GPU.
-        Returns (index int32-as-u32 [Q, k_eff], score f64 [Q, k_eff]) CUDA tensors, identical on every rank."""
-        import torch
-        m = _native.metric_from_str(metric)
-        Q, D = d_queries.shape
-        n_local = d_corpus_shard.shape[0]
-        k_eff = min(int(k), int(n_total))
-        if k_eff > 128:
-            raise _native.PmmError(_native.PMM_ERR_UNSUPPORTED, "sharded top-k supports k <= 128")
-        code = {torch.float16: _native.DTYPE_F16, torch.float32: _native.DTYPE_F32}[d_queries.dtype]
-        ccode = {torch.float16: _native.DTYPE_F16, torch.float32: _native.DTYPE_F32}[d_corpus_shard.dtype]
-        stream = torch.cuda.current_stream().cuda_stream
-        k_local = min(k_eff, n_local)
-        cand = torch.zeros((Q, k_eff), dtype=torch.int64, device=d_queries.device)  # 0 = empty slot
-        if k_local > 0:
-            local = cand if k_local == k_eff else torch.empty((Q, k_local), dtype=torch.int64, device=d_queries.device)
-            _native.dev_topk(_native.dev_matrix(d_queries.data_ptr(), Q, D, code),
-                             _native.dev_matrix(d_corpus_shard.data_ptr(), n_local, D, ccode),
-                             k_local, m, index_base=index_base, cand_ptr=local.data_ptr(), stream=stream)
-            if local is not cand:
-                cand[:, :k_local] = local
-        gathered = all_gather_candidates(cand, self.group) if self.world > 1 else cand.unsqueeze(0)
-        idx = torch.empty((Q, k_eff), dtype=torch.int32, device=d_queries.device)
-        sc = torch.empty((Q, k_eff), dtype=torch.float64, device=d_queries.device)
-        _native.dev_merge_candidates(gathered.data_ptr(), gathered.shape[0], Q, k_eff, k_eff, m,
-                                     idx.data_ptr(), sc.data_ptr(), stream=stream)
+    def close(self):
+        if self._h:
+            _native.lib().pmm_group_destroy(self._h)
+            self._h = ctypes.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LocalGroup(_Group):
+    """All (or the first n) GPUs of the box driven by this process."""
+
+    def __init__(self, n_devices: int = 0):
+        super().__init__()
+        _native.check(_native.lib().pmm_group_init_local(int(n_devices), ctypes.byref(self._h)))
+
+    def topk(self, queries, corpus, k: int, metric: str):
+        """Host buffers in (NumPy / Arrow / HostMatrix), (index u32 [Q,k_eff], score f64 [Q,k_eff]) out."""
+        from .arrow import to_host_matrix
+        q, c = to_host_matrix(queries), to_host_matrix(corpus)
+        if k < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        keff = min(int(k), c.n_rows)
+        idx = _native.result_empty((q.n_rows, keff), np.uint32)
+        sc = _native.result_empty((q.n_rows, keff), np.float64)
+        ka = ctypes.c_int64(0)
+        qs, cs = q.c_struct(), c.c_struct()
+        _native.check(_native.lib().pmm_group_topk(self._h, ctypes.byref(qs), ctypes.byref(cs), int(k), str(metric).encode(),
+                                                   idx.ctypes.data, sc.ctypes.data, ctypes.byref(ka)))
         return idx, sc
 
-    def topk_host(self, queries, corpus_shard, index_base: int, n_total: int, k: int, metric: str):
-        """End-to-end variant: host buffers in (NumPy / Arrow / HostMatrix; pinned memory is copied without
-        staging), host arrays out. The shard upload overlaps the fused kernel inside libpmm_b200
-        (pmm_topk_shard); only the Q x k candidates cross NVLink."""
-        import torch
-        import torch.distributed as dist
+
+class RankGroup(_Group):
+    """This process is rank `rank` of `world`; its GPU is the calling thread's current device (pmm_set_device)."""
+
+    def __init__(self, uid: bytes, rank: int, world: int):
+        super().__init__()
+        self.rank, self.world = int(rank), int(world)
+        _native.check(_native.lib().pmm_group_init_rank(uid, self.rank, self.world, ctypes.byref(self._h)))
+
+    def query_slice(self, n_queries: int) -> Tuple[int, int]:
+        """Rows of the result this rank merges (and, in the *_SLICE output modes, the only rows it fills)."""
+        return shard_bounds(n_queries, self.world)[self.rank]
+
+    def topk_shard_raw(self, q_desc, c_desc, index_base: int, n_total: int, k: int, metric: int, flags: int,
+                       index_ptr: int, score_ptr: int) -> None:
+        _native.check(_native.lib().pmm_group_topk_shard(self._h, ctypes.byref(q_desc), ctypes.byref(c_desc), int(index_base),
+                                                         int(n_total), int(k), int(metric), int(flags), index_ptr, score_ptr))
+
+    def topk_device(self, q_ptr: int, n_queries: int, dim: int, q_dtype: int, c_ptr: int, n_local: int, c_dtype: int,
+                    index_base: int, n_total: int, k: int, metric: str, index_ptr: int, score_ptr: int,
+                    full: bool = True) -> None:
+        """Device-resident queries and shard; index/score device buffers [Q, k_eff] (u32 / f64).  full=True: every rank
+        receives the whole result, else only this rank's query slice is written."""
+        m = _native.metric_from_str(metric)
+        on = _native.PMM_MATRIX_ON_DEVICE
+        self.topk_shard_raw(_native.dev_matrix(q_ptr, n_queries, dim, q_dtype, flags=on),
+                            _native.dev_matrix(c_ptr, n_local, dim, c_dtype, flags=on), index_base, n_total, k, m,
+                            OUT_DEVICE_FULL if full else OUT_DEVICE_SLICE, index_ptr, score_ptr)
+
+    def topk_host(self, queries, corpus_shard, index_base: int, n_total: int, k: int, metric: str, full: bool = False,
+                  queries_from_root: bool = True):
+        """Host buffers in, host arrays [Q, k_eff] out.  full=False (default): only this rank's query slice
+        (`query_slice`) is filled — the whole-job result is the union over the ranks and crosses PCIe once;
+        full=True: every rank reads the whole result back."""
         from .arrow import to_host_matrix
         m = _native.metric_from_str(metric)
         q, c = to_host_matrix(queries), to_host_matrix(corpus_shard)
-        Q = q.n_rows
-        k_eff = min(int(k), int(n_total))
-        if k_eff > 128:
-            raise _native.PmmError(_native.PMM_ERR_UNSUPPORTED, "sharded top-k supports k <= 128")
-        k_local = min(k_eff, c.n_rows)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        cand = torch.zeros((Q, k_eff), dtype=torch.int64, device=dev)
-        if k_local > 0:
-            local = cand if k_local == k_eff else torch.empty((Q, k_local), dtype=torch.int64, device=dev)
-            q_arg = q
-            if self.world > 1 and q.offsets is None and q.validity is None and q.row_validity is None and q.values.size:
-                # the query batch is the same on every rank: one rank sends it through its host link, the others get
-                # it over NVLink (8 ranks: 2.5 GB less through the host per C3 step)
-                tq = torch.empty((Q, q.dim), dtype=torch.from_numpy(q.values[:1]).dtype, device=dev)
-                src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
-                if self.rank == 0:
-                    tq.copy_(torch.from_numpy(q.values).view(Q, q.dim), non_blocking=True)
-                dist.broadcast(tq, src=src, group=self.group)
-                q_arg = _native.dev_matrix(tq.data_ptr(), Q, q.dim, q.dtype_code, flags=_native.PMM_MATRIX_ON_DEVICE)
-            torch.cuda.current_stream().synchronize()          # cand is zeroed (and the queries have arrived) before the library runs
-            _native.topk_shard(q_arg, c, k_local, m, index_base, local.data_ptr())
-            if local is not cand:
-                cand[:, :k_local] = local
-        gathered = all_gather_candidates(cand, self.group) if self.world > 1 else cand.unsqueeze(0)
-        idx = torch.empty((Q, k_eff), dtype=torch.int32, device=dev)
-        sc = torch.empty((Q, k_eff), dtype=torch.float64, device=dev)
-        _native.dev_merge_candidates(gathered.data_ptr(), gathered.shape[0], Q, k_eff, k_eff, m,
-                                     idx.data_ptr(), sc.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
-        # results land in pooled page-locked buffers (device->host at PCIe rate, no pageable staging)
-        out_i = _native.result_empty((Q, k_eff), np.int32)
-        out_s = _native.result_empty((Q, k_eff), np.float64)
-        torch.from_numpy(out_i).copy_(idx)
-        torch.from_numpy(out_s).copy_(sc)
-        return out_i.view(np.uint32), out_s
+        keff = min(int(k), int(n_total))
+        idx = _native.result_empty((q.n_rows, keff), np.uint32)
+        sc = _native.result_empty((q.n_rows, keff), np.float64)
+        flags = (OUT_HOST_FULL if full else OUT_HOST_SLICE) | (QUERIES_FROM_ROOT if queries_from_root else 0)
+        self.topk_shard_raw(q.c_struct(), c.c_struct(), index_base, n_total, k, m, flags, idx.ctypes.data, sc.ctypes.data)
+        return idx, sc

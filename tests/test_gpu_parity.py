@@ -107,20 +107,47 @@ def test_generic_path_bit_exact(native, oracle, metric, dtype):
 def test_generic_path_large_k_and_clamp(native, oracle):
     rng = np.random.default_rng(8)
     q, c = _randn(rng, 9, 24), _randn(rng, 700, 24)
-    for k in (129, 300, 700, 5000):  # > 128 routes to the SIMT path; 5000 clamps to N (src/matmul.rs:443)
-        idx, sc = native.topk(_hm(q), _hm(c), k, "dot")
+    for k in (129, 200, 248, 249, 300, 700, 5000):  # <= 248: fused path with 256-entry lists; above: SIMT slab path;
+        idx, sc = native.topk(_hm(q), _hm(c), k, "dot")   # 5000 clamps to N (src/matmul.rs:443)
         assert idx.shape == (9, min(k, 700))
         parity.check_topk(idx, sc, q, c, k, "dot", oracle, exact=True)
+    q2, c2 = _randn(rng, 140, 72), _randn(rng, 20_000, 72)
+    c2[rng.integers(0, 20_000, size=400)] = c2[rng.integers(0, 20_000, size=400)]
+    for metric, k in (("cosine", 130), ("euclidean", 248), ("dot", 199)):
+        native.reset_stats()
+        native.set_option("profile", 1)
+        try:
+            idx, sc = native.topk(_hm(q2), _hm(c2), k, metric)
+            assert native.get_stat("select_f32_launches") == 0 and native.get_stat("tc_topk_f16r_kp256_launches") >= 1
+        finally:
+            native.set_option("profile", 0)
+        parity.check_topk(idx, sc, q2, c2, k, metric, oracle, exact=True)
 
 
 def test_f64_path(native, oracle):
     rng = np.random.default_rng(9)
     q, c = _randn(rng, 64, 64, dtype=np.float64), _randn(rng, 2000, 64, dtype=np.float64)
-    # default: DMMA (mma.sync.m8n8k4.f64) — within 1e-12 relative of the oracle, indices equal up to near-ties
-    for metric in ("cosine", "dot", "euclidean"):
-        idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
-        frac = parity.check_topk(idx, sc, q, c, 10, metric, oracle)
-        assert frac == 1.0
+    # default: tensor-core filter on operands rounded to f16 + exact f64 re-scoring (sequential FMA, the oracle's order)
+    # + per-query losslessness proof: scores and indices bit-identical to the oracle, no Q x N slab
+    native.reset_stats()
+    native.set_option("profile", 1)
+    try:
+        for metric in ("cosine", "dot", "euclidean"):
+            idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
+            parity.check_topk(idx, sc, q, c, 10, metric, oracle, exact=True)
+        assert native.get_stat("rescore_f64_launches") == 3 and native.get_stat("select_f64_launches") == 0
+        assert native.get_stat("scores_f64_dmma_launches") == 0
+    finally:
+        native.set_option("profile", 0)
+    # the slab path (DMMA scores + select): within 1e-12 relative, indices equal up to near-ties
+    native.set_option("f64_tc", 0)
+    try:
+        for metric in ("cosine", "dot", "euclidean"):
+            idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
+            frac = parity.check_topk(idx, sc, q, c, 10, metric, oracle)
+            assert frac == 1.0
+    finally:
+        native.set_option("f64_tc", 1)
     out = native.matmul(_hm(q), _hm(c))
     assert out.dtype == np.float64
     parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float64)
@@ -129,6 +156,7 @@ def test_f64_path(native, oracle):
     parity.check_matmul(native.matmul(_hm(q2), _hm(c2)), q2, c2, oracle.matmul(q2, c2), np.float64)
     # sequential-FMA kernel: bit-identical
     native.set_option("f64_simt", 1)
+    native.set_option("f64_tc", 0)
     try:
         for metric in ("cosine", "dot", "euclidean"):
             idx, sc = native.topk(_hm(q), _hm(c), 10, metric)
@@ -136,6 +164,42 @@ def test_f64_path(native, oracle):
         assert np.array_equal(native.matmul(_hm(q), _hm(c)), oracle.matmul(q, c))
     finally:
         native.set_option("f64_simt", 0)
+        native.set_option("f64_tc", 1)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+def test_f64_fused_path_shapes_and_levels(native, oracle, metric):
+    """f64 working precision on the fused path: shapes with row/column/k tails, mixed storage dtypes (widened exactly,
+    src/matmul.rs:308), k up to 248, magnitudes outside the f16 and f32 ranges (the proof must escalate: f16-rounded ->
+    3xTF32 -> exact f64 SIMT), exact ties. Always bit-identical to the oracle."""
+    rng = np.random.default_rng(90)
+    for nq, n, d, k in ((300, 5000, 96, 10), (33, 700, 257, 100), (5, 3000, 64, 200), (1, 40, 3, 40)):
+        q, c = _randn(rng, nq, d, dtype=np.float64), _randn(rng, n, d, dtype=np.float64)
+        idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+        parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+    q, c = _randn(rng, 40, 48, dtype=np.float64), _randn(rng, 3000, 48, dtype=np.float64)
+    # mixed f32 / f64 and f16 / f64 storage
+    for qd, cd in ((np.float32, np.float64), (np.float64, np.float32), (np.float16, np.float64)):
+        qq, cc = q.astype(qd), c.astype(cd)
+        idx, sc = native.topk(_hm(qq), _hm(cc), 7, metric)
+        parity.check_topk(idx, sc, qq.astype(np.float64), cc.astype(np.float64), 7, metric, oracle, working_dtype=np.float64, exact=True)
+    # beyond the f16 range (1e6), beyond the f32 range (1e60), far below both (1e-50), mixed in one corpus
+    big = c.copy()
+    big[::5] *= 1e6
+    huge = c.copy()
+    huge[::11] *= 1e60
+    tiny = np.concatenate([c[:1500], c[1500:] * 1e-50])
+    native.reset_stats()
+    for corpus in (big, huge, tiny):
+        idx, sc = native.topk(_hm(q), _hm(corpus), 9, metric)
+        parity.check_topk(idx, sc, q, corpus, 9, metric, oracle, exact=True)
+    assert native.get_stat("requeried_tf32x3") > 0 and native.get_stat("fallback_queries") > 0
+    # exact ties: integer data and duplicated rows
+    qi = rng.integers(-3, 4, size=(30, 20)).astype(np.float64)
+    ci = rng.integers(-3, 4, size=(900, 20)).astype(np.float64)
+    ci[500:700] = ci[:200]
+    idx, sc = native.topk(_hm(qi), _hm(ci), 50, metric)
+    parity.check_topk(idx, sc, qi, ci, 50, metric, oracle, exact=True)
 
 
 def test_mixed_dtype_uses_f64(native, oracle):
@@ -555,7 +619,7 @@ def test_host_shard_entry_point(native, oracle):
     """pmm_topk_shard: host shard in, exact candidates on the device; two shards merged == unsharded oracle.
     The second shard is large enough (>= 64 MB) to take the chunked/overlapped upload path."""
     import torch
-    from polars_matmul_b200.sharded import ShardedTopk, shard_bounds
+    from polars_matmul_b200.sharded import shard_bounds
     rng = np.random.default_rng(31)
     q, c = _randn(rng, 150, 256), _randn(rng, 80_000, 256)
     k = 12
@@ -571,10 +635,74 @@ def test_host_shard_entry_point(native, oracle):
                                     stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         parity.check_topk(idx.cpu().numpy().view(np.uint32), sc.cpu().numpy(), q, c, k, metric_name, oracle, exact=True)
-    # the single-rank driver (world size 1) end to end
-    i2, s2 = ShardedTopk().topk_host(q, c, 0, c.shape[0], k, "cosine")
-    parity.check_topk(i2, s2, q, c, k, "cosine", oracle, exact=True)
+    # a one-rank group (world size 1) end to end, host and device variants
+    from polars_matmul_b200.sharded import RankGroup, unique_id
+    grp = RankGroup(unique_id(), 0, 1)
+    try:
+        i2, s2 = grp.topk_host(q, c, 0, c.shape[0], k, "cosine")
+        parity.check_topk(i2, s2, q, c, k, "cosine", oracle, exact=True)
+        dq, dc = torch.from_numpy(q).cuda(), torch.from_numpy(c).cuda()
+        di = torch.empty((150, k), dtype=torch.int32, device="cuda")
+        ds = torch.empty((150, k), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        grp.topk_device(dq.data_ptr(), 150, 256, 1, dc.data_ptr(), c.shape[0], 1, 0, c.shape[0], k, "euclidean",
+                        di.data_ptr(), ds.data_ptr())
+        parity.check_topk(di.cpu().numpy().view(np.uint32), ds.cpu().numpy(), q, c, k, "euclidean", oracle, exact=True)
+    finally:
+        grp.close()
     assert shard_bounds(80_000, 2) == [(0, 40_000), (40_000, 80_000)]
+
+
+def _gpu_count(native):
+    return native.device_count()
+
+
+def test_single_process_group_over_all_gpus(native, oracle):
+    """The multi-GPU driver behind the C ABI (north_star item 6): one process, one host thread per GPU, corpus rows
+    sharded, NCCL all-to-all of packed candidates, merge. Needs >= 2 GPUs (skipped on the single-GPU test box; run with
+    gpurun --gpus 2)."""
+    if _gpu_count(native) < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from polars_matmul_b200.sharded import LocalGroup
+    rng = np.random.default_rng(50)
+    q, c = _randn(rng, 333, 128), _randn(rng, 150_000, 128)          # 77 MB: every shard takes the chunked host path
+    c[[10, 80_000, 149_999]] = c[3]                                   # exact ties across shards
+    g = LocalGroup()
+    try:
+        assert g.size == _gpu_count(native)
+        for metric, k in (("cosine", 10), ("dot", 100), ("euclidean", 200)):
+            idx, sc = g.topk(q, c, k, metric)
+            parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+        # fewer corpus rows than GPUs x 256: the last shards are empty, k > rows of a shard
+        small = _randn(rng, 300, 128)
+        idx, sc = g.topk(q[:20], small, 200, "dot")
+        parity.check_topk(idx, sc, q[:20], small, 200, "dot", oracle, exact=True)
+    finally:
+        g.close()
+    # the plugin call itself spreads over the box once the call is large enough (threshold lowered for the test)
+    native.set_option("multi_gpu_min_gflop", 1)
+    native.set_option("profile", 1)
+    native.reset_stats()
+    try:
+        idx, sc = native.topk(_hm(q), _hm(c), 50, "cosine")
+        assert native.get_stat("group_merge_launches") == _gpu_count(native)
+        parity.check_topk(idx, sc, q, c, 50, "cosine", oracle, exact=True)
+        # raw matmul: output rows sharded, no collective
+        big_q = _randn(rng, 4096, 128)
+        out = native.matmul(_hm(big_q), _hm(c[:20_000]))
+        parity.check_matmul(out, big_q, c[:20_000], oracle.matmul(big_q, c[:20_000]), np.float32)
+        out64 = native.matmul(_hm(big_q[:2048].astype(np.float64)), _hm(c[:5000].astype(np.float64)))
+        parity.check_matmul(out64, big_q[:2048].astype(np.float64), c[:5000].astype(np.float64),
+                            oracle.matmul(big_q[:2048].astype(np.float64), c[:5000].astype(np.float64)), np.float64)
+    finally:
+        native.set_option("multi_gpu_min_gflop", 4000)
+        native.set_option("profile", 0)
+    native.set_option("multi_gpu", 0)
+    try:
+        i1, s1 = native.topk(_hm(q), _hm(c), 50, "cosine")           # single GPU: identical answer
+    finally:
+        native.set_option("multi_gpu", 1)
+    assert np.array_equal(i1, idx) and np.array_equal(s1, sc)
 
 
 def test_device_norms_bit_exact(native, oracle):
@@ -602,17 +730,20 @@ def test_device_norms_bit_exact(native, oracle):
             assert np.array_equal(out.cpu().numpy(), oracle.norms(h.astype(np.float32), squared=squared)), dim
 
 
-def test_full_size_c3_properties(native, oracle):
-    """BASELINE.json configs[2] at full size (100k x 1M x 768, k=100): too large for the oracle as a
-    whole, so check size-independent properties plus the oracle on a query sample."""
+def _full_size_device_case(native, oracle, Q, N, D, k, metrics, seed):
+    """Full-size configuration with device-resident Gaussian inputs: size-independent properties on the whole result plus
+    bit-identity with the oracle for 16 sampled queries against the FULL corpus."""
     import torch
-    Q, N, D, k = 100_000, 1_000_000, 768, 100
-    g = torch.Generator(device="cuda").manual_seed(42)
+    g = torch.Generator(device="cuda").manual_seed(seed)
     dq = torch.randn((Q, D), generator=g, device="cuda", dtype=torch.float32)
     dc = torch.randn((N, D), generator=g, device="cuda", dtype=torch.float32)
     idx = torch.empty((Q, k), dtype=torch.int32, device="cuda")
     sc = torch.empty((Q, k), dtype=torch.float64, device="cuda")
-    for metric_name, metric in (("dot", 1), ("euclidean", 2)):
+    ch = dc.cpu().numpy()
+    sample = np.arange(0, Q, Q // 16)[:16]
+    ts = torch.from_numpy(sample).cuda()
+    qs = dq[ts].cpu().numpy()
+    for metric_name, metric in metrics:
         native.dev_topk(native.dev_matrix(dq.data_ptr(), Q, D, 1), native.dev_matrix(dc.data_ptr(), N, D, 1), k, metric,
                         index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(),
                         stream=torch.cuda.current_stream().cuda_stream)
@@ -620,7 +751,7 @@ def test_full_size_c3_properties(native, oracle):
         i64 = idx.long() & 0xFFFFFFFF
         # sorted best-first, indices in range and unique per row
         d = sc[:, 1:] - sc[:, :-1]
-        assert bool((d <= 0).all()) if metric == 1 else bool((d >= 0).all())
+        assert bool((d >= 0).all()) if metric == 2 else bool((d <= 0).all())
         assert int(i64.max()) < N
         srt, _ = torch.sort(i64, dim=1)
         assert bool((srt[:, 1:] > srt[:, :-1]).all())
@@ -629,12 +760,272 @@ def test_full_size_c3_properties(native, oracle):
         cq = dq[rows].double()
         cc = dc[i64[rows]].double()                              # [r, k, D]
         dot = torch.einsum("rd,rkd->rk", cq, cc)
-        ref = dot if metric == 1 else torch.sqrt(torch.clamp((cq * cq).sum(1)[:, None] + (cc * cc).sum(2) - 2 * dot, min=0))
-        assert torch.allclose(sc[rows], ref, rtol=1e-5, atol=0)
-        # oracle on a sample of queries against the FULL corpus
-        sample = np.arange(0, Q, Q // 16)[:16]
-        qs = dq[torch.from_numpy(sample).cuda()].cpu().numpy()
-        ch = dc.cpu().numpy()
-        frac = parity.check_topk(idx[torch.from_numpy(sample).cuda()].cpu().numpy().view(np.uint32),
-                                 sc[torch.from_numpy(sample).cuda()].cpu().numpy(), qs, ch, k, metric_name, oracle)
-        assert frac > 0.995
+        if metric == 1:
+            ref = dot
+        elif metric == 0:
+            ref = dot / (cq.norm(dim=1)[:, None] * cc.norm(dim=2))
+        else:
+            ref = torch.sqrt(torch.clamp((cq * cq).sum(1)[:, None] + (cc * cc).sum(2) - 2 * dot, min=0))
+        assert torch.allclose(sc[rows], ref, rtol=1e-5, atol=1e-6 if metric == 0 else 0)
+        # the oracle on a sample of queries against the FULL corpus: bit-identical scores and indices
+        parity.check_topk(idx[ts].cpu().numpy().view(np.uint32), sc[ts].cpu().numpy(), qs, ch, k, metric_name, oracle, exact=True)
+
+
+def test_full_size_c3_properties(native, oracle):
+    """BASELINE.json configs[2] at full size (100k x 1M x 768 f32, k=100), all three metrics."""
+    _full_size_device_case(native, oracle, 100_000, 1_000_000, 768, 100, (("dot", 1), ("euclidean", 2), ("cosine", 0)), 42)
+
+
+def test_full_size_c4_shard_shape(native, oracle):
+    """BASELINE.json configs[3], the share of one of 8 GPUs: 100k queries x 1.25M corpus rows x 768 f32, cosine, k=100."""
+    _full_size_device_case(native, oracle, 100_000, 1_250_000, 768, 100, (("cosine", 0),), 43)
+
+
+def test_full_size_c5_shard_shape_f16_list(pmm, native, oracle):
+    """BASELINE.json configs[4], the share of one of 8 GPUs, in its stated container: f16-stored 1024-d embeddings as
+    pl.List (Arrow LargeList<halffloat> with i64 offsets, flattened on the device), 1M queries x 125k corpus rows,
+    cosine, k=10 - through the host entry point (chunked, staged upload). Oracle on 16 sampled queries, exact."""
+    import pyarrow as pa
+    Q, N, D, k = 1_000_000, 125_000, 1024, 10
+    rng = np.random.default_rng(44)
+
+    def f16_list(rows):
+        vals = np.empty((rows, D), np.float16)
+        for lo in range(0, rows, 65536):
+            hi = min(rows, lo + 65536)
+            vals[lo:hi] = rng.standard_normal((hi - lo, D), dtype=np.float32).astype(np.float16)
+        offsets = np.arange(rows + 1, dtype=np.int64) * D
+        return vals, pa.LargeListArray.from_arrays(pa.array(offsets), pa.array(vals.reshape(-1)))
+
+    qv, qa = f16_list(Q)
+    cv, ca = f16_list(N)
+    assert qa.type == pa.large_list(pa.float16())
+    idx, sc = pmm.topk_arrays(qa, ca, k, "cosine")
+    assert idx.shape == (Q, k)
+    assert (np.diff(sc, axis=1) <= 0).all()
+    sample = np.arange(0, Q, Q // 16)[:16]
+    parity.check_topk(idx[sample], sc[sample], qv[sample].astype(np.float32), cv.astype(np.float32), k, "cosine", oracle,
+                      working_dtype=np.float32, exact=True)
+
+
+def test_f16_list_container_with_offsets_nulls_and_short_rows(pmm, native, oracle):
+    """f16 storage COMBINED with list offsets (never covered in round 1): ragged rows, a null row, a null element."""
+    import pyarrow as pa
+    rng = np.random.default_rng(45)
+    dense = _randn(rng, 3000, 40).astype(np.float16)
+    rows = [r.tolist() for r in dense]
+    rows[7] = rows[7][:11]
+    rows[9] = None
+    rows[12][3] = None
+    dense[7, 11:] = 0
+    dense[9] = 0
+    dense[12, 3] = 0
+    arr = pa.array(rows, type=pa.large_list(pa.float16()))
+    q16 = _randn(rng, 50, 40).astype(np.float16)
+    qarr = pa.array([r.tolist() for r in q16], type=pa.list_(pa.float16()))
+    for metric in ("cosine", "dot", "euclidean"):
+        idx, sc = pmm.topk_arrays(qarr, arr, 12, metric)
+        parity.check_topk(idx, sc, q16.astype(np.float32), dense.astype(np.float32), 12, metric, oracle,
+                          working_dtype=np.float32, exact=True)
+
+
+def test_pageable_inputs_are_staged_by_the_library(native, oracle):
+    """Pageable host buffers (what Polars / Arrow hand over) go through the library's page-locked staging ring; buffers
+    that are already page-locked are copied directly. Same results either way, and with staging switched off."""
+    rng = np.random.default_rng(46)
+    q, c = _randn(rng, 400, 256), _randn(rng, 120_000, 256)          # 123 MB corpus: chunked host path
+    c[60_000] = c[5]
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q), _hm(c), 20, "cosine")
+    staged = native.get_stat("staged_h2d_bytes")
+    assert staged >= c.nbytes, staged                                  # the corpus went through the ring
+    parity.check_topk(idx, sc, q, c, 20, "cosine", oracle, exact=True)
+    cp = native.result_empty(c.shape, np.float32)                      # page-locked (pmm_host_alloc)
+    cp[...] = c
+    native.reset_stats()
+    i2, s2 = native.topk(_hm(q), _hm(cp), 20, "cosine")
+    assert native.get_stat("staged_h2d_bytes") < c.nbytes / 2          # only the (pageable) queries
+    assert np.array_equal(i2, idx) and np.array_equal(s2, sc)
+    native.set_option("stage", 0)
+    try:
+        native.reset_stats()
+        i3, s3 = native.topk(_hm(q), _hm(c), 20, "cosine")
+        assert native.get_stat("staged_h2d_bytes") == 0
+    finally:
+        native.set_option("stage", 1)
+    assert np.array_equal(i3, idx) and np.array_equal(s3, sc)
+    # small ring (4 slots of 1 MB), one copy thread: many pieces per chunk, slots recycled while the GPU works
+    native.set_option("stage_slot_mb", 1)
+    native.set_option("stage_threads", 1)
+    try:
+        i4, s4 = native.topk(_hm(q), _hm(c), 20, "cosine")
+        out = native.matmul(_hm(q), _hm(c[:9000]))                    # 14 MB result into a pageable buffer
+    finally:
+        native.set_option("stage_slot_mb", 32)
+        native.set_option("stage_threads", 0)
+    assert np.array_equal(i4, idx) and np.array_equal(s4, sc)
+    parity.check_matmul(out, q, c[:9000], oracle.matmul(q, c[:9000]), np.float32)
+    # pageable result buffers through the C ABI directly (a binding that allocates a plain Vec)
+    import ctypes
+    oi = np.empty((400, 20), np.uint32)
+    os_ = np.empty((400, 20), np.float64)
+    ka = ctypes.c_int64(0)
+    qs, cs = _hm(q).c_struct(), _hm(c).c_struct()
+    native.check(native.lib().pmm_topk(ctypes.byref(qs), ctypes.byref(cs), 20, b"cosine", oi.ctypes.data, os_.ctypes.data, ctypes.byref(ka)))
+    assert np.array_equal(oi, idx) and np.array_equal(os_, sc)
+
+
+def test_two_threads_call_concurrently(native, oracle):
+    """The reference releases the GIL and is re-entrant (src/lib.rs:25,45; tests/test_polars_matmul.py:551-572 runs
+    queries from a thread pool). Two threads, different corpora and per-thread options, interleaved calls: every
+    result exact."""
+    import threading
+    rng = np.random.default_rng(47)
+    jobs = [(_randn(rng, 300, 96), _randn(rng, 40_000, 96), 10, "cosine", 3),
+            (_randn(rng, 200, 128), _randn(rng, 30_000, 128), 50, "euclidean", 2)]
+    errors = []
+
+    def work(q, c, k, metric, levels):
+        try:
+            native.set_thread_option("tc_levels", levels)           # per-thread: the other thread keeps its own
+            for _ in range(6):
+                idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+                parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+            native.set_thread_option(None)
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
+def test_seeded_requery_levels(native, oracle):
+    """Queries the first level cannot prove are re-run from SEEDED thresholds (the exact k-th score at hand minus the
+    next level's error bound): same answers with and without seeding, and the seeded launch is the one that ran."""
+    rng = np.random.default_rng(48)
+    d, n, k = 64, 50_000, 10
+    c = _randn(rng, n, d)
+    base = _randn(rng, 1, d)
+    c[:60] = base * (1.0 + 1e-5 * np.arange(60, dtype=np.float32)[:, None]) * 3.0     # near ties at the top
+    c[1000:1400] = base * (1.0 + 2e-6 * np.arange(400, dtype=np.float32)[:, None]) * 2.9
+    q = np.concatenate([np.repeat(base, 8, axis=0) + 1e-3 * _randn(rng, 8, d), _randn(rng, 120, d)])
+    res = {}
+    for seeded in (1, 0):
+        native.set_option("seed_retry", seeded)
+        native.set_option("profile", 1)
+        native.reset_stats()
+        try:
+            for metric in ("dot", "cosine", "euclidean"):
+                res[(seeded, metric)] = native.topk(_hm(q), _hm(c), k, metric)
+            assert native.get_stat("requeried_f16_wide") > 0
+            if seeded:
+                assert native.get_stat("tc_topk_f16r_seeded_launches") >= 3 and native.get_stat("tc_topk_f16r_kp256_launches") == 0
+            else:
+                assert native.get_stat("tc_topk_f16r_seeded_launches") == 0 and native.get_stat("tc_topk_f16r_kp256_launches") >= 3
+        finally:
+            native.set_option("seed_retry", 1)
+            native.set_option("profile", 0)
+    for metric in ("dot", "cosine", "euclidean"):
+        i1, s1 = res[(1, metric)]
+        i0, s0 = res[(0, metric)]
+        assert np.array_equal(i1, i0) and np.array_equal(s1, s0)
+        parity.check_topk(i1, s1, q, c, k, metric, oracle, exact=True)
+
+
+def test_corpus_cache_in_the_plugin_call(pmm, native, oracle):
+    """`_topk` keeps a corpus resident from its second sighting on: five calls on the same Arrow
+    corpus upload it twice (streamed, then made resident) and afterwards only the queries cross PCIe. Results identical
+    to the oracle every time; writable NumPy corpora are never cached; explicit invalidation works."""
+    import pyarrow as pa
+    rng = np.random.default_rng(60)
+    c = _randn(rng, 30_000, 64)
+    carr = pa.FixedSizeListArray.from_arrays(pa.array(c.reshape(-1)), 64)
+    pmm.corpus_cache_clear()
+    growth = []
+    for i in range(5):
+        q = _randn(rng, 100, 64)
+        native.reset_stats()
+        out = pmm._topk(q, carr, 5, "cosine")
+        growth.append(native.get_stat("h2d_bytes"))
+        idx = np.asarray(out.values.field("index")).reshape(100, 5)
+        sc = np.asarray(out.values.field("score")).reshape(100, 5)
+        parity.check_topk(idx, sc, q, c, 5, "cosine", oracle, exact=True)
+    assert growth[0] >= c.nbytes and growth[1] >= c.nbytes
+    assert all(g < c.nbytes / 10 for g in growth[2:]), growth              # only the queries from the third call on
+    # a different query dtype is a different entry (working precision f64): streamed again, still correct
+    q64 = _randn(rng, 20, 64, dtype=np.float64)
+    out = pmm._topk(q64, carr, 5, "dot")
+    idx = np.asarray(out.values.field("index")).reshape(20, 5)
+    sc = np.asarray(out.values.field("score")).reshape(20, 5)
+    parity.check_topk(idx, sc, q64, c.astype(np.float64), 5, "dot", oracle, working_dtype=np.float64, exact=True)
+    # writable NumPy corpus: mutation in place must be seen
+    cw = c.copy()
+    for _ in range(3):
+        native.reset_stats()
+        pmm._topk(q, cw, 5, "dot")
+        assert native.get_stat("h2d_bytes") >= cw.nbytes
+    cw[17] = q[0] * 100
+    out = pmm._topk(q[:1], cw, 1, "dot")
+    assert out.to_pylist()[0][0]["index"] == 17
+    pmm.corpus_cache_clear()
+    native.reset_stats()
+    pmm._topk(q, carr, 5, "cosine")
+    assert native.get_stat("h2d_bytes") >= c.nbytes                         # invalidated: streamed again
+    pmm.corpus_cache_configure(enabled=False)
+    try:
+        for _ in range(3):
+            native.reset_stats()
+            pmm._topk(q, carr, 5, "cosine")
+            assert native.get_stat("h2d_bytes") >= c.nbytes
+    finally:
+        pmm.corpus_cache_configure(enabled=True)
+
+
+def test_multi_chunk_columns_upload_chunk_by_chunk(pmm, native, oracle):
+    """A Series with several chunks (the reference's zero-copy path gives up at src/matmul.rs:53):
+    the chunks go to the device one after the other, for queries and corpus, on the plain and on the chunked/overlapped
+    host path, for top-k, matmul and the resident handle."""
+    import pyarrow as pa
+    rng = np.random.default_rng(61)
+
+    def chunked(a, cuts):
+        parts = [a[lo:hi] for lo, hi in zip([0] + cuts, cuts + [a.shape[0]])]
+        return pa.chunked_array([pa.FixedSizeListArray.from_arrays(pa.array(p.reshape(-1)), a.shape[1]) for p in parts])
+
+    q, c = _randn(rng, 300, 96), _randn(rng, 7000, 96)
+    qa, ca = chunked(q, [1, 130]), chunked(c, [999, 1000, 4097])
+    from polars_matmul_b200.arrow import to_host_matrix
+    assert to_host_matrix(ca).chunks is not None
+    for metric in ("cosine", "dot", "euclidean"):
+        idx, sc = pmm.topk_arrays(qa, ca, 9, metric)
+        parity.check_topk(idx, sc, q, c, 9, metric, oracle, exact=True)
+    out = pmm.matmul_array(qa, ca)
+    parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float32)
+    # large corpus: the overlapped host path cuts ITS chunks across the column's chunk boundaries
+    big = _randn(rng, 200_000, 96)                                         # 77 MB
+    big[[3, 70_001, 199_999]] = big[5]
+    ba = chunked(big, [50_000, 70_000, 70_001, 160_000])
+    idx, sc = pmm.topk_arrays(qa, ba, 20, "dot")
+    parity.check_topk(idx, sc, q, big, 20, "dot", oracle, exact=True)
+    pmm.corpus_cache_clear()
+    for _ in range(3):                                                     # third call: resident handle built from chunks
+        out = pmm._topk(qa, ba, 20, "dot")
+    idx2 = np.asarray(out.values.field("index")).reshape(300, 20)
+    assert np.array_equal(idx2, idx)
+    pmm.corpus_cache_clear()
+
+
+def test_flatten_returns_the_flat_buffer(pmm, oracle):
+    import pyarrow as pa
+    rng = np.random.default_rng(62)
+    q, c = _randn(rng, 17, 8), _randn(rng, 23, 8)
+    flat = pmm._matmul(q, c, flatten=True)
+    assert flat.type == pa.float32() and len(flat) == 17 * 23
+    arr = pmm._matmul(q, c)
+    assert np.array_equal(np.asarray(flat), np.asarray(arr.values))         # row-major flatten == explode() of Array[T, N]
+    assert len(pmm._matmul(np.empty((0, 8), np.float32), c, flatten=True)) == 0
+    parity.check_matmul(np.asarray(flat).reshape(17, 23), q, c, oracle.matmul(q, c), np.float32)

@@ -101,8 +101,18 @@ def test_arrow_marshalling():
         to_host_matrix(pa.array([None, [1.0]], type=pa.list_(pa.float32())))
     ch = pa.chunked_array([pa.array([[1.0, 2.0]], type=pa.list_(pa.float32(), 2)),
                            pa.array([[3.0, 4.0]], type=pa.list_(pa.float32(), 2))])
-    h = to_host_matrix(ch)
-    assert h.n_rows == 2 and h.values.tolist() == [1.0, 2.0, 3.0, 4.0]
+    h = to_host_matrix(ch)      # multi-chunk Array column: views of the chunks' own buffers, no host-side concatenation
+    assert h.n_rows == 2 and h.dim == 2 and [c.tolist() for c in h.chunks] == [[1.0, 2.0], [3.0, 4.0]]
+    m = h.c_struct()
+    assert m.reserved == 2 and m.n_rows == 2 and m.offsets is None
+    chn = pa.chunked_array([pa.array([[1.0, None]], type=pa.list_(pa.float32(), 2)),      # nulls: concatenated on the host
+                            pa.array([[3.0, 4.0]], type=pa.list_(pa.float32(), 2))])
+    h = to_host_matrix(chn)
+    assert h.chunks is None and h.n_rows == 2 and h.validity is not None
+    chl = pa.chunked_array([pa.array([[1.0, 2.0]], type=pa.large_list(pa.float32())),      # List columns likewise
+                            pa.array([[3.0, 4.0]], type=pa.large_list(pa.float32()))])
+    h = to_host_matrix(chl)
+    assert h.chunks is None and h.n_rows == 2 and h.values.tolist() == [1.0, 2.0, 3.0, 4.0]
     h = to_host_matrix(np.arange(6, dtype=np.int32).reshape(2, 3))
     assert h.values.dtype == np.float64
     h = to_host_matrix(np.ones((2, 3), np.float16))
