@@ -303,6 +303,8 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *                              64 MB) of the chunked upload; tests lower both to drive tiny corpora through it
  *   "f64_simt" (0/1)           f64 contraction (raw matmul, slab path) on FP64 FMA instead of DMMA
  *   "generic_workspace_mb"     score slab of the SIMT path
+ *   "matmul_tc_max_dim"        longest vector the raw matmul sends through the tensor cores (0 = auto: 256 for f32 via
+ *                              3xTF32, 1024 for f16 storage; longer vectors use the exact sequential-FMA kernel)
  *   "multi_gpu" (0/1, default 1), "multi_gpu_min_gflop" (default 4000)   pmm_topk / pmm_matmul spread one call over all
  *                              visible GPUs when the call has at least that many GFLOP of contraction work
  * Acting immediately, process-wide (not part of the snapshot):

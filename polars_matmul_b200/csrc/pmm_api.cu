@@ -58,7 +58,7 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0;
     int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
@@ -92,6 +92,7 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "host_chunked") o.host_chunked = value ? 1 : 0;
     else if (k == "tc_sync_tiles") o.tc_sync_tiles = value < 0 ? 0 : (int)value;  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") o.generic_ws_mb = value < 1 ? 1 : value;
+    else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
     else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
     else if (k == "multi_gpu_min_gflop") o.multi_gpu_min_gflop = value < 0 ? 0 : value;
     else return false;
@@ -355,7 +356,8 @@ size_t plane_bytes(int mode, int64_t rows, int64_t dim, int64_t row_tile) {
 
 // Runs the prep kernel on a device-resident matrix. row_tile: pad rows to this multiple (planes only).
 int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool want_norm, bool want_sq, int *d_err,
-            cudaStream_t s, Prepared *out, bool want_max = false, unsigned int *shared_max = nullptr) {
+            cudaStream_t s, Prepared *out, bool want_max = false, unsigned int *shared_max = nullptr,
+            unsigned char *nonfinite_rows = nullptr, unsigned int *nonfinite_count = nullptr) {
     out->mode = mode;
     out->f64 = f64;
     out->n_rows = m.n_rows;
@@ -403,6 +405,8 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     a.zero_guard_sq = f64 ? 1e-20f : 1e-12f;   // square of the cosine zero-norm guard (1e-10 f64 / 1e-6 f32)
     a.max_sq_out = out->max_sq_ptr;
     a.error_flag = d_err;
+    a.nonfinite_rows = nonfinite_rows;
+    a.nonfinite_count = nonfinite_count;
     CUDA_TRY(launch_counted("prep", s, [&] { return launch_prep(a, m.dtype, mode, f64 ? 1 : 0, s); }));
     return PMM_OK;
 }
@@ -894,15 +898,40 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
     return PMM_OK;
 }
 
+// Longest vector the raw matmul still sends through the tensor cores.  The matmul's result IS the output (no exact
+// re-scoring behind it), and tcgen05 accumulates with truncation: measured against the oracle (tests/test_gpu_bound.py,
+// profiles/matmul_precision_r2.md) the 3xTF32 result is off by ~1e-8 * D relative on same-sign data and by up to
+// ~1e-6 |q||c| on Gaussian data at D >= 384 - beyond the stated 1e-5 * max(|x|, 0.05 |q||c|) - while exact f16 planes
+// (one MMA per 16 elements, exact products) hold it up to D = 1024.  Longer vectors take the exact SIMT kernel
+// (sequential FMA: bit-identical to the oracle), which raw matmul can afford: end to end the path is bound by the
+// device->host copy of the Q x N result, not by the contraction.
+int matmul_tc_dim_limit(int mode) {
+    if (t_opt.matmul_tc_max_dim > 0) return t_opt.matmul_tc_max_dim;
+    return mode == PREP_F16 ? 1024 : 256;
+}
+
 int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, cudaStream_t s) {
     PathChoice pc = choose_path(dl->dtype, dr->dtype, 1, false);
+    if (pc.tc && dl->dim > matmul_tc_dim_limit(pc.mode)) {
+        pc.tc = false;
+        pc.mode = PREP_DENSE;
+    }
     DevBuf err;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared l, r;
-    int rc = prepare(*dl, pc.mode, pc.f64, 2 * TC_TILE_M, false, false, err.as<int>(), s, &l);
+    // f32 on the tensor cores: rows with inf / NaN elements are marked by the prep pass and fixed up afterwards
+    DevBuf nf;
+    const bool track = pc.tc && pc.mode == PREP_TF32;
+    if (track) {
+        CUDA_TRY(nf.alloc((size_t)(dl->n_rows + dr->n_rows) + 16, s));
+        CUDA_TRY(cudaMemsetAsync(nf.p, 0, 16, s));   // [0], [1]: counts for left / right (the row flags are written by every row)
+    }
+    unsigned int *nf_count = nf.as<unsigned int>();
+    unsigned char *nf_left = track ? nf.as<unsigned char>() + 16 : nullptr, *nf_right = track ? nf_left + dl->n_rows : nullptr;
+    int rc = prepare(*dl, pc.mode, pc.f64, 2 * TC_TILE_M, false, false, err.as<int>(), s, &l, false, nullptr, nf_left, track ? nf_count : nullptr);
     if (rc) return rc;
-    rc = prepare(*dr, pc.mode, pc.f64, TC_TILE_N, false, false, err.as<int>(), s, &r);
+    rc = prepare(*dr, pc.mode, pc.f64, TC_TILE_N, false, false, err.as<int>(), s, &r, false, nullptr, nf_right, track ? nf_count + 1 : nullptr);
     if (rc) return rc;
     const int64_t Q = dl->n_rows, N = dr->n_rows, D = dl->dim;
     if (pc.tc) {
@@ -928,6 +957,10 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         cudaError_t e = launch_counted(a.f16 ? "tc_matmul_f16" : "tc_matmul_tf32x3", s, [&] { return launch_tc_matmul(a, s); });
         if (e != cudaSuccess)
             return fail(PMM_ERR_CUDA, "tensor-core matmul launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
+        if (track)   // +-inf inputs: 0 * inf inside the split gives NaN where the reference propagates the infinity
+            CUDA_TRY(launch_counted("matmul_fixup", s, [&] {
+                return launch_matmul_nonfinite_fixup(raw_of(*dl), raw_of(*dr), nf_left, nf_right, nf_count, (float *)d_out, s);
+            }));
     } else if (pc.f64) {
         for (int64_t q0 = 0; q0 < Q; q0 += (1 << 20)) {
             int64_t nq = Q - q0 < (1 << 20) ? Q - q0 : (1 << 20);

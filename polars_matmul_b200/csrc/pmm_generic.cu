@@ -87,9 +87,111 @@ static cudaError_t launch_scores_t(const T *q, const T *c, const T *qa, const T 
     scores_kernel<T><<<grid, 256, 0, s>>>(q, c, qa, ca, nq, n, d, metric, out, ldo);
     return cudaGetLastError();
 }
+// f32, larger shapes: 128 x 128 x 16 block tile, 8 x 8 outputs per thread (two 4-wide quadrants per side so that the
+// shared-memory reads are conflict-free float4s), global -> register -> shared double buffering.  Still ONE FMA per
+// element and output, k ascending: bit-identical to scores_kernel and to the oracle.  This is the exact path of the raw
+// f32 matmul for vector lengths where the tensor-core split no longer holds 1e-5 (pmm_api.cu: matmul_tc_max_dim) and
+// of the exact top-k fallback; about 3x the rate of the 64 x 64 kernel.
+template <bool VEC>
+__global__ void __launch_bounds__(256) scores_f32_tiled_kernel(const float *__restrict__ q, const float *__restrict__ c,
+                                                               const float *__restrict__ qa, const float *__restrict__ ca,
+                                                               int64_t nq, int64_t n, int64_t d, int metric,
+                                                               float *__restrict__ out, int64_t ldo) {
+    constexpr int BM = 128, BN = 128, BK = 16, P = BM + 4;
+    __shared__ __align__(16) float As[2][BK][P];
+    __shared__ __align__(16) float Bs[2][BK][P];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: rows lr and lr + 64, k offset lk..lk+3
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    float ra[2][4], rb[2][4];
+    auto gload = [&](int64_t k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t ar = m0 + lr + 64 * h, br = n0 + lr + 64 * h, kk = k0 + lk;
+            if (VEC) {   // d % 4 == 0 and 16-byte aligned bases: whole float4s are in or out
+                float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                if (kk < d) {
+                    if (ar < nq) va = __ldg((const float4 *)(q + ar * d + kk));
+                    if (br < n) vb = __ldg((const float4 *)(c + br * d + kk));
+                }
+                ra[h][0] = va.x; ra[h][1] = va.y; ra[h][2] = va.z; ra[h][3] = va.w;
+                rb[h][0] = vb.x; rb[h][1] = vb.y; rb[h][2] = vb.z; rb[h][3] = vb.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ra[h][u] = (ar < nq && kk + u < d) ? __ldg(q + ar * d + kk + u) : 0.0f;
+                    rb[h][u] = (br < n && kk + u < d) ? __ldg(c + br * d + kk + u) : 0.0f;
+                }
+            }
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                As[buf][lk + u][lr + 64 * h] = ra[h][u];
+                Bs[buf][lk + u][lr + 64 * h] = rb[h][u];
+            }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t k0 = 0; k0 < d; k0 += BK) {
+        const bool more = k0 + BK < d;
+        if (more) gload(k0 + BK);   // next slice's global loads fly while this one is multiplied
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *(const float4 *)&As[buf][kk][ty * 4], a1 = *(const float4 *)&As[buf][kk][64 + ty * 4];
+            const float4 b0 = *(const float4 *)&Bs[buf][kk][tx * 4], b1 = *(const float4 *)&Bs[buf][kk][64 + tx * 4];
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    const bool aux = metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= nq) continue;
+        const float qav = aux ? qa[r] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t cc = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (cc >= n) continue;
+            float v = acc[i][j];
+            if (aux) v = metric_finish(v, metric, qav, ca[cc]);
+            out[r * ldo + cc] = v;
+        }
+    }
+}
+
 cudaError_t launch_scores_f32(const float *q, const float *c, const float *qa, const float *ca, int64_t nq,
                               int64_t n, int64_t d, int metric, float *out, int64_t ldo, cudaStream_t s) {
-    return launch_scores_t<float>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
+    if (nq <= 0 || n <= 0) return cudaSuccess;
+    if (nq < 96 || n < 96) return launch_scores_t<float>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);   // small: finer tiles
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)((nq + 127) / 128));
+    const bool vec = (d % 4) == 0 && (((uintptr_t)q | (uintptr_t)c) & 15) == 0;
+    if (vec) scores_f32_tiled_kernel<true><<<grid, 256, 0, s>>>(q, c, qa, ca, nq, n, d, metric, out, ldo);
+    else scores_f32_tiled_kernel<false><<<grid, 256, 0, s>>>(q, c, qa, ca, nq, n, d, metric, out, ldo);
+    return cudaGetLastError();
 }
 cudaError_t launch_scores_f64(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
                               int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s) {

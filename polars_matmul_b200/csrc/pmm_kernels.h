@@ -25,6 +25,8 @@ struct PrepArgs {
     float zero_guard_sq;          // rows with a squared norm at or below this do not enter the "smallest norm" statistic
     unsigned int *max_sq_out;     // f32 working type only: atomicMax of the squared norms' bit patterns, or NULL
     int *error_flag;              // set to 1 when a list row is longer than dim
+    unsigned char *nonfinite_rows;  // [n_rows] set to 1 for rows holding an inf / NaN element, or NULL
+    unsigned int *nonfinite_count;  // number of such rows (atomicAdd), with nonfinite_rows
 };
 enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2, PREP_F16R = 3 };  // = MODE_* of pmm_prep.cu
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s);
@@ -123,6 +125,12 @@ cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, 
 cudaError_t launch_rescore_f64(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm, const double *q_aux,
                                const double *c_aux, int metric, int64_t index_base, int k_out, uint32_t *out_idx,
                                double *out_score, const RescoreCheck &chk, cudaStream_t s);
+// Raw f32 matmul through the 3xTF32 split turns an INFINITE input element into NaN (0 * inf in the lo*hi term) where the
+// reference propagates +-inf (src/metrics.rs:160-202).  The prep pass marks rows with non-finite elements; this kernel
+// recomputes every output that involves a marked row with the reference's arithmetic (one FMA per element, sequential
+// in d).  Launched unconditionally with a small grid; exits at once when nothing is marked - no host synchronisation.
+cudaError_t launch_matmul_nonfinite_fixup(const RawMatrix &left, const RawMatrix &right, const unsigned char *nf_left,
+                                          const unsigned char *nf_right, const unsigned int *nf_count, float *out, cudaStream_t s);
 cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, void *out, int out_f64, cudaStream_t s);
 cudaError_t launch_scatter_results(const int64_t *ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,
                                    const uint64_t *sc, uint32_t *di, double *ds, uint64_t *dc, cudaStream_t s);

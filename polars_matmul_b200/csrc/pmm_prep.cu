@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
         if (a.validity && !((a.validity[p >> 3] >> (p & 7)) & 1)) return (W)0;
         return SrcLoad<SRC>::template get<W>(values + p);
     };
+    bool bad = false;   // this lane saw an inf / NaN element (raw matmul only: a.nonfinite_rows)
     auto emit = [&](int64_t i, W x) {
+        if (MODE == MODE_TF32) bad |= !(fabs((double)x) <= 3.4028234663852886e38);
         if (MODE == MODE_DENSE) {
             dense[row * ld + i] = x;
         } else if (MODE == MODE_TF32) {
@@ -148,6 +150,13 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
         for (int64_t i = dim + sub; i < ld; i += 8) {  // zero the padding columns
             if (MODE == MODE_TF32) { hi[row * ld + i] = 0.0f; lo[row * ld + i] = 0.0f; }
             else hp[row * ld + i] = __float2half_rn(0.0f);
+        }
+    }
+    if (MODE == MODE_TF32 && a.nonfinite_rows) {
+        const bool any_bad = __any_sync(gmask, bad);
+        if (sub == 0 && row < a.n_rows) {
+            a.nonfinite_rows[row] = any_bad ? 1 : 0;
+            if (any_bad) atomicAdd(a.nonfinite_count, 1u);
         }
     }
     if (sub == 0) {

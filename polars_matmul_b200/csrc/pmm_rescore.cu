@@ -526,6 +526,43 @@ cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, 
     return cudaGetLastError();
 }
 
+// ---- raw matmul: outputs that involve a row with inf / NaN elements, recomputed with IEEE arithmetic ---------------
+__global__ void __launch_bounds__(256) matmul_nonfinite_fixup_kernel(RawMatrix lm, RawMatrix rm, const unsigned char *__restrict__ nf_left,
+                                                                      const unsigned char *__restrict__ nf_right,
+                                                                      const unsigned int *__restrict__ nf_count, float *__restrict__ out) {
+    if (nf_count[0] == 0 && nf_count[1] == 0) return;   // the common case: nothing to do
+    const int64_t Q = lm.n_rows, N = rm.n_rows, D = lm.dim;
+    auto elem = [&](const RawMatrix &m, int64_t b, int64_t l, int64_t i) {
+        return m.dtype == 0 ? raw_fetch<__half>(m, b, l, i) : raw_fetch<float>(m, b, l, i);
+    };
+    // marked LEFT rows: the whole output row; marked RIGHT rows: the whole output column
+    for (int64_t i = blockIdx.x; i < Q + N; i += gridDim.x) {
+        const bool is_left = i < Q;
+        const int64_t r = is_left ? i : i - Q;
+        if (!(is_left ? nf_left[r] : nf_right[r])) continue;
+        int64_t ab, al;
+        raw_row(is_left ? lm : rm, r, ab, al);
+        const int64_t others = is_left ? N : Q;
+        for (int64_t j = threadIdx.x; j < others; j += blockDim.x) {
+            int64_t bb, bl;
+            raw_row(is_left ? rm : lm, j, bb, bl);
+            float acc = 0.0f;
+            for (int64_t d = 0; d < D; ++d) {
+                const float x = elem(is_left ? lm : rm, ab, al, d), y = elem(is_left ? rm : lm, bb, bl, d);
+                acc = is_left ? __fmaf_rn(x, y, acc) : __fmaf_rn(y, x, acc);
+            }
+            if (is_left) out[r * N + j] = acc;
+            else out[j * N + r] = acc;
+        }
+    }
+}
+cudaError_t launch_matmul_nonfinite_fixup(const RawMatrix &left, const RawMatrix &right, const unsigned char *nf_left,
+                                          const unsigned char *nf_right, const unsigned int *nf_count, float *out, cudaStream_t s) {
+    if (left.n_rows <= 0 || right.n_rows <= 0) return cudaSuccess;
+    matmul_nonfinite_fixup_kernel<<<296, 256, 0, s>>>(left, right, nf_left, nf_right, nf_count, out);
+    return cudaGetLastError();
+}
+
 // ---- fallback plumbing: gather flagged query rows into a dense f32 matrix, scatter their results back ----
 template <typename OUT>
 __global__ void gather_rows_kernel(RawMatrix qm, const int64_t *__restrict__ ids, int64_t n_ids, OUT *__restrict__ out) {

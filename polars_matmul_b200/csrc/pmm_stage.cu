@@ -281,8 +281,9 @@ cudaError_t stage_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStr
 }
 
 void stage_take_counters(double *h2d, double *d2h) {
-    if (h2d) *h2d = (double)g_staged_h2d.exchange(0);
-    if (d2h) *d2h = (double)g_staged_d2h.exchange(0);
+    const uint64_t a = g_staged_h2d.exchange(0), b = g_staged_d2h.exchange(0);
+    if (h2d) *h2d = (double)a;
+    if (d2h) *d2h = (double)b;
 }
 
 void stage_release_thread_ring() { t_ring.release(); }

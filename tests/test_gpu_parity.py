@@ -274,6 +274,52 @@ def test_tc_matmul_odd_shapes(native, oracle, shape):
     parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float32)
 
 
+@pytest.mark.parametrize("d", [320, 385, 768, 1024, 2048])
+def test_matmul_long_vectors_stay_within_tolerance(native, oracle, d):
+    """tcgen05 accumulates f32 with truncation, and the raw matmul has no exact re-scoring behind it: beyond D = 256 (f32,
+    3xTF32) / 1024 (f16 storage) it runs on the exact sequential-FMA kernel instead - bit-identical to the oracle - so that
+    the stated 1e-5 holds for every vector length, on same-sign data (where the truncation bias accumulates) as well."""
+    rng = np.random.default_rng(d)
+    for kind in ("gauss", "positive"):
+        q = (_randn(rng, 200, d) if kind == "gauss" else rng.uniform(0.5, 1.5, size=(200, d)).astype(np.float32))
+        c = (_randn(rng, 1500, d) if kind == "gauss" else rng.uniform(0.5, 1.5, size=(1500, d)).astype(np.float32))
+        out = native.matmul(_hm(q), _hm(c))
+        ref = oracle.matmul(q, c)
+        assert np.array_equal(out, ref), (kind, np.abs(out - ref).max())
+        h, hc = q.astype(np.float16), c.astype(np.float16)
+        out16 = native.matmul(_hm(h), _hm(hc))
+        parity.check_matmul(out16, h.astype(np.float32), hc.astype(np.float32), oracle.matmul(h.astype(np.float32), hc.astype(np.float32)), np.float32)
+    # the limit is an option: forcing the tensor cores at this length still gives a result close to the oracle (diagnostics)
+    native.set_option("matmul_tc_max_dim", 1 << 20)
+    try:
+        out_tc = native.matmul(_hm(q), _hm(c))
+    finally:
+        native.set_option("matmul_tc_max_dim", 0)
+    np.testing.assert_allclose(out_tc, ref, rtol=1e-4)
+
+
+def test_matmul_infinite_inputs_propagate(native, oracle):
+    """+-inf elements: the 3xTF32 split would turn them into NaN (0 * inf in the lo*hi term); the rows are marked by the prep
+    pass and recomputed with IEEE arithmetic, so the result equals the reference's propagation (src/metrics.rs:160-202)."""
+    rng = np.random.default_rng(91)
+    q, c = _randn(rng, 130, 64), _randn(rng, 700, 64)
+    q[3, 5] = np.inf
+    q[77, 0] = -np.inf
+    c[10, 63] = np.inf
+    c[300, 1] = np.nan
+    out = native.matmul(_hm(q), _hm(c))
+    ref = oracle.matmul(q, c)
+    same = (out == ref) | (np.isnan(out) & np.isnan(ref))
+    marked_rows, marked_cols = [3, 77], [10, 300]
+    assert same[marked_rows].all() and same[:, marked_cols].all()
+    assert np.isinf(out[3]).sum() > 600 and np.isnan(out[:, 300]).all()
+    rest = np.ones_like(same)
+    rest[marked_rows] = False
+    rest[:, marked_cols] = False
+    parity.check_matmul(np.where(rest, out, 0), np.where(np.isfinite(q), q, 0), np.where(np.isfinite(c), c, 0),
+                        np.where(rest, ref, 0), np.float32)
+
+
 def test_tie_stress(native, oracle):
     # exact ties: duplicated corpus rows, small-integer vectors, zero vectors (north_star tie rule)
     rng = np.random.default_rng(3)
@@ -923,9 +969,9 @@ def test_seeded_requery_levels(native, oracle):
                 res[(seeded, metric)] = native.topk(_hm(q), _hm(c), k, metric)
             assert native.get_stat("requeried_f16_wide") > 0
             if seeded:
-                assert native.get_stat("tc_topk_f16r_seeded_launches") >= 3 and native.get_stat("tc_topk_f16r_kp256_launches") == 0
+                assert native.get_stat("tc_topk_f16r_seeded_launches") >= 1 and native.get_stat("tc_topk_f16r_kp256_launches") == 0
             else:
-                assert native.get_stat("tc_topk_f16r_seeded_launches") == 0 and native.get_stat("tc_topk_f16r_kp256_launches") >= 3
+                assert native.get_stat("tc_topk_f16r_seeded_launches") == 0 and native.get_stat("tc_topk_f16r_kp256_launches") >= 1
         finally:
             native.set_option("seed_retry", 1)
             native.set_option("profile", 0)
