@@ -318,6 +318,7 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="override the corpus rows per GPU (profiling runs only)")
     ap.add_argument("--metric", default=None)
     ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments only; recorded in config)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, emit)
@@ -335,6 +336,9 @@ def main():
     _native.lib()
     _native.set_device(local_rank)
     _native.set_option("multi_gpu", 0)     # one process per GPU here: the library must not spread a call over the box itself
+    for kv in args.opt:
+        key, _, val = kv.partition("=")
+        _native.set_option(key, int(val))
     numa = None
     group = None
     if world > 1:
@@ -630,7 +634,7 @@ def main():
                                     "packed candidates exchanged all-to-all over NCCL inside libpmm_b200 (rank g merges 1/N of the queries), "
                                     "merged slices broadcast so every rank holds the full result") if world > 1 else "single GPU",
                        "value_definition": "n_gpus * Q / step time: every rank scans its own shard for all Q queries",
-                       "host_placement": numa or "not bound",
+                       "host_placement": numa or "not bound", "options": args.opt or None,
                        "l2": "inputs (3.4 GB per rank) are far larger than the 126 MB L2; no explicit flush",
                        "arithmetic": "tcgen05 filter on f32 operands rounded to f16 (kind::f16, 11 significant bits; 3xTF32 hi/lo "
                                      "split on demand), f32 accumulate in TMEM; exact f32 re-scoring + per-query losslessness "

@@ -286,6 +286,9 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *   "f16r_wide" (0/1, default 1)  queries the f16-rounded first level cannot prove are first re-run against the same
  *                              planes with 256-entry lists, then with 3xTF32
  *   "seed_retry" (0/1, default 1) re-query levels start from thresholds seeded by the exact k-th scores at hand
+ *   "pipeline" (0/1, default 1)   large query batches: one filter launch per round of query tiles, the merge and exact
+ *                              re-scoring of a round overlap the filter of the next one (second stream);
+ *                              "pipeline_min_gflop" (default 2000): rounds below this much work are not split off
  *   "f64_tc" (0/1, default 1)  f64 top-k: tensor-core filter + exact f64 re-scoring; 0: DMMA score slab + select
  *   "tc_cg" (1|2)              tcgen05 cta_group of the fused kernels (default 2)
  *   "tc_group"                 CTA groups sharing a query tile (0 = auto)

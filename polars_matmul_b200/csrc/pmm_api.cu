@@ -58,8 +58,8 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0;
-    int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, pipeline = 1;
+    int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000, pipeline_min_gflop = 2000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
 std::mutex g_opt_mu;
@@ -92,6 +92,8 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "host_chunked") o.host_chunked = value ? 1 : 0;
     else if (k == "tc_sync_tiles") o.tc_sync_tiles = value < 0 ? 0 : (int)value;  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") o.generic_ws_mb = value < 1 ? 1 : value;
+    else if (k == "pipeline") o.pipeline = value ? 1 : 0;                       // per-round filter launches with overlapped merge + re-scoring
+    else if (k == "pipeline_min_gflop") o.pipeline_min_gflop = value < 0 ? 0 : value;   // smallest round worth a launch of its own
     else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
     else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
     else if (k == "multi_gpu_min_gflop") o.multi_gpu_min_gflop = value < 0 ? 0 : value;
@@ -547,8 +549,30 @@ const char *tc_kernel_stat_name(const Prepared &q, int terms, int kp, bool seede
     return terms == 1 ? "tc_topk_tf32x1" : "tc_topk_tf32x3";
 }
 
+// pipe: the merge of the launch's corpus pieces runs on pipe->s2 (after an event on s) out of pipe->partial, a list buffer
+// the CALLER owns and recycles, instead of on s out of a buffer of this launch - the next filter launch can then start
+// on s while s2 still merges (filter_rescore_pipelined).
+struct TcPipe {
+    cudaStream_t s2 = nullptr;
+    DevBuf *partial = nullptr;
+    cudaEvent_t filter_done = nullptr;
+};
+
+cudaStream_t aux_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    static thread_local int dev_of_stream = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!s || dev_of_stream != dev) {
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        dev_of_stream = dev;
+    }
+    return s;
+}
+
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
-              cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3, const float *seed = nullptr) {
+              cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3, const float *seed = nullptr,
+              TcPipe *pipe = nullptr) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -588,7 +612,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.kp = kp;
     a.k = kp;
     DevBuf own_partial, rsync, staged;
-    DevBuf &partial = carry ? carry->partial : own_partial;
+    DevBuf &partial = pipe ? *pipe->partial : carry ? carry->partial : own_partial;
     const int esets = tc_epilogue_sets(a.f16, a.terms);
     if (!carry || (phase & 1)) CUDA_TRY(partial.alloc((size_t)a.sched.total_slots() * esets * gs * TC_TILE_M * a.kp * 8, s));
     a.resume = (carry && !(phase & 1)) ? 1 : 0;
@@ -606,9 +630,15 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     cudaError_t e = launch_counted(tc_kernel_stat_name(q, a.terms, kp, seed != nullptr), s, [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
+    cudaStream_t ms = s;
+    if (pipe) {
+        CUDA_TRY(cudaEventRecord(pipe->filter_done, s));
+        CUDA_TRY(cudaStreamWaitEvent(pipe->s2, pipe->filter_done, 0));
+        ms = pipe->s2;
+    }
     if (phase & 2)
-        CUDA_TRY(launch_counted("merge", s, [&] {
-            return launch_merge_tiles(a.partial, a.sched, gs, esets, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, s);
+        CUDA_TRY(launch_counted("merge", ms, [&] {
+            return launch_merge_tiles(a.partial, a.sched, gs, esets, a.kp, q.n_rows, a.kp, true, nullptr, nullptr, kept, ms);
         }));
     return PMM_OK;
 }
@@ -661,46 +691,93 @@ pmm_matrix_t slice_rows(const pmm_matrix_t &m, int64_t r0, int64_t rows) {
 // filter; 0: the exact SIMT path.  Re-query levels on the tensor cores start from SEEDED thresholds (option
 // "seed_retry"): the flagged query's exact k-th score among the candidates at hand bounds what can still matter.
 // May synchronise the stream.
+struct RescoreJob {   // buffers and parameters of one level's exact re-scoring + losslessness check
+    DevBuf flags, count, kth;
+    RescoreCheck chk;          // pointers for query 0 of the level
+    bool verify = false;
+    const void *q_aux = nullptr, *c_aux = nullptr;   // working type
+    int kp = 0;
+};
+
+int rescore_setup(const VerifyCtx &vc, const Prepared &q, int64_t Q, int kp, LevelErr le, const float *seed, RescoreJob *job) {
+    cudaStream_t s = vc.s;
+    job->kp = kp;
+    job->q_aux = vc.metric == PMM_METRIC_COSINE ? q.norm.p : vc.metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.p : nullptr;
+    job->c_aux = vc.metric == PMM_METRIC_COSINE ? vc.c_norm : vc.metric == PMM_METRIC_EUCLIDEAN ? vc.c_sq : nullptr;
+    memset(&job->chk, 0, sizeof(job->chk));
+    const float *q_sq32 = q.sq_f32();
+    job->verify = t_opt.verify && q_sq32 && vc.c_range;
+    if (job->verify) {
+        CUDA_TRY(job->flags.alloc((size_t)Q, s));
+        CUDA_TRY(job->count.alloc(sizeof(unsigned int), s));
+        CUDA_TRY(job->kth.alloc((size_t)Q * 4, s));
+        CUDA_TRY(cudaMemsetAsync(job->flags.p, 0, (size_t)Q, s));
+        CUDA_TRY(cudaMemsetAsync(job->count.p, 0, sizeof(unsigned int), s));
+        job->chk.q_sq = q_sq32;
+        job->chk.c_max_sq = vc.c_range;
+        job->chk.eps = le.eps;
+        job->chk.abs_err = le.abs_err;
+        job->chk.max_norm = le.max_norm;
+        job->chk.seed = seed;
+        job->chk.flags = job->flags.as<unsigned char>();
+        job->chk.flag_count = job->count.as<unsigned int>();
+        job->chk.kth_units = job->kth.as<float>();
+    }
+    return PMM_OK;
+}
+
+// Re-scores the queries [q0, q0 + rows) of the level (q0 a multiple of 256) on `stream`; `kept` and `o` are the level's
+// whole buffers.
+int rescore_launch(const VerifyCtx &vc, const RescoreJob &job, const pmm_matrix_t &raw_q, const uint64_t *kept, int64_t q0, int64_t rows,
+                   TopkOut o, cudaStream_t stream) {
+    const int64_t keff = vc.keff;
+    const pmm_matrix_t rq = (q0 == 0 && rows == raw_q.n_rows) ? raw_q : slice_rows(raw_q, q0, rows);
+    RescoreCheck chk = job.chk;
+    if (job.verify) {
+        chk.q_sq += q0;
+        chk.flags += q0;
+        chk.kth_units += q0;
+        if (chk.seed) chk.seed += q0;
+    }
+    const int64_t wsz = vc.f64 ? 8 : 4;
+    const void *qa = job.q_aux ? (const char *)job.q_aux + q0 * wsz : nullptr;
+    uint32_t *oi = o.index ? o.index + q0 * keff : nullptr;
+    double *os = o.score ? o.score + q0 * keff : nullptr;
+    uint64_t *oc = o.cand ? o.cand + q0 * keff : nullptr;
+    if (vc.f64) {
+        if (o.cand) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
+        CUDA_TRY(launch_counted("rescore_f64", stream, [&] {
+            return launch_rescore_f64(kept + q0 * job.kp, job.kp, raw_of(rq), raw_of(vc.raw_c), (const double *)qa, (const double *)job.c_aux,
+                                      vc.metric, vc.index_base, (int)keff, oi, os, chk, stream);
+        }));
+    } else {
+        CUDA_TRY(launch_counted("rescore", stream, [&] {
+            return launch_rescore(kept + q0 * job.kp, job.kp, raw_of(rq), raw_of(vc.raw_c), (const float *)qa, (const float *)job.c_aux,
+                                  vc.metric, vc.index_base, (int)keff, oi, os, oc, chk, stream);
+        }));
+    }
+    return PMM_OK;
+}
+
+int rescore_finish(const VerifyCtx &vc, RescoreJob &job, const pmm_matrix_t &raw_q, const Prepared *c_planes, int next_terms, TopkOut o);
+
 int rescore_and_verify(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const uint64_t *kept, int kp,
                        const Prepared *c_planes, LevelErr le, int next_terms, const float *seed, TopkOut o) {
+    RescoreJob job;
+    int rc;
+    if ((rc = rescore_setup(vc, q, raw_q.n_rows, kp, le, seed, &job))) return rc;
+    if ((rc = rescore_launch(vc, job, raw_q, kept, 0, raw_q.n_rows, o, vc.s))) return rc;
+    return rescore_finish(vc, job, raw_q, c_planes, next_terms, o);
+}
+
+// The flagged queries of a level -> the next level (see rescore_and_verify's comment above).
+int rescore_finish(const VerifyCtx &vc, RescoreJob &job, const pmm_matrix_t &raw_q, const Prepared *c_planes, int next_terms, TopkOut o) {
     cudaStream_t s = vc.s;
     const int metric = vc.metric;
     const int64_t Q = raw_q.n_rows, keff = vc.keff;
-    const void *q_aux = metric == PMM_METRIC_COSINE ? q.norm.p : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.p : nullptr;
-    const void *c_aux = metric == PMM_METRIC_COSINE ? vc.c_norm : metric == PMM_METRIC_EUCLIDEAN ? vc.c_sq : nullptr;
-    DevBuf flags, count, kth;
-    RescoreCheck chk;
-    memset(&chk, 0, sizeof(chk));
-    const float *q_sq32 = q.sq_f32();
-    const bool verify = t_opt.verify && q_sq32 && vc.c_range;
-    if (verify) {
-        CUDA_TRY(flags.alloc((size_t)Q, s));
-        CUDA_TRY(count.alloc(sizeof(unsigned int), s));
-        CUDA_TRY(kth.alloc((size_t)Q * 4, s));
-        CUDA_TRY(cudaMemsetAsync(flags.p, 0, (size_t)Q, s));
-        CUDA_TRY(cudaMemsetAsync(count.p, 0, sizeof(unsigned int), s));
-        chk.q_sq = q_sq32;
-        chk.c_max_sq = vc.c_range;
-        chk.eps = le.eps;
-        chk.abs_err = le.abs_err;
-        chk.max_norm = le.max_norm;
-        chk.seed = seed;
-        chk.flags = flags.as<unsigned char>();
-        chk.flag_count = count.as<unsigned int>();
-        chk.kth_units = kth.as<float>();
-    }
-    if (vc.f64) {
-        if (o.cand) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
-        CUDA_TRY(launch_counted("rescore_f64", s, [&] {
-            return launch_rescore_f64(kept, kp, raw_of(raw_q), raw_of(vc.raw_c), (const double *)q_aux, (const double *)c_aux, metric,
-                                      vc.index_base, (int)keff, o.index, o.score, chk, s);
-        }));
-    } else {
-        CUDA_TRY(launch_counted("rescore", s, [&] {
-            return launch_rescore(kept, kp, raw_of(raw_q), raw_of(vc.raw_c), (const float *)q_aux, (const float *)c_aux, metric,
-                                  vc.index_base, (int)keff, o.index, o.score, o.cand, chk, s);
-        }));
-    }
+    const bool verify = job.verify;
+    DevBuf &flags = job.flags, &count = job.count, &kth = job.kth;
+    RescoreCheck &chk = job.chk;
     if (!verify) return PMM_OK;
     unsigned int n_flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_flag, count.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -797,6 +874,101 @@ int rescore_and_verify(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_
     return PMM_OK;
 }
 
+// ---- pipelined first level --------------------------------------------------------------------------------------
+// Query rows per filter launch of the pipelined first level = one ROUND of the persistent schedule (every scheduling
+// unit takes one query tile and sweeps the whole corpus), or 0 when pipelining is off / pointless.
+int64_t pipeline_part_rows(const Prepared &q, const Prepared &c, int terms) {
+    if (!t_opt.pipeline) return 0;
+    DevInfo &di = dev_info();
+    const bool f16 = q.mode == PREP_F16 || q.mode == PREP_F16R;
+    const int cg = (terms == 1 && !f16) ? 2 : t_opt.tc_cg;
+    const int gs = cg * ((cg == 2 && t_opt.tc_clm == 2) ? 2 : 1);
+    int units = di.num_sms / gs;
+    if (t_opt.tc_max_units > 0 && units > t_opt.tc_max_units) units = t_opt.tc_max_units;
+    const int g = tc_group_for(c.n_rows, q.ld, f16 || terms == 1, units, gs);
+    const int mc = units / (g < 1 ? 1 : g);
+    if (mc < 1) return 0;
+    // a round must be long enough to hide a launch boundary (~20 us) and a merge + re-scoring of the previous one
+    const double round_flop = 2.0 * (double)mc * TC_TILE_M * gs * (double)c.n_rows * (double)q.dim;
+    if (round_flop < 1.0e9 * (double)t_opt.pipeline_min_gflop) return 0;
+    return (int64_t)mc * TC_TILE_M * gs;
+}
+
+// Rows [q0, q0 + rows) of prepared query operands as an operand set of its own (views, nothing is copied).
+void view_query_rows(const Prepared &q, int64_t q0, int64_t rows, cudaStream_t s, Prepared *v) {
+    const bool half_plane = q.mode == PREP_F16 || q.mode == PREP_F16R;
+    const int64_t es = half_plane ? 2 : 4, wsz = q.f64 ? 8 : 4;
+    v->mode = q.mode;
+    v->f64 = q.f64;
+    v->n_rows = rows;
+    v->dim = q.dim;
+    v->ld = q.ld;
+    v->rows_pad = q.rows_pad - q0;
+    const size_t pb = (size_t)v->rows_pad * q.ld * es;
+    v->p0.borrow((char *)q.p0.p + (size_t)q0 * q.ld * es, pb, s);
+    if (q.p1.p) v->p1.borrow((char *)q.p1.p + (size_t)q0 * q.ld * es, pb, s);
+    if (q.norm.p) v->norm.borrow((char *)q.norm.p + q0 * wsz, (size_t)v->rows_pad * wsz, s);
+    if (q.sqnorm.p) v->sqnorm.borrow((char *)q.sqnorm.p + q0 * wsz, (size_t)v->rows_pad * wsz, s);
+    if (q.norm32.p) v->norm32.borrow((char *)q.norm32.p + q0 * 4, (size_t)v->rows_pad * 4, s);
+    if (q.sqnorm32.p) v->sqnorm32.borrow((char *)q.sqnorm32.p + q0 * 4, (size_t)v->rows_pad * 4, s);
+    v->max_sq_ptr = q.max_sq_ptr;
+}
+
+int filter_rescore_pipelined(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared &c, int terms, int kp,
+                             int64_t part_rows, uint64_t *kept, const RescoreJob &job, TopkOut o) {
+    cudaStream_t s = vc.s, s2 = aux_stream();
+    const int64_t Q = q.n_rows;
+    const int n_parts = (int)((Q + part_rows - 1) / part_rows);
+    DevBuf partial[2];
+    struct Events {
+        std::vector<cudaEvent_t> ev;
+        ~Events() {
+            for (cudaEvent_t e : ev)
+                if (e) cudaEventDestroy(e);
+        }
+        cudaError_t make(cudaEvent_t *e) {
+            cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+            if (r == cudaSuccess) ev.push_back(*e);
+            return r;
+        }
+    } events;
+    // every way out joins the second stream into s first: buffers freed on s afterwards must not be in use on s2
+    struct Join {
+        cudaStream_t s, s2;
+        ~Join() {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(e, s2);
+                cudaStreamWaitEvent(s, e, 0);
+                cudaEventDestroy(e);
+            } else {
+                cudaStreamSynchronize(s2);
+            }
+        }
+    } join{s, s2};
+    cudaEvent_t start;
+    CUDA_TRY(events.make(&start));
+    CUDA_TRY(cudaEventRecord(start, s));                 // everything prepared on s so far (planes, norms, flag buffers)
+    CUDA_TRY(cudaStreamWaitEvent(s2, start, 0));
+    std::vector<cudaEvent_t> part_done(n_parts, nullptr);
+    for (int p = 0; p < n_parts; ++p) {
+        const int64_t q0 = (int64_t)p * part_rows, rows = std::min<int64_t>(part_rows, Q - q0);
+        Prepared qv;
+        view_query_rows(q, q0, rows, s, &qv);
+        if (p >= 2) CUDA_TRY(cudaStreamWaitEvent(s, part_done[p - 2], 0));   // its list buffer is being recycled
+        TcPipe pipe;
+        pipe.s2 = s2;
+        pipe.partial = &partial[p & 1];
+        CUDA_TRY(events.make(&pipe.filter_done));
+        int rc = tc_filter(qv, c, kp, vc.metric, vc.index_base, kept + q0 * kp, s, terms, nullptr, 3, nullptr, &pipe);
+        if (rc) return rc;
+        if ((rc = rescore_launch(vc, job, raw_q, kept, q0, rows, o, s2))) return rc;
+        CUDA_TRY(events.make(&part_done[p]));
+        CUDA_TRY(cudaEventRecord(part_done[p], s2));
+    }
+    return PMM_OK;   // ~Join: s waits for s2
+}
+
 // Filter at `terms` (unless the kept lists are supplied) -> exact re-scoring -> verification -> next level.
 // c may be NULL only when kept_in is given.
 int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared *c, int terms,
@@ -806,9 +978,24 @@ int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t 
     const bool f16r = q.mode == PREP_F16R;   // input rounded to f16: TF32-x1-like error, then 3xTF32 on demand
     DevBuf kept;
     const uint64_t *kept_ptr = kept_in;
+    const LevelErr le = level_err(q.mode, f16r ? 1 : terms, vc.f64, raw_q.dim);
+    // next level for the queries the proof rejects (see below)
+    const bool wide_ = f16r && c && kp < 256 && !seed && t_opt.f16r_wide;
+    const int next_terms_ = wide_ ? 1 : (f16r || (!f16 && terms == 1)) ? 3 : 0;
     if (!kept_ptr) {
         CUDA_TRY(kept.alloc((size_t)q.n_rows * kp * 8, vc.s));
-        int rc = tc_filter(q, *c, kp, vc.metric, vc.index_base, kept.as<uint64_t>(), vc.s, terms, nullptr, 3, seed);
+        // Large query batches: one filter launch per ROUND of query tiles, and the merge + exact re-scoring of a round
+        // run on a second stream while the tensor cores filter the next one (the filter leaves DRAM ~98 % idle, the
+        // re-scoring is a DRAM gather; its blocks fit beside the persistent filter CTAs).
+        int rc = PMM_OK;
+        const int64_t part_rows = pipeline_part_rows(q, *c, terms);
+        if (part_rows > 0 && !seed && !kp_override && q.n_rows >= 2 * part_rows) {
+            RescoreJob job;
+            if ((rc = rescore_setup(vc, q, raw_q.n_rows, kp, le, seed, &job))) return rc;
+            if ((rc = filter_rescore_pipelined(vc, q, raw_q, *c, terms, kp, part_rows, kept.as<uint64_t>(), job, o))) return rc;
+            return rescore_finish(vc, job, raw_q, (f16r && !wide_) ? nullptr : c, next_terms_, o);
+        }
+        rc = tc_filter(q, *c, kp, vc.metric, vc.index_base, kept.as<uint64_t>(), vc.s, terms, nullptr, 3, seed);
         if (rc) return rc;
         kept_ptr = kept.as<uint64_t>();
     }

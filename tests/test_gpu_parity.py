@@ -949,6 +949,56 @@ def test_two_threads_call_concurrently(native, oracle):
     assert not errors, errors
 
 
+def test_pipelined_rounds_overlap_rescoring(native, oracle):
+    """Large query batches run one filter launch per round of query tiles while the merge + exact re-scoring of the
+    previous round run on a second stream. Forced onto small data here (two scheduling units, no size threshold): 600
+    queries -> two 512-row parts... same answers as the single-launch path, flagged queries still escalate."""
+    import torch
+    rng = np.random.default_rng(49)
+    q, c = _randn(rng, 1700, 96), _randn(rng, 30_000, 96)
+    c[:40] = c[40:80] * np.float32(1.00001)                    # near ties: some queries need the retry levels
+    q[5] = c[41]
+    dq, dc = torch.from_numpy(q).cuda(), torch.from_numpy(c).cuda()
+    res = {}
+    for pipe in (1, 0):
+        native.set_option("pipeline", pipe)
+        native.set_option("pipeline_min_gflop", 0)
+        native.set_option("tc_max_units", 2)                   # a round = 2 units x 256 query rows
+        native.set_option("profile", 1)
+        native.reset_stats()
+        try:
+            for metric_name, metric, k in (("dot", 1, 100), ("cosine", 0, 10), ("euclidean", 2, 30)):
+                idx = torch.empty((1700, k), dtype=torch.int32, device="cuda")
+                sc = torch.empty((1700, k), dtype=torch.float64, device="cuda")
+                native.dev_topk(native.dev_matrix(dq.data_ptr(), 1700, 96, 1), native.dev_matrix(dc.data_ptr(), 30_000, 96, 1), k, metric,
+                                index_ptr=idx.data_ptr(), score_ptr=sc.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                res[(pipe, metric_name)] = (idx.cpu().numpy().view(np.uint32), sc.cpu().numpy())
+            n_filter = native.get_stat("tc_topk_f16r_launches")
+            assert n_filter == (3 * 4 if pipe else 3), n_filter     # 1700 rows = 3 rounds of 512 + a remainder
+            assert native.get_stat("rescore_launches") >= n_filter
+        finally:
+            native.set_option("pipeline", 1)
+            native.set_option("pipeline_min_gflop", 2000)
+            native.set_option("tc_max_units", 0)
+            native.set_option("profile", 0)
+    for metric_name, k in (("dot", 100), ("cosine", 10), ("euclidean", 30)):
+        i1, s1 = res[(1, metric_name)]
+        i0, s0 = res[(0, metric_name)]
+        assert np.array_equal(i1, i0) and np.array_equal(s1, s0)
+        parity.check_topk(i1, s1, q, c, k, metric_name, oracle, exact=True)
+    # f64 working precision through the same pipeline
+    native.set_option("pipeline_min_gflop", 0)
+    native.set_option("tc_max_units", 2)
+    try:
+        q64, c64 = q[:1100].astype(np.float64), c[:8000].astype(np.float64)
+        idx, sc = native.topk(_hm(q64), _hm(c64), 10, "cosine")
+    finally:
+        native.set_option("pipeline_min_gflop", 2000)
+        native.set_option("tc_max_units", 0)
+    parity.check_topk(idx, sc, q64, c64, 10, "cosine", oracle, exact=True)
+
+
 def test_seeded_requery_levels(native, oracle):
     """Queries the first level cannot prove are re-run from SEEDED thresholds (the exact k-th score at hand minus the
     next level's error bound): same answers with and without seeding, and the seeded launch is the one that ran."""
