@@ -598,7 +598,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        flops_per_launch = 2.0 * Q * N * D
+        # Dominant kernel: algorithmic FLOPs of one step (2 Q N D per rank) over the kernel's time per step.  By default
+        # the first level is ONE launch per step; with the pipelined first level (option pipeline=1) it is one launch per
+        # round of query tiles, which together still cover every query x corpus pair exactly once.
+        launches_per_step = k_launches / max(1, args.steps)
+        flops_per_launch = 2.0 * Q * N * D / max(1.0, launches_per_step)
         k_avg_ms = k_ms / max(1.0, k_launches)
         achieved = flops_per_launch / (k_avg_ms / 1000.0) / 1e12 if k_avg_ms > 0 else None
         # Tensor-pipe peak for ALGORITHMIC flops: the default first level rounds the operands to f16 (11 significant bits,
@@ -613,8 +617,8 @@ def main():
                     "traffic": tr["dram_bytes_per_launch"] if tr else None,
                     "traffic_note": tr["source"] if tr else "no ncu capture committed for this workload",
                     "ncu_tensor_pipe_active_pct": tr.get("tensor_pipe_active_pct_of_elapsed") if tr else None,
-                    "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms,
-                    "kernel_share_of_step": (k_avg_ms / ms_step) if ms_step else None,
+                    "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms_avg": k_avg_ms, "launches_per_step": launches_per_step,
+                    "kernel_share_of_step": (k_avg_ms * launches_per_step / ms_step) if ms_step else None,
                     "peak_note": f"{peak_src}: bf16_tflops_sustained / {rate_div:g} ("
                                  + ("one kind::f16 MMA per MAC on f16-rounded operands" if kname.endswith("f16r") else
                                     f"TF32 = 1/2 bf16 rate, {terms} TF32 MMA(s) per MAC")

@@ -286,9 +286,13 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *   "f16r_wide" (0/1, default 1)  queries the f16-rounded first level cannot prove are first re-run against the same
  *                              planes with 256-entry lists, then with 3xTF32
  *   "seed_retry" (0/1, default 1) re-query levels start from thresholds seeded by the exact k-th scores at hand
- *   "pipeline" (0/1, default 1)   large query batches: one filter launch per round of query tiles, the merge and exact
- *                              re-scoring of a round overlap the filter of the next one (second stream);
- *                              "pipeline_min_gflop" (default 2000): rounds below this much work are not split off
+ *   "pipeline" (0/1/2, default 0) large query batches: one filter launch per round of query tiles, the merge and exact
+ *                              re-scoring of a round overlap the filter of the next one (second stream).  Off by default:
+ *                              the part runs against its power cap during the filter, so the overlapped re-scoring slows
+ *                              the filter by what it saves (measured: 127.2 -> 126.7 ms at C3, profiles/sweep_r2.md);
+ *                              2 = per-round launches without the overlap (measurement);
+ *                              "pipeline_min_gflop" (default 2000): rounds below this much work are not split off;
+ *                              "rescore_stream_loads" (default 1): the overlapped re-scoring gathers with evict-first loads
  *   "f64_tc" (0/1, default 1)  f64 top-k: tensor-core filter + exact f64 re-scoring; 0: DMMA score slab + select
  *   "tc_cg" (1|2)              tcgen05 cta_group of the fused kernels (default 2)
  *   "tc_group"                 CTA groups sharing a query tile (0 = auto)
@@ -315,6 +319,7 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *                              0: plain cudaMemcpyAsync, staged by the driver
  *   "stage_threads"            host threads per staged copy (0 = auto: half the cores, at most 8)
  *   "stage_slot_mb", "stage_slots"   ring geometry (default 4 slots of 32 MB per calling thread)
+ *   "prep_fast" (0/1, default 1)  128-bit loads / stores in the plane-building pass where the layout allows
  *   "workspace_cache_mb"       device blocks (>= 32 MB) a thread keeps parked between calls for reuse (default 24576)
  *   "release_workspace"        return the calling thread's parked device blocks and its staging ring
  * Unknown keys return PMM_ERR_INVALID. */

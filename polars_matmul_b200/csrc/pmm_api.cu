@@ -58,7 +58,7 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, pipeline = 1;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, pipeline = 0, rescore_stream_loads = 1;
     int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000, pipeline_min_gflop = 2000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
@@ -92,7 +92,9 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "host_chunked") o.host_chunked = value ? 1 : 0;
     else if (k == "tc_sync_tiles") o.tc_sync_tiles = value < 0 ? 0 : (int)value;  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") o.generic_ws_mb = value < 1 ? 1 : value;
-    else if (k == "pipeline") o.pipeline = value ? 1 : 0;                       // per-round filter launches with overlapped merge + re-scoring
+    else if (k == "rescore_stream_loads") o.rescore_stream_loads = value ? 1 : 0;
+    else if (k == "pipeline") o.pipeline = value < 0 ? 0 : value > 2 ? 2 : (int)value;   // 2: per-round launches WITHOUT the overlap (measurement)
+    else if (k == "__unused_pipeline") o.pipeline = value ? 1 : 0;                       // per-round filter launches with overlapped merge + re-scoring
     else if (k == "pipeline_min_gflop") o.pipeline_min_gflop = value < 0 ? 0 : value;   // smallest round worth a launch of its own
     else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
     else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
@@ -733,6 +735,7 @@ int rescore_launch(const VerifyCtx &vc, const RescoreJob &job, const pmm_matrix_
     const int64_t keff = vc.keff;
     const pmm_matrix_t rq = (q0 == 0 && rows == raw_q.n_rows) ? raw_q : slice_rows(raw_q, q0, rows);
     RescoreCheck chk = job.chk;
+    chk.stream_loads = (stream != vc.s && t_opt.rescore_stream_loads) ? 1 : 0;
     if (job.verify) {
         chk.q_sq += q0;
         chk.flags += q0;
@@ -916,7 +919,7 @@ void view_query_rows(const Prepared &q, int64_t q0, int64_t rows, cudaStream_t s
 
 int filter_rescore_pipelined(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared &c, int terms, int kp,
                              int64_t part_rows, uint64_t *kept, const RescoreJob &job, TopkOut o) {
-    cudaStream_t s = vc.s, s2 = aux_stream();
+    cudaStream_t s = vc.s, s2 = t_opt.pipeline == 2 ? vc.s : aux_stream();
     const int64_t Q = q.n_rows;
     const int n_parts = (int)((Q + part_rows - 1) / part_rows);
     DevBuf partial[2];
@@ -2095,6 +2098,7 @@ static int immediate_option(const std::string &k, int64_t value) {
         return 1;
     }
     if (k == "workspace_cache_mb") { g_block_cache_cap_mb.store(value < 0 ? 0 : value); return 1; }
+    if (k == "prep_fast") { prep_set_fast(value != 0); return 1; }
     if (k == "stage") { stage_set_enabled(value != 0); return 1; }
     if (k == "stage_threads") { stage_set_threads((int)value); return 1; }
     if (k == "stage_slot_mb") { stage_set_ring((size_t)(value < 1 ? 1 : value) << 20, g_stage_slots.load()); g_stage_slot_mb.store(value < 1 ? 1 : value); return 1; }

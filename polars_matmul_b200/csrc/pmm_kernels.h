@@ -31,6 +31,7 @@ struct PrepArgs {
 enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2, PREP_F16R = 3 };  // = MODE_* of pmm_prep.cu
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s);
 cudaError_t launch_norms(const PrepArgs &a, int src_dtype, cudaStream_t s);
+void prep_set_fast(bool on);   // vectorised fast path of the plane modes (default on)
 
 // ---- generic SIMT path (pmm_generic.cu) -----------------------------------------------------------
 // scores[i*ldo + j] = metric(dot(q_i, c_j)); metric < 0 => raw dot. Sequential FMA over the vector
@@ -111,6 +112,7 @@ struct RescoreCheck {
     unsigned char *flags;          // [n_queries] set to 1 when not provable
     unsigned int *flag_count;
     float *kth_units;              // [n_queries] out (flagged queries): the exact k-th score in filter units, or NULL
+    int stream_loads;              // gather the candidate rows with evict-first loads (re-scoring beside the fused kernel)
 };
 // cand [n_queries][kp_in] packed candidates (approximate keys, global indices) -> exact top-k_out.
 cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,

@@ -56,6 +56,8 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
 }
 
 enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2, MODE_F16R = 3 };
+static bool g_prep_fast = true;   // prep_set_fast(): A/B switch for measurements and tests
+void prep_set_fast(bool on) { g_prep_fast = on; }
 
 template <typename SRC, typename W, int MODE>
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
@@ -179,10 +181,151 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path of the plane modes for the common layout: fixed-size rows, no bitmaps, f32 working precision, row length a
+// multiple of 32 (f32 source) / 64 (f16 source), 16-byte aligned rows.  Same thread mapping (8 lanes per row, lane j owns
+// partial sum p_j) and therefore the same norm bits as prep_kernel, but every lane moves 16 bytes at a time: one 128-bit
+// load per lane covers a 128-byte line of the row, the plane stores are 8 (f16 from f32), 16 (f16 copy) or 2 x 16 bytes
+// (TF32 hi/lo) per lane instead of 2- / 4-byte scalars, and the elements a lane needs for ITS residue class come back
+// through a per-warp shared-memory tile (the line is written as loaded and read back transposed).
+template <typename SRC, int MODE>
+__global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
+    constexpr int EPL = 16 / (int)sizeof(SRC);          // elements per lane and step: 4 (f32) or 8 (f16)
+    constexpr int STEP = 8 * EPL;                       // elements per row and step: 32 or 64
+    constexpr int PITCH = STEP + 8;                     // floats per tile row: rows start 8 banks apart
+    __shared__ __align__(16) float tiles[8][2][4][PITCH];   // per warp: double-buffered 4-row tile (as floats)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7, rw = lane >> 3;
+    const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 4 + rw;
+    const unsigned gmask = 0xffu << (lane & 24);
+    if (row >= a.rows_out) return;  // whole 8-lane group leaves together
+    const int64_t dim = a.dim, ld = a.ld_out;
+    const bool live = row < a.n_rows;
+    const SRC *src = (const SRC *)a.values + row * dim;
+    float *hi = (float *)a.out0 + row * ld, *lo = (float *)a.out1 + row * ld;
+    __half *hp = (__half *)a.out0 + row * ld;
+    float p = 0.0f;
+    bool bad = false;
+    int buf = 0;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    // one 16-byte piece of the row (already loaded) at element offset t: planes + this lane's share of the norm
+    auto process = [&](const uint4 raw, int64_t t) {
+        float x[EPL];
+        if (sizeof(SRC) == 4) {
+            x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y); x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
+        } else {
+            const __half2 *h2 = (const __half2 *)&raw;
+#pragma unroll
+            for (int u = 0; u < EPL / 2; ++u) {
+                const float2 f = __half22float2(h2[u]);
+                x[2 * u] = f.x;
+                x[2 * u + 1] = f.y;
+            }
+            if (MODE == MODE_F16) *((uint4 *)(hp + t) + sub) = raw;   // exact plane of f16 input: the line as loaded
+        }
+        if (MODE == MODE_F16R || (MODE == MODE_F16 && sizeof(SRC) == 4)) {
+            __half2 h[EPL / 2];
+#pragma unroll
+            for (int u = 0; u < EPL / 2; ++u) h[u] = __floats2half2_rn(x[2 * u], x[2 * u + 1]);
+            if (EPL == 4) *((uint2 *)(hp + t) + sub) = *(const uint2 *)h;
+            else *((uint4 *)(hp + t) + sub) = *(const uint4 *)h;
+        } else if (MODE == MODE_TF32) {
+            float h4[EPL], l4[EPL];
+#pragma unroll
+            for (int u = 0; u < EPL; ++u) {
+                tf32_split(x[u], h4[u], l4[u]);
+                bad |= !(fabsf(x[u]) <= 3.4028234663852886e38f);
+            }
+#pragma unroll
+            for (int u = 0; u < EPL; u += 4) {
+                *((float4 *)(hi + t + EPL * sub + u)) = make_float4(h4[u], h4[u + 1], h4[u + 2], h4[u + 3]);
+                *((float4 *)(lo + t + EPL * sub + u)) = make_float4(l4[u], l4[u + 1], l4[u + 2], l4[u + 3]);
+            }
+        }
+        // norm: lane `sub` adds the elements of ITS residue class (mod 8) in index order, as ndarray's unrolled_dot
+        float *tile = tiles[warp][buf][rw];
+#pragma unroll
+        for (int u = 0; u < EPL; u += 4) *(float4 *)(tile + EPL * sub + u) = make_float4(x[u], x[u + 1], x[u + 2], x[u + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < STEP / 8; ++c) {
+            const float y = tile[8 * c + sub];
+            p = add_rn(p, mul_rn(y, y));
+        }
+        buf ^= 1;   // (no second barrier: the next piece writes the OTHER buffer, the one after that is behind the next __syncwarp)
+    };
+    const uint4 *src16 = (const uint4 *)src;   // row as 16-byte pieces: piece index = (t / EPL) + sub
+    int64_t t = 0;
+    for (; t + 4 * STEP <= dim; t += 4 * STEP) {   // four 128-byte lines of the row in flight per lane group
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = live ? __ldg(src16 + (t + u * STEP) / EPL + sub) : zero4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) process(r[u], t + u * STEP);
+    }
+    for (; t < dim; t += STEP) process(live ? __ldg(src16 + t / EPL + sub) : zero4, t);
+    for (int64_t i = dim + 8 * sub; i < ld; i += 64) {   // zero the padding columns (ld - dim is 0 or 32 here)
+        if (MODE == MODE_TF32) {
+#pragma unroll
+            for (int u = 0; u < 8 && i + u < ld; ++u) { hi[i + u] = 0.0f; lo[i + u] = 0.0f; }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8 && i + u < ld; ++u) hp[i + u] = __float2half_rn(0.0f);
+        }
+    }
+    // (p0+p4), (p1+p5), (p2+p6), (p3+p7) then a sequential sum, as ndarray's unrolled_dot (no tail: dim % 8 == 0)
+    const int gbase = lane & 24;
+    const float other = __shfl_sync(gmask, p, gbase + ((sub + 4) & 7));
+    const float pair = add_rn(p, other);
+    const float s0 = __shfl_sync(gmask, pair, gbase + 0), s1 = __shfl_sync(gmask, pair, gbase + 1);
+    const float s2 = __shfl_sync(gmask, pair, gbase + 2), s3 = __shfl_sync(gmask, pair, gbase + 3);
+    float sum = add_rn(0.0f, s0);
+    sum = add_rn(sum, s1);
+    sum = add_rn(sum, s2);
+    sum = add_rn(sum, s3);
+    if (MODE == MODE_TF32 && a.nonfinite_rows) {
+        const bool any_bad = __any_sync(gmask, bad);
+        if (sub == 0 && live) {
+            a.nonfinite_rows[row] = any_bad ? 1 : 0;
+            if (any_bad) atomicAdd(a.nonfinite_count, 1u);
+        }
+    }
+    if (sub == 0) {
+        if (a.sqnorm_out) ((float *)a.sqnorm_out)[row] = sum;
+        if (a.norm_out) ((float *)a.norm_out)[row] = sqrt_rn(sum);
+    }
+    if (a.max_sq_out) {
+        unsigned int bits = (sub == 0 && live && sum == sum) ? __float_as_uint(sum) : 0u;
+        const unsigned am = __activemask();
+        bits = __reduce_max_sync(am, bits);
+        if (lane == __ffs(am) - 1 && bits) atomicMax(a.max_sq_out, bits);
+        unsigned int lo_bits = (sub == 0 && live && sum > a.zero_guard_sq) ? __float_as_uint(sum) : 0x7f800000u;
+        lo_bits = __reduce_min_sync(am, lo_bits);
+        if (lane == __ffs(am) - 1 && lo_bits != 0x7f800000u) atomicMin(a.max_sq_out + 1, lo_bits);
+    }
+}
+
+template <typename SRC>
+static bool prep_fast_ok(const PrepArgs &a) {
+    const int step = 8 * (16 / (int)sizeof(SRC));
+    return !a.offsets && !a.validity && !a.row_validity && !a.norm32_out && !a.sqnorm32_out && a.dim > 0 && (a.dim % step) == 0 &&
+           (a.ld_out % 8) == 0 && (((uintptr_t)a.values) & 15) == 0 && (((uintptr_t)a.out0) & 15) == 0 && (((uintptr_t)a.out1) & 15) == 0;
+}
+
+template <typename SRC, int MODE>
+static cudaError_t launch_prep_fast(const PrepArgs &a, int64_t groups, cudaStream_t s) {
+    prep_fast_kernel<SRC, MODE><<<(unsigned)groups, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <typename SRC, typename W, int MODE>
 static cudaError_t launch_prep_t(const PrepArgs &a, cudaStream_t s) {
     int64_t groups = (a.rows_out + 31) / 32;
     if (groups <= 0) return cudaSuccess;
+    if (MODE != MODE_DENSE && sizeof(W) == 4 && sizeof(SRC) <= 4 && g_prep_fast && prep_fast_ok<SRC>(a)) {
+        if (sizeof(SRC) == 4) return launch_prep_fast<float, MODE == MODE_DENSE ? MODE_F16R : MODE>(a, groups, s);
+        return launch_prep_fast<__half, MODE == MODE_DENSE ? MODE_F16R : MODE>(a, groups, s);
+    }
     prep_kernel<SRC, W, MODE><<<(unsigned)groups, 256, 0, s>>>(a);
     return cudaGetLastError();
 }

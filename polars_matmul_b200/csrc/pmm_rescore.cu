@@ -47,7 +47,9 @@ __device__ __forceinline__ void raw_row(const RawMatrix &m, int64_t row, int64_t
 // One 32-element step of the gather: element `e` of candidate rows [0, n_act) of the warp, in batches of 8 rows
 // (a warp-uniform guard per batch, no branch per row: every batch is in flight before the first value is consumed).
 // PLAIN: no element validity bitmap (the usual case) -> one predicated load per row.
-template <typename CSRC, bool PLAIN>
+// STREAM: evict-first loads (ld.global.cs) - the gathered rows are used once; keeps them from displacing the fused
+// kernel's L2-resident operand planes when the re-scoring runs beside it (pipelined first level).
+template <typename CSRC, bool PLAIN, bool STREAM>
 __device__ __forceinline__ void gather_step(float (&x)[32], const RawMatrix &cm, const int64_t *rowb, const int *rowl, int w0,
                                             int n_act, int e) {
 #pragma unroll
@@ -57,7 +59,8 @@ __device__ __forceinline__ void gather_step(float (&x)[32], const RawMatrix &cm,
             for (int i = g; i < g + 8; ++i) {
                 const int64_t cbi = rowb[w0 + i];
                 const int cli = rowl[w0 + i];
-                if (PLAIN) x[i] = e < cli ? RsLoad<CSRC>::get(cm.values, cbi + e) : 0.0f;
+                if (PLAIN && STREAM && sizeof(CSRC) == 4) x[i] = e < cli ? __ldcs((const float *)cm.values + cbi + e) : 0.0f;
+                else if (PLAIN) x[i] = e < cli ? RsLoad<CSRC>::get(cm.values, cbi + e) : 0.0f;
                 else x[i] = raw_fetch<CSRC>(cm, cbi, cli, e);
             }
         }
@@ -181,8 +184,9 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
         const bool plain = !cm.validity;
         for (int d0 = 0; d0 < dim; d0 += 32) {
             float x[32];
-            if (plain) gather_step<CSRC, true>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
-            else gather_step<CSRC, false>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
+            if (plain && chk.stream_loads) gather_step<CSRC, true, true>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
+            else if (plain) gather_step<CSRC, true, false>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
+            else gather_step<CSRC, false, false>(x, cm, rowb, rowl, w0, n_act, d0 + lane);
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
                 if (g < n_act) {

@@ -978,7 +978,7 @@ def test_pipelined_rounds_overlap_rescoring(native, oracle):
             assert n_filter == (3 * 4 if pipe else 3), n_filter     # 1700 rows = 3 rounds of 512 + a remainder
             assert native.get_stat("rescore_launches") >= n_filter
         finally:
-            native.set_option("pipeline", 1)
+            native.set_option("pipeline", 0)
             native.set_option("pipeline_min_gflop", 2000)
             native.set_option("tc_max_units", 0)
             native.set_option("profile", 0)
@@ -988,12 +988,14 @@ def test_pipelined_rounds_overlap_rescoring(native, oracle):
         assert np.array_equal(i1, i0) and np.array_equal(s1, s0)
         parity.check_topk(i1, s1, q, c, k, metric_name, oracle, exact=True)
     # f64 working precision through the same pipeline
+    native.set_option("pipeline", 1)
     native.set_option("pipeline_min_gflop", 0)
     native.set_option("tc_max_units", 2)
     try:
         q64, c64 = q[:1100].astype(np.float64), c[:8000].astype(np.float64)
         idx, sc = native.topk(_hm(q64), _hm(c64), 10, "cosine")
     finally:
+        native.set_option("pipeline", 0)
         native.set_option("pipeline_min_gflop", 2000)
         native.set_option("tc_max_units", 0)
     parity.check_topk(idx, sc, q64, c64, 10, "cosine", oracle, exact=True)
