@@ -165,8 +165,9 @@ PMM_API int pmm_topk_corpus(const pmm_matrix_t *queries, const pmm_corpus_t *cor
  *                       (score best-first, lower index first), so shards merge by plain u64 max.
  *                       f32 working precision only.
  * Path: k_eff <= 248 runs the fused tcgen05 filter (operands rounded to f16 / TF32 planes) + exact re-scoring in the
- * working precision (f32 or f64; sequential FMA like the reference) + a per-query losslessness proof; larger k takes
- * the SIMT score-slab path.  Either way scores and indices equal the reference arithmetic's.
+ * working precision (f32 or f64; sequential FMA like the reference) + a per-query losslessness proof; f32 with
+ * 248 < k_eff <= 2000 runs several passes of it; anything larger (or f64 beyond 248) takes the SIMT score-slab path.
+ * Either way scores and indices equal the reference arithmetic's.
  */
 PMM_API int pmm_dev_topk(const pmm_matrix_t *d_queries, const pmm_matrix_t *d_corpus, int64_t k, int32_t metric,
                  int64_t index_base, uint32_t *d_index, double *d_score, uint64_t *d_candidates,
@@ -293,6 +294,8 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *                              2 = per-round launches without the overlap (measurement);
  *                              "pipeline_min_gflop" (default 2000): rounds below this much work are not split off;
  *                              "rescore_stream_loads" (default 1): the overlapped re-scoring gathers with evict-first loads
+ *   "multipass" (0/1, default 1)  f32 top-k with 248 < k <= 2000: several passes of the fused filter (256 candidates each,
+ *                              pass p+1 below the worst candidate pass p kept) instead of the score-slab path
  *   "f64_tc" (0/1, default 1)  f64 top-k: tensor-core filter + exact f64 re-scoring; 0: DMMA score slab + select
  *   "tc_cg" (1|2)              tcgen05 cta_group of the fused kernels (default 2)
  *   "tc_group"                 CTA groups sharing a query tile (0 = auto)

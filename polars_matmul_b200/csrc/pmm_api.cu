@@ -58,7 +58,7 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, pipeline = 0, rescore_stream_loads = 1;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
     int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000, pipeline_min_gflop = 2000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
@@ -92,6 +92,7 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "host_chunked") o.host_chunked = value ? 1 : 0;
     else if (k == "tc_sync_tiles") o.tc_sync_tiles = value < 0 ? 0 : (int)value;  // 0 = no pacing barriers
     else if (k == "generic_workspace_mb") o.generic_ws_mb = value < 1 ? 1 : value;
+    else if (k == "multipass") o.multipass = value ? 1 : 0;                     // 248 < k <= 2000 on the fused path (several filter passes)
     else if (k == "rescore_stream_loads") o.rescore_stream_loads = value ? 1 : 0;
     else if (k == "pipeline") o.pipeline = value < 0 ? 0 : value > 2 ? 2 : (int)value;   // 2: per-round launches WITHOUT the overlap (measurement)
     else if (k == "__unused_pipeline") o.pipeline = value ? 1 : 0;                       // per-round filter launches with overlapped merge + re-scoring
@@ -574,7 +575,7 @@ cudaStream_t aux_stream() {
 
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
               cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3, const float *seed = nullptr,
-              TcPipe *pipe = nullptr) {
+              TcPipe *pipe = nullptr, const uint64_t *ceil = nullptr) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -609,6 +610,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     // exact pass treats as non-zero is never zeroed by the filter (the other way round only costs a list slot)
     a.norm_guard = q.f64 ? 0.999999e-10f : 0.0f;
     a.seed_thr = seed;
+    a.ceil = ceil;
     a.index_base = index_base;
     a.metric = metric;
     a.kp = kp;
@@ -1039,10 +1041,54 @@ int topk_tc(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, con
     return tc_topk_verified(verify_ctx(c, raw_c, keff, metric, index_base, s), q, raw_q, &c, first_level_terms(q), nullptr, o);
 }
 
+// k > 248 on the fused path (f32 working precision): P passes of the first-level filter with 256-entry lists; pass p+1
+// admits only candidates strictly BELOW the worst one pass p kept (per-query ceilings), so the passes collect
+// consecutive, disjoint ranks of the filter order - 256 P candidates per query in all.  Every pass's candidates are
+// re-scored exactly; the P sorted lists are sorted as one, the best k are emitted, and the usual proof is made against
+// the LAST pass's worst filter value; queries it cannot clear go to the exact SIMT path.  No Q x N slab.
+constexpr int64_t TC_MAX_K_MULTIPASS = 2000;
+int topk_tc_multipass(const Prepared &q, const Prepared &c, const pmm_matrix_t &raw_q, const pmm_matrix_t &raw_c, int64_t keff,
+                      int metric, int64_t index_base, TopkOut o, cudaStream_t s) {
+    const int kp = 256;
+    const int P = (int)((keff + 8 + kp - 1) / kp);
+    const int64_t Q = q.n_rows;
+    const int terms = first_level_terms(q);
+    VerifyCtx vc = verify_ctx(c, raw_c, keff, metric, index_base, s);
+    DevBuf kept_all, exact, ceil;
+    CUDA_TRY(kept_all.alloc((size_t)P * Q * kp * 8, s));
+    CUDA_TRY(exact.alloc((size_t)P * Q * kp * 8, s));
+    CUDA_TRY(ceil.alloc((size_t)q.rows_pad * 8, s));
+    const void *q_aux = metric == PMM_METRIC_COSINE ? q.norm.p : metric == PMM_METRIC_EUCLIDEAN ? q.sqnorm.p : nullptr;
+    const void *c_aux = metric == PMM_METRIC_COSINE ? vc.c_norm : metric == PMM_METRIC_EUCLIDEAN ? vc.c_sq : nullptr;
+    RescoreCheck none;
+    memset(&none, 0, sizeof(none));
+    int rc;
+    for (int p = 0; p < P; ++p) {
+        uint64_t *kept_p = kept_all.as<uint64_t>() + (size_t)p * Q * kp;
+        if ((rc = tc_filter(q, c, kp, metric, index_base, kept_p, s, terms, nullptr, 3, nullptr, nullptr, p > 0 ? ceil.as<uint64_t>() : nullptr)))
+            return rc;
+        CUDA_TRY(launch_counted("rescore", s, [&] {   // exact scores of ALL candidates of the pass (k_out = kp), as packed candidates
+            return launch_rescore(kept_p, kp, raw_of(raw_q), raw_of(raw_c), (const float *)q_aux, (const float *)c_aux, metric, index_base, kp,
+                                  nullptr, nullptr, exact.as<uint64_t>() + (size_t)p * Q * kp, none, s);
+        }));
+        if (p + 1 < P)
+            CUDA_TRY(launch_counted("ceilings", s, [&] { return launch_next_ceilings(kept_p, kp, Q, q.rows_pad, ceil.as<uint64_t>(), s); }));
+    }
+    RescoreJob job;
+    if ((rc = rescore_setup(vc, q, Q, kp, level_err(q.mode, q.mode == PREP_F16R ? 1 : terms, false, raw_q.dim), nullptr, &job))) return rc;
+    CUDA_TRY(launch_counted("sort_lists", s, [&] {
+        return launch_sort_lists(exact.as<uint64_t>(), P, Q * kp, kp, Q, (int)keff, metric, kept_all.as<uint64_t>() + (size_t)(P - 1) * Q * kp,
+                                 o.index, o.score, o.cand, job.chk, s);
+    }));
+    if (!job.verify) return PMM_OK;
+    return rescore_finish(vc, job, raw_q, nullptr, 0, o);
+}
+
 struct PathChoice {
     bool tc;
     bool f64;
     int mode;  // prep mode for both operands
+    bool multipass = false;  // tc && k > 248: topk_tc_multipass
 };
 // for_topk: the top-k starts with f16-rounded planes ("tc_levels" >= 3, the default) whatever the working precision -
 // the filter only selects, the exact scores come from the re-scoring in f32 or f64; raw matmul needs 3xTF32 (f32) or
@@ -1051,6 +1097,10 @@ PathChoice choose_path(int q_dtype, int c_dtype, int64_t keff, bool for_topk = t
     PathChoice pc;
     pc.f64 = pmm_working_dtype(q_dtype, c_dtype) == PMM_DTYPE_F64;
     pc.tc = keff <= TC_MAX_K && !t_opt.force_generic && dev_info().tc && (!pc.f64 || (for_topk && t_opt.f64_tc));
+    if (!pc.tc && for_topk && !pc.f64 && keff > TC_MAX_K && keff <= TC_MAX_K_MULTIPASS && t_opt.multipass && !t_opt.force_generic && dev_info().tc) {
+        pc.tc = true;
+        pc.multipass = true;
+    }
     pc.mode = !pc.tc ? PREP_DENSE : (q_dtype == PMM_DTYPE_F16 && c_dtype == PMM_DTYPE_F16) ? PREP_F16 : PREP_TF32;
     if (pc.mode == PREP_TF32 && for_topk && t_opt.tc_levels >= 3 && t_opt.tc_cg == 2) pc.mode = PREP_F16R;
     return pc;
@@ -1082,7 +1132,9 @@ int dev_topk_impl(const pmm_matrix_t *dq, const pmm_matrix_t *dc, const Prepared
         if (rc) return rc;
         c = &c_local;
     }
-    rc = pc.tc ? topk_tc(q, *c, *dq, *dc, keff, metric, index_base, o, s) : topk_generic(q, *c, keff, metric, index_base, o, s);
+    rc = pc.multipass ? topk_tc_multipass(q, *c, *dq, *dc, keff, metric, index_base, o, s)
+         : pc.tc      ? topk_tc(q, *c, *dq, *dc, keff, metric, index_base, o, s)
+                      : topk_generic(q, *c, keff, metric, index_base, o, s);
     if (rc) return rc;
     if (dq->offsets || dc->offsets) return finish_error_flag(err.as<int>(), s);
     return PMM_OK;
@@ -1323,7 +1375,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     // included) both streams are drained before a buffer is released: the copy stream may still be writing into the
     // corpus buffer, and the caller's host buffers must not be in use by a DMA after we return.
     Uploaded uq, uc;
-    DevBuf err, kept, c_aux_all, d_idx, d_sc, c_max;
+    DevBuf err, kept, c_aux_all, c_aux32_all, d_idx, d_sc, c_max;
     Prepared q, call;
     TcCarry carry;
     struct Drain {
@@ -1443,7 +1495,9 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
-    if ((rc = prepare(uq.dm, pc.mode, false, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
+    if (pc.f64 && d_cand) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
+    const int64_t wsz = pc.f64 ? 8 : 4;   // working type of the norms; f64 keeps f32 copies for the filter beside them
+    if ((rc = prepare(uq.dm, pc.mode, pc.f64, 4 * TC_TILE_M, want_norm, true, err.as<int>(), s, &q))) return rc;
     CUDA_TRY(c_max.alloc(2 * sizeof(unsigned int), s));
     CUDA_TRY(init_norm_range(c_max.as<unsigned int>(), s));
     const int kp = tc_list_capacity(keff);
@@ -1452,10 +1506,14 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     carry.layout_rows = N;
     for (int i = 0; i < n_chunks; ++i) carry.layout_rows = std::min<int64_t>(carry.layout_rows, cut[i + 1] - cut[i]);
     CUDA_TRY(kept.alloc((size_t)Q * kp * 8, s));
-    if (want_norm || want_sq) CUDA_TRY(c_aux_all.alloc((size_t)round_up(N, TC_TILE_N) * 4, s));  // chunks write their padded tails too
+    if (want_norm || want_sq) {   // chunks write their padded tails too
+        CUDA_TRY(c_aux_all.alloc((size_t)round_up(N, TC_TILE_N) * wsz, s));
+        if (pc.f64) CUDA_TRY(c_aux32_all.alloc((size_t)round_up(N, TC_TILE_N) * 4, s));
+    }
     // Plane buffers for the WHOLE corpus; every chunk is prepared into its slice (chunk starts are multiples of the
     // corpus tile), so that after the last chunk the planes of the full corpus are at hand for the re-query levels.
     call.mode = pc.mode;
+    call.f64 = pc.f64;
     call.n_rows = N;
     call.dim = D;
     call.rows_pad = round_up(N, TC_TILE_N);
@@ -1472,16 +1530,21 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         const size_t off = (size_t)r0 * call.ld * plane_es, pb = plane_bytes(pc.mode, rows, D, TC_TILE_N);
         c.p0.borrow((char *)call.p0.p + off, pb, s);
         if (pc.mode == PREP_TF32) c.p1.borrow((char *)call.p1.p + off, pb, s);
-        if (want_norm) c.norm.borrow(c_aux_all.as<float>() + r0, (size_t)round_up(rows, TC_TILE_N) * 4, s);
-        if (want_sq) c.sqnorm.borrow(c_aux_all.as<float>() + r0, (size_t)round_up(rows, TC_TILE_N) * 4, s);
-        if ((rc = prepare(dm, pc.mode, false, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
+        const size_t aux_rows = (size_t)round_up(rows, TC_TILE_N);
+        if (want_norm) c.norm.borrow((char *)c_aux_all.p + (size_t)r0 * wsz, aux_rows * wsz, s);
+        if (want_sq) c.sqnorm.borrow((char *)c_aux_all.p + (size_t)r0 * wsz, aux_rows * wsz, s);
+        if (pc.f64 && want_norm) c.norm32.borrow(c_aux32_all.as<float>() + r0, aux_rows * 4, s);
+        if (pc.f64 && want_sq) c.sqnorm32.borrow(c_aux32_all.as<float>() + r0, aux_rows * 4, s);
+        if ((rc = prepare(dm, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
         // the candidate lists are carried from chunk to chunk; the last launch merges them into `kept`
         if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept.as<uint64_t>(), s, terms0, &carry,
                             (i == 0 ? 1 : 0) | (i == n_chunks - 1 ? 2 : 0))))
             return rc;
     }
-    if (want_norm) call.norm.borrow(c_aux_all.p, (size_t)call.rows_pad * 4, s);
-    if (want_sq) call.sqnorm.borrow(c_aux_all.p, (size_t)call.rows_pad * 4, s);
+    if (want_norm) call.norm.borrow(c_aux_all.p, (size_t)call.rows_pad * wsz, s);
+    if (want_sq) call.sqnorm.borrow(c_aux_all.p, (size_t)call.rows_pad * wsz, s);
+    if (pc.f64 && want_norm) call.norm32.borrow(c_aux32_all.p, (size_t)call.rows_pad * 4, s);
+    if (pc.f64 && want_sq) call.sqnorm32.borrow(c_aux32_all.p, (size_t)call.rows_pad * 4, s);
     call.max_sq_ptr = c_max.as<unsigned int>();
     const uint64_t *kept_ptr = kept.as<uint64_t>();
     const size_t cnt = (size_t)Q * keff;
@@ -1526,7 +1589,7 @@ int shard_candidates(const pmm_matrix_t *queries, const pmm_matrix_t *corpus_sha
     if (keff == 0) return PMM_OK;
     PathChoice pc = choose_path(queries->dtype, corpus_shard->dtype, keff);
     if (pc.f64) return fail(PMM_ERR_UNSUPPORTED, "packed candidates exist for f32 working precision only");
-    if (pc.tc && t_opt.host_chunked &&
+    if (pc.tc && !pc.multipass && t_opt.host_chunked &&
         (double)corpus_shard->n_rows * corpus_shard->dim * esize(corpus_shard->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
         return host_topk_chunked(queries, corpus_shard, keff, metric, pc, index_base, nullptr, nullptr, d_candidates);
     cudaStream_t s = host_stream();
@@ -2323,7 +2386,7 @@ int pmm_topk(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, int64_t k,
     cudaStream_t s = host_stream();
     {
         PathChoice pc = choose_path(queries->dtype, corpus->dtype, keff);
-        if (pc.tc && !pc.f64 && t_opt.host_chunked && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
+        if (pc.tc && !pc.multipass && t_opt.host_chunked && (double)corpus->n_rows * corpus->dim * esize(corpus->dtype) >= 1e6 * t_opt.host_chunk_min_mb)
             return host_topk_chunked(queries, corpus, keff, m, pc, 0, out_index, out_score, nullptr);
     }
     Uploaded uq, uc;

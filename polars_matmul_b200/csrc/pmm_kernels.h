@@ -133,6 +133,15 @@ cudaError_t launch_rescore_f64(const uint64_t *cand, int kp_in, const RawMatrix 
 // in d).  Launched unconditionally with a small grid; exits at once when nothing is marked - no host synchronisation.
 cudaError_t launch_matmul_nonfinite_fixup(const RawMatrix &left, const RawMatrix &right, const unsigned char *nf_left,
                                           const unsigned char *nf_right, const unsigned int *nf_count, float *out, cudaStream_t s);
+// Multi-pass top-k (k > 248): ceilings of the next pass = the worst candidate each query kept in this one
+// (kept [nq][kp], sorted best first; 0 = list not full -> ceiling 0: nothing more to collect); rows [nq, n_pad) get 0.
+cudaError_t launch_next_ceilings(const uint64_t *kept, int kp, int64_t nq, int64_t n_pad, uint64_t *ceil_out, cudaStream_t s);
+// Final stage of the multi-pass top-k: per query the `n_lists` x `kp` EXACT packed candidates (each list sorted) are
+// sorted as one (n_lists * kp <= 4096), the best k_out are emitted, and the losslessness of the whole collection is
+// checked against the LAST pass's worst filter value (kept_last [nq][kp]): same proof as rescore_kernel.
+cudaError_t launch_sort_lists(const uint64_t *lists, int n_lists, int64_t list_stride, int kp, int64_t nq, int k_out, int metric,
+                              const uint64_t *kept_last, uint32_t *out_idx, double *out_score, uint64_t *out_cand,
+                              const RescoreCheck &chk, cudaStream_t s);
 cudaError_t launch_gather_rows(const RawMatrix &qm, const int64_t *ids, int64_t n_ids, void *out, int out_f64, cudaStream_t s);
 cudaError_t launch_scatter_results(const int64_t *ids, int64_t n_ids, int k, const uint32_t *si, const double *ss,
                                    const uint64_t *sc, uint32_t *di, double *ds, uint64_t *dc, cudaStream_t s);
@@ -199,6 +208,9 @@ struct TcArgs {
     const float *seed_thr;         // top-k: [q_rows_pad] initial per-query thresholds in filter units (NaN = none) or NULL.
                                    // Everything with a filter value <= the seed is dropped from the start: the caller
                                    // must know that nothing at or below it can matter (re-query levels, pmm_api.cu)
+    const uint64_t *ceil;          // top-k: [q_rows_pad] per-query ceilings (packed candidates) or NULL: only candidates strictly
+                                   // below the ceiling are admitted - pass p+1 of a multi-pass top-k collects "the next
+                                   // list-full below what pass p kept" (k > 248)
     uint64_t *staged;              // top-k: scratch of tc_staged_bytes(grid CTAs) bytes (unsorted candidates per CTA and row)
     // matmul mode
     float *out;                    // [nq x n] row-major

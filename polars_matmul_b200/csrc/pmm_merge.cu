@@ -70,6 +70,61 @@ __global__ void __launch_bounds__(256) merge_tiles_kernel(const uint64_t *__rest
     merge_query<R>(ptr, sched.pieces(mt) * esets, KP, k_out, higher, q, out_idx, out_score, out_cand, lane);
 }
 
+// Many pieces per query (a handful of re-queried rows shared by all scheduling units: 74 lists of 256 entries each): one
+// BLOCK per query, warp w merges the pieces l = w, w + 8, ... into a partial list in shared memory, warp 0 merges the
+// eight partial lists.  The chain of dependent list loads shrinks from `pieces` to pieces / 8 + 8.
+template <int R>
+__global__ void __launch_bounds__(256) merge_tiles_block_kernel(const uint64_t *__restrict__ lists, TcSchedule sched, int cg, int esets,
+                                                                int64_t nq, int k_out, bool higher, uint32_t *out_idx,
+                                                                double *out_score, uint64_t *out_cand) {
+    constexpr int KP = 32 * R;
+    __shared__ uint64_t part[8][KP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t q = blockIdx.x;
+    if (q >= nq) return;
+    const int tile_rows = TC_TILE_M * cg;
+    const int mt = (int)(q / tile_rows), r = (int)(q % tile_rows);
+    const uint64_t *base = lists + (sched.slot_base(mt) * esets * tile_rows + r) * KP;
+    const int64_t piece_stride = (int64_t)tile_rows * KP;
+    const int n_lists = sched.pieces(mt) * esets;
+    uint64_t L[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) L[rr] = 0ull;
+    for (int l = w; l < n_lists; l += 8) {
+        const uint64_t *p = base + l * piece_stride;
+        uint64_t M[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) M[rr] = __ldg(p + (KP - 1 - (32 * rr + lane)));   // reversed read
+        warp_merge_topk_desc<R>(L, M, lane);
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) part[w][32 * rr + lane] = L[rr];
+    __syncthreads();
+    if (w != 0) return;
+    auto ptr = [&](int l) { return (const uint64_t *)part[l]; };
+    // (merge_query reads with __ldg semantics on generic pointers: shared memory is fine for plain loads)
+    uint64_t F[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) F[rr] = 0ull;
+    for (int l = 0; l < 8; ++l) {
+        const uint64_t *p = ptr(l);
+        uint64_t M[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) M[rr] = p[KP - 1 - (32 * rr + lane)];
+        warp_merge_topk_desc<R>(F, M, lane);
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+        const int t = 32 * rr + lane;
+        if (t < k_out) {
+            const uint64_t cnd = F[rr];
+            if (out_idx) out_idx[q * k_out + t] = candidate_index(cnd);
+            if (out_score) out_score[q * k_out + t] = (double)key_score(candidate_key(cnd), higher);
+            if (out_cand) out_cand[q * k_out + t] = cnd;
+        }
+    }
+}
+
 cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t list_stride, int64_t row_stride,
                                  int64_t nq, int k_in, int k_out, bool higher, uint32_t *out_idx,
                                  double *out_score, uint64_t *out_cand, cudaStream_t s) {
@@ -90,6 +145,17 @@ cudaError_t launch_merge_regular(const uint64_t *lists, int64_t n_lists, int64_t
 cudaError_t launch_merge_tiles(const uint64_t *lists, TcSchedule sched, int cg, int esets, int kp, int64_t nq, int k_out, bool higher,
                                uint32_t *out_idx, double *out_score, uint64_t *out_cand, cudaStream_t s) {
     if (nq <= 0 || k_out <= 0) return cudaSuccess;
+    // few queries, many pieces each (re-query launches): one block per query
+    const int max_lists = (sched.g > sched.g_rem ? sched.g : sched.g_rem) * esets;
+    if (max_lists >= 16 && nq <= 8192) {
+        const unsigned bg = (unsigned)nq;
+        if (kp == 32) merge_tiles_block_kernel<1><<<bg, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
+        else if (kp == 64) merge_tiles_block_kernel<2><<<bg, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
+        else if (kp == 128) merge_tiles_block_kernel<4><<<bg, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
+        else if (kp == 256) merge_tiles_block_kernel<8><<<bg, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    }
     unsigned grid = (unsigned)((nq + 7) / 8);
     if (kp == 32)
         merge_tiles_kernel<1><<<grid, 256, 0, s>>>(lists, sched, cg, esets, nq, k_out, higher, out_idx, out_score, out_cand);

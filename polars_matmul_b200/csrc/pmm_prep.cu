@@ -183,16 +183,17 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Fast path of the plane modes for the common layout: fixed-size rows, no bitmaps, f32 working precision, row length a
-// multiple of 32 (f32 source) / 64 (f16 source), 16-byte aligned rows.  Same thread mapping (8 lanes per row, lane j owns
-// partial sum p_j) and therefore the same norm bits as prep_kernel, but every lane moves 16 bytes at a time: one 128-bit
-// load per lane covers a 128-byte line of the row, the plane stores are 8 (f16 from f32), 16 (f16 copy) or 2 x 16 bytes
-// (TF32 hi/lo) per lane instead of 2- / 4-byte scalars, and the elements a lane needs for ITS residue class come back
-// through a per-warp shared-memory tile (the line is written as loaded and read back transposed).
+// multiple of 64, 16-byte aligned rows.  Same thread mapping (8 lanes per row, lane j owns partial sum p_j) and therefore
+// the same norm bits as prep_kernel, but every lane moves 8 consecutive elements at a time: 128-bit loads, and plane stores
+// of 16 bytes per lane (f16 plane: the 8 lanes of a row write one whole 128-byte line per step; TF32 hi/lo: 256 bytes each)
+// instead of 2- / 4-byte scalars; the elements a lane needs for ITS residue class come back through a per-warp
+// shared-memory tile (the piece is written as loaded and read back transposed).
 template <typename SRC, int MODE>
 __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
-    constexpr int EPL = 16 / (int)sizeof(SRC);          // elements per lane and step: 4 (f32) or 8 (f16)
-    constexpr int STEP = 8 * EPL;                       // elements per row and step: 32 or 64
+    constexpr int EPL = 8;                              // elements per lane and step: 32 bytes of f32 or 16 bytes of f16
+    constexpr int STEP = 8 * EPL;                       // 64 elements per row and step: 256 / 128 bytes, whole lines
     constexpr int PITCH = STEP + 8;                     // floats per tile row: rows start 8 banks apart
+    constexpr int NL = sizeof(SRC) == 4 ? 2 : 1;        // 16-byte loads per lane and step
     __shared__ __align__(16) float tiles[8][2][4][PITCH];   // per warp: double-buffered 4-row tile (as floats)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, rw = lane >> 3;
@@ -208,27 +209,40 @@ __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
     bool bad = false;
     int buf = 0;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    // one 16-byte piece of the row (already loaded) at element offset t: planes + this lane's share of the norm
-    auto process = [&](const uint4 raw, int64_t t) {
+    struct Piece {
+        uint4 v[NL];
+    };
+    auto load = [&](int64_t t) {   // this lane's 8 consecutive elements [t + 8 sub, t + 8 sub + 8) of the row
+        Piece pc;
+        const uint4 *s16 = (const uint4 *)(src + t + EPL * sub);
+#pragma unroll
+        for (int u = 0; u < NL; ++u) pc.v[u] = live ? __ldg(s16 + u) : zero4;
+        return pc;
+    };
+    // one piece of the row (already loaded) at element offset t: planes + this lane's share of the norm
+    auto process = [&](const Piece &pc, int64_t t) {
         float x[EPL];
         if (sizeof(SRC) == 4) {
-            x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y); x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
+#pragma unroll
+            for (int u = 0; u < NL; ++u) {
+                x[4 * u] = __uint_as_float(pc.v[u].x); x[4 * u + 1] = __uint_as_float(pc.v[u].y);
+                x[4 * u + 2] = __uint_as_float(pc.v[u].z); x[4 * u + 3] = __uint_as_float(pc.v[u].w);
+            }
         } else {
-            const __half2 *h2 = (const __half2 *)&raw;
+            const __half2 *h2 = (const __half2 *)&pc.v[0];
 #pragma unroll
             for (int u = 0; u < EPL / 2; ++u) {
                 const float2 f = __half22float2(h2[u]);
                 x[2 * u] = f.x;
                 x[2 * u + 1] = f.y;
             }
-            if (MODE == MODE_F16) *((uint4 *)(hp + t) + sub) = raw;   // exact plane of f16 input: the line as loaded
+            if (MODE == MODE_F16) *((uint4 *)(hp + t) + sub) = pc.v[0];   // exact plane of f16 input: the line as loaded
         }
         if (MODE == MODE_F16R || (MODE == MODE_F16 && sizeof(SRC) == 4)) {
-            __half2 h[EPL / 2];
+            __half2 h[EPL / 2];   // 8 halves = 16 bytes per lane: the 8 lanes of a row write one whole 128-byte line
 #pragma unroll
             for (int u = 0; u < EPL / 2; ++u) h[u] = __floats2half2_rn(x[2 * u], x[2 * u + 1]);
-            if (EPL == 4) *((uint2 *)(hp + t) + sub) = *(const uint2 *)h;
-            else *((uint4 *)(hp + t) + sub) = *(const uint4 *)h;
+            *((uint4 *)(hp + t) + sub) = *(const uint4 *)h;
         } else if (MODE == MODE_TF32) {
             float h4[EPL], l4[EPL];
 #pragma unroll
@@ -254,25 +268,16 @@ __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
         }
         buf ^= 1;   // (no second barrier: the next piece writes the OTHER buffer, the one after that is behind the next __syncwarp)
     };
-    const uint4 *src16 = (const uint4 *)src;   // row as 16-byte pieces: piece index = (t / EPL) + sub
     int64_t t = 0;
-    for (; t + 4 * STEP <= dim; t += 4 * STEP) {   // four 128-byte lines of the row in flight per lane group
-        uint4 r[4];
+    for (; t + 4 * STEP <= dim; t += 4 * STEP) {   // four pieces (1 KB of f32 per row) in flight per lane group
+        Piece r[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) r[u] = live ? __ldg(src16 + (t + u * STEP) / EPL + sub) : zero4;
+        for (int u = 0; u < 4; ++u) r[u] = load(t + u * STEP);
 #pragma unroll
         for (int u = 0; u < 4; ++u) process(r[u], t + u * STEP);
     }
-    for (; t < dim; t += STEP) process(live ? __ldg(src16 + t / EPL + sub) : zero4, t);
-    for (int64_t i = dim + 8 * sub; i < ld; i += 64) {   // zero the padding columns (ld - dim is 0 or 32 here)
-        if (MODE == MODE_TF32) {
-#pragma unroll
-            for (int u = 0; u < 8 && i + u < ld; ++u) { hi[i + u] = 0.0f; lo[i + u] = 0.0f; }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 8 && i + u < ld; ++u) hp[i + u] = __float2half_rn(0.0f);
-        }
-    }
+    for (; t < dim; t += STEP) process(load(t), t);
+    // (dim is a multiple of 64 here, and so is every plane's leading dimension: no padding columns to zero)
     // (p0+p4), (p1+p5), (p2+p6), (p3+p7) then a sequential sum, as ndarray's unrolled_dot (no tail: dim % 8 == 0)
     const int gbase = lane & 24;
     const float other = __shfl_sync(gmask, p, gbase + ((sub + 4) & 7));
@@ -307,9 +312,9 @@ __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
 
 template <typename SRC>
 static bool prep_fast_ok(const PrepArgs &a) {
-    const int step = 8 * (16 / (int)sizeof(SRC));
+    const int step = 64;
     return !a.offsets && !a.validity && !a.row_validity && !a.norm32_out && !a.sqnorm32_out && a.dim > 0 && (a.dim % step) == 0 &&
-           (a.ld_out % 8) == 0 && (((uintptr_t)a.values) & 15) == 0 && (((uintptr_t)a.out0) & 15) == 0 && (((uintptr_t)a.out1) & 15) == 0;
+           a.ld_out == a.dim && (((uintptr_t)a.values) & 15) == 0 && (((uintptr_t)a.out0) & 15) == 0 && (((uintptr_t)a.out1) & 15) == 0;
 }
 
 template <typename SRC, int MODE>

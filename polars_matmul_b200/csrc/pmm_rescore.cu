@@ -500,6 +500,87 @@ cudaError_t launch_rescore_f64(const uint64_t *cand, int kp_in, const RawMatrix 
     return cudaGetLastError();
 }
 
+// ---- multi-pass top-k (k > 248) ----------------------------------------------------------------------------------
+__global__ void next_ceilings_kernel(const uint64_t *__restrict__ kept, int kp, int64_t nq, int64_t n_pad, uint64_t *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    out[r] = r < nq ? kept[r * kp + kp - 1] : 0ull;
+}
+cudaError_t launch_next_ceilings(const uint64_t *kept, int kp, int64_t nq, int64_t n_pad, uint64_t *ceil_out, cudaStream_t s) {
+    if (n_pad <= 0) return cudaSuccess;
+    next_ceilings_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(kept, kp, nq, n_pad, ceil_out);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) sort_lists_kernel(const uint64_t *__restrict__ lists, int n_lists, int64_t list_stride, int kp, int npad,
+                                                         int k_out, int metric, const uint64_t *__restrict__ kept_last, uint32_t *out_idx,
+                                                         double *out_score, uint64_t *out_cand, RescoreCheck chk) {
+    extern __shared__ __align__(16) unsigned char sl_smem[];
+    uint64_t *buf = (uint64_t *)sl_smem;
+    const int64_t q = blockIdx.x;
+    const int t = threadIdx.x, n = n_lists * kp;
+    const bool higher = higher_is_better(metric);
+    for (int i = t; i < npad; i += 256) buf[i] = i < n ? lists[(int64_t)(i / kp) * list_stride + q * kp + (i % kp)] : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = t; i < npad; i += 256) {
+                const int p = i ^ stride;
+                if (p > i) {
+                    const bool desc = (i & size) == 0;
+                    const uint64_t a = buf[i], b = buf[p];
+                    if ((a > b) != desc) { buf[i] = b; buf[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (t == 0 && chk.flags) {
+        // everything dropped by ALL passes has a filter value <= the last pass's worst kept one (0: its list did not
+        // fill, i.e. every candidate that exists was collected)
+        const uint64_t last = kept_last[q * kp + kp - 1];
+        bool ok = true;
+        if (last != 0ull && k_out > 0) {
+            const float f_last = key_score(candidate_key(last), true);
+            const float tk = key_score(candidate_key(buf[k_out - 1]), higher);
+            const float qn = sqrtf(chk.q_sq[q]);
+            const float cmax = sqrtf(__uint_as_float(chk.c_max_sq[0])), cmin = sqrtf(__uint_as_float(chk.c_max_sq[1]));
+            const float e = filter_error_bound(chk.eps, chk.abs_err, metric, qn, cmax, cmin);
+            if (metric == METRIC_DOT) {
+                ok = tk > f_last + e;
+            } else if (metric == METRIC_COSINE) {
+                ok = qn > 1e-6f && tk > (f_last + e) / qn;
+            } else {
+                const float sq_floor = -f_last - e;
+                ok = sq_floor > 0.0f && tk < sqrtf(sq_floor) * (1.0f - 1e-6f);
+            }
+            if (chk.max_norm > 0.0f && !(qn <= chk.max_norm && cmax <= chk.max_norm)) ok = false;
+            if (!(ok)) ok = false;
+        }
+        if (!ok) {
+            chk.flags[q] = 1;
+            atomicAdd(chk.flag_count, 1u);
+        }
+    }
+    for (int i = t; i < k_out; i += 256) {
+        const uint64_t r = buf[i];
+        if (out_idx) out_idx[q * k_out + i] = candidate_index(r);
+        if (out_score) out_score[q * k_out + i] = (double)key_score(candidate_key(r), higher);
+        if (out_cand) out_cand[q * k_out + i] = r;
+    }
+}
+cudaError_t launch_sort_lists(const uint64_t *lists, int n_lists, int64_t list_stride, int kp, int64_t nq, int k_out, int metric,
+                              const uint64_t *kept_last, uint32_t *out_idx, double *out_score, uint64_t *out_cand,
+                              const RescoreCheck &chk, cudaStream_t s) {
+    if (nq <= 0 || k_out <= 0) return cudaSuccess;
+    int npad = 64;
+    while (npad < n_lists * kp) npad <<= 1;
+    if (npad > 4096 || k_out > n_lists * kp) return cudaErrorInvalidValue;
+    sort_lists_kernel<<<(unsigned)nq, 256, (size_t)npad * 8, s>>>(lists, n_lists, list_stride, kp, npad, k_out, metric, kept_last, out_idx,
+                                                                  out_score, out_cand, chk);
+    return cudaGetLastError();
+}
+
 // ---- seeds of a re-query level --------------------------------------------------------------------------------
 // A flagged query's exact k-th score t (from the candidates the previous level kept) is a LOWER bound of its true
 // k-th score, so a candidate that belongs to the top k (or ties into it) has an exact score >= t and therefore a

@@ -111,6 +111,7 @@ struct TcKParams {
     int max_flush;   // row merges per warp at the end of a tile (rate limit; rows above URGENT_AT always go)
     float norm_guard;       // cosine: norms at or below this count as zero (1e-6 f32; just under 1e-10 for f64 sources)
     const float *seed_thr;  // per query row (padded like q_aux): initial threshold in filter units, NaN = none; or NULL
+    const uint64_t *ceil;   // per query row (padded): only candidates strictly BELOW this packed value are admitted; or NULL
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
@@ -230,7 +231,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t a
                                              uint32_t look_s /* shared address: the warp's 32 x LOOK_PITCH floats */, float rowc,
                                              int64_t col0, int64_t n, int64_t index_base, uint64_t *stg /* warp's staging rows */,
                                              uint64_t *list_base, int lane, int k, uint64_t &thr, float &thr_f, int &cnt,
-                                             uint64_t seed_c) {
+                                             uint64_t seed_c, uint64_t ceil_c) {
     float f[32];
 #pragma unroll
     for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -273,7 +274,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint32_t a
             const int64_t col = col0 + j;
             if (col < n) {
                 const uint64_t cand = pack_candidate(score_key(fv, true), (uint32_t)(index_base + col));
-                if (cand > thr) {
+                if (cand > thr && cand < ceil_c) {   // (ceil_c: multi-pass top-k, "the next 256 below what is already kept")
                     stg[lane * SC + cnt] = cand;
                     ++cnt;
                 }
@@ -576,7 +577,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             unsigned rot = 0;
             const int max_flush = p.max_flush;
             float rowc = 0.0f;
-            uint64_t seed_c = 0ull;
+            uint64_t seed_c = 0ull, ceil_c = ~0ull;
             uint64_t *list_base = nullptr;
             if (EPI == EPI_TOPK) {
                 constexpr int KP = 32 * R;
@@ -588,6 +589,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     thr = kth;
                     thr_f = kth == 0ull ? __uint_as_float(0x7fc00000u) : key_score(candidate_key(kth), true);
                 }
+                if (p.ceil) ceil_c = p.ceil[qrow];
                 if (p.seed_thr) {  // "collect everything above this filter value" (NaN: no seed for this row)
                     const float sf = p.seed_thr[qrow];   // padded to the tile grid like q_aux
                     if (sf == sf) seed_c = pack_candidate(score_key(sf, true), 0xffffffffu);
@@ -659,13 +661,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         }
                     } else if (p.metric == METRIC_DOT) {
                         filter_chunk<METRIC_DOT, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane, kk,
-                                                    thr, thr_f, cnt, seed_c);
+                                                    thr, thr_f, cnt, seed_c, ceil_c);
                     } else if (p.metric == METRIC_COSINE) {
                         filter_chunk<METRIC_COSINE, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base, lane,
-                                                       kk, thr, thr_f, cnt, seed_c);
+                                                       kk, thr, thr_f, cnt, seed_c, ceil_c);
                     } else {
                         filter_chunk<METRIC_EUCLIDEAN, R>(v, aux_sa + (ch - ch0) * 128, look_sa, rowc, col0, p.n, p.index_base, stg, list_base,
-                                                          lane, kk, thr, thr_f, cnt, seed_c);
+                                                          lane, kk, thr, thr_f, cnt, seed_c, ceil_c);
                     }
                 }
                 if (edbg && lane == 0)
@@ -821,6 +823,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.debug_skip = a.debug_skip;
     p.resume = a.resume;
     p.seed_thr = a.seed_thr;
+    p.ceil = a.ceil;
     p.norm_guard = a.norm_guard > 0.0f ? a.norm_guard : 1e-6f;
     p.soft_at = a.soft_at > 0 ? a.soft_at : SOFT_AT;
     // merges that fit beside one tile's MMA time: a merge costs about as much as 8 k-blocks of one plane

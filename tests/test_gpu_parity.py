@@ -124,6 +124,56 @@ def test_generic_path_large_k_and_clamp(native, oracle):
         parity.check_topk(idx, sc, q2, c2, k, metric, oracle, exact=True)
 
 
+def test_large_k_runs_several_fused_passes(native, oracle):
+    """248 < k <= 2000 (f32): P passes of the fused filter with 256-entry lists, pass p+1 restricted to candidates below
+    the worst one pass p kept; all 256 P candidates re-scored exactly, sorted as one, proven against the last pass.
+    No score slab (the select kernel never runs); beyond 2000 the slab path takes over. Always the oracle's answer."""
+    rng = np.random.default_rng(81)
+    q, c = _randn(rng, 150, 80), _randn(rng, 30_000, 80)
+    c[rng.integers(0, 30_000, size=600)] = c[rng.integers(0, 30_000, size=600)]      # exact ties at arbitrary ranks
+    for metric, k, passes in (("dot", 249, 2), ("cosine", 1000, 4), ("euclidean", 600, 3), ("dot", 2000, 8)):
+        native.reset_stats()
+        native.set_option("profile", 1)
+        try:
+            idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+            assert native.get_stat("tc_topk_f16r_kp256_launches") == passes, (k, native.get_stat("tc_topk_f16r_kp256_launches"))
+            assert native.get_stat("sort_lists_launches") == 1
+            # the score-slab kernels run only for queries the proof hands to the exact fallback (ties beyond the lists)
+            assert native.get_stat("select_f32_launches") == (1 if native.get_stat("fallback_queries") > 0 else 0)
+        finally:
+            native.set_option("profile", 0)
+        parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+    native.set_option("profile", 1)
+    native.reset_stats()
+    try:
+        idx, sc = native.topk(_hm(q[:20]), _hm(c), 2001, "dot")                       # beyond the multi-pass range: slab path
+        assert native.get_stat("select_f32_launches") >= 1
+    finally:
+        native.set_option("profile", 0)
+    parity.check_topk(idx, sc, q[:20], c, 2001, "dot", oracle, exact=True)
+    # massive duplication: more exact ties than all passes collect -> the proof fails -> exact fallback, lower index first
+    base = _randn(rng, 3, 80)
+    cd = np.concatenate([base[rng.integers(0, 3, size=4000)], _randn(rng, 500, 80)])
+    native.reset_stats()
+    idx, sc = native.topk(_hm(q[:16]), _hm(cd), 300, "cosine")
+    assert native.get_stat("fallback_queries") > 0
+    parity.check_topk(idx, sc, q[:16], cd, 300, "cosine", oracle, exact=True)
+    # the resident handle serves large k from the same planes
+    h = native.ResidentCorpus(_hm(c), native.DTYPE_F32)
+    try:
+        i2, s2 = h.topk(_hm(q), 500, "dot")
+    finally:
+        h.close()
+    parity.check_topk(i2, s2, q, c, 500, "dot", oracle, exact=True)
+    # switched off: the slab path, same answer
+    native.set_option("multipass", 0)
+    try:
+        i3, s3 = native.topk(_hm(q), _hm(c), 500, "dot")
+    finally:
+        native.set_option("multipass", 1)
+    assert np.array_equal(i3, i2) and np.array_equal(s3, s2)
+
+
 def test_f64_path(native, oracle):
     rng = np.random.default_rng(9)
     q, c = _randn(rng, 64, 64, dtype=np.float64), _randn(rng, 2000, 64, dtype=np.float64)
@@ -580,6 +630,15 @@ def test_host_chunked_upload_path(pmm, native, oracle):
         native.set_option("host_chunked", 1)
     i1, s1 = native.topk(_hm(q), _hm(c), 20, "cosine")
     assert np.array_equal(i0, i1) and np.array_equal(s0, s1)
+    # f64 working precision takes the same overlapped path (f16-rounded planes for the filter, exact f64 norms and
+    # re-scoring): 74 MB of f64 rows, and an f32 corpus queried with f64 vectors
+    c64 = c[:48_000].astype(np.float64)
+    q64 = q.astype(np.float64)
+    for metric in ("cosine", "euclidean"):
+        idx, sc = native.topk(_hm(q64), _hm(c64), 20, metric)
+        parity.check_topk(idx, sc, q64, c64, 20, metric, oracle, exact=True)
+    idx, sc = native.topk(_hm(q64), _hm(c), 20, "dot")
+    parity.check_topk(idx, sc, q64, c.astype(np.float64), 20, "dot", oracle, working_dtype=np.float64, exact=True)
     # list layout: offsets + a null row + a null element + a short row, spread over both chunks
     flat = pa.array(c.reshape(-1))
     offsets = np.arange(0, (c.shape[0] + 1) * 192, 192, dtype=np.int64)
