@@ -258,6 +258,53 @@ def hbm_extras(_native, torch, peaks):
                                                      "hbm" if (t_tc is None or t_hbm >= t_tc) else "tensor"),
                                 "frac_tensor": (tf / tensor_peak) if tensor_peak else None}
         del a, b, o
+    # FP64 peak of the box (cuBLAS DGEMM through torch; MEASURED_PEAKS.json has no f64 figure) -> fraction for the DMMA matmul
+    try:
+        a64 = torch.randn((6144, 6144), generator=g, device="cuda", dtype=torch.float64)
+        b64 = torch.randn((6144, 6144), generator=g, device="cuda", dtype=torch.float64)
+        torch.matmul(a64, b64)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(3):
+            e0.record()
+            torch.matmul(a64, b64)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        fp64_peak = 2.0 * 6144 ** 3 / best / 1e9
+        out["fp64_tflops_cublas_6144"] = fp64_peak
+        m64 = out["matmul"].get("C2_f64_1000x10000x256")
+        if m64:
+            m64["frac_fp64_cublas"] = m64["TFLOPs"] / fp64_peak
+        del a64, b64
+    except Exception as ex:
+        out["fp64_tflops_cublas_6144"] = repr(ex)
+    # f64 top-k (what Polars hands the reference by default): fused filter on f16-rounded operands + exact f64 re-scoring,
+    # no Q x N slab. Round 1: 12.1 ms per step at this shape on the slab path.
+    try:
+        Q6, N6, D6, k6 = 2000, 100_000, 256, 10
+        q6 = torch.randn((Q6, D6), generator=g, device="cuda", dtype=torch.float64)
+        c6 = torch.randn((N6, D6), generator=g, device="cuda", dtype=torch.float64)
+        i6 = torch.empty((Q6, k6), dtype=torch.int32, device="cuda")
+        s6 = torch.empty((Q6, k6), dtype=torch.float64, device="cuda")
+        fn6 = lambda: _native.dev_topk(_native.dev_matrix(q6.data_ptr(), Q6, D6, 2), _native.dev_matrix(c6.data_ptr(), N6, D6, 2), k6, 0,
+                                       index_ptr=i6.data_ptr(), score_ptr=s6.data_ptr(), stream=st)
+        for _ in range(3):
+            fn6()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn6()
+        e1.record()
+        torch.cuda.synchronize()
+        r6 = run(fn6, ("prep", "tc_topk_f16r", "rescore_f64", "merge", "scores_f64_dmma", "select_f64"))
+        out["f64_topk_2000x100000x256_cosine_k10"] = {"step_ms": e0.elapsed_time(e1) / 10, "per_kernel_ms": r6,
+                                                      "round1_step_ms": 12.1, "path": "tcgen05 filter (f16-rounded planes) + exact f64 re-scoring"}
+        del q6, c6
+    except Exception as ex:
+        out["f64_topk_2000x100000x256_cosine_k10"] = {"error": repr(ex)}
     for (N, D, dt) in ((1_000_000, 768, torch.float32), (4_000_000, 256, torch.float32), (1_000_000, 1024, torch.float16)):
         x = torch.randn((N, D), generator=g, device="cuda", dtype=torch.float32).to(dt)
         o = torch.empty(N, dtype=torch.float32, device="cuda")

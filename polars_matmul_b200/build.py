@@ -40,11 +40,11 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
-    objs = []
+    objs, todo = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
@@ -53,8 +53,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
+            todo.append(cmd)
+    if todo:   # the translation units are independent: compile them side by side (the tensor-core file dominates)
+        from concurrent.futures import ThreadPoolExecutor
+        jobs = jobs or min(len(todo), os.cpu_count() or 1)
+
+        def run(cmd):
+            if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
+
+        with ThreadPoolExecutor(max_workers=max(1, jobs)) as ex:
+            list(ex.map(run, todo))
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++",
                "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-ldl", "-lpthread"]

@@ -1358,13 +1358,14 @@ cudaStream_t copy_stream() {
     return s;
 }
 
-// Host top-k on the tensor-core path with the corpus upload overlapped with compute (north_star item 5:
-// the Arrow buffer feeds H2D copies directly). The corpus is cut into row chunks; chunk i+1 is copied on
-// a second stream while chunk i runs prep + the fused filter; the per-chunk candidate lists are merged
-// and re-scored once against the whole (now resident) corpus. A small first chunk starts the tensor
-// cores early; the rest of the upload hides behind it.
-// Outputs: host index/score buffers and/or exact packed candidates left on the device (d_cand, for the
-// multi-GPU exchange); corpus row j is reported as index_base + j.
+// Host top-k on the tensor-core path with the corpus upload overlapped with compute (north_star item 5: the Arrow
+// buffer feeds the H2D copies directly - through the page-locked staging ring when it is pageable).  The corpus is cut
+// into row chunks; chunk i+1 is copied on a second stream while chunk i runs prep + the fused filter.  The candidate
+// lists are CARRIED from launch to launch (TcCarry), so nothing is merged across chunks and only the first chunk pays
+// the list warm-up; every chunk is prepared into its slice of whole-corpus plane buffers, so the re-query levels find the
+// full planes afterwards; the kept candidates are re-scored once against the whole (now resident) corpus.
+// Outputs: host index/score buffers and/or exact packed candidates left on the device (d_cand, for the multi-GPU
+// exchange); corpus row j is reported as index_base + j.
 // Sustained algorithmic FLOP/s of the first filter level on f32 planes (TF32 x1 with two levels, else 3xTF32).
 double terms0_rate(int mode) { return (mode == PREP_TF32 && t_opt.tc_levels >= 2 && t_opt.tc_cg == 2) ? 7.5e14 : 2.6e14; }
 
@@ -1393,10 +1394,10 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     const int64_t Q = queries->n_rows, N = corpus->n_rows, D = corpus->dim;
     const int es = esize(corpus->dtype);
     // Chunk boundaries in rows (multiples of 256 so bitmaps can be re-based by whole bytes).  The filter of chunk i
-    // runs while chunk i+1 is copied, so only the first copy is exposed: start small (N/16) and let the chunks grow
-    // by the ratio of filter time to copy time per row (2 Q / tensor rate vs element size / PCIe rate, about 3.5 at
-    // Q = 100k f32), so that each copy finishes just before the filter wants it.  Copy-bound shapes (few queries)
-    // get equal chunks instead.
+    // runs while chunk i+1 is copied, so only the first copy is exposed: start small (N/32) and let the chunks grow
+    // by the ratio of filter time to copy time per row (2 Q / tensor rate vs element size / host-link rate: about 1.6
+    // at Q = 100k f32 from page-locked memory, below 1 through the staging ring), the first term of a geometric series
+    // of at most eight chunks that sums to N.  Copy-bound shapes (few queries, pageable sources) get equal chunks.
     const bool copy_up_front = !stage_enabled() || host_ptr_is_pinned(first_host_values(corpus));
     std::vector<int64_t> cut{0};
     {
