@@ -562,7 +562,10 @@ def main():
             t = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             h2d, d2h = float(t[0].item()), float(t[1].item())
-            bytes_note = "; bytes are whole-job totals over all ranks (the replicated queries cross ONE host link and are broadcast over NVLink; every rank reads back only its query slice)"
+            bytes_note = ("; bytes are whole-job totals over all ranks (the replicated queries cross ONE host link and are broadcast over NVLink; "
+                          "every rank reads back only its query slice). With pageable inputs the ranks share ONE host: every staged byte is read, "
+                          "written to the ring and read again by the DMA engine, so the leg is bound by host-memory bandwidth, not by the GPUs "
+                          "(pinned_inputs shows the same leg without the staging copy)")
         e2e = {"value": world * Q / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "inputs": "pageable",
                "staged_h2d_bytes_per_step_rank0": int(staged),
