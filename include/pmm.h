@@ -323,6 +323,8 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *   "stage_threads"            host threads per staged copy (0 = auto: half the cores, at most 8)
  *   "stage_slot_mb", "stage_slots"   ring geometry (default 4 slots of 32 MB per calling thread)
  *   "prep_fast" (0/1, default 1)  128-bit loads / stores in the plane-building pass where the layout allows
+ *   "rescore_fixed" (0/1, default 0)  cp.async gather in the exact re-scoring of plain f32 corpora (faster kernel, slower
+ *                              step on a power-capped part: profiles/sweep_r2.md)
  *   "workspace_cache_mb"       device blocks (>= 32 MB) a thread keeps parked between calls for reuse (default 24576)
  *   "release_workspace"        return the calling thread's parked device blocks and its staging ring
  * Unknown keys return PMM_ERR_INVALID. */

@@ -2163,6 +2163,7 @@ static int immediate_option(const std::string &k, int64_t value) {
     }
     if (k == "workspace_cache_mb") { g_block_cache_cap_mb.store(value < 0 ? 0 : value); return 1; }
     if (k == "prep_fast") { prep_set_fast(value != 0); return 1; }
+    if (k == "rescore_fixed") { rescore_set_fixed(value != 0); return 1; }
     if (k == "stage") { stage_set_enabled(value != 0); return 1; }
     if (k == "stage_threads") { stage_set_threads((int)value); return 1; }
     if (k == "stage_slot_mb") { stage_set_ring((size_t)(value < 1 ? 1 : value) << 20, g_stage_slots.load()); g_stage_slot_mb.store(value < 1 ? 1 : value); return 1; }

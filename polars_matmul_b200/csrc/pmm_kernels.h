@@ -119,6 +119,7 @@ cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm,
                            const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
                            uint32_t *out_idx, double *out_score, uint64_t *out_cand, const RescoreCheck &chk,
                            cudaStream_t s);
+void rescore_set_fixed(bool on);   // cp.async gather of the re-scoring for plain f32 corpora (default on)
 // Seeds for a re-query level: out[r] = kth_units[ids[r]] - E_next(query) - margin for r < n_ids, NaN for the padding
 // rows [n_ids, n_pad).  `next` carries the NEXT level's eps / abs_err / max_norm and the norm inputs.
 cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, const float *kth_units,

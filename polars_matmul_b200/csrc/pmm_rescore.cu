@@ -67,7 +67,26 @@ __device__ __forceinline__ void gather_step(float (&x)[32], const RawMatrix &cm,
     }
 }
 
-template <typename CSRC, int NT>
+// FIXED (f32 corpus, fixed-size rows, no bitmaps, dim % 4 == 0, 16-byte aligned rows - the C3 / C4 case): the gather runs
+// on cp.async.  Eight lanes copy one 128-byte line of a candidate row (16 bytes each) straight into the warp's
+// shared-memory tile, so ONE instruction moves the lines of four candidates and a lane only ever needs the row pointers
+// of its own 8 candidates - they live in registers.  Per 32-element step a warp issues 8 copies instead of 32 loads +
+// 64 shared-memory reads of row offsets + 32 stores: about 80 instead of 280 instructions.  Two tile stages per warp keep
+// the next step's lines in flight under the FMAs.  Measured at C3 (profiles/sweep_r2.md): the kernel itself gets faster
+// (9.8 -> 9.2 ms in the step) but the NEXT step's filter launch slows down by more (112.5 -> 114.7 ms) - the part runs
+// against its power cap and the denser re-scoring eats the headroom the filter starts with - so the step is 1.3-1.8 ms
+// SLOWER.  Kept behind pmm_set_option("rescore_fixed", 1), off by default.
+constexpr int RS_STAGES = 2;
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src, unsigned src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename CSRC, int NT, bool FIXED = false>
 __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict__ cand, int kp_in, RawMatrix qm,
                                                      RawMatrix cm, const float *__restrict__ q_aux,
                                                      const float *__restrict__ c_aux, int metric,
@@ -127,7 +146,49 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     unsigned char *tile_base = rs_smem + NT * 12 + (size_t)((dim + 3) & ~3) * 4;
     // f16 rows without nulls: 64 elements per step, one half2 per lane (128-byte requests per row)
     const bool wide16 = sizeof(CSRC) == 2 && !cm.offsets && !cm.validity && (dim & 1) == 0;
-    if (wide16) {
+    if (FIXED) {
+        float (*tiles)[32][RS_PITCH32] = (float (*)[32][RS_PITCH32])(tile_base + (size_t)wrp * RS_STAGES * 32 * RS_PITCH32 * 4);
+        const int seg = lane & 7, cgrp = lane >> 3;       // my 16-byte segment of a line; my candidates are 4 j + cgrp
+        const char *rp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rp[j] = (const char *)cm.values + (size_t)rowb[w0 + 4 * j + cgrp] * 4 + seg * 16;
+        const int n_steps = (dim + 31) >> 5;
+        auto issue = [&](int step, int stage) {
+            const int e0 = step * 32 + seg * 4;             // first element of my segment (dim % 4 == 0: all or nothing)
+            const unsigned sz = e0 < dim ? 16u : 0u;        // beyond the row: zero fill, nothing is read
+            const size_t off = sz ? (size_t)step * 128 : 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (4 * j + cgrp < n_act) cp_async_16(smem_addr(&tiles[stage][4 * j + cgrp][seg * 4]), rp[j] + off, sz);
+            cp_async_commit();
+        };
+        issue(0, 0);
+        for (int step = 0; step < n_steps; ++step) {
+            const int d0 = step * 32;
+            if (step + 1 < n_steps) {
+                issue(step + 1, (step + 1) & 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const float (*tile)[RS_PITCH32] = tiles[step & 1];
+            const int jn = dim - d0 < 32 ? dim - d0 : 32;
+            if (jn == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 qv = *(const float4 *)&qs[d0 + j], cv = *(const float4 *)&tile[lane][j];
+                    acc = __fmaf_rn(qv.x, cv.x, acc);
+                    acc = __fmaf_rn(qv.y, cv.y, acc);
+                    acc = __fmaf_rn(qv.z, cv.z, acc);
+                    acc = __fmaf_rn(qv.w, cv.w, acc);
+                }
+            } else {
+                for (int j = 0; j < jn; ++j) acc = __fmaf_rn(qs[d0 + j], tile[lane][j], acc);
+            }
+            __syncwarp();   // the stage is overwritten by the copies of step + 2
+        }
+    } else if (wide16) {
         // the tile keeps the rows as f16 pairs (36-word pitch like the f32 tile: half the shared memory and registers
         // of an upcast tile, so more blocks are resident); the upcast happens at the FMA
         __half2 (*tileh)[RS_PITCH32] = (__half2 (*)[RS_PITCH32])(tile_base + (size_t)wrp * 32 * RS_PITCH32 * 4);
@@ -281,6 +342,9 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const uint64_t *__restrict_
     }
 }
 
+static bool g_rescore_fixed = false;  // rescore_set_fixed(): off by default - see the note at rescore_kernel (measured: no net gain)
+void rescore_set_fixed(bool on) { g_rescore_fixed = on; }
+
 template <typename CSRC>
 static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMatrix &qm, const RawMatrix &cm,
                                     const float *q_aux, const float *c_aux, int metric, int64_t index_base, int k_out,
@@ -288,21 +352,29 @@ static cudaError_t launch_rescore_t(const uint64_t *cand, int kp_in, const RawMa
                                     cudaStream_t s) {
     const unsigned grid = (unsigned)qm.n_rows;
     const size_t smem_q = (size_t)((qm.dim + 3) & ~(int64_t)3) * 4;
-#define PMM_RS(NT)                                                                                                  \
+    const bool fixed = sizeof(CSRC) == 4 && g_rescore_fixed && !cm.offsets && !cm.validity && !cm.row_validity && (cm.dim % 4) == 0 &&
+                       (((uintptr_t)cm.values) & 15) == 0;
+#define PMM_RS_LAUNCH(NT, FX, TILES)                                                                                 \
     {                                                                                                               \
-        size_t smem = NT * 12 + smem_q + (size_t)(NT / 32) * 32 * RS_PITCH32 * 4;                                                                              \
+        size_t smem = NT * 12 + smem_q + (size_t)(NT / 32) * (TILES) * 32 * RS_PITCH32 * 4;                         \
         if (smem > 48 * 1024) {                                                                                     \
-            cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaError_t e = cudaFuncSetAttribute(rescore_kernel<CSRC, NT, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                         \
         }                                                                                                           \
-        rescore_kernel<CSRC, NT><<<grid, NT, smem, s>>>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, \
-                                                        out_idx, out_score, out_cand, chk);                         \
+        rescore_kernel<CSRC, NT, FX><<<grid, NT, smem, s>>>(cand, kp_in, qm, cm, q_aux, c_aux, metric, index_base, k_out, \
+                                                            out_idx, out_score, out_cand, chk);                     \
+    }
+#define PMM_RS(NT)                                                                                                  \
+    {                                                                                                               \
+        if (fixed) PMM_RS_LAUNCH(NT, true, RS_STAGES)                                                               \
+        else PMM_RS_LAUNCH(NT, false, 1)                                                                            \
     }
     if (kp_in <= 32) PMM_RS(32)
     else if (kp_in <= 64) PMM_RS(64)
     else if (kp_in <= 128) PMM_RS(128)
     else if (kp_in <= 256) PMM_RS(256)
     else return cudaErrorInvalidValue;
+#undef PMM_RS_LAUNCH
 #undef PMM_RS
     return cudaGetLastError();
 }

@@ -1060,6 +1060,21 @@ def test_pipelined_rounds_overlap_rescoring(native, oracle):
     parity.check_topk(idx, sc, q64, c64, 10, "cosine", oracle, exact=True)
 
 
+def test_rescore_cp_async_variant(native, oracle):
+    """The cp.async gather of the re-scoring kernel (option rescore_fixed, off by default): identical results, on row lengths
+    with and without a partial last step, skipped candidates and every list capacity."""
+    rng = np.random.default_rng(52)
+    native.set_option("rescore_fixed", 1)
+    try:
+        for nq, n, d, k, metric in ((300, 9000, 768, 100, "dot"), (77, 5000, 100, 10, "cosine"), (130, 7000, 36, 50, "euclidean"),
+                                    (64, 3000, 4, 200, "dot"), (9, 400, 1028, 7, "cosine")):
+            q, c = _randn(rng, nq, d), _randn(rng, n, d)
+            idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+            parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+    finally:
+        native.set_option("rescore_fixed", 0)
+
+
 def test_seeded_requery_levels(native, oracle):
     """Queries the first level cannot prove are re-run from SEEDED thresholds (the exact k-th score at hand minus the
     next level's error bound): same answers with and without seeding, and the seeded launch is the one that ran."""

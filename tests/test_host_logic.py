@@ -191,7 +191,7 @@ def test_every_documented_option_is_accepted_and_unknown_ones_are_not():
     defaults = {"tc_levels": 3, "tc_cg": 2, "tc_sync_tiles": 32, "host_chunked": 1, "verify": 1, "f16r_wide": 1, "tc_clm": 1,
                 "host_chunk_min_rows": 16384, "host_chunk_min_mb": 64, "generic_workspace_mb": 0, "seed_retry": 1, "f64_tc": 1,
                 "multi_gpu": 1, "multi_gpu_min_gflop": 4000, "stage": 1, "stage_slot_mb": 32, "stage_slots": 4,
-                "workspace_cache_mb": 24576, "pipeline": 0, "pipeline_min_gflop": 2000, "prep_fast": 1, "rescore_stream_loads": 1, "multipass": 1}
+                "workspace_cache_mb": 24576, "pipeline": 0, "pipeline_min_gflop": 2000, "prep_fast": 1, "rescore_stream_loads": 1, "multipass": 1, "rescore_fixed": 0}
     for n in sorted(names):
         if n in ("release_workspace", "generic_workspace_mb") or n.startswith("tc_dbg"):
             continue
