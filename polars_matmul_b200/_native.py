@@ -151,6 +151,7 @@ class HostMatrix:
     chunks: Optional[list] = None            # multi-chunk column: list of 1-D value views (fixed-size rows, no nulls);
                                              # `values` is then an empty array that only carries the dtype
     owner: object = None                     # whatever keeps the viewed buffers alive (an Arrow array, a Series)
+    offsets_id: object = None                # identity of the source offsets buffer when `offsets` is a derived copy
 
     @property
     def dtype_code(self) -> int:
@@ -175,7 +176,8 @@ class HostMatrix:
         def addr(a):
             return 0 if a is None else a.ctypes.data
         vals = tuple((c.ctypes.data, c.size) for c in self.chunks) if self.chunks is not None else ((addr(self.values), self.values.size),)
-        return (vals, self.n_rows, self.dim, self.dtype_code, addr(self.offsets), addr(self.validity), addr(self.row_validity))
+        offs = self.offsets_id if self.offsets_id is not None else addr(self.offsets)
+        return (vals, self.n_rows, self.dim, self.dtype_code, offs, addr(self.validity), addr(self.row_validity))
 
 
 def metric_from_str(name: str) -> int:

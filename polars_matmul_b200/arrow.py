@@ -108,19 +108,24 @@ def from_arrow(arr: Any) -> HostMatrix:
     if pa.types.is_list(t) or pa.types.is_large_list(t):
         odt = np.int64 if pa.types.is_large_list(t) else np.int32
         obuf = arr.buffers()[1]
+        vals, validity, child_off = _child_to_numpy(arr.values)
+        offsets_id = None
         if obuf is None or n_rows == 0:
             offsets = np.zeros(1, np.int64)
         else:
-            offsets = np.frombuffer(obuf, dtype=odt, count=arr.offset + n_rows + 1)[arr.offset:].astype(np.int64)
-        vals, validity, child_off = _child_to_numpy(arr.values)
-        offsets = offsets + child_off  # absolute positions in the child buffer
+            raw = np.frombuffer(obuf, dtype=odt, count=arr.offset + n_rows + 1)[arr.offset:]
+            if odt is np.int64 and child_off == 0:
+                offsets = raw                                   # Polars' List layout: the Arrow buffer itself, no copy
+            else:                                               # 32-bit offsets or a sliced child: widened / re-based copy
+                offsets = raw.astype(np.int64) + child_off      # absolute positions in the child buffer
+                offsets_id = (obuf.address, arr.offset, child_off)   # identity of the SOURCE buffer (resident-corpus cache key)
         row_valid = _bitmap(arr)
         dim = 0
         if n_rows > 0:
             if row_valid is not None and not (row_valid[0] & 1):
                 raise RuntimeError("First element is null")  # src/matmul.rs:238
             dim = int(offsets[1] - offsets[0])               # row 0 defines the dimension
-        return HostMatrix(vals, n_rows, dim, np.ascontiguousarray(offsets), validity, row_valid, owner=arr)
+        return HostMatrix(vals, n_rows, dim, np.ascontiguousarray(offsets), validity, row_valid, owner=arr, offsets_id=offsets_id)
     raise RuntimeError(f"expected a List or Array (fixed-size list) column of numbers, got {t}")
 
 

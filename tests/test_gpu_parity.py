@@ -565,9 +565,13 @@ def test_f16_storage(native, oracle):
     out = native.matmul(_hm(q16), _hm(c16))
     assert out.dtype == np.float32
     parity.check_matmul(out, q32, c32, oracle.matmul(q32, c32), np.float32)
-    # mixed f16 / f32 stays on the f32 path
+    # mixed f16 / f32 stays on the f32 path (planes built from f16 AND f32 sources; D = 128: the vectorised plane pass)
     idx, sc = native.topk(_hm(q32), _hm(c16), 10, "cosine")
-    parity.check_topk(idx, sc, q32, c32, 10, "cosine", oracle, working_dtype=np.float32)
+    parity.check_topk(idx, sc, q32, c32, 10, "cosine", oracle, working_dtype=np.float32, exact=True)
+    out = native.matmul(_hm(q32), _hm(c16))
+    parity.check_matmul(out, q32, c32, oracle.matmul(q32, c32), np.float32)
+    out = native.matmul(_hm(q16), _hm(c32))
+    parity.check_matmul(out, q32, c32, oracle.matmul(q32, c32), np.float32)
 
 
 def test_result_containers(pmm):
@@ -1128,6 +1132,19 @@ def test_corpus_cache_in_the_plugin_call(pmm, native, oracle):
         parity.check_topk(idx, sc, q, c, 5, "cosine", oracle, exact=True)
     assert growth[0] >= c.nbytes and growth[1] >= c.nbytes
     assert all(g < c.nbytes / 10 for g in growth[2:]), growth              # only the queries from the third call on
+    # pl.List layout (i64 offsets): keyed on the Arrow offsets buffer, so it is recognised from call to call as well
+    larr = pa.LargeListArray.from_arrays(pa.array(np.arange(c.shape[0] + 1, dtype=np.int64) * 64), pa.array(c.reshape(-1)))
+    l32 = pa.ListArray.from_arrays(pa.array(np.arange(c.shape[0] + 1, dtype=np.int32) * 64), pa.array(c.reshape(-1)))
+    for arr_ in (larr, l32):
+        seen = []
+        for i in range(4):
+            native.reset_stats()
+            out = pmm._topk(q, arr_, 5, "cosine")
+            seen.append(native.get_stat("h2d_bytes"))
+        assert seen[0] >= c.nbytes and all(g < c.nbytes / 10 for g in seen[2:]), seen
+        idx = np.asarray(out.values.field("index")).reshape(100, 5)
+        sc = np.asarray(out.values.field("score")).reshape(100, 5)
+        parity.check_topk(idx, sc, q, c, 5, "cosine", oracle, exact=True)
     # a different query dtype is a different entry (working precision f64): streamed again, still correct
     q64 = _randn(rng, 20, 64, dtype=np.float64)
     out = pmm._topk(q64, carr, 5, "dot")

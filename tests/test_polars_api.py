@@ -149,6 +149,12 @@ class TestFloat32Support:  # :366-464
         assert df64.select(pl.col("embedding").pmm.matmul(c64).alias("s"))["s"].dtype == pl.Array(pl.Float64, 2)
         # mixed f32 query / f64 corpus -> f64 (src/matmul.rs:308)
         assert df32.select(pl.col("embedding").pmm.matmul(pl.Series("e", [[1.0, 0.0]])).alias("s"))["s"].dtype == pl.Array(pl.Float64, 1)
+        # f16-stored corpus (not in the reference, whose README says "cast to f32 first"): storage is upcast exactly and
+        # the result is f32 - the dtype the namespace declares must be the one that comes back (round-1 advisor finding)
+        if hasattr(pl, "Float16"):
+            c16 = c32.cast(pl.List(pl.Float16))
+            assert df32.select(pl.col("embedding").pmm.matmul(c16).alias("s"))["s"].dtype == pl.Array(pl.Float32, 2)
+            assert df32.select(pl.col("embedding").pmm.matmul(c16, flatten=True).alias("s"))["s"].dtype == pl.Float32
 
     def test_topk_f32(self):
         np.random.seed(42)
