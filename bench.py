@@ -328,6 +328,15 @@ def c1_e2e(pmm):
     for label, conv in (("list", lambda a: pa.LargeListArray.from_arrays(pa.array(np.arange(a.shape[0] + 1, dtype=np.int64) * a.shape[1]), pa.array(a.reshape(-1)))),
                         ("array", lambda a: pa.FixedSizeListArray.from_arrays(pa.array(a.reshape(-1)), a.shape[1]))):
         qa, ca = conv(q), conv(c)
+        pmm.corpus_cache_clear()
+        cold = []
+        for _ in range(3):   # no residency: the corpus is uploaded and prepared inside every call, as the reference re-marshals it
+            pmm.corpus_cache_configure(enabled=False)
+            t0 = time.perf_counter()
+            pmm._topk(qa, ca, 10, "cosine")
+            cold.append((time.perf_counter() - t0) * 1e3)
+        pmm.corpus_cache_configure(enabled=True)
+        res[label + "_ms_corpus_uploaded_every_call"] = min(cold[1:])
         for _ in range(2):
             pmm._topk(qa, ca, 10, "cosine")
         ts = []
@@ -337,7 +346,9 @@ def c1_e2e(pmm):
             ts.append((time.perf_counter() - t0) * 1e3)
         res[label + "_ms_median"] = statistics.median(ts)
     res["reference_readme_ms"] = 45.0
-    res["note"] = "polars_matmul_b200._topk(Arrow in, Arrow out), pageable inputs, H2D + D2H + result assembly inside; README figure: hardware unstated"
+    res["note"] = ("polars_matmul_b200._topk(Arrow in, Arrow out), pageable inputs, H2D + D2H + result assembly inside. *_ms_median: repeated "
+                   "calls on the same Arrow corpus - from the second call on `_topk` keeps it resident (only the queries cross PCIe); "
+                   "*_ms_corpus_uploaded_every_call: residency switched off. README figure: hardware unstated")
     return res
 
 
