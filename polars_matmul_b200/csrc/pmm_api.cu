@@ -816,7 +816,9 @@ int rescore_finish(const VerifyCtx &vc, RescoreJob &job, const pmm_matrix_t &raw
     if (o.cand) CUDA_TRY(t_cand.alloc((size_t)F * keff * 8, s));
     TopkOut t{t_idx.as<uint32_t>(), t_sc.as<double>(), o.cand ? t_cand.as<uint64_t>() : nullptr};
     const bool want_norm = metric == PMM_METRIC_COSINE, want_sq = metric == PMM_METRIC_EUCLIDEAN;
-    const int64_t q_tile = 4 * TC_TILE_M;
+    // the few re-queried rows are padded to ONE scheduling unit's query tile (256 rows for CTA pairs), not to the 512 the
+    // bulk path uses: a second, all-padding query tile would make half of the units stream the corpus planes for nothing
+    const int64_t q_tile = (int64_t)TC_TILE_M * std::max(2, t_opt.tc_cg * (t_opt.tc_cg == 2 && t_opt.tc_clm == 2 ? 2 : 1));
     const float *seed_next = nullptr;
     if (next_terms != 0 && t_opt.seed_retry) {
         const int64_t n_pad = round_up(F, q_tile);

@@ -55,7 +55,7 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
     lo = __uint_as_float(tf32_rna(__fsub_rn(x, hi)));
 }
 
-enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2, MODE_F16R = 3 };
+enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2, MODE_F16R = 3, MODE_NONE = 4 /* prep_fast_kernel only: norms, no planes */ };
 static bool g_prep_fast = true;   // prep_set_fast(): A/B switch for measurements and tests
 void prep_set_fast(bool on) { g_prep_fast = on; }
 
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
                 x[2 * u] = f.x;
                 x[2 * u + 1] = f.y;
             }
-            if (MODE == MODE_F16) *((uint4 *)(hp + t) + sub) = pc.v[0];   // exact plane of f16 input: the line as loaded
+            if (MODE == MODE_F16 && a.out0) *((uint4 *)(hp + t) + sub) = pc.v[0];   // exact plane of f16 input: the line as loaded
         }
         if (MODE == MODE_F16R || (MODE == MODE_F16 && sizeof(SRC) == 4)) {
             __half2 h[EPL / 2];   // 8 halves = 16 bytes per lane: the 8 lanes of a row write one whole 128-byte line
@@ -457,6 +457,13 @@ __global__ void __launch_bounds__(256) norms_kernel(PrepArgs a) {
 cudaError_t launch_norms(const PrepArgs &a, int src_dtype, cudaStream_t s) {
     int64_t groups = (a.n_rows + 31) / 32;
     if (groups <= 0) return cudaSuccess;
+    // f16 rows of a plain layout: the 16-byte-load pass of the plane builder without its plane stores (4-byte pair loads
+    // keep too few bytes in flight: 0.61 of HBM)
+    PrepArgs b = a;
+    b.ld_out = a.dim;
+    b.out0 = b.out1 = nullptr;
+    b.zero_guard_sq = 1e-12f;
+    if (src_dtype == 0 && g_prep_fast && a.rows_out == a.n_rows && prep_fast_ok<__half>(b)) return launch_prep_fast<__half, MODE_NONE>(b, groups, s);
     if (src_dtype == 0) norms_kernel<__half, float><<<(unsigned)groups, 256, 0, s>>>(a);
     else if (src_dtype == 1) norms_kernel<float, float><<<(unsigned)groups, 256, 0, s>>>(a);
     else norms_kernel<double, double><<<(unsigned)groups, 256, 0, s>>>(a);
