@@ -2511,6 +2511,8 @@ int pmm_group_topk(pmm_group_t *g, const pmm_matrix_t *queries, const pmm_matrix
     int rc;
     if (!g || !g->local) return fail(PMM_ERR_INVALID, "pmm_group_topk needs a single-process group (pmm_group_init_local)");
     if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus, "corpus"))) return rc;
+    if (is_chunked(queries) || is_chunked(corpus))
+        return fail(PMM_ERR_UNSUPPORTED, "the group entry points take single-buffer columns (multi-chunk columns: pmm_topk on one GPU)");
     if (k < 0) return fail(PMM_ERR_INVALID, "k must be non-negative (can't convert negative int to unsigned)");
     const int64_t keff = k < corpus->n_rows ? k : corpus->n_rows;
     if (k_actual) *k_actual = keff;
@@ -2532,6 +2534,8 @@ int pmm_group_topk_shard(pmm_group_t *g, const pmm_matrix_t *queries, const pmm_
     if (!g || g->local || g->members.size() != 1)
         return fail(PMM_ERR_INVALID, "pmm_group_topk_shard needs a one-rank-per-process group (pmm_group_init_rank)");
     if ((rc = check_matrix(queries, "queries")) || (rc = check_matrix(corpus_shard, "corpus"))) return rc;
+    if (is_chunked(queries) || is_chunked(corpus_shard))
+        return fail(PMM_ERR_UNSUPPORTED, "the group entry points take single-buffer columns (multi-chunk columns: pmm_topk on one GPU)");
     if (k < 0 || n_total < corpus_shard->n_rows || index_base < 0) return fail(PMM_ERR_INVALID, "bad k / n_total / index_base");
     if (metric < 0 || metric > 2) return fail(PMM_ERR_INVALID, "Unknown metric: '%d'. Supported: cosine, dot, euclidean", metric);
     if (queries->n_rows == 0) return PMM_OK;

@@ -88,13 +88,14 @@ def _exact_in_filter_units(oracle, q32, c32, metric):
 
 
 def _check(native, oracle, q, c, level, metric, label):
-    q32, c32 = q.astype(np.float32), c.astype(np.float32)
+    wd = np.float64 if (q.dtype == np.float64 or c.dtype == np.float64) else np.float32   # working precision of the exact score
+    q32, c32 = q.astype(wd), c.astype(wd)
     f = _filter_values(native, q, c, metric, level)
     assert not np.isnan(f).any(), f"{label}: pairs missing from the kept lists"
     exact = _exact_in_filter_units(oracle, q32, c32, metric)
     qn = np.sqrt(oracle.norms(q32, squared=True).astype(np.float64))
     cn = np.sqrt(oracle.norms(c32, squared=True).astype(np.float64))
-    code = {np.dtype(np.float16): 0, np.dtype(np.float32): 1}
+    code = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
     worst = 0.0
     for i in range(q.shape[0]):
         e, max_norm = native.filter_error_bound(level, code[q.dtype], code[c.dtype], q.shape[1], metric, float(qn[i]),
@@ -147,6 +148,20 @@ def test_exact_f16_planes_within_bound(native, oracle, d, kind):
     q16, c16 = q.astype(np.float16), c.astype(np.float16)
     for metric in (DOT, COSINE, EUCLIDEAN):
         _check(native, oracle, q16, c16, 0, metric, f"f16 d={d} {kind} metric={metric}")
+
+
+@pytest.mark.parametrize("d", [768, 4096])
+@pytest.mark.parametrize("kind", ["positive", "gauss", "small"])
+def test_f64_sources_within_bound(native, oracle, d, kind):
+    """f64 working precision: the planes are rounded from the f64 value (f16 level) or split after an f64 -> f32 rounding
+    (3xTF32 level); the exact counterpart is the oracle's f64 score."""
+    rng = np.random.default_rng(11 * d + len(kind))
+    q, c = _data(kind, 96, 256, d, rng)
+    q64 = q.astype(np.float64) * (1.0 + 1e-9 * rng.standard_normal(q.shape))    # not representable in f32
+    c64 = c.astype(np.float64) * (1.0 + 1e-9 * rng.standard_normal(c.shape))
+    for level in (0, 3):
+        for metric in (DOT, COSINE, EUCLIDEAN):
+            _check(native, oracle, q64, c64, level, metric, f"f64 level={level} d={d} {kind} metric={metric}")
 
 
 def test_bound_is_not_vacuous(native, oracle):

@@ -116,17 +116,17 @@ def test_topk_f16_input_bit_exact(native, oracle, p):
     parity.check_topk(idx, sc, q16.astype(np.float32), c16.astype(np.float32), k, metric, oracle, exact=True)
 
 
-@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=max(15, EXAMPLES // 2), deadline=None, suppress_health_check=list(HealthCheck))
 @given(problems())
 def test_topk_f64_vs_oracle(native, oracle, p):
     nq, n, d, k, metric, seed, kind = p
-    q, c = _data(min(nq, 64), n, d, seed, kind, np.float64)
+    q, c = _data(min(nq, 64) if n * d > 200_000 else nq, n, d, seed, kind, np.float64)
     idx, sc = native.topk(_hm(q), _hm(c), k, metric)
     # f64 top-k = tensor-core filter + exact f64 re-scoring (sequential FMA): bit-identical to the oracle for every kind
     parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
 
 
-@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=max(15, EXAMPLES // 4), deadline=None, suppress_health_check=list(HealthCheck))
 @given(problems())
 def test_matmul_vs_oracle(native, oracle, p):
     nq, n, d, k, metric, seed, kind = p
@@ -141,7 +141,7 @@ def test_matmul_vs_oracle(native, oracle, p):
             parity.check_matmul(out, q, c, ref, dtype)
 
 
-@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=max(15, EXAMPLES // 4), deadline=None, suppress_health_check=list(HealthCheck))
 @given(st.integers(1, 60), st.integers(1, 400), st.integers(1, 40), st.integers(1, 30), st.sampled_from(["cosine", "dot", "euclidean"]),
        st.integers(0, 2**31 - 1))
 def test_list_container_nulls_and_ragged(native, oracle, nq, n, d, k, metric, seed):
