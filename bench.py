@@ -503,16 +503,19 @@ def main():
     value = world * Q / (ms_step / 1000.0)
 
     # ---- self-check of the timed result: oracle on a query sample against the GLOBAL corpus ------------------------
-    def selfcheck(index_dev, score_dev, c_shard_host, base, label_metric, kk):
+    def selfcheck(index_dev, score_dev, c_shard_host, base, label_metric, kk, q_dev=None):
         """Every rank scans ITS shard with the CPU oracle for the sampled queries; rank 0 merges the per-shard lists
         under (score best first, lower index first) and compares with the product's merged result: bit-identical
         scores and indices, or exact=false."""
         from oracle import pmm_oracle as oracle
         oracle.build()
         oracle.set_num_threads(max(1, host_threads() // world))
-        sample = np.arange(0, Q, max(1, Q // SELFCHECK_QUERIES))[:SELFCHECK_QUERIES]
+        q_dev = dq if q_dev is None else q_dev
+        nq_ = q_dev.shape[0]
+        sample = np.arange(0, nq_, max(1, nq_ // SELFCHECK_QUERIES))[:SELFCHECK_QUERIES]
         ts = torch.from_numpy(sample).to(dev)
-        qs = dq[ts].cpu().numpy()
+        qs = q_dev[ts].float().cpu().numpy()
+        c_shard_host = np.asarray(c_shard_host, dtype=np.float32)      # f16 storage: the reference contract is an exact upcast
         li, ls = oracle.topk(qs, c_shard_host, min(kk, c_shard_host.shape[0]), label_metric)
         li = li.astype(np.int64) + base
         if world > 1:
@@ -532,7 +535,7 @@ def main():
         msc = score_dev[ts].cpu().numpy()
         exact = bool(np.array_equal(mi, oi) and np.array_equal(msc, osc))
         return {"queries": int(len(sample)), "exact": exact, "index_match_frac": float((mi == oi).mean()),
-                "max_abs_score_diff": float(np.abs(msc - osc).max()), "corpus_rows": int(n_total if c_shard_host is c_host else c_shard_host.shape[0] * world),
+                "max_abs_score_diff": float(np.nanmax(np.abs(msc - osc))), "corpus_rows": int(c_shard_host.shape[0] * world),
                 "how": "CPU oracle (oracle/pmm_oracle.c) per shard on every rank, merged on rank 0 under (score, lower index); compared "
                        "bit for bit with the result of the last timed resident step"}
 
@@ -656,6 +659,56 @@ def main():
                 del dc4, c4_host
             except Exception as ex:
                 extra["c4_strong"] = {"error": repr(ex)}
+    # BASELINE.json configs[4]: f16-stored 1024-d embeddings, 1M queries x 1M corpus, cosine, k=10, corpus sharded over the
+    # ranks (N=1: the share of one of 8 GPUs, 125k rows).  Resident timing; exact kind::f16 planes (no rounding level).
+    if not args.no_extras and not args.small:
+        try:
+            if "dc" in dir():
+                del dc
+            torch.cuda.empty_cache()
+            Q5, D5, k5 = 1_000_000, 1024, 10
+            n5 = 1_000_000 // max(world, 8 if world == 1 else world)
+            g5 = torch.Generator(device=dev).manual_seed(5000)
+            q5 = torch.empty((Q5, D5), dtype=torch.float16, device=dev)
+            for lo in range(0, Q5, 1 << 18):
+                q5[lo:lo + (1 << 18)] = torch.randn((min(Q5, lo + (1 << 18)) - lo, D5), generator=g5, device=dev, dtype=torch.float32).half()
+            g5c = torch.Generator(device=dev).manual_seed(5100 + rank)
+            c5 = torch.randn((n5, D5), generator=g5c, device=dev, dtype=torch.float32).half()
+            i5 = torch.empty((Q5, k5), dtype=torch.int32, device=dev)
+            s5 = torch.empty((Q5, k5), dtype=torch.float64, device=dev)
+
+            def step5():
+                if world == 1:
+                    _native.dev_topk(_native.dev_matrix(q5.data_ptr(), Q5, D5, _native.DTYPE_F16), _native.dev_matrix(c5.data_ptr(), n5, D5, _native.DTYPE_F16),
+                                     k5, _native.METRIC_COSINE, index_ptr=i5.data_ptr(), score_ptr=s5.data_ptr(), stream=stream)
+                else:
+                    group.topk_device(q5.data_ptr(), Q5, D5, _native.DTYPE_F16, c5.data_ptr(), n5, _native.DTYPE_F16, rank * n5, n5 * world,
+                                      k5, "cosine", i5.data_ptr(), s5.data_ptr(), full=True)
+            step5()
+            barrier()
+            _native.set_option("profile", 1)
+            _native.reset_stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(tstream)
+            for _ in range(2):
+                step5()
+            e1.record(tstream)
+            barrier()
+            ms5, _ = reduce_ranks(e0.elapsed_time(e1) / 2)
+            k5ms = _native.get_stat("tc_topk_f16_ms") / max(1.0, _native.get_stat("tc_topk_f16_launches"))
+            _native.set_option("profile", 0)
+            chk5 = selfcheck(i5, s5, c5.cpu().numpy(), rank * n5, "cosine", k5, q_dev=q5)
+            tf5 = 2.0 * Q5 * n5 * D5 / (k5ms / 1e3) / 1e12 if k5ms > 0 else None
+            if rank == 0:
+                extra["c5"] = {"workload": f"C5: {Q5} queries x {n5 * world} corpus rows ({n5} per rank), {D5}d f16-stored, cosine, k={k5}, {world} GPU(s)"
+                                           + (" - the share of one of 8 GPUs" if world == 1 else ""),
+                               "ms_per_step": ms5, "queries_per_sec": Q5 / (ms5 / 1e3), "filter_kernel_ms_rank0": k5ms, "filter_tflops_per_gpu": tf5,
+                               "frac_of_bf16_sustained_per_gpu": (tf5 / peaks.get("bf16_tflops_sustained", 1400.0)) if tf5 else None,
+                               "steps": 2, "selfcheck": chk5}
+            del q5, c5
+        except Exception as ex:
+            if rank == 0:
+                extra["c5"] = {"error": repr(ex)}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
