@@ -244,12 +244,13 @@ def hbm_extras(_native, torch, peaks):
         b = torch.randn((N, D), generator=g, device="cuda", dtype=torch.float32).to(dt)
         o = torch.empty((Q, N), dtype=torch.float64 if dt == torch.float64 else torch.float32, device="cuda")
         r = run(lambda: _native.dev_matmul(_native.dev_matrix(a.data_ptr(), Q, D, code[dt]), _native.dev_matrix(b.data_ptr(), N, D, code[dt]),
-                                           o.data_ptr(), st), ("tc_matmul_tf32x3", "tc_matmul_f16", "scores_f64_dmma", "scores_f32", "prep"))
+                                           o.data_ptr(), st), ("tc_matmul_f16x3", "tc_matmul_tf32x3", "tc_matmul_f16", "scores_f64_dmma", "scores_f32", "prep"))
         kern = [k for k in r if k != "prep"][0]
         gb = (Q * N * o.element_size() + (Q + N) * D * a.element_size()) / 1e9
         tf = 2.0 * Q * N * D / r[kern] / 1e9
         # which roofline binds the shape: HBM (write-bound) when the contraction is cheaper than the writes
-        tensor_peak = {"tc_matmul_tf32x3": peaks.get("bf16_tflops_sustained", 1400.0) / 6.0, "tc_matmul_f16": peaks.get("bf16_tflops_sustained", 1400.0)}.get(kern)
+        tensor_peak = {"tc_matmul_tf32x3": peaks.get("bf16_tflops_sustained", 1400.0) / 6.0, "tc_matmul_f16x3": peaks.get("bf16_tflops_sustained", 1400.0) / 3.0,
+                       "tc_matmul_f16": peaks.get("bf16_tflops_sustained", 1400.0)}.get(kern)
         t_hbm = gb / hbm * 1e3
         t_tc = (2.0 * Q * N * D / 1e12 / tensor_peak * 1e3) if tensor_peak else None
         out["matmul"][label] = {"kernel": kern, "kernel_ms": r[kern], "prep_ms": r.get("prep"), "algorithmic_GB": gb,

@@ -58,7 +58,7 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, matmul_split16 = 1, matmul_exact_max_dim = 8, matmul_flat = -1, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
     int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000, pipeline_min_gflop = 2000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
@@ -98,6 +98,9 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "__unused_pipeline") o.pipeline = value ? 1 : 0;                       // per-round filter launches with overlapped merge + re-scoring
     else if (k == "pipeline_min_gflop") o.pipeline_min_gflop = value < 0 ? 0 : value;   // smallest round worth a launch of its own
     else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
+    else if (k == "matmul_exact_max_dim") o.matmul_exact_max_dim = value < 0 ? 0 : (int)value;   // f32 vectors this short: exact SIMT kernel
+    else if (k == "matmul_flat") o.matmul_flat = value < 0 ? -1 : value ? 1 : 0;   // tile schedule of the tensor-core matmul: -1 automatic
+    else if (k == "matmul_split16") o.matmul_split16 = value ? 1 : 0;           // raw f32 matmul: hi/lo f16 planes (1) or the 3xTF32 split (0)
     else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
     else if (k == "multi_gpu_min_gflop") o.multi_gpu_min_gflop = value < 0 ? 0 : value;
     else return false;
@@ -338,6 +341,7 @@ struct Prepared {
     bool f64 = false;        // working precision of norm / sqnorm (and of the DENSE copy)
     int64_t n_rows = 0, dim = 0, rows_pad = 0, ld = 0;
     DevBuf p0, p1, norm, sqnorm, norm32, sqnorm32, max_sq;
+    DevBuf scale;            // PREP_SPLIT16: [rows_pad] factors that undo the rows' power-of-two scaling
     unsigned int *max_sq_ptr = nullptr;  // own (max_sq) or shared across corpus chunks
     // f32 views of the norms for the tensor-core filter and its proof: the working-type buffers themselves for f32
     // working precision, rounded copies written by the same prep pass for f64
@@ -354,7 +358,7 @@ cudaError_t init_norm_range(unsigned int *d, cudaStream_t s) {
 
 // Bytes of one operand plane prepare() allocates for `rows` x `dim` (tensor-core modes).
 size_t plane_bytes(int mode, int64_t rows, int64_t dim, int64_t row_tile) {
-    const bool half_plane = mode == PREP_F16 || mode == PREP_F16R;
+    const bool half_plane = mode == PREP_F16 || mode == PREP_F16R || mode == PREP_SPLIT16;
     const int64_t kq = half_plane ? 64 : 32, es = half_plane ? 2 : 4;
     return (size_t)(round_up(rows, row_tile) * round_up(dim, kq) * es);
 }
@@ -373,13 +377,14 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
         out->ld = m.dim;
         CUDA_TRY(out->p0.alloc((size_t)(m.n_rows * m.dim * wsz), s));
     } else {
-        const bool half_plane = mode == PREP_F16 || mode == PREP_F16R;
+        const bool half_plane = mode == PREP_F16 || mode == PREP_F16R || mode == PREP_SPLIT16;
         const int64_t kq = half_plane ? 64 : 32;
         const int64_t es = half_plane ? 2 : 4;
         out->rows_pad = round_up(m.n_rows, row_tile);
         out->ld = round_up(m.dim, kq);
         CUDA_TRY(out->p0.alloc((size_t)(out->rows_pad * out->ld * es), s));
-        if (mode == PREP_TF32) CUDA_TRY(out->p1.alloc((size_t)(out->rows_pad * out->ld * es), s));
+        if (mode == PREP_TF32 || mode == PREP_SPLIT16) CUDA_TRY(out->p1.alloc((size_t)(out->rows_pad * out->ld * es), s));
+        if (mode == PREP_SPLIT16) CUDA_TRY(out->scale.alloc((size_t)(out->rows_pad * 4), s));
     }
     if (want_norm) CUDA_TRY(out->norm.alloc((size_t)(out->rows_pad * wsz), s));
     if (want_sq) CUDA_TRY(out->sqnorm.alloc((size_t)(out->rows_pad * wsz), s));
@@ -412,6 +417,7 @@ int prepare(const pmm_matrix_t &m, int mode, bool f64, int64_t row_tile, bool wa
     a.error_flag = d_err;
     a.nonfinite_rows = nonfinite_rows;
     a.nonfinite_count = nonfinite_count;
+    a.scale_out = out->scale.as<float>();
     CUDA_TRY(launch_counted("prep", s, [&] { return launch_prep(a, m.dtype, mode, f64 ? 1 : 0, s); }));
     return PMM_OK;
 }
@@ -1153,6 +1159,11 @@ int matmul_tc_dim_limit(int mode) {
     if (t_opt.matmul_tc_max_dim > 0) return t_opt.matmul_tc_max_dim;
     return mode == PREP_F16 ? 1024 : 256;
 }
+// f32 operands of the tensor-core matmul: row-scaled hi/lo f16 planes (PREP_SPLIT16; CTA-pair kernel), three kind::f16
+// MMAs per 16 elements with the small terms swept first - twice the rate of the 3xTF32 split and a sixth of its
+// accumulate truncations on the full-size sum (profiles/matmul_soak_r2*.json: worst |error| / tolerance 1.13 -> see
+// DESIGN 4.5).  `matmul_split16 = 0` or cta_group::1 keep the 3xTF32 planes.
+int matmul_f32_mode() { return (t_opt.matmul_split16 && t_opt.tc_cg == 2) ? PREP_SPLIT16 : PREP_TF32; }
 
 int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out, cudaStream_t s) {
     PathChoice pc = choose_path(dl->dtype, dr->dtype, 1, false);
@@ -1160,13 +1171,23 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         pc.tc = false;
         pc.mode = PREP_DENSE;
     }
+    // Very short f32 vectors: a 22-bit split is off by up to 2^-21 |q||c| per product and nothing averages out over two or
+    // three elements (measured: 0.6 of the tolerance at D = 2, 3), while one FMA per element costs nothing against the
+    // Q x N writes - the exact kernel serves them.  Up to 32 elements the TF32 planes (32-element K-blocks) are the
+    // cheaper operands; beyond, the f16 split (64-element K-blocks) wins on rate and on accumulate truncations.
+    if (pc.tc && pc.mode == PREP_TF32 && dl->dim <= t_opt.matmul_exact_max_dim) {
+        pc.tc = false;
+        pc.mode = PREP_DENSE;
+    }
+    if (pc.tc && pc.mode == PREP_TF32 && dl->dim > 32 && dl->dim <= 256) pc.mode = matmul_f32_mode();   // (resident query planes: D <= 256)
     DevBuf err;
     CUDA_TRY(err.alloc(sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     Prepared l, r;
-    // f32 on the tensor cores: rows with inf / NaN elements are marked by the prep pass and fixed up afterwards
+    // f32 on the tensor cores: rows with inf / NaN elements (f16 split: also rows beyond the scalable range) are marked
+    // by the prep pass and fixed up afterwards
     DevBuf nf;
-    const bool track = pc.tc && pc.mode == PREP_TF32;
+    const bool track = pc.tc && (pc.mode == PREP_TF32 || pc.mode == PREP_SPLIT16);
     if (track) {
         CUDA_TRY(nf.alloc((size_t)(dl->n_rows + dr->n_rows) + 16, s));
         CUDA_TRY(cudaMemsetAsync(nf.p, 0, 16, s));   // [0], [1]: counts for left / right (the row flags are written by every row)
@@ -1191,14 +1212,32 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
         a.dim_pad = l.ld;
         a.nq = Q;
         a.n = N;
-        a.f16 = pc.mode == PREP_F16 ? 1 : 0;
+        a.f16 = (pc.mode == PREP_F16 || pc.mode == PREP_SPLIT16) ? 1 : 0;
+        a.terms = pc.mode == PREP_SPLIT16 ? 2 : 3;
+        if (pc.mode == PREP_SPLIT16) {
+            a.q_aux = l.scale.as<float>();
+            a.c_aux = r.scale.as<float>();
+        }
         a.cg = t_opt.tc_cg;
+        a.debug_skip = t_opt.tc_debug_skip == 8 ? 8 : 0;   // wait-cycle counters of the MMA warps (diagnostics)
+        // Classic schedule: whole query tiles per unit, all units sweep the corpus tiles in the same order (a corpus tile
+        // is fetched from HBM once and hit in L2 by everyone else).  When the number of query tiles leaves many units
+        // idle, the flat schedule (equal shares of the tile list, unaligned sweeps: measured 15-30 % slower per tile)
+        // wins anyway.
         a.sched = make_tc_schedule(Q, N, di.num_sms / a.cg, 1, a.cg);
+        {
+            const TcSchedule &c = a.sched;
+            const int64_t classic = (int64_t)c.rounds * ((c.n_tiles + c.g - 1) / c.g) + (c.m_rem > 0 ? (c.n_tiles + c.g_rem - 1) / c.g_rem : 0);
+            const TcSchedule f = make_tc_schedule_flat(Q, N, di.num_sms / a.cg, a.cg);
+            const int64_t flat = ((int64_t)f.m_tiles * f.n_tiles + f.num_ctas - 1) / f.num_ctas;
+            if (t_opt.matmul_flat == 1 || (t_opt.matmul_flat < 0 && flat * 13 < classic * 10)) a.sched = f;
+        }
         a.metric = PMM_METRIC_DOT;
         a.k = 1;
         a.kp = 32;
         a.out = (float *)d_out;
-        cudaError_t e = launch_counted(a.f16 ? "tc_matmul_f16" : "tc_matmul_tf32x3", s, [&] { return launch_tc_matmul(a, s); });
+        cudaError_t e = launch_counted(pc.mode == PREP_SPLIT16 ? "tc_matmul_f16x3" : a.f16 ? "tc_matmul_f16" : "tc_matmul_tf32x3", s,
+                                       [&] { return launch_tc_matmul(a, s); });
         if (e != cudaSuccess)
             return fail(PMM_ERR_CUDA, "tensor-core matmul launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
         if (track)   // +-inf inputs: 0 * inf inside the split gives NaN where the reference propagates the infinity

@@ -27,8 +27,13 @@ struct PrepArgs {
     int *error_flag;              // set to 1 when a list row is longer than dim
     unsigned char *nonfinite_rows;  // [n_rows] set to 1 for rows holding an inf / NaN element, or NULL
     unsigned int *nonfinite_count;  // number of such rows (atomicAdd), with nonfinite_rows
+    float *scale_out;               // PREP_SPLIT16: [rows_out] factor 2^-e that undoes the row's power-of-two scaling
 };
-enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2, PREP_F16R = 3 };  // = MODE_* of pmm_prep.cu
+// PREP_SPLIT16 (raw f32 matmul): every row scaled by a power of two so that its largest element lands in [2^14, 2^15),
+// then split into two f16 planes hi = f16(x), lo = f16(x - hi): 22 significant bits like the TF32 split, at the f16 rate.
+// Rows the scaling cannot serve (inf / NaN elements, a largest element outside [2^-60, 2^60]) are written as zeros and
+// marked in nonfinite_rows; the caller recomputes them with IEEE arithmetic.
+enum { PREP_DENSE = 0, PREP_TF32 = 1, PREP_F16 = 2, PREP_F16R = 3, PREP_SPLIT16 = 5 };  // = MODE_* of pmm_prep.cu
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s);
 cudaError_t launch_norms(const PrepArgs &a, int src_dtype, cudaStream_t s);
 void prep_set_fast(bool on);   // vectorised fast path of the plane modes (default on)
@@ -165,6 +170,8 @@ struct TcSchedule {
     int m_full;     // = rounds * mc
     int m_rem;      // = m_tiles - m_full
     int g_rem;      // CTAs per query tile in the last round (0 when m_rem == 0)
+    int flat;       // raw matmul (no lists to merge): unit u takes tiles [T u / U, T (u+1) / U) of the row-major list of all
+                    // T = m_tiles x n_tiles tiles; `rounds` = the most query tiles one unit touches, m_rem = 0
     __host__ __device__ int pieces(int m_tile) const { return m_tile < m_full ? g : g_rem; }
     __host__ __device__ int64_t slot_base(int m_tile) const {
         return m_tile < m_full ? (int64_t)m_tile * g : (int64_t)m_full * g + (int64_t)(m_tile - m_full) * g_rem;
@@ -172,6 +179,7 @@ struct TcSchedule {
     __host__ __device__ int64_t total_slots() const { return (int64_t)m_full * g + (int64_t)m_rem * g_rem; }
 };
 TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg, int64_t layout_rows = 0);
+TcSchedule make_tc_schedule_flat(int64_t q_rows, int64_t c_rows, int num_units, int cg);   // raw matmul: every unit busy, equal shares
 // Diagnostics: reads and clears the wait-cycle counters filled when TcArgs::debug_skip == 8.
 void tc_debug_wait_cycles(unsigned long long out[52]);
 int tc_epilogue_sets(int f16, int terms);  // epilogue warp sets of the top-k kernel variant: lists per (slot, row)
@@ -187,7 +195,7 @@ struct TcArgs {
     const void *c_hi, *c_lo;       // planes [c_rows_pad x dim_pad]
     int64_t q_rows_pad, c_rows_pad, dim_pad;
     int64_t nq, n;                 // real rows
-    int f16;                       // 1: kind::f16 single MMA, 0: 3xTF32
+    int f16;                       // 1: kind::f16 (one plane; or the hi/lo f16 split with terms == 2), 0: TF32
     int cg;                        // tcgen05 cta_group: 1, or 2 (CTA pairs, UMMA M=256)
     int cluster4;                  // cg == 2, clm == 1: launch two independent pairs per cluster of 4
     int soft_at;                   // end-of-tile merge threshold in staged candidates (0 = default 48)
@@ -196,7 +204,9 @@ struct TcArgs {
     int max_flush;                 // list merges per epilogue warp and tile (0 = auto from the tile's MMA time)
     int debug_skip;                // measurement only: 1 = epilogue loads TMEM but does not filter, 2 = one load per tile
     int clm;                       // CTA pairs per cluster: 1, or 2 (corpus tile multicast; needs cg == 2)
-    int terms;                     // f32 top-k: 3 = 3xTF32 split, 1 = hi*hi only (first-level filter, needs cg == 2)
+    int terms;                     // f32 top-k: 3 = 3xTF32 split, 1 = hi*hi only (first-level filter, needs cg == 2);
+                                   // raw matmul with f16 == 1: 2 = hi/lo f16 split (PREP_SPLIT16 planes, q_aux / c_aux = the
+                                   // rows' scale factors, needs cg == 2)
     TcSchedule sched;
     // top-k mode
     const float *q_aux, *c_aux;    // norms (cosine) / squared norms (euclidean) / NULL (dot)

@@ -12,6 +12,7 @@
 //   MODE_DENSE : dense [n_rows x dim] copy in the working type (f32 or f64) for the SIMT path;
 //   MODE_TF32  : hi/lo TF32 planes [rows_pad x dim_pad] for the 3xTF32 split
 //                (hi = rna_tf32(x), lo = rna_tf32(x - hi); x = hi + lo to ~2^-24 relative);
+//   MODE_SPLIT16: row-scaled hi/lo f16 planes + per-row scale factors for the raw f32 matmul (prep_split16_kernel);
 //   MODE_F16   : f16 plane [rows_pad x dim_pad] for f16-stored input (exact upcast, kind::f16 MMA);
 //   MODE_F16R  : f16 plane of f32 input ROUNDED to f16 (round to nearest even): 11 significant bits, the same
 //                unit roundoff 2^-11 as TF32, at twice the tensor rate and half the bytes - the first-level
@@ -55,7 +56,8 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
     lo = __uint_as_float(tf32_rna(__fsub_rn(x, hi)));
 }
 
-enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2, MODE_F16R = 3, MODE_NONE = 4 /* prep_fast_kernel only: norms, no planes */ };
+enum { MODE_DENSE = 0, MODE_TF32 = 1, MODE_F16 = 2, MODE_F16R = 3, MODE_NONE = 4 /* prep_fast_kernel only: norms, no planes */,
+       MODE_SPLIT16 = 5 /* prep_split16_kernel */ };
 static bool g_prep_fast = true;   // prep_set_fast(): A/B switch for measurements and tests
 void prep_set_fast(bool on) { g_prep_fast = on; }
 
@@ -310,6 +312,84 @@ __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
     }
 }
 
+// ---- MODE_SPLIT16: row-scaled hi/lo f16 planes for the raw f32 matmul -----------------------------------------------
+// One warp per output row.  Pass 1: largest |element| of the row (and: any inf / NaN?).  The row is scaled by 2^e with
+// e = 14 - floor(log2(max)), an exact operation, so that the largest element lands in [2^14, 2^15) - inside the f16
+// range with four binades of head room for the 16-element sums of the MMA - and every element within 2^-17 of the
+// largest keeps a NORMAL lo part.  Pass 2 (the row is still in L1/L2): hi = f16(x 2^e), lo = f16(x 2^e - hi); smaller
+// elements round with an absolute error <= 2^-25 in scaled units, i.e. <= 2^-39 of the row's largest element.
+// scale_out[row] = 2^-e undoes the scaling in the matmul epilogue (two exact multiplications per output).
+// Rows holding inf / NaN, or whose largest element lies outside [2^-60, 2^60] (the two factors of an output must stay
+// representable), are written as zeros and marked for the IEEE fix-up pass like the non-finite rows of the TF32 split.
+template <typename SRC>
+__global__ void __launch_bounds__(256) prep_split16_kernel(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= a.rows_out) return;
+    const SRC *values = (const SRC *)a.values;
+    int64_t base = 0, len = 0;
+    if (row < a.n_rows) {
+        const bool row_ok = !a.row_validity || ((a.row_validity[row >> 3] >> (row & 7)) & 1);
+        if (a.offsets) {
+            base = a.offsets[row];
+            len = a.offsets[row + 1] - base;
+            if (len > a.dim) {
+                if (lane == 0) *a.error_flag = 1;
+                len = a.dim;
+            }
+        } else {
+            base = row * a.dim;
+            len = a.dim;
+        }
+        if (!row_ok) len = 0;
+    }
+    auto fetch = [&](int64_t i) -> float {
+        if (i >= len) return 0.0f;
+        const int64_t p = base + i;
+        if (a.validity && !((a.validity[p >> 3] >> (p & 7)) & 1)) return 0.0f;
+        return SrcLoad<SRC>::template get<float>(values + p);
+    };
+    float mx = 0.0f;
+    bool bad = false;
+    for (int64_t i = lane; i < len; i += 32) {
+        const float x = fetch(i);
+        bad |= (__float_as_uint(x) & 0x7f800000u) == 0x7f800000u;
+        mx = fmaxf(mx, fabsf(x));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad = __any_sync(0xffffffffu, bad);
+    int e = 0;
+    if (mx > 0.0f) {
+        const int lg = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;   // floor(log2(mx)) for normal mx; -127 for subnormals
+        if (lg < -60 || lg > 60) bad = true;
+        e = 14 - lg;
+    }
+    if (bad) e = 0;
+    const float up = __uint_as_float((uint32_t)(127 + e) << 23);      // 2^e   (|e| <= 74)
+    const float down = __uint_as_float((uint32_t)(127 - e) << 23);    // 2^-e
+    __half2 *hi = (__half2 *)((__half *)a.out0 + row * a.ld_out);
+    __half2 *lo = (__half2 *)((__half *)a.out1 + row * a.ld_out);
+    for (int64_t i = 2 * lane; i < a.ld_out; i += 64) {   // ld_out is a multiple of 64: full 128-byte stores per warp
+        float x0 = 0.0f, x1 = 0.0f;
+        if (!bad) {
+            x0 = fetch(i) * up;
+            x1 = fetch(i + 1) * up;
+        }
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        const __half l0 = __float2half_rn(__fsub_rn(x0, __half2float(h0))), l1 = __float2half_rn(__fsub_rn(x1, __half2float(h1)));
+        hi[i >> 1] = __halves2half2(h0, h1);
+        lo[i >> 1] = __halves2half2(l0, l1);
+    }
+    if (lane == 0) {
+        if (a.scale_out) a.scale_out[row] = down;
+        if (a.nonfinite_rows && row < a.n_rows) {
+            a.nonfinite_rows[row] = bad ? 1 : 0;
+            if (bad) atomicAdd(a.nonfinite_count, 1u);
+        }
+    }
+}
+
 template <typename SRC>
 static bool prep_fast_ok(const PrepArgs &a) {
     const int step = 64;
@@ -339,6 +419,14 @@ static cudaError_t launch_prep_t(const PrepArgs &a, cudaStream_t s) {
 // are computed and written in (and of the DENSE copy).  Plane modes with f64 working precision: the planes are the
 // tensor-core FILTER's operands (rounded to f16 / split to TF32 from the f64 value), the norms stay exact f64.
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s) {
+    if (mode == MODE_SPLIT16) {   // raw f32 matmul operands: planes + scale factors, no norms
+        if (work_f64 || src_dtype > 1 || !a.out0 || !a.out1 || (a.ld_out & 63)) return cudaErrorInvalidValue;
+        const int64_t blocks = (a.rows_out + 7) / 8;
+        if (blocks <= 0) return cudaSuccess;
+        if (src_dtype == 1) prep_split16_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(a);
+        else prep_split16_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(a);
+        return cudaGetLastError();
+    }
     if (work_f64 && (mode == MODE_F16R || mode == MODE_TF32)) {
         if (mode == MODE_F16R) {
             if (src_dtype == 0) return launch_prep_t<__half, double, MODE_F16R>(a, s);

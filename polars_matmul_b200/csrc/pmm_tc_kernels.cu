@@ -70,24 +70,33 @@ constexpr int SOFT_AT = 48;
 //        (128 rows), so corpus bytes per SM halve and a third pipeline stage fits.
 // TERMS = tcgen05 MMAs per K-step for f32 data: 3 = the 3xTF32 split (hi/lo planes), 1 = hi*hi only (TF32
 //         precision, |error| <= 2^-11 |q||c|; used as the first-level filter, see pmm_api.cu).
+//         With F16: 2 = the hi/lo f16 split of the raw f32 matmul (row-scaled planes from prep_split16_kernel, see
+//         the MMA issuer), any other value = one exact / rounded f16 plane.
 // CLM  = CTA pairs per cluster (cta_group::2 only): 2 = a cluster of 4 CTAs works on two query tiles against the
 //        SAME corpus tile; each CTA fetches a quarter of the corpus tile and TMA-multicasts it to the CTA of the
 //        other pair that needs the same half, so corpus bytes L2 -> shared memory halve again.
 template <bool F16, int ROWB, int CG, int TERMS, int CLM = 1, int ESETS = 1>
 struct TcCfg {
-    static constexpr int PLANES = (F16 || TERMS == 1) ? 1 : 2;
+    static constexpr int PLANES = (F16 || TERMS == 1) ? 1 : 2;   // operand planes per matrix IN A STAGE (the f16 hi/lo split
+                                                                 // stages one plane of each matrix at a time)
     static constexpr int BK = ROWB / (F16 ? 2 : 4);  // elements of K per stage
     static constexpr int KSTEPS = ROWB / 32;         // 32 bytes of K per tcgen05.mma
     static constexpr int B_ROWS = BN / CG;           // corpus rows this CTA stages per tile
     static constexpr int A_BYTES = BM * ROWB;
     static constexpr int B_BYTES = B_ROWS * ROWB;
-    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    static constexpr bool SPLIT16 = F16 && TERMS == 2;   // raw f32 matmul on hi/lo f16 planes: the query planes of the item stay
+                                                         // resident in shared memory, a stage holds one K-block of one corpus plane
+    static constexpr int STAGE_BYTES = SPLIT16 ? B_BYTES : PLANES * (A_BYTES + B_BYTES);
     static constexpr int STAGING_BYTES = ESETS * 4 * 32 * LOOK_PITCH * 4;  // per epilogue warp: one chunk of filter values (hit lookup)
     static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of its columns of the tile
     static constexpr int STORE_BYTES = 4 * 2 * 4096; // matmul epilogue: per warp two 32x32 f32 TMA-store tiles
     static constexpr int EPI_BYTES = (STAGING_BYTES + AUX_BYTES) > STORE_BYTES ? (STAGING_BYTES + AUX_BYTES) : STORE_BYTES;
-    static constexpr int STAGES = (232448 - EPI_BYTES - 256 - 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
+    static constexpr int COLF_BYTES = (F16 && TERMS == 2) ? BN * 4 : 0;   // f16 split: the tile's column scale factors (one copy per CTA)
+    // f16 split: [epilogue][barriers, column factors: 2 KB][resident query planes: 2 x num_kb x A_BYTES][stage ring]; the
+    // ring takes what is left of the 227 KB (12 - 2 num_kb stages, at most STAGES = 8: the barrier arrays' size)
+    static constexpr int SPLIT_FIXED = EPI_BYTES + 2048;
+    static constexpr int STAGES = SPLIT16 ? 8 : (232448 - EPI_BYTES - 256 - COLF_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = SPLIT16 ? 232448 : STAGES * STAGE_BYTES + EPI_BYTES + 256 + COLF_BYTES + 1024;
 };
 
 struct TcKParams {
@@ -130,7 +139,22 @@ __device__ unsigned long long g_tc_wait[4 + 48];  // [20 + b] / [36 + b]: epilog
 
 // Work of CTA `cta` in round `it`. Returns false when the CTA idles in that round.
 __device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int it, int &m_tile, int &n_start,
-                                              int &n_step, int64_t &slot) {
+                                              int &n_step, int64_t &slot, int &n_end) {
+    n_end = s.n_tiles;
+    if (s.flat) {   // raw matmul: this unit's share of the row-major tile list, one query tile per "round"
+        const int64_t total = (int64_t)s.m_tiles * s.n_tiles;
+        const int64_t t0 = total * cta / s.num_ctas, t1 = total * (cta + 1) / s.num_ctas;
+        if (cta >= s.num_ctas || t0 >= t1) return false;
+        const int m0 = (int)(t0 / s.n_tiles);
+        m_tile = m0 + it;
+        if ((int64_t)m_tile * s.n_tiles >= t1) return false;
+        n_start = it == 0 ? (int)(t0 - (int64_t)m0 * s.n_tiles) : 0;
+        const int64_t left = t1 - (int64_t)m_tile * s.n_tiles;
+        if (left < n_end) n_end = (int)left;
+        n_step = 1;
+        slot = 0;
+        return true;
+    }
     if (it < s.rounds) {
         if (cta >= s.mc * s.g) return false;
         int grp = cta / s.g, rank = cta - grp * s.g;
@@ -221,6 +245,13 @@ __device__ __forceinline__ float filter_value(float acc, float aux, float rowc) 
     return acc;
 }
 
+// (x, y) <- ((x r) c0, (y r) c1) with two packed f32x2 multiplications (FMUL2): the matmul epilogue of the f16 split.
+__device__ __forceinline__ void scale2(uint32_t &x, uint32_t &y, float r, float c0, float c1) {
+    asm("{ .reg .b64 va, vr, vc; mov.b64 va, {%0, %1}; mov.b64 vr, {%2, %2}; mov.b64 vc, {%3, %4};\n\t"
+        "mul.rn.f32x2 va, va, vr; mul.rn.f32x2 va, va, vc; mov.b64 {%0, %1}, va; }"
+        : "+r"(x), "+r"(y) : "f"(r), "f"(c0), "f"(c1));
+}
+
 // One 32-column chunk of the accumulator tile for this thread's row.
 // Common case: no score of the chunk beats any row's threshold. It costs the filter values, a max tree
 // (one FMNMX per score; fmaxf drops NaN, and NaN can only matter while a list is not full, when thr_f is NaN
@@ -293,15 +324,32 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     constexpr int ESETS = tc_esets(F16, EPI, TERMS);
     constexpr int CPS = BN / 32 / ESETS;      // 32-column chunks of a tile per epilogue warp
     typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS> Cfg;
-    constexpr bool ONE = F16 || TERMS == 1;   // one operand plane per matrix, one MMA per K-step
+    constexpr bool ONE = Cfg::PLANES == 1;    // one operand plane per matrix, one MMA per K-step
+    // Raw f32 matmul on f16 hi/lo planes: x = hi + lo to 22 bits, products hi*hi + hi*lo + lo*hi at the f16 rate.
+    // tcgen05 truncates the f32 accumulator once per MMA, and a truncation costs up to one ulp of the RUNNING SUM, so
+    // the order matters: the K range is swept TWICE - first all lo*hi and hi*lo terms (the sum is ~2^-11 of the result
+    // while they are added, their truncations vanish), then the hi*hi terms.  Only D/16 truncations hit the full-size
+    // sum (the 3xTF32 order: 3 D/8).  The unit of work sweeps all corpus tiles for ONE query tile, so both query planes
+    // of the item (2 x num_kb x 16 KB, D <= 256) stay resident in shared memory and only corpus planes stream through
+    // the stage ring, one K-block of one plane (16 KB) per stage: per K-block (c hi), (c lo) in the first sweep -
+    // multiplied with q lo and q hi - and (c hi) again in the second.  Operand bytes L2 -> SM per tile: 12 x 16 KB per
+    // CTA at D = 256 instead of 24 - the kernel had been bound by the SM <-> L2 fabric (operands in, results out).
+    constexpr bool SPLIT16 = Cfg::SPLIT16;
     constexpr int GS = CG * CLM;              // CTAs per scheduling unit (= cluster size)
     static_assert(CLM == 1 || CG == 2, "corpus multicast is built on CTA pairs");
+    static_assert(!SPLIT16 || (CG == 2 && CLM == 1 && EPI == EPI_MATMUL), "the f16 split is the CTA-pair matmul kernel");
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
-    float *aux_tiles = (float *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
-    uint64_t *bars = (uint64_t *)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    // offsets of the epilogue area and of the stage ring (f16 split: see TcCfg)
+    const int a_bytes = SPLIT16 ? 2 * p.num_kb * Cfg::A_BYTES : 0;
+    const uint32_t epi_off = SPLIT16 ? 0u : (uint32_t)(Cfg::STAGES * Cfg::STAGE_BYTES);
+    const uint32_t a_off = (uint32_t)Cfg::SPLIT_FIXED;
+    const uint32_t ring_off = SPLIT16 ? a_off + (uint32_t)a_bytes : 0u;
+    const int nst = SPLIT16 ? (12 - 2 * p.num_kb < Cfg::STAGES ? 12 - 2 * p.num_kb : Cfg::STAGES) : Cfg::STAGES;   // stages in the ring
+    float *aux_tiles = (float *)(smem + epi_off + Cfg::STAGING_BYTES);
+    uint64_t *bars = (uint64_t *)(smem + epi_off + Cfg::EPI_BYTES);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -309,6 +357,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
     auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };  // CLM == 2: "peer CTA's stage landed"
     volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(bars + 3 * Cfg::STAGES + 4);
+    const uint32_t colf_sa = bar_base + 256u;   // f16 split: BN floats, 256-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank4 = GS > 1 ? cluster_ctarank() : 0u;    // rank inside the cluster
@@ -322,7 +371,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_qhi);
         prefetch_tensormap(&tm_chi);
-        if (!ONE) {
+        if (!ONE || SPLIT16) {
             prefetch_tensormap(&tm_qlo);
             prefetch_tensormap(&tm_clo);
         }
@@ -351,7 +400,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         // The whole warp walks the schedule (warp-uniform control flow and addresses); one elected lane issues.
         const bool issuer = elect_one();
         int stage = 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, aphase = 0;
         const int n_sync_full = p.round_sync ? ((S.n_tiles + S.g - 1) / S.g + p.sync_tiles - 1) / p.sync_tiles : 0;
         bool pace = true;  // cleared by the first timeout: this CTA keeps arriving but no longer waits (the grid is
                            // evidently not co-resident, e.g. another kernel holds SMs; waiting again would cost 4 ms a time)
@@ -364,17 +413,32 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             const int step_r = it < S.rounds ? S.g : S.g_rem;
             const int n_sync = p.round_sync ? ((S.n_tiles + step_r - 1) / step_r + p.sync_tiles - 1) / p.sync_tiles : 0;
             unsigned int *sync_base = p.round_sync + (it < S.rounds ? it * n_sync_full : S.rounds * n_sync_full);
-            int m_tile, n_start, n_step;
+            int m_tile, n_start, n_step, n_end;
             int64_t slot;
-            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) {
+            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot, n_end)) {
                 if (issuer)
                     for (int sp = 0; sp < n_sync; ++sp) atomicAdd(sync_base + sp, 1u);
                 __syncwarp();
                 continue;
             }
             const int32_t arow = ((m_tile * CLM + (int)pairc) * CG + (int)crank) * BM;   // this CTA's 128 query rows
+            if (SPLIT16) {
+                // the item's query planes, resident for all of its tiles: hi K-blocks, then lo K-blocks.  The region is
+                // free once the MMAs of the previous item have retired (aempty: committed by the MMA warp).
+                mbar_wait(pfull_bar(1), aphase ^ 1u);
+                if (issuer) {
+                    const uint32_t afb = mapa_u32(pfull_bar(0), leader_rank);
+                    if (crank == 0) mbar_arrive_expect_tx(pfull_bar(0), 2u * (uint32_t)a_bytes);
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        tma_load_2d_pair(smem_base + a_off + (uint32_t)(kb * Cfg::A_BYTES), &tm_qhi, afb, kb * Cfg::BK, arow);
+                        tma_load_2d_pair(smem_base + a_off + (uint32_t)((p.num_kb + kb) * Cfg::A_BYTES), &tm_qlo, afb, kb * Cfg::BK, arow);
+                    }
+                }
+                __syncwarp();
+                aphase ^= 1u;
+            }
             int j = 0;  // tile counter of this CTA inside the round
-            for (int nt = n_start; nt < S.n_tiles; nt += n_step, ++j) {
+            for (int nt = n_start; nt < n_end; nt += n_step, ++j) {
                 const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
                 if (n_sync && j % p.sync_tiles == 0) {
                     if (issuer) {
@@ -398,11 +462,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     }
                     __syncwarp();
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int kb_total = SPLIT16 ? 3 * p.num_kb : p.num_kb;   // f16 split: stage uses, see above
+                for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sa = smem_base + ring_off + stage * Cfg::STAGE_BYTES;
                     if (issuer) {
-                        if (CG == 1) {
+                        if (SPLIT16) {   // one K-block of one corpus plane
+                            const bool first = kb < 2 * p.num_kb;
+                            const int k0 = (first ? (kb >> 1) : kb - 2 * p.num_kb) * Cfg::BK;
+                            const uint32_t fb = mapa_u32(full_bar(stage), leader_rank);
+                            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+                            tma_load_2d_pair(sa, (first && (kb & 1)) ? &tm_clo : &tm_chi, fb, k0, brow);
+                        } else if (CG == 1) {
                             const uint32_t fb = full_bar(stage);
                             mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
                             tma_load_2d(sa, &tm_qhi, fb, kb * Cfg::BK, arow);
@@ -437,7 +508,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         }
                     }
                     __syncwarp();
-                    if (++stage == Cfg::STAGES) {
+                    if (++stage == nst) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -459,16 +530,21 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             int abuf = 0;
-            uint32_t aphase = 0;
+            uint32_t aphase = 0, qphase = 0;
             const bool dbg = p.debug_skip == 8;
             long long w_tempty = 0, w_full = 0;
             const long long w_start = dbg ? clock64() : 0ll;
             for (int it = 0; it < total_rounds; ++it) {
-                int m_tile, n_start, n_step;
+                int m_tile, n_start, n_step, n_end;
                 int64_t slot;
-                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot, n_end)) continue;
+                if (SPLIT16) {   // the item's query planes have landed (both CTAs' bytes count on the leader's barrier)
+                    mbar_wait(pfull_bar(0), qphase);
+                    qphase ^= 1u;
+                    tc_fence_after();
+                }
                 int jt = 0;
-                for (int nt = n_start; nt < S.n_tiles; nt += n_step, ++jt) {
+                for (int nt = n_start; nt < n_end; nt += n_step, ++jt) {
                     const long long w0 = dbg ? clock64() : 0ll;
                     mbar_wait(tempty_bar(abuf), aphase ^ 1u);
                     if (dbg) {
@@ -478,19 +554,30 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     }
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(abuf * BN);
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const int kb_total = SPLIT16 ? 3 * p.num_kb : p.num_kb;
+                    for (int kb = 0; kb < kb_total; ++kb) {
                         const long long w1 = dbg ? clock64() : 0ll;
                         mbar_wait(full_bar(stage), phase);
                         if (dbg) w_full += clock64() - w1;
                         if (CLM == 2) mbar_wait(pfull_bar(stage), phase);   // the peer CTA's half of the stage landed too
                         tc_fence_after();
-                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sa = smem_base + ring_off + stage * Cfg::STAGE_BYTES;
                         // descriptors of the stage's four tiles; a K-step of 32 bytes adds 2 to the address field
                         const uint64_t d_ah = umma_smem_desc<ROWB>(sa);
                         const uint64_t d_al = d_ah + (uint64_t)(Cfg::A_BYTES >> 4);
                         const uint64_t d_bh = d_ah + (uint64_t)((Cfg::PLANES * Cfg::A_BYTES) >> 4);
                         const uint64_t d_bl = d_bh + (uint64_t)(Cfg::B_BYTES >> 4);
-                        if (issuer) {
+                        if (issuer && SPLIT16) {
+                            // the stage holds a corpus plane's K-block; its partner is the resident query plane:
+                            // first sweep (c hi) x q lo, (c lo) x q hi; second sweep (c hi) x q hi
+                            const bool first = kb < 2 * p.num_kb;
+                            const int kq = first ? (kb >> 1) : kb - 2 * p.num_kb;
+                            const bool q_lo = first && !(kb & 1);
+                            const uint64_t d_q = umma_smem_desc<ROWB>(smem_base + a_off + (uint32_t)(((q_lo ? p.num_kb : 0) + kq) * Cfg::A_BYTES));
+#pragma unroll
+                            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) umma<CG, true>(tmem_d, d_q + 2 * ks, d_ah + 2 * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                            umma_commit_pair(empty_bar(stage), (uint16_t)(3u << leader_rank));
+                        } else if (issuer) {
 #pragma unroll
                             for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
                                 const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
@@ -510,7 +597,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                             else umma_commit_pair(empty_bar(stage), CLM == 2 ? (uint16_t)0xF : (uint16_t)(3u << leader_rank));
                         }
                         __syncwarp();
-                        if (++stage == Cfg::STAGES) {
+                        if (++stage == nst) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -521,6 +608,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     __syncwarp();
                     abuf ^= 1;
                     if (abuf == 0) aphase ^= 1u;
+                }
+                if (SPLIT16) {   // every MMA that reads the resident query planes has been issued: free them on retirement
+                    if (issuer) umma_commit_pair(pfull_bar(1), (uint16_t)(3u << leader_rank));
+                    __syncwarp();
                 }
             }
             if (dbg && issuer) {
@@ -534,15 +625,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < total_rounds; ++it) {
-                int m_tile, n_start, n_step;
+                int m_tile, n_start, n_step, n_end;
                 int64_t slot;
-                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
-                for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+                if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot, n_end)) continue;
+                for (int nt = n_start; nt < n_end; nt += n_step) {
                     for (int kb = 0; kb < p.num_kb; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         if (lane == 0) mbar_arrive_cluster(pfull_bar(stage), leader_rank);
                         __syncwarp();
-                        if (++stage == Cfg::STAGES) {
+                        if (++stage == nst) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -558,16 +649,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
         const int eset = (warp - 2) >> 2;  // epilogue set: columns [eset * BN / ESETS, (eset + 1) * BN / ESETS) of every tile
         const int ch0 = eset * CPS;
         float *aux_s = aux_tiles + (warp - 2) * (BN / ESETS);
-        const uint32_t look_sa = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (uint32_t)((warp - 2) * 32 * LOOK_PITCH * 4);
+        const uint32_t look_sa = smem_base + epi_off + (uint32_t)((warp - 2) * 32 * LOOK_PITCH * 4);
         // this warp's 32 staging rows
         uint64_t *stg = EPI == EPI_TOPK ? p.staged + (((int64_t)blockIdx.x * ESETS + eset) * BM + row0) * SC : nullptr;
         const uint32_t aux_sa = smem_u32(aux_s);
         int abuf = 0;
         uint32_t aphase = 0;
         for (int it = 0; it < total_rounds; ++it) {
-            int m_tile, n_start, n_step;
+            int m_tile, n_start, n_step, n_end;
             int64_t slot;
-            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot)) continue;
+            if (!tc_round_item(S, cta, it, m_tile, n_start, n_step, slot, n_end)) continue;
             const int64_t qrow = (((int64_t)m_tile * CLM + pairc) * CG + crank) * BM + row;
             uint64_t thr = 0ull;
             float thr_f = PMM_DSKIP(p, 3) ? 103.0f : __uint_as_float(0x7fc00000u);
@@ -603,7 +694,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                 if (p.metric == METRIC_EUCLIDEAN) rowc = p.q_aux[qrow];
                 __syncwarp();
             }
-            for (int nt = n_start; nt < S.n_tiles; nt += n_step) {
+            if (SPLIT16) rowc = p.q_aux[qrow];   // this row's scale factor (padded to the tile grid)
+            for (int nt = n_start; nt < n_end; nt += n_step) {
                 const int64_t col_tile = (int64_t)nt * BN;
                 if (EPI == EPI_TOPK && p.metric != METRIC_DOT) {  // stage this tile's corpus aux values (per warp)
                     __syncwarp();
@@ -613,6 +705,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         aux_s[i * 32 + lane] = p.metric == METRIC_COSINE ? (a > p.norm_guard ? __frcp_rn(a) : 0.0f) : a;
                     }
                     __syncwarp();
+                }
+                if (SPLIT16) {
+                    // The tile's 256 column scale factors, ONE copy per CTA: each of the four epilogue warps fetches a
+                    // quarter (the load is in flight across the first barrier), the warps meet before the copy is
+                    // overwritten (everyone is done with the previous tile's factors) and after it is complete.
+                    const float2 mine = __ldg((const float2 *)(p.c_aux + col_tile + (warp - 2) * 64) + lane);   // padded to the tile grid
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(colf_sa + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(mine.x), "f"(mine.y) : "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
                 mbar_wait(tfull_bar(abuf), aphase);
                 tc_fence_after();
@@ -633,11 +734,20 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     }
                     const int64_t col0 = col_tile + ch * 32;
                     if (EPI == EPI_TOPK && (PMM_DSKIP(p, 1) || PMM_DSKIP(p, 2))) continue;
+                    if (EPI == EPI_MATMUL && SPLIT16) {   // undo the rows' power-of-two scaling: two exact multiplications
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {   // broadcast reads of the chunk's 32 factors; packed f32x2 multiplies
+                            float c0, c1, c2, c3;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0), "=f"(c1), "=f"(c2), "=f"(c3) : "r"(colf_sa + (uint32_t)(ch * 128 + i * 16)));
+                            scale2(v[4 * i + 0], v[4 * i + 1], rowc, c0, c1);
+                            scale2(v[4 * i + 2], v[4 * i + 3], rowc, c2, c3);
+                        }
+                    }
                     if (EPI == EPI_MATMUL) {
                         if (p.out_tma) {
                             // registers -> swizzled 32x32 smem tile -> one TMA store per warp and chunk: full 128-byte
                             // lines, bounds clipped by the hardware
-                            const uint32_t sbuf = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (uint32_t)((lg * 2 + (ch & 1)) * 4096);
+                            const uint32_t sbuf = smem_base + epi_off + (uint32_t)((lg * 2 + (ch & 1)) * 4096);
                             if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
                             __syncwarp();
 #pragma unroll
@@ -787,7 +897,7 @@ template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM = 1>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     constexpr int ESETS = tc_esets(F16, EPI, TERMS);
     typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS> Cfg;
-    constexpr bool ONE = F16 || TERMS == 1;
+    constexpr bool ONE = Cfg::PLANES == 1 && !(F16 && TERMS == 2);   // the f16 split needs the lo planes' maps as well
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
     if (!make_plane_map(&tc_hi, a.c_hi, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS / CLM, F16, ROWB)) return cudaErrorInvalidValue;
@@ -795,8 +905,8 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
         tq_lo = tq_hi;
         tc_lo = tc_hi;
     } else {
-        if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, false, ROWB)) return cudaErrorInvalidValue;
-        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS / CLM, false, ROWB)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tq_lo, a.q_lo, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&tc_lo, a.c_lo, a.c_rows_pad, a.dim_pad, Cfg::B_ROWS / CLM, F16, ROWB)) return cudaErrorInvalidValue;
     }
     CUtensorMap t_out = tq_hi;  // placeholder for the top-k kernels
     int out_tma = 0;
@@ -896,10 +1006,27 @@ TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int g
         if (s.g_rem > cap_tiles) s.g_rem = cap_tiles;
         if (s.g_rem < 1) s.g_rem = 1;
     }
+    s.flat = 0;
     int used_full = s.rounds > 0 ? s.mc * s.g : 0;
     int used_rem = s.m_rem * s.g_rem;
     s.num_ctas = used_full > used_rem ? used_full : used_rem;
     if (s.num_ctas < 1) s.num_ctas = 1;
+    return s;
+}
+
+TcSchedule make_tc_schedule_flat(int64_t q_rows, int64_t c_rows, int num_units, int cg) {
+    TcSchedule s = make_tc_schedule(q_rows, c_rows, num_units, 1, cg);
+    const int64_t total = (int64_t)s.m_tiles * s.n_tiles;
+    s.flat = 1;
+    s.num_ctas = (int)(total < (int64_t)(num_units > 0 ? num_units : 1) ? (total > 0 ? total : 1) : (num_units > 0 ? num_units : 1));
+    const int64_t per = (total + s.num_ctas - 1) / s.num_ctas;   // the largest share; it may start anywhere inside a query tile
+    s.rounds = (int)((per + s.n_tiles - 2) / s.n_tiles) + 1;
+    if (s.rounds > s.m_tiles) s.rounds = s.m_tiles;
+    s.g = 1;
+    s.mc = s.num_ctas;
+    s.m_full = s.m_tiles;
+    s.m_rem = 0;
+    s.g_rem = 0;
     return s;
 }
 
@@ -937,6 +1064,10 @@ cudaError_t launch_tc_topk(const TcArgs &a, cudaStream_t s) {
 }
 
 cudaError_t launch_tc_matmul(const TcArgs &a, cudaStream_t s) {
+    if (a.f16 && a.terms == 2) {   // hi/lo f16 split of f32 operands (CTA pairs only; resident query planes: D <= 256)
+        if (a.cg != 2 || !a.q_lo || !a.c_lo || !a.q_aux || !a.c_aux || a.dim_pad > 256) return cudaErrorInvalidValue;
+        return launch_t2<true, EPI_MATMUL, 1, 128, 2, 2>(a, s);
+    }
     if (a.f16) return launch_t<true, EPI_MATMUL, 1>(a, s);
     return launch_t<false, EPI_MATMUL, 1>(a, s);
 }

@@ -23,7 +23,7 @@ from tests.test_gpu_property import _data                    # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", type=int, default=1500)
+    ap.add_argument("--cases", type=int, default=20000)
     ap.add_argument("--max-dim", type=int, default=256)
     ap.add_argument("--seconds", type=float, default=150.0)
     ap.add_argument("--option", action="append", default=[])
@@ -45,7 +45,7 @@ def main():
         if time.time() - t0 > args.seconds:
             break
         kind = kinds[case % len(kinds)]
-        d = int(rng.integers(1, args.max_dim + 1)) if case % 3 else int(rng.choice([args.max_dim, args.max_dim - 1, args.max_dim // 2, 1, 2, 3, 8, 33]))
+        d = int(rng.integers(1, args.max_dim + 1)) if case % 3 else int(rng.choice([args.max_dim, args.max_dim - 1, args.max_dim // 2, 9, 10, 12, 16, 20, 31, 32, 33, 48]))
         nq, n = int(rng.integers(1, 301)), int(rng.integers(1, 2501))
         seed = int(rng.integers(0, 2**31 - 1))
         if kind == "positive":
@@ -63,7 +63,7 @@ def main():
             ratio = np.where(diff == 0, 0.0, diff / tol)
         ratio = np.nan_to_num(ratio, nan=0.0, posinf=1e30)
         worst = float(ratio.max())
-        key = f"{kind}:{'<=64' if d <= 64 else '<=128' if d <= 128 else '<=192' if d <= 192 else '<=256' if d <= 256 else '>256'}"
+        key = f"{kind}:" + next((f"<={b:03d}" for b in (4, 8, 16, 32, 64, 128, 192, 256, 512, 1024) if d <= b), ">1024")
         b = buckets.setdefault(key, {"worst_ratio": 0.0, "entries": 0, "cases": 0})
         b["worst_ratio"] = max(b["worst_ratio"], worst)
         b["entries"] += int(ratio.size)

@@ -324,6 +324,115 @@ def test_tc_matmul_odd_shapes(native, oracle, shape):
     parity.check_matmul(out, q, c, oracle.matmul(q, c), np.float32)
 
 
+@pytest.mark.parametrize("d", [1, 8, 9, 32, 33, 64, 65, 130, 192, 255, 256])
+def test_matmul_f16_split_planes(native, oracle, d):
+    """Raw f32 matmul on the tensor cores runs on row-scaled hi/lo f16 planes (one, several and an odd number of 64-element
+    K-blocks; the second sweep packs two K-blocks per stage) for 32 < D <= 256; up to 8 elements the exact kernel, up to 32
+    the TF32 planes.  Per-row magnitudes over 13 decades exercise the power-of-two scaling; small integers must come out
+    exactly; the 3xTF32 planes stay available as an option."""
+    rng = np.random.default_rng(1000 + d)
+    q, c = _randn(rng, 150, d), _randn(rng, 1100, d)
+    native.set_option("profile", 1)
+    try:
+        native.reset_stats()
+        out = native.matmul(_hm(q), _hm(c))
+        assert native.get_stat("scores_f32_launches" if d <= 8 else "tc_matmul_tf32x3_launches" if d <= 32 else "tc_matmul_f16x3_launches") == 1
+    finally:
+        native.set_option("profile", 0)
+    ref = oracle.matmul(q, c)
+    if d <= 8:
+        assert np.array_equal(out, ref)
+    parity.check_matmul(out, q, c, ref, np.float32)
+    qs = q * (10.0 ** rng.uniform(-8, 5, size=(150, 1))).astype(np.float32)
+    cs = c * (10.0 ** rng.uniform(-8, 5, size=(1100, 1))).astype(np.float32)
+    parity.check_matmul(native.matmul(_hm(qs), _hm(cs)), qs, cs, oracle.matmul(qs, cs), np.float32)
+    qi = rng.integers(-3, 4, size=(150, d)).astype(np.float32)
+    ci = rng.integers(-3, 4, size=(1100, d)).astype(np.float32)
+    assert np.array_equal(native.matmul(_hm(qi), _hm(ci)), oracle.matmul(qi, ci))
+    native.set_option("matmul_split16", 0)
+    native.set_option("profile", 1)
+    try:
+        native.reset_stats()
+        out3 = native.matmul(_hm(q), _hm(c))
+        assert native.get_stat("tc_matmul_tf32x3_launches") == (1 if d > 8 else 0)
+    finally:
+        native.set_option("matmul_split16", 1)
+        native.set_option("profile", 0)
+    assert np.abs(out3 - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(2600, 1500, 96), (300, 5000, 200), (5000, 300, 24)])
+def test_matmul_tile_schedules_agree(native, oracle, shape):
+    """The flat tile schedule (equal shares of the tile list per CTA pair: shares start and end inside a query tile, the
+    resident query planes are reloaded at the boundary) and the classic one give the same matrix."""
+    nq, n, d = shape
+    rng = np.random.default_rng(nq + n)
+    q, c = _randn(rng, nq, d), _randn(rng, n, d)
+    outs = []
+    for flat in (1, 0):
+        native.set_option("matmul_flat", flat)
+        try:
+            outs.append(native.matmul(_hm(q), _hm(c)))
+        finally:
+            native.set_option("matmul_flat", -1)
+    assert np.array_equal(outs[0], outs[1])
+    parity.check_matmul(outs[0], q, c, oracle.matmul(q, c), np.float32)
+
+
+def test_matmul_f16_split_extreme_rows(native, oracle):
+    """Rows the power-of-two scaling cannot serve - a largest element beyond 2^+-60, inf / NaN, all-zero rows, elements
+    25 binades below the row's largest - keep the reference's result: the first two are recomputed with IEEE arithmetic
+    (bit-identical to the oracle), zero rows give zeros, tiny elements are off by far less than the tolerance."""
+    rng = np.random.default_rng(77)
+    q, c = _randn(rng, 70, 96), _randn(rng, 900, 96)
+    q[3] *= np.float32(1e25)
+    q[4] *= np.float32(1e-25)
+    q[5] = 0
+    q[6, ::2] *= np.float32(3e-8)
+    q[7, 10] = np.inf
+    c[11] *= np.float32(1e-30)
+    c[12] *= np.float32(1e22)
+    c[13] = 0
+    c[14, 5] = np.nan
+    c[15, 1::3] *= np.float32(1e-9)
+    out = native.matmul(_hm(q), _hm(c))
+    ref = oracle.matmul(q, c)
+    special_q, special_c = [3, 4, 7], [11, 12, 14]
+    assert np.array_equal(out[special_q], ref[special_q], equal_nan=True)
+    assert np.array_equal(out[:, special_c], ref[:, special_c], equal_nan=True)
+    keep_q = [i for i in range(70) if i not in special_q]
+    keep_c = [j for j in range(900) if j not in special_c]
+    assert not out[5][keep_c].any() and not out[keep_q, 13].any()
+    parity.check_matmul(out[np.ix_(keep_q, keep_c)], q[keep_q], c[keep_c], ref[np.ix_(keep_q, keep_c)], np.float32)
+
+
+def test_matmul_f16_split_mixed_storage_and_lists(native, oracle):
+    """f16-stored rows beside f32 rows (working precision f32, src/matmul.rs:13-19 as relaxed by the README contract) and a
+    pl.List column with nulls and short rows go through the same split planes."""
+    import pyarrow as pa
+    rng = np.random.default_rng(5)
+    q, c = _randn(rng, 90, 100), _randn(rng, 700, 100).astype(np.float16)
+    out = native.matmul(_hm(q), _hm(c))
+    parity.check_matmul(out, q, c.astype(np.float32), oracle.matmul(q, c.astype(np.float32)), np.float32)
+    rows, dense = [], np.zeros((90, 100), np.float32)
+    for i in range(90):
+        if i % 11 == 5:
+            rows.append(None)
+            continue
+        ln = 100 if i == 0 or i % 7 else int(rng.integers(0, 100))
+        vals = rng.standard_normal(ln).astype(np.float32)
+        dense[i, :ln] = vals
+        r = vals.tolist()
+        if ln > 3 and i % 5 == 0:
+            r[2] = None
+            dense[i, 2] = 0
+        rows.append(r)
+    col = pa.array(rows, type=pa.large_list(pa.float32()))
+    cf = c.astype(np.float32)
+    out = native.matmul(_hm(col), _hm(cf))
+    parity.check_matmul(out, dense, cf, oracle.matmul(dense, cf), np.float32)
+
+
 @pytest.mark.parametrize("d", [320, 385, 768, 1024, 2048])
 def test_matmul_long_vectors_stay_within_tolerance(native, oracle, d):
     """tcgen05 accumulates f32 with truncation, and the raw matmul has no exact re-scoring behind it: beyond D = 256 (f32,
