@@ -58,7 +58,7 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, matmul_split16 = 1, matmul_exact_max_dim = 8, matmul_flat = -1, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, matmul_split16 = 1, matmul_exact_max_dim = 8, matmul_flat = -1, d2h_direct = 1, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
     int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000, pipeline_min_gflop = 2000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
@@ -99,6 +99,7 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "pipeline_min_gflop") o.pipeline_min_gflop = value < 0 ? 0 : value;   // smallest round worth a launch of its own
     else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
     else if (k == "matmul_exact_max_dim") o.matmul_exact_max_dim = value < 0 ? 0 : (int)value;   // f32 vectors this short: exact SIMT kernel
+    else if (k == "d2h_direct") o.d2h_direct = value ? 1 : 0;   // top-k results written straight into page-locked result buffers
     else if (k == "matmul_flat") o.matmul_flat = value < 0 ? -1 : value ? 1 : 0;   // tile schedule of the tensor-core matmul: -1 automatic
     else if (k == "matmul_split16") o.matmul_split16 = value ? 1 : 0;           // raw f32 matmul: hi/lo f16 planes (1) or the 3xTF32 split (0)
     else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
@@ -1590,14 +1591,23 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     call.max_sq_ptr = c_max.as<unsigned int>();
     const uint64_t *kept_ptr = kept.as<uint64_t>();
     const size_t cnt = (size_t)Q * keff;
-    CUDA_TRY(d_idx.alloc(cnt * 4, s));
-    CUDA_TRY(d_sc.alloc(cnt * 8, s));
-    TopkOut o{d_idx.as<uint32_t>(), d_sc.as<double>(), d_cand};
+    // Page-locked result buffers (the Python shim's pooled ones) are addressable from the device: the re-scoring kernel
+    // then stores its coalesced rows straight into them - the 12 bytes per result cross PCIe while the kernel runs and
+    // there is no trailing copy.  Pageable buffers get device buffers and the staged copy.
+    uint32_t *direct_idx = nullptr;
+    double *direct_sc = nullptr;
+    const bool direct = t_opt.d2h_direct && out_index && out_score && host_device_view(out_index, (void **)&direct_idx) &&
+                        host_device_view(out_score, (void **)&direct_sc);
+    if (!direct) {
+        CUDA_TRY(d_idx.alloc(cnt * 4, s));
+        CUDA_TRY(d_sc.alloc(cnt * 8, s));
+    }
+    TopkOut o{direct ? direct_idx : d_idx.as<uint32_t>(), direct ? direct_sc : d_sc.as<double>(), d_cand};
     // c_aux_all holds the corpus norms (cosine) or squared norms (euclidean) of the whole corpus
     VerifyCtx vc = verify_ctx(call, uc.dm, keff, metric, index_base, s);
     if ((rc = tc_topk_verified(vc, q, uq.dm, &call, terms0, kept_ptr, o))) return rc;
-    if (out_index) CUDA_TRY(stage_d2h(out_index, d_idx.p, cnt * 4, s));
-    if (out_score) CUDA_TRY(stage_d2h(out_score, d_sc.p, cnt * 8, s));
+    if (!direct && out_index) CUDA_TRY(stage_d2h(out_index, d_idx.p, cnt * 4, s));
+    if (!direct && out_score) CUDA_TRY(stage_d2h(out_score, d_sc.p, cnt * 8, s));
     if (out_index || out_score) stat_add("d2h_bytes", (double)cnt * 12);
     if (queries->offsets || corpus->offsets) rc = finish_error_flag(err.as<int>(), s);
     CUDA_TRY(cudaStreamSynchronize(s));

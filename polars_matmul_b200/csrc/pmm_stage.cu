@@ -216,6 +216,18 @@ bool host_ptr_is_pinned(const void *p) {
     return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
 }
 
+// Page-locked host memory the current device can address: *dev = the device-side pointer (UVA: normally the same address).
+bool host_device_view(const void *p, void **dev) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return false;
+    *dev = attr.devicePointer;
+    return true;
+}
+
 cudaError_t stage_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream) {
     if (bytes == 0) return cudaSuccess;
     if (bytes < kDirectBelow || !g_enabled.load() || host_ptr_is_pinned(src_host))

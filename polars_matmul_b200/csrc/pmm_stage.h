@@ -25,6 +25,8 @@ void stage_set_ring(size_t slot_bytes, int slots);
 
 // True when `p` is page-locked (cudaHostAlloc / cudaHostRegister) or managed memory: cudaMemcpyAsync can DMA it.
 bool host_ptr_is_pinned(const void *p);
+// True when `p` is page-locked host memory the current device can address; *dev = the pointer to use in kernels.
+bool host_device_view(const void *p, void **dev);
 
 // Enqueue a host -> device copy of `bytes` on `stream`.  Page-locked sources: one cudaMemcpyAsync.  Pageable sources:
 // staged through the calling thread's ring; the call returns when the last piece has been ENQUEUED (the source

@@ -726,6 +726,46 @@ def test_resident_corpus_handle(native, oracle):
         h.close()
 
 
+def test_results_written_straight_into_page_locked_buffers(native, oracle):
+    """Host path with page-locked result buffers: the re-scoring kernel (and the scatter of re-queried rows) store into them
+    directly, no trailing device->host copy; pageable buffers take the staged copy.  Same bits either way, incl. queries
+    that go through the re-query levels (duplicated corpus rows: ties beyond the list)."""
+    import ctypes
+    rng = np.random.default_rng(123)
+    q, c = _randn(rng, 3000, 192), _randn(rng, 90_000, 192)          # 69 MB corpus -> chunked host path
+    c[1000:1300] = c[7]                                               # 300 identical rows: some queries need the exact fallback
+    k = 40
+    hq, hc = _hm(q), _hm(c)
+    outs = {}
+    for label, direct, pinned in (("direct", 1, True), ("copied", 0, True), ("pageable", 1, False)):
+        if pinned:
+            blocks = []
+            for nbytes in (3000 * k * 4, 3000 * k * 8):
+                p = ctypes.c_void_p()
+                native.check(native.lib().pmm_host_alloc(nbytes, ctypes.byref(p)))
+                blocks.append(p)
+            idx = np.ctypeslib.as_array(ctypes.cast(blocks[0], ctypes.POINTER(ctypes.c_uint32)), shape=(3000, k))
+            sc = np.ctypeslib.as_array(ctypes.cast(blocks[1], ctypes.POINTER(ctypes.c_double)), shape=(3000, k))
+        else:
+            blocks, idx, sc = [], np.empty((3000, k), np.uint32), np.empty((3000, k), np.float64)
+        idx[:] = 0xdeadbeef
+        sc[:] = -7.0
+        ka = ctypes.c_int64(0)
+        qs, cs = hq.c_struct(), hc.c_struct()
+        native.set_option("d2h_direct", direct)
+        try:
+            native.check(native.lib().pmm_topk(ctypes.byref(qs), ctypes.byref(cs), k, b"dot", idx.ctypes.data, sc.ctypes.data, ctypes.byref(ka)))
+        finally:
+            native.set_option("d2h_direct", 1)
+        assert ka.value == k
+        outs[label] = (idx.copy(), sc.copy())
+        for p in blocks:
+            native.check(native.lib().pmm_host_free(p))
+    parity.check_topk(outs["direct"][0], outs["direct"][1], q, c, k, "dot", oracle, exact=True)
+    for label in ("copied", "pageable"):
+        assert np.array_equal(outs[label][0], outs["direct"][0]) and np.array_equal(outs[label][1], outs["direct"][1])
+
+
 def test_host_chunked_upload_path(pmm, native, oracle):
     """Corpora >= 64 MB take the chunked host path (upload of chunk i+1 overlaps compute of chunk i):
     same result as the oracle, for fixed-size rows and for list offsets with nulls."""
