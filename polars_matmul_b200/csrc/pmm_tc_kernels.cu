@@ -49,7 +49,10 @@ constexpr int BN = TC_TILE_N;
 // accumulator tile and keeps its own candidate lists (merged with the others by pmm_merge.cu).  Two warps per
 // scheduler also hide each other's TMEM-load and dependent-issue latencies.  The 3xTF32 and matmul kernels are
 // MMA- resp. store-bound and keep one set (and the deeper operand pipeline).
-__host__ __device__ constexpr int tc_esets(bool f16, int epi, int terms) { return (epi == 0 && f16) ? 2 : 1; }
+// The matmul epilogue is a latency chain per warp and 32-column chunk (TMEM load -> registers -> swizzled shared tile ->
+// TMA store); four warps could not keep the result stream at HBM rate (4.3 us per 256 x 256 tile against 3.0 at the
+// write rate), eight - two per scheduler, half of the columns each, one store tile per warp - can.
+__host__ __device__ constexpr int tc_esets(bool f16, int epi, int terms) { return ((epi == 0 && f16) || epi == 1) ? 2 : 1; }
 __host__ __device__ constexpr int tc_threads(int esets) { return 64 + 128 * esets; }
 // Candidates that beat a row's threshold are APPENDED to a per-row staging area in global memory (L2-resident,
 // one per CTA and row, reused by every item of the CTA) and merged into the row's sorted list in batches: the
@@ -75,7 +78,7 @@ constexpr int SOFT_AT = 48;
 // CLM  = CTA pairs per cluster (cta_group::2 only): 2 = a cluster of 4 CTAs works on two query tiles against the
 //        SAME corpus tile; each CTA fetches a quarter of the corpus tile and TMA-multicasts it to the CTA of the
 //        other pair that needs the same half, so corpus bytes L2 -> shared memory halve again.
-template <bool F16, int ROWB, int CG, int TERMS, int CLM = 1, int ESETS = 1>
+template <bool F16, int ROWB, int CG, int TERMS, int CLM = 1, int ESETS = 1, int EPI = 0>
 struct TcCfg {
     static constexpr int PLANES = (F16 || TERMS == 1) ? 1 : 2;   // operand planes per matrix IN A STAGE (the f16 hi/lo split
                                                                  // stages one plane of each matrix at a time)
@@ -90,7 +93,7 @@ struct TcCfg {
     static constexpr int STAGING_BYTES = ESETS * 4 * 32 * LOOK_PITCH * 4;  // per epilogue warp: one chunk of filter values (hit lookup)
     static constexpr int AUX_BYTES = 4 * BN * 4;     // per epilogue warp: the corpus aux values of its columns of the tile
     static constexpr int STORE_BYTES = 4 * 2 * 4096; // matmul epilogue: per warp two 32x32 f32 TMA-store tiles
-    static constexpr int EPI_BYTES = (STAGING_BYTES + AUX_BYTES) > STORE_BYTES ? (STAGING_BYTES + AUX_BYTES) : STORE_BYTES;
+    static constexpr int EPI_BYTES = EPI == 1 ? STORE_BYTES : (STAGING_BYTES + AUX_BYTES);   // matmul: the store tiles only
     static constexpr int COLF_BYTES = (F16 && TERMS == 2) ? BN * 4 : 0;   // f16 split: the tile's column scale factors (one copy per CTA)
     // f16 split: [epilogue][barriers, column factors: 2 KB][resident query planes: 2 x num_kb x A_BYTES][stage ring]; the
     // ring takes what is left of the 227 KB (12 - 2 num_kb stages, at most STAGES = 8: the barrier arrays' size)
@@ -323,7 +326,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
           const __grid_constant__ CUtensorMap tm_out, const TcKParams p) {
     constexpr int ESETS = tc_esets(F16, EPI, TERMS);
     constexpr int CPS = BN / 32 / ESETS;      // 32-column chunks of a tile per epilogue warp
-    typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS> Cfg;
+    typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS, EPI> Cfg;
     constexpr bool ONE = Cfg::PLANES == 1;    // one operand plane per matrix, one MMA per K-step
     // Raw f32 matmul on f16 hi/lo planes: x = hi + lo to 22 bits, products hi*hi + hi*lo + lo*hi at the f16 rate.
     // tcgen05 truncates the f32 accumulator once per MMA, and a truncation costs up to one ulp of the RUNNING SUM, so
@@ -707,13 +710,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                     __syncwarp();
                 }
                 if (SPLIT16) {
-                    // The tile's 256 column scale factors, ONE copy per CTA: each of the four epilogue warps fetches a
-                    // quarter (the load is in flight across the first barrier), the warps meet before the copy is
+                    // The tile's 256 column scale factors, ONE copy per CTA: each of the eight epilogue warps fetches an
+                    // eighth (the load is in flight across the first barrier), the warps meet before the copy is
                     // overwritten (everyone is done with the previous tile's factors) and after it is complete.
-                    const float2 mine = __ldg((const float2 *)(p.c_aux + col_tile + (warp - 2) * 64) + lane);   // padded to the tile grid
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(colf_sa + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(mine.x), "f"(mine.y) : "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    static_assert(ESETS == 2 || !SPLIT16, "eight epilogue warps stage 32 column factors each");
+                    const float mine = __ldg(p.c_aux + col_tile + (warp - 2) * 32 + lane);   // padded to the tile grid
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(colf_sa + (uint32_t)(((warp - 2) * 32 + lane) * 4)), "f"(mine) : "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
                 mbar_wait(tfull_bar(abuf), aphase);
                 tc_fence_after();
@@ -747,8 +751,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
                         if (p.out_tma) {
                             // registers -> swizzled 32x32 smem tile -> one TMA store per warp and chunk: full 128-byte
                             // lines, bounds clipped by the hardware
-                            const uint32_t sbuf = smem_base + epi_off + (uint32_t)((lg * 2 + (ch & 1)) * 4096);
-                            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+                            // one 4 KB store tile per warp (eight warps) or two per warp (four)
+                            const uint32_t sbuf = smem_base + epi_off + (uint32_t)((ESETS == 2 ? (warp - 2) : (lg * 2 + (ch & 1))) * 4096);
+                            if (lane == 0) tma_store_wait_read<ESETS == 2 ? 0 : 1>();  // the store that last used this buffer has read it
                             __syncwarp();
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
@@ -896,7 +901,7 @@ bool make_out_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols) 
 template <bool F16, int EPI, int R, int ROWB, int CG, int TERMS, int CLM = 1>
 cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     constexpr int ESETS = tc_esets(F16, EPI, TERMS);
-    typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS> Cfg;
+    typedef TcCfg<F16, ROWB, CG, TERMS, CLM, ESETS, EPI> Cfg;
     constexpr bool ONE = Cfg::PLANES == 1 && !(F16 && TERMS == 2);   // the f16 split needs the lo planes' maps as well
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     if (!make_plane_map(&tq_hi, a.q_hi, a.q_rows_pad, a.dim_pad, BM, F16, ROWB)) return cudaErrorInvalidValue;
