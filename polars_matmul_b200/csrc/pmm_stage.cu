@@ -1,6 +1,7 @@
 // pmm_stage.cu — page-locked staging ring + host copy threads (see pmm_stage.h).
 #include "pmm_stage.h"
 
+#include <emmintrin.h>
 #include <string.h>
 
 #include <atomic>
@@ -18,6 +19,32 @@ std::atomic<size_t> g_slot_bytes{(size_t)32 << 20};
 std::atomic<int> g_slots{4};
 std::atomic<uint64_t> g_staged_h2d{0}, g_staged_d2h{0};
 std::atomic<int> g_enabled{1};
+
+std::atomic<int> g_nt_stores{1};
+
+// One range of a staged copy.  Into the ring (pageable -> page-locked) the bytes are written with non-temporal stores: the
+// destination is read next by the DMA engine, not by a core, so pulling its lines into the cache first (read for
+// ownership) only costs memory bandwidth - a third of the copy's traffic.  glibc's memcpy does the same, but only above a
+// size threshold that the per-thread ranges (a few MB) stay below.
+void copy_range(void *dst, const void *src, size_t bytes, bool stream_dst) {
+    if (!stream_dst || !g_nt_stores.load(std::memory_order_relaxed) || (((uintptr_t)dst) & 15) || bytes < 4096) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t n64 = bytes / 64;
+    const __m128i *s = (const __m128i *)src;
+    __m128i *d = (__m128i *)dst;
+    for (size_t i = 0; i < n64; ++i) {
+        const __m128i a = _mm_loadu_si128(s + 4 * i), b = _mm_loadu_si128(s + 4 * i + 1);
+        const __m128i c = _mm_loadu_si128(s + 4 * i + 2), e = _mm_loadu_si128(s + 4 * i + 3);
+        _mm_stream_si128(d + 4 * i, a);
+        _mm_stream_si128(d + 4 * i + 1, b);
+        _mm_stream_si128(d + 4 * i + 2, c);
+        _mm_stream_si128(d + 4 * i + 3, e);
+    }
+    _mm_sfence();
+    if (bytes & 63) memcpy((char *)dst + n64 * 64, (const char *)src + n64 * 64, bytes & 63);
+}
 
 int auto_threads() {
     unsigned hc = std::thread::hardware_concurrency();
@@ -37,6 +64,7 @@ class CopyPool {
         const void *src;
         size_t bytes;
         std::atomic<int> *pending;
+        bool stream_dst;
     };
     static CopyPool &get() {
         static CopyPool *p = new CopyPool();  // leaked on purpose: helper threads may outlive static destructors
@@ -67,7 +95,7 @@ class CopyPool {
                 }
             }
             if (have) {
-                memcpy(j.dst, j.src, j.bytes);
+                copy_range(j.dst, j.src, j.bytes, j.stream_dst);
                 j.pending->fetch_sub(1, std::memory_order_release);
             } else {
                 std::this_thread::yield();
@@ -85,7 +113,7 @@ class CopyPool {
                 j = q_.front();
                 q_.pop_front();
             }
-            memcpy(j.dst, j.src, j.bytes);
+            copy_range(j.dst, j.src, j.bytes, j.stream_dst);
             j.pending->fetch_sub(1, std::memory_order_release);
         }
     }
@@ -95,10 +123,11 @@ class CopyPool {
     std::vector<std::thread> workers_;
 };
 
-void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+// stream_dst: the destination is a ring slot (see copy_range)
+void parallel_memcpy(void *dst, const void *src, size_t bytes, bool stream_dst = false) {
     const int nt = stage_threads();
     if (nt <= 1 || bytes < ((size_t)1 << 20)) {
-        memcpy(dst, src, bytes);
+        copy_range(dst, src, bytes, stream_dst);
         return;
     }
     CopyPool &pool = CopyPool::get();
@@ -111,9 +140,9 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     pending.store(n_jobs, std::memory_order_relaxed);
     for (off = part; off < bytes; off += part) {
         const size_t n = bytes - off < part ? bytes - off : part;
-        pool.submit(CopyPool::Job{(char *)dst + off, (const char *)src + off, n, &pending});
+        pool.submit(CopyPool::Job{(char *)dst + off, (const char *)src + off, n, &pending, stream_dst});
     }
-    memcpy(dst, src, part < bytes ? part : bytes);
+    copy_range(dst, src, part < bytes ? part : bytes, stream_dst);
     pool.wait(&pending);
 }
 
@@ -194,6 +223,7 @@ constexpr size_t kDirectBelow = (size_t)256 << 10;  // small pageable copies: th
 
 void stage_set_enabled(int on) { g_enabled.store(on ? 1 : 0); }
 bool stage_enabled() { return g_enabled.load() != 0; }
+void stage_set_nt_stores(int on) { g_nt_stores.store(on ? 1 : 0); }
 void stage_set_threads(int n) { g_threads.store(n < 0 ? 0 : n > 64 ? 64 : n); }
 int stage_threads() {
     const int n = g_threads.load();
@@ -242,7 +272,7 @@ cudaError_t stage_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStr
         const size_t n = bytes - off < S ? bytes - off : S;
         Ring::Slot *s;
         if ((e = t_ring.acquire(&s)) != cudaSuccess) return e;
-        parallel_memcpy(s->p, (const char *)src_host + off, n);
+        parallel_memcpy(s->p, (const char *)src_host + off, n, true);
         if ((e = cudaMemcpyAsync((char *)dst_dev + off, s->p, n, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(s->ev, stream)) != cudaSuccess) return e;
         s->busy = true;

@@ -19,6 +19,8 @@ void stage_set_enabled(int on);
 bool stage_enabled();
 // Number of host threads one staged copy is spread over (including the caller). 0 = automatic.
 void stage_set_threads(int n);
+// Non-temporal stores for copies INTO the ring (default on).
+void stage_set_nt_stores(int on);
 int stage_threads();
 // Slot size in bytes (>= 1 MB) and slot count (>= 2) of rings created afterwards.
 void stage_set_ring(size_t slot_bytes, int slots);
