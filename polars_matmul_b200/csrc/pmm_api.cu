@@ -100,7 +100,7 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
     else if (k == "matmul_exact_max_dim") o.matmul_exact_max_dim = value < 0 ? 0 : (int)value;   // f32 vectors this short: exact SIMT kernel
     else if (k == "d2h_direct") o.d2h_direct = value ? 1 : 0;   // top-k results written straight into page-locked result buffers
-    else if (k == "matmul_flat") o.matmul_flat = value < 0 ? -1 : value ? 1 : 0;   // tile schedule of the tensor-core matmul: -1 automatic
+    else if (k == "matmul_flat") o.matmul_flat = value < 0 ? -1 : value > 2 ? 2 : (int)value;   // tile schedule of the tensor-core matmul: -1 automatic, 0 classic, 1 flat, 2 hybrid
     else if (k == "matmul_split16") o.matmul_split16 = value ? 1 : 0;           // raw f32 matmul: hi/lo f16 planes (1) or the 3xTF32 split (0)
     else if (k == "multi_gpu") o.multi_gpu = value ? 1 : 0;                     // host entry points may spread one call over all GPUs
     else if (k == "multi_gpu_min_gflop") o.multi_gpu_min_gflop = value < 0 ? 0 : value;
@@ -1232,6 +1232,12 @@ int dev_matmul_impl(const pmm_matrix_t *dl, const pmm_matrix_t *dr, void *d_out,
             const TcSchedule f = make_tc_schedule_flat(Q, N, di.num_sms / a.cg, a.cg);
             const int64_t flat = ((int64_t)f.m_tiles * f.n_tiles + f.num_ctas - 1) / f.num_ctas;
             if (t_opt.matmul_flat == 1 || (t_opt.matmul_flat < 0 && flat * 13 < classic * 10)) a.sched = f;
+            // between half and all of the units holding a query tile: the idle ones take over the tails of the sweeps -
+            // unless the shape is write-bound and few units idle (measured at 64 of 74: D = 32 classic 0.76 / hybrid 0.86 ms,
+            // D = 64 equal, D = 128 0.98 / 0.92, D = 256 1.63 / 1.58; at 47 of 74, D = 128: 1.11 / 0.74 ms)
+            else if (t_opt.matmul_flat == 2 ||
+                     (t_opt.matmul_flat < 0 && (D > 64 || (di.num_sms / a.cg - c.m_tiles) * 5 > di.num_sms / a.cg)))
+                a.sched = make_tc_schedule_hybrid(Q, N, di.num_sms / a.cg, a.cg);
         }
         a.metric = PMM_METRIC_DOT;
         a.k = 1;

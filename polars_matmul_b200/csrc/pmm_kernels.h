@@ -170,8 +170,12 @@ struct TcSchedule {
     int m_full;     // = rounds * mc
     int m_rem;      // = m_tiles - m_full
     int g_rem;      // CTAs per query tile in the last round (0 when m_rem == 0)
-    int flat;       // raw matmul (no lists to merge): unit u takes tiles [T u / U, T (u+1) / U) of the row-major list of all
-                    // T = m_tiles x n_tiles tiles; `rounds` = the most query tiles one unit touches, m_rem = 0
+    int flat;       // raw matmul (no lists to merge).  1: unit u takes tiles [T u / U, T (u+1) / U) of the row-major list of all
+                    // T = m_tiles x n_tiles tiles; `rounds` = the most query tiles one unit touches, m_rem = 0.
+                    // 2 (hybrid, G/2 < m_tiles < G units): unit m < m_tiles sweeps corpus tiles [0, n_main) of query tile m -
+                    // all of them in the same order, like the classic schedule - and the remaining units share the tails
+                    // [n_main, n_tiles) of all query tiles, so that no unit idles
+    int n_main;     // flat == 2: corpus tiles per main sweep
     __host__ __device__ int pieces(int m_tile) const { return m_tile < m_full ? g : g_rem; }
     __host__ __device__ int64_t slot_base(int m_tile) const {
         return m_tile < m_full ? (int64_t)m_tile * g : (int64_t)m_full * g + (int64_t)(m_tile - m_full) * g_rem;
@@ -180,6 +184,8 @@ struct TcSchedule {
 };
 TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int group, int cg, int64_t layout_rows = 0);
 TcSchedule make_tc_schedule_flat(int64_t q_rows, int64_t c_rows, int num_units, int cg);   // raw matmul: every unit busy, equal shares
+// raw matmul, hybrid (TcSchedule::flat == 2); returns a classic schedule when the shape does not qualify
+TcSchedule make_tc_schedule_hybrid(int64_t q_rows, int64_t c_rows, int num_units, int cg);
 // Diagnostics: reads and clears the wait-cycle counters filled when TcArgs::debug_skip == 8.
 void tc_debug_wait_cycles(unsigned long long out[52]);
 int tc_epilogue_sets(int f16, int terms);  // epilogue warp sets of the top-k kernel variant: lists per (slot, row)

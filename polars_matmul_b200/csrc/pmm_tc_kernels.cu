@@ -144,6 +144,27 @@ __device__ unsigned long long g_tc_wait[4 + 48];  // [20 + b] / [36 + b]: epilog
 __device__ __forceinline__ bool tc_round_item(const TcSchedule &s, int cta, int it, int &m_tile, int &n_start,
                                               int &n_step, int64_t &slot, int &n_end) {
     n_end = s.n_tiles;
+    if (s.flat == 2) {   // raw matmul, hybrid: main sweeps + helpers on the tails
+        n_step = 1;
+        slot = 0;
+        if (cta < s.m_tiles) {
+            m_tile = cta;
+            n_start = 0;
+            n_end = s.n_main;
+            return it == 0;
+        }
+        const int H = s.num_ctas - s.m_tiles, h = cta - s.m_tiles, tail = s.n_tiles - s.n_main;
+        const int64_t total = (int64_t)s.m_tiles * tail;
+        const int64_t t0 = total * h / H, t1 = total * (h + 1) / H;
+        if (cta >= s.num_ctas || t0 >= t1) return false;
+        const int m0 = (int)(t0 / tail);
+        m_tile = m0 + it;
+        if ((int64_t)m_tile * tail >= t1) return false;
+        n_start = s.n_main + (it == 0 ? (int)(t0 - (int64_t)m0 * tail) : 0);
+        const int64_t left = t1 - (int64_t)m_tile * tail;
+        n_end = s.n_main + (int)(left < tail ? left : tail);
+        return true;
+    }
     if (s.flat) {   // raw matmul: this unit's share of the row-major tile list, one query tile per "round"
         const int64_t total = (int64_t)s.m_tiles * s.n_tiles;
         const int64_t t0 = total * cta / s.num_ctas, t1 = total * (cta + 1) / s.num_ctas;
@@ -1012,6 +1033,7 @@ TcSchedule make_tc_schedule(int64_t q_rows, int64_t c_rows, int num_units, int g
         if (s.g_rem < 1) s.g_rem = 1;
     }
     s.flat = 0;
+    s.n_main = 0;
     int used_full = s.rounds > 0 ? s.mc * s.g : 0;
     int used_rem = s.m_rem * s.g_rem;
     s.num_ctas = used_full > used_rem ? used_full : used_rem;
@@ -1029,6 +1051,28 @@ TcSchedule make_tc_schedule_flat(int64_t q_rows, int64_t c_rows, int num_units, 
     if (s.rounds > s.m_tiles) s.rounds = s.m_tiles;
     s.g = 1;
     s.mc = s.num_ctas;
+    s.m_full = s.m_tiles;
+    s.m_rem = 0;
+    s.g_rem = 0;
+    return s;
+}
+
+TcSchedule make_tc_schedule_hybrid(int64_t q_rows, int64_t c_rows, int num_units, int cg) {
+    TcSchedule s = make_tc_schedule(q_rows, c_rows, num_units, 1, cg);
+    const int G = num_units > 0 ? num_units : 1;
+    if (s.rounds != 0 || s.g_rem != 1 || s.m_tiles >= G || s.m_tiles < 1) return s;
+    const int n_main = (int)(((int64_t)s.n_tiles * s.m_tiles + G - 1) / G);
+    if (n_main < 1 || n_main >= s.n_tiles) return s;
+    const int H = G - s.m_tiles, tail = s.n_tiles - n_main;
+    const int64_t per = ((int64_t)s.m_tiles * tail + H - 1) / H;   // the largest helper share; it may start inside a tail
+    s.flat = 2;
+    s.n_main = n_main;
+    s.num_ctas = G;
+    s.rounds = (int)((per + tail - 2) / tail) + 1;
+    if (s.rounds > s.m_tiles) s.rounds = s.m_tiles;
+    if (s.rounds < 1) s.rounds = 1;
+    s.g = 1;
+    s.mc = G;
     s.m_full = s.m_tiles;
     s.m_rem = 0;
     s.g_rem = 0;

@@ -361,21 +361,22 @@ def test_matmul_f16_split_planes(native, oracle, d):
     assert np.abs(out3 - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("shape", [(2600, 1500, 96), (300, 5000, 200), (5000, 300, 24)])
+@pytest.mark.parametrize("shape", [(2600, 1500, 96), (300, 5000, 200), (5000, 300, 24), (10000, 3000, 96), (12000, 2000, 20)])
 def test_matmul_tile_schedules_agree(native, oracle, shape):
     """The flat tile schedule (equal shares of the tile list per CTA pair: shares start and end inside a query tile, the
-    resident query planes are reloaded at the boundary) and the classic one give the same matrix."""
+    resident query planes are reloaded at the boundary), the hybrid one (main sweeps + helper pairs on the sweeps' tails,
+    for 37 < query tiles < 74: the last two shapes) and the classic one give the same matrix."""
     nq, n, d = shape
     rng = np.random.default_rng(nq + n)
     q, c = _randn(rng, nq, d), _randn(rng, n, d)
     outs = []
-    for flat in (1, 0):
+    for flat in (1, 2, 0):
         native.set_option("matmul_flat", flat)
         try:
             outs.append(native.matmul(_hm(q), _hm(c)))
         finally:
             native.set_option("matmul_flat", -1)
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     parity.check_matmul(outs[0], q, c, oracle.matmul(q, c), np.float32)
 
 
