@@ -2224,6 +2224,7 @@ static int immediate_option(const std::string &k, int64_t value) {
     if (k == "stage") { stage_set_enabled(value != 0); return 1; }
     if (k == "stage_threads") { stage_set_threads((int)value); return 1; }
     if (k == "stage_nt") { stage_set_nt_stores((int)value); return 1; }
+    if (k == "f64_dmma_async") { dmma_set_async((int)value); return 1; }
     if (k == "stage_slot_mb") { stage_set_ring((size_t)(value < 1 ? 1 : value) << 20, g_stage_slots.load()); g_stage_slot_mb.store(value < 1 ? 1 : value); return 1; }
     if (k == "stage_slots") { g_stage_slots.store((int)value); stage_set_ring((size_t)g_stage_slot_mb.load() << 20, (int)value); return 1; }
     return 0;

@@ -283,9 +283,132 @@ __global__ void __launch_bounds__(256) scores_f64_dmma_kernel(const double *__re
     }
 }
 
+// Same tile and fragment mapping, operands through a three-stage cp.async ring (8-byte copies: any row pitch; rows and
+// K positions beyond the matrix are zero-filled by the copy itself): one block barrier per K-tile instead of two, two
+// K-tiles of loads in flight, no staging registers (two blocks per SM stay resident).
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+// MI = 8-row fragments per warp in M: 4 (warp tile 32 x 32, block tile 128 x 64, two blocks per SM) or 8 (64 x 32, block
+// tile 256 x 64, one block per SM: 12 instead of 8 fragment loads per 32 resp. 16 DMMAs, 32 independent accumulators).
+// MI = 2 (warp tile 16 x 32, block tile 64 x 64, <= 64 registers): three or four blocks per SM - DMMA has a long latency
+// and a warp keeps few of them in flight, so resident WARPS are what fills the FP64 pipe (measured: 8 / 16 warps per SM
+// -> 7.7 / 5.0 ms at 8192 x 8192 x 1024).  ST = ring stages (2: the copy of tile kt+1 overlaps tile kt only).
+template <int MI, int ST, int MINB>
+__global__ void __launch_bounds__(256, MINB) scores_f64_dmma_async_kernel(const double *__restrict__ q, const double *__restrict__ c,
+                                                                                 const double *__restrict__ qa, const double *__restrict__ ca,
+                                                                                 int64_t nq, int64_t n, int64_t d, int metric,
+                                                                                 double *__restrict__ out, int64_t ldo) {
+    constexpr int BM = 32 * MI, BN = 64, BK = 16, LD = BK + 4, APT = BM * BK / 256;   // APT: A elements per thread and K-tile
+    extern __shared__ __align__(16) double dmma_smem[];
+    double *As = dmma_smem;                       // [ST][BM * LD]
+    double *Bs = dmma_smem + ST * BM * LD;        // [ST][BN * LD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int ar = tid / (BK / APT), ak = (tid % (BK / APT)) * APT;
+    const int br = tid >> 2, bk = (tid & 3) * 4;
+    const bool a_row = m0 + ar < nq, b_row = n0 + br < n;
+    const double *a_src = q + (a_row ? (m0 + ar) : 0) * d;
+    const double *b_src = c + (b_row ? (n0 + br) : 0) * d;
+    const int nkt = (int)((d + BK - 1) / BK);
+    auto issue = [&](int kt) {
+        if (kt < nkt) {
+            const int slot = kt % ST;
+            const int64_t k0 = (int64_t)kt * BK;
+            double *ad = As + slot * BM * LD + ar * LD + ak;
+            double *bd = Bs + slot * BN * LD + br * LD + bk;
+#pragma unroll
+            for (int u = 0; u < APT; ++u) {
+                const bool ok = a_row && k0 + ak + u < d;
+                cp_async8(ad + u, a_src + (ok ? k0 + ak + u : 0), ok);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = b_row && k0 + bk + u < d;
+                cp_async8(bd + u, b_src + (ok ? k0 + bk + u : 0), ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the wait counts uniform)
+    };
+    double acc[MI][4][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    issue(0);
+    if (ST > 2) issue(1);
+    for (int kt = 0; kt < nkt; ++kt) {
+        if (ST > 2) asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of tile kt have landed ...
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                        // ... everyone's have, and tile kt-1's slot is free
+        issue(kt + ST - 1);
+        const double *at = As + (kt % ST) * BM * LD, *bt = Bs + (kt % ST) * BN * LD;
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 4) {
+            double a[MI], b[4];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = at[(wm * 8 * MI + i * 8 + (lane >> 2)) * LD + ks + (lane & 3)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = bt[(wn * 32 + j * 8 + (lane >> 2)) * LD + ks + (lane & 3)];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const bool aux = metric == METRIC_COSINE || metric == METRIC_EUCLIDEAN;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int64_t r = m0 + wm * 8 * MI + i * 8 + (lane >> 2);
+        if (r >= nq) continue;
+        const double qav = aux ? qa[r] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t cc = n0 + wn * 32 + j * 8 + (lane & 3) * 2 + e;
+                if (cc >= n) continue;
+                double v = acc[i][j][e];
+                if (aux) v = metric_finish(v, metric, qav, ca[cc]);
+                out[r * ldo + cc] = v;
+            }
+        }
+    }
+}
+
+static int g_dmma_async = 3;   // dmma_set_async(): 0 register-staged kernel; cp.async ring with 1: 32 x 32 warp tiles, 2 blocks per SM,
+                                // 2: 64 x 32, 1 block, 3 (default): 16 x 32, 4 blocks, two stages, 4: 16 x 32, 3 blocks, three stages
+void dmma_set_async(int mode) { g_dmma_async = mode; }
+
+template <int MI, int ST, int MINB>
+static cudaError_t launch_dmma_async(const double *q, const double *c, const double *qa, const double *ca, int64_t nq, int64_t n,
+                                     int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s) {
+    constexpr int smem = ST * (32 * MI + 64) * 20 * 8;
+    static bool attr_set[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(scores_f64_dmma_async_kernel<MI, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 15] = true;
+    }
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((nq + 32 * MI - 1) / (32 * MI)));
+    scores_f64_dmma_async_kernel<MI, ST, MINB><<<grid, 256, smem, s>>>(q, c, qa, ca, nq, n, d, metric, out, ldo);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scores_f64_dmma(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
                                    int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s) {
     if (nq <= 0 || n <= 0) return cudaSuccess;
+    if (g_dmma_async == 4) return launch_dmma_async<2, 3, 3>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
+    if (g_dmma_async == 3) return launch_dmma_async<2, 2, 4>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
+    if (g_dmma_async == 2) return launch_dmma_async<8, 3, 1>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
+    if (g_dmma_async == 1) return launch_dmma_async<4, 3, 2>(q, c, qa, ca, nq, n, d, metric, out, ldo, s);
     dim3 grid((unsigned)((n + 63) / 64), (unsigned)((nq + 127) / 128));
     scores_f64_dmma_kernel<<<grid, 256, 0, s>>>(q, c, qa, ca, nq, n, d, metric, out, ldo);
     return cudaGetLastError();

@@ -48,6 +48,7 @@ cudaError_t launch_scores_f64(const double *q, const double *c, const double *qa
 // Same contract on the FP64 tensor path (mma.sync.m8n8k4.f64); agrees to ~1e-15 relative, not bit for bit.
 cudaError_t launch_scores_f64_dmma(const double *q, const double *c, const double *qa, const double *ca, int64_t nq,
                                    int64_t n, int64_t d, int metric, double *out, int64_t ldo, cudaStream_t s);
+void dmma_set_async(int mode);   // variant of the DMMA kernel (pmm_generic.cu; default 3: 16 x 32 warp tiles, four blocks per SM)
 // Per-row exact top-k of a score slab (radix select + ordered tie collection + bitonic sort).
 // scratch: nq * kpad * 12 bytes when kpad > select_smem_kpad_limit(), else unused.
 int select_kpad(int64_t k);
