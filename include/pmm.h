@@ -313,14 +313,22 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *                              64 MB) of the chunked upload; tests lower both to drive tiny corpora through it
  *   "f64_simt" (0/1)           f64 contraction (raw matmul, slab path) on FP64 FMA instead of DMMA
  *   "generic_workspace_mb"     score slab of the SIMT path
- *   "matmul_tc_max_dim"        longest vector the raw matmul sends through the tensor cores (0 = auto: 256 for f32 via
- *                              3xTF32, 1024 for f16 storage; longer vectors use the exact sequential-FMA kernel)
+ *   "matmul_tc_max_dim"        longest vector the raw matmul sends through the tensor cores (0 = auto: 256 for f32,
+ *                              1024 for f16 storage; longer vectors use the exact sequential-FMA kernel)
+ *   "matmul_split16" (0/1, default 1)  f32 operands with 32 < D <= 256: row-scaled hi/lo f16 planes, small terms accumulated
+ *                              first (1), or the 3xTF32 planes (0); D <= 32 always uses the TF32 planes
+ *   "matmul_exact_max_dim"     f32 vectors this short (default 8) take the exact kernel: a 22-bit split does not average out
+ *   "matmul_flat" (-1/0/1/2)   tile schedule of the tensor-core matmul: classic (0), flat (1), hybrid (2), automatic (-1, default)
+ *   "d2h_direct" (0/1, default 1)  host top-k with page-locked result buffers: the re-scoring kernel stores straight into them
  *   "multi_gpu" (0/1, default 1), "multi_gpu_min_gflop" (default 4000)   pmm_topk / pmm_matmul spread one call over all
  *                              visible GPUs when the call has at least that many GFLOP of contraction work
  * Acting immediately, process-wide (not part of the snapshot):
  *   "stage" (0/1, default 1)   pageable host buffers go through the library's page-locked staging ring (pmm_stage.h);
  *                              0: plain cudaMemcpyAsync, staged by the driver
  *   "stage_threads"            host threads per staged copy (0 = auto: half the cores, at most 8)
+ *   "stage_nt" (0/1, default 1)  non-temporal stores for the copies into the ring (a third less host-memory traffic)
+ *   "f64_dmma_async"           variant of the f64 DMMA matmul kernel (default 3: 16 x 32 warp tiles, four blocks per SM,
+ *                              cp.async operand ring; 0: the register-staged round-1 kernel; see pmm_generic.cu)
  *   "stage_slot_mb", "stage_slots"   ring geometry (default 4 slots of 32 MB per calling thread)
  *   "prep_fast" (0/1, default 1)  128-bit loads / stores in the plane-building pass where the layout allows
  *   "rescore_fixed" (0/1, default 0)  cp.async gather in the exact re-scoring of plain f32 corpora (faster kernel, slower
