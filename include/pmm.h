@@ -319,6 +319,8 @@ PMM_API void pmm_reset_kernel_launch_count(void);
  *                              first (1), or the 3xTF32 planes (0); D <= 32 always uses the TF32 planes
  *   "matmul_exact_max_dim"     f32 vectors this short (default 8) take the exact kernel: a 22-bit split does not average out
  *   "matmul_flat" (-1/0/1/2)   tile schedule of the tensor-core matmul: classic (0), flat (1), hybrid (2), automatic (-1, default)
+ *   "warm_seed" (0/1, default 1)  large top-k calls start the first filter level from thresholds of a sample pre-pass
+ *                              (DESIGN 4.2); "warm_rows" (default 4096: cap of the sample size), "warm_rank" (0 = auto)
  *   "d2h_direct" (0/1, default 1)  host top-k with page-locked result buffers: the re-scoring kernel stores straight into them
  *   "multi_gpu" (0/1, default 1), "multi_gpu_min_gflop" (default 4000)   pmm_topk / pmm_matmul spread one call over all
  *                              visible GPUs when the call has at least that many GFLOP of contraction work

@@ -58,7 +58,7 @@ struct Options {
     int force_generic = 0, profile = 0, tc_group = 0, tc_cg = 2, tc_sync_tiles = 32, host_chunked = 1, f64_simt = 0, verify = 1,
         tc_levels = 3, tc_clm = 1, tc_cluster4 = 0, tc_max_units = 0, tc_debug_skip = 0, tc_sync_slack = 0, tc_max_flush = 0,
         host_chunk_ratio_pct = 0, host_chunk_first_div = 0, f16r_wide = 1, host_chunk_min_rows = 16384, host_chunk_min_mb = 64,
-        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, matmul_split16 = 1, matmul_exact_max_dim = 8, matmul_flat = -1, d2h_direct = 1, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
+        tc_soft_at = 0, f64_tc = 1, multi_gpu = 1, seed_retry = 1, matmul_tc_max_dim = 0, matmul_split16 = 1, matmul_exact_max_dim = 8, matmul_flat = -1, d2h_direct = 1, warm_seed = 1, warm_rows = 4096, warm_rank = 0, pipeline = 0, rescore_stream_loads = 1, multipass = 1;
     int64_t generic_ws_mb = 1024, multi_gpu_min_gflop = 4000, pipeline_min_gflop = 2000;
 };
 Options g_opt;                 // process-wide defaults, guarded by g_opt_mu
@@ -99,6 +99,9 @@ bool apply_option(Options &o, const std::string &k, int64_t value) {
     else if (k == "pipeline_min_gflop") o.pipeline_min_gflop = value < 0 ? 0 : value;   // smallest round worth a launch of its own
     else if (k == "matmul_tc_max_dim") o.matmul_tc_max_dim = value < 0 ? 0 : (int)value;   // 0 = automatic (see dev_matmul_impl)
     else if (k == "matmul_exact_max_dim") o.matmul_exact_max_dim = value < 0 ? 0 : (int)value;   // f32 vectors this short: exact SIMT kernel
+    else if (k == "warm_seed") o.warm_seed = value ? 1 : 0;     // first filter level starts from thresholds of a sample pre-pass
+    else if (k == "warm_rows") o.warm_rows = value < 256 ? 256 : value > 65536 ? 65536 : (int)(value / 256 * 256);   // sample size (rows)
+    else if (k == "warm_rank") o.warm_rank = value < 0 ? 0 : value > 32 ? 32 : (int)value;   // sample rank that becomes the seed (0 = auto)
     else if (k == "d2h_direct") o.d2h_direct = value ? 1 : 0;   // top-k results written straight into page-locked result buffers
     else if (k == "matmul_flat") o.matmul_flat = value < 0 ? -1 : value > 2 ? 2 : (int)value;   // tile schedule of the tensor-core matmul: -1 automatic, 0 classic, 1 flat, 2 hybrid
     else if (k == "matmul_split16") o.matmul_split16 = value ? 1 : 0;           // raw f32 matmul: hi/lo f16 planes (1) or the 3xTF32 split (0)
@@ -582,7 +585,7 @@ cudaStream_t aux_stream() {
 
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
               cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3, const float *seed = nullptr,
-              TcPipe *pipe = nullptr, const uint64_t *ceil = nullptr) {
+              TcPipe *pipe = nullptr, const uint64_t *ceil = nullptr, int k_thr = 0, const char *stat_name = nullptr) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -621,7 +624,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     a.index_base = index_base;
     a.metric = metric;
     a.kp = kp;
-    a.k = kp;
+    a.k = (k_thr > 0 && k_thr <= kp) ? k_thr : kp;   // list position that sets a row's threshold
     DevBuf own_partial, rsync, staged;
     DevBuf &partial = pipe ? *pipe->partial : carry ? carry->partial : own_partial;
     const int esets = tc_epilogue_sets(a.f16, a.terms);
@@ -638,7 +641,7 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     }
     a.partial = partial.as<uint64_t>();
     // (256-entry lists and seeded launches are the retry levels: statistics of their own)
-    cudaError_t e = launch_counted(tc_kernel_stat_name(q, a.terms, kp, seed != nullptr), s, [&] { return launch_tc_topk(a, s); });
+    cudaError_t e = launch_counted(stat_name ? stat_name : tc_kernel_stat_name(q, a.terms, kp, seed != nullptr), s, [&] { return launch_tc_topk(a, s); });
     if (e != cudaSuccess)
         return fail(PMM_ERR_CUDA, "tensor-core top-k launch failed: %s %s", cudaGetErrorString(e), tc_last_error());
     cudaStream_t ms = s;
@@ -679,8 +682,10 @@ struct VerifyCtx {
     cudaStream_t s = nullptr;
 };
 
+// seed: thresholds of a RE-QUERY level (guaranteed lower bounds).  warm: thresholds a first level started from (warm
+// seeds, below) when the caller ran the filter itself (kept_in): the losslessness check has to know them.
 int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared *c, int terms,
-                     const uint64_t *kept_in, TopkOut o, int kp_override = 0, const float *seed = nullptr);
+                     const uint64_t *kept_in, TopkOut o, int kp_override = 0, const float *seed = nullptr, const float *warm = nullptr);
 
 // Rows [r0, r0 + rows) of a device-resident matrix as a matrix of its own. r0 must be a multiple of 256 (element
 // validity bitmaps are re-based by whole bytes).
@@ -985,12 +990,69 @@ int filter_rescore_pipelined(const VerifyCtx &vc, const Prepared &q, const pmm_m
 
 // Filter at `terms` (unless the kept lists are supplied) -> exact re-scoring -> verification -> next level.
 // c may be NULL only when kept_in is given.
+// ---- warm seeds: thresholds for the first filter level from a sample pre-pass -----------------------------------------
+// The first tiles of every query tile's sweep are dominated by list maintenance: with open thresholds every score is a
+// candidate, and the tensor cores wait for the epilogue (measured at C3, scripts/filter_wait_histogram.py: 85 % of the
+// MMA warps' accumulator waits fall into the first 512 of 3906 tiles, the first 64 tiles alone cost ~6 % of the launch).
+// A pre-pass filters the first 1024-4096 corpus rows with 32-entry lists whose r-th entry sets the threshold (cheap to
+// maintain), and the r-th best sample value of a query seeds its row in the real launch: "collect what beats the best
+// 0.2-0.8 % of a sample" (C3: 114.7 -> 108.7 ms for a 2.0 ms pre-pass; sweep in profiles/sweep_r2.md).  The seed is a lower bound of the final k-th best only with overwhelming probability (it needs k
+// corpus rows above the r-th best of the sample) - which is all it has to be: a seeded row whose list does not fill is dropped
+// by the losslessness check like any other unprovable row and re-queried one level up.  Applied when the corpus is at
+// least 16 k / r samples long, so that the expected number of rows above the seed is >= 16 k.
+// Sample size: the pre-pass costs sample / corpus of the launch's MMA work plus its own list warm-up, so short corpora
+// (C5: 125k rows per GPU, a million queries) get a smaller sample: N / 128 rows, within [1024, "warm_rows" = 4096].
+int64_t warm_rows_for(int64_t c_rows_total) {
+    int64_t s = c_rows_total / 128 / 256 * 256;
+    if (s < 1024) s = 1024;
+    if (s > t_opt.warm_rows) s = t_opt.warm_rows;
+    return s;
+}
+// The sample rank that becomes the seed: the smallest r >= 8 (a stable order statistic) for which the corpus is expected
+// to hold >= 16 k rows above the r-th best of the samples; 0 = no seeds (r would exceed the 32-entry sample lists).
+int warm_seed_rank(int64_t c_rows_total, int64_t keff) {
+    if (t_opt.warm_rank > 0) return t_opt.warm_rank;
+    const int64_t need = (16 * keff * warm_rows_for(c_rows_total) + c_rows_total - 1) / (c_rows_total > 0 ? c_rows_total : 1);
+    return need > 32 ? 0 : need < 8 ? 8 : (int)need;
+}
+bool warm_seed_applies(const Prepared &q, int64_t c_rows_total, int64_t c_rows_at_hand, int64_t keff, int kp) {
+    if (!t_opt.warm_seed || !(q.mode == PREP_F16R || q.mode == PREP_F16) || kp > 256) return false;
+    const int64_t rows = warm_rows_for(c_rows_total);
+    if (q.n_rows < 2048 || c_rows_at_hand < rows) return false;
+    return c_rows_total >= 16 * rows && warm_seed_rank(c_rows_total, keff) > 0;
+}
+// c: prepared planes holding at least warm_rows_for(c_rows_total) rows (the corpus, or its first chunk).  out: [q.rows_pad] floats.
+int warm_seeds(const Prepared &q, const Prepared &c, int64_t c_rows_total, int64_t keff, int metric, int terms, cudaStream_t s, DevBuf *out) {
+    const int64_t WARM_ROWS = warm_rows_for(c_rows_total);
+    Prepared cs;   // view of the first WARM_ROWS rows
+    cs.mode = c.mode;
+    cs.f64 = c.f64;
+    cs.n_rows = WARM_ROWS;
+    cs.dim = c.dim;
+    cs.rows_pad = WARM_ROWS;
+    cs.ld = c.ld;
+    cs.p0.borrow(c.p0.p, (size_t)WARM_ROWS * c.ld * 2, s);
+    const int64_t wsz = c.f64 ? 8 : 4;
+    if (c.norm.p) cs.norm.borrow(c.norm.p, (size_t)WARM_ROWS * wsz, s);
+    if (c.sqnorm.p) cs.sqnorm.borrow(c.sqnorm.p, (size_t)WARM_ROWS * wsz, s);
+    if (c.norm32.p) cs.norm32.borrow(c.norm32.p, (size_t)WARM_ROWS * 4, s);
+    if (c.sqnorm32.p) cs.sqnorm32.borrow(c.sqnorm32.p, (size_t)WARM_ROWS * 4, s);
+    DevBuf kept_s;
+    CUDA_TRY(kept_s.alloc((size_t)q.n_rows * 32 * 8, s));
+    const int r = warm_seed_rank(c_rows_total, keff);
+    int rc = tc_filter(q, cs, 32, metric, 0, kept_s.as<uint64_t>(), s, terms, nullptr, 3, nullptr, nullptr, nullptr, r, "tc_topk_warm");
+    if (rc) return rc;
+    CUDA_TRY(out->alloc((size_t)q.rows_pad * 4, s));
+    CUDA_TRY(launch_counted("seeds", s, [&] { return launch_seeds_from_lists(kept_s.as<uint64_t>(), 32, r, q.n_rows, q.rows_pad, out->as<float>(), s); }));
+    return PMM_OK;
+}
+
 int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t &raw_q, const Prepared *c, int terms,
-                     const uint64_t *kept_in, TopkOut o, int kp_override, const float *seed) {
+                     const uint64_t *kept_in, TopkOut o, int kp_override, const float *seed, const float *warm) {
     const int kp = kp_override ? kp_override : tc_list_capacity(vc.keff);
     const bool f16 = q.mode == PREP_F16;     // exact f16 planes
     const bool f16r = q.mode == PREP_F16R;   // input rounded to f16: TF32-x1-like error, then 3xTF32 on demand
-    DevBuf kept;
+    DevBuf kept, warm_buf;
     const uint64_t *kept_ptr = kept_in;
     const LevelErr le = level_err(q.mode, f16r ? 1 : terms, vc.f64, raw_q.dim);
     // next level for the queries the proof rejects (see below)
@@ -1009,7 +1071,13 @@ int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t 
             if ((rc = filter_rescore_pipelined(vc, q, raw_q, *c, terms, kp, part_rows, kept.as<uint64_t>(), job, o))) return rc;
             return rescore_finish(vc, job, raw_q, (f16r && !wide_) ? nullptr : c, next_terms_, o);
         }
-        rc = tc_filter(q, *c, kp, vc.metric, vc.index_base, kept.as<uint64_t>(), vc.s, terms, nullptr, 3, seed);
+        if (!seed && !kp_override && warm_seed_applies(q, c->n_rows, c->n_rows, vc.keff, kp)) {
+            if ((rc = warm_seeds(q, *c, c->n_rows, vc.keff, vc.metric, terms, vc.s, &warm_buf))) return rc;
+            warm = warm_buf.as<float>();
+        }
+        // (a warm-seeded first level keeps the first level's statistics name; "..._seeded" are the re-query levels)
+        rc = tc_filter(q, *c, kp, vc.metric, vc.index_base, kept.as<uint64_t>(), vc.s, terms, nullptr, 3, seed ? seed : warm, nullptr, nullptr, 0,
+                       seed ? nullptr : tc_kernel_stat_name(q, f16r ? 1 : terms, kp, false));
         if (rc) return rc;
         kept_ptr = kept.as<uint64_t>();
     }
@@ -1022,7 +1090,7 @@ int tc_topk_verified(const VerifyCtx &vc, const Prepared &q, const pmm_matrix_t 
     const int next_terms = wide ? 1 : (f16r || (!f16 && terms == 1)) ? 3 : 0;
     // f16 planes cannot serve the 3xTF32 level: it rebuilds TF32 planes piece by piece (c_planes = NULL)
     return rescore_and_verify(vc, q, raw_q, kept_ptr, kp, (f16r && !wide) ? nullptr : c, level_err(q.mode, f16r ? 1 : terms, vc.f64, raw_q.dim),
-                              next_terms, seed, o);
+                              next_terms, seed ? seed : warm, o);
 }
 
 // First filter level for f32 planes: TF32 x1 unless switched off ("tc_levels" = 1) or cta_group::1 was forced.
@@ -1424,7 +1492,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     // included) both streams are drained before a buffer is released: the copy stream may still be writing into the
     // corpus buffer, and the caller's host buffers must not be in use by a DMA after we return.
     Uploaded uq, uc;
-    DevBuf err, kept, c_aux_all, c_aux32_all, d_idx, d_sc, c_max;
+    DevBuf err, kept, c_aux_all, c_aux32_all, d_idx, d_sc, c_max, warm_buf;
     Prepared q, call;
     TcCarry carry;
     struct Drain {
@@ -1551,6 +1619,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     CUDA_TRY(init_norm_range(c_max.as<unsigned int>(), s));
     const int kp = tc_list_capacity(keff);
     const int terms0 = first_level_terms(q);
+    const float *warm = nullptr;
     carry.corpus_rows_total = N;
     carry.layout_rows = N;
     for (int i = 0; i < n_chunks; ++i) carry.layout_rows = std::min<int64_t>(carry.layout_rows, cut[i + 1] - cut[i]);
@@ -1585,9 +1654,14 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         if (pc.f64 && want_norm) c.norm32.borrow(c_aux32_all.as<float>() + r0, aux_rows * 4, s);
         if (pc.f64 && want_sq) c.sqnorm32.borrow(c_aux32_all.as<float>() + r0, aux_rows * 4, s);
         if ((rc = prepare(dm, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
+        // warm seeds (see warm_seeds) from the first rows of the first chunk; every chunk's launch starts from them
+        if (i == 0 && warm_seed_applies(q, N, rows, keff, kp)) {
+            if ((rc = warm_seeds(q, c, N, keff, metric, terms0, s, &warm_buf))) return rc;
+            warm = warm_buf.as<float>();
+        }
         // the candidate lists are carried from chunk to chunk; the last launch merges them into `kept`
         if ((rc = tc_filter(q, c, kp, metric, index_base + r0, kept.as<uint64_t>(), s, terms0, &carry,
-                            (i == 0 ? 1 : 0) | (i == n_chunks - 1 ? 2 : 0))))
+                            (i == 0 ? 1 : 0) | (i == n_chunks - 1 ? 2 : 0), warm, nullptr, nullptr, 0, tc_kernel_stat_name(q, terms0, kp, false))))
             return rc;
     }
     if (want_norm) call.norm.borrow(c_aux_all.p, (size_t)call.rows_pad * wsz, s);
@@ -1611,7 +1685,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     TopkOut o{direct ? direct_idx : d_idx.as<uint32_t>(), direct ? direct_sc : d_sc.as<double>(), d_cand};
     // c_aux_all holds the corpus norms (cosine) or squared norms (euclidean) of the whole corpus
     VerifyCtx vc = verify_ctx(call, uc.dm, keff, metric, index_base, s);
-    if ((rc = tc_topk_verified(vc, q, uq.dm, &call, terms0, kept_ptr, o))) return rc;
+    if ((rc = tc_topk_verified(vc, q, uq.dm, &call, terms0, kept_ptr, o, 0, nullptr, warm))) return rc;
     if (!direct && out_index) CUDA_TRY(stage_d2h(out_index, d_idx.p, cnt * 4, s));
     if (!direct && out_score) CUDA_TRY(stage_d2h(out_score, d_sc.p, cnt * 8, s));
     if (out_index || out_score) stat_add("d2h_bytes", (double)cnt * 12);

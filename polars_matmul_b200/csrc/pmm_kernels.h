@@ -128,6 +128,7 @@ cudaError_t launch_rescore(const uint64_t *cand, int kp_in, const RawMatrix &qm,
 void rescore_set_fixed(bool on);   // cp.async gather of the re-scoring for plain f32 corpora (default on)
 // Seeds for a re-query level: out[r] = kth_units[ids[r]] - E_next(query) - margin for r < n_ids, NaN for the padding
 // rows [n_ids, n_pad).  `next` carries the NEXT level's eps / abs_err / max_norm and the norm inputs.
+cudaError_t launch_seeds_from_lists(const uint64_t *lists, int kp, int r, int64_t n_queries, int64_t n_pad, float *out, cudaStream_t s);
 cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, const float *kth_units,
                               const RescoreCheck &next, int metric, float *out, cudaStream_t s);
 // f64 working precision: exact f64 scores of the kept candidates (raw columns may be f16 / f32 / f64).

@@ -683,6 +683,29 @@ cudaError_t launch_make_seeds(const int64_t *ids, int64_t n_ids, int64_t n_pad, 
     return cudaGetLastError();
 }
 
+// ---- warm seeds of a first filter level: the r-th best filter value of a sample pre-pass, per query ---------------------
+// lists [n_queries][kp]: merged candidate lists of the pre-pass (sorted, best first; 0 = empty slot).  out [n_pad]: the
+// filter value of entry r - 1, NaN (no seed) for rows whose sample list is shorter, holds a NaN score, or is padding.
+__global__ void seeds_from_lists_kernel(const uint64_t *__restrict__ lists, int kp, int r, int64_t n_queries, int64_t n_pad,
+                                        float *__restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pad) return;
+    float seed = __uint_as_float(0x7fc00000u);
+    if (q < n_queries) {
+        const uint64_t c = lists[q * kp + (r - 1)];
+        if (c != 0ull && candidate_key(c) != 0u) {
+            const float v = key_score(candidate_key(c), true);
+            if (v == v && fabsf(v) <= 3.0e38f) seed = v;
+        }
+    }
+    out[q] = seed;
+}
+cudaError_t launch_seeds_from_lists(const uint64_t *lists, int kp, int r, int64_t n_queries, int64_t n_pad, float *out, cudaStream_t s) {
+    if (n_pad <= 0) return cudaSuccess;
+    seeds_from_lists_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(lists, kp, r, n_queries, n_pad, out);
+    return cudaGetLastError();
+}
+
 // ---- raw matmul: outputs that involve a row with inf / NaN elements, recomputed with IEEE arithmetic ---------------
 __global__ void __launch_bounds__(256) matmul_nonfinite_fixup_kernel(RawMatrix lm, RawMatrix rm, const unsigned char *__restrict__ nf_left,
                                                                       const unsigned char *__restrict__ nf_right,

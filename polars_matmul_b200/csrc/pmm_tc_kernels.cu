@@ -8,19 +8,24 @@
 //              thread owns one query row of the 128 x 256 accumulator tile in TMEM, applies the metric
 //              in f32 exactly as the reference does, packs (score key, ~index) into a u64 and keeps
 //              only candidates that beat the row's current k-th best.
-//   * matmul : replaces matmul_slice_f32 (src/metrics.rs:160-202): 128-bit stores of the tile rows.
+//   * matmul : replaces matmul_slice_f32 (src/metrics.rs:160-202): the tile goes registers -> swizzled shared tile -> TMA
+//              store (full 128-byte lines), on eight epilogue warps.  f32 operands with 32 < D <= 256 arrive as row-scaled
+//              hi/lo f16 planes (pmm_prep.cu: prep_split16_kernel) and are contracted with three kind::f16 MMAs per 16
+//              elements, the small terms swept first, the query planes of the item resident in shared memory (SPLIT16
+//              below); shorter f32 vectors use the 3xTF32 planes, f16-stored input one exact plane.
 //
 // Precision: the top-k epilogue is a FILTER - final scores come from the exact re-scoring kernel (pmm_rescore.cu)
 // and every query carries a proof that the filter dropped nothing relevant - so the operand format is an internal
 // choice per level: f32 (or f64) inputs rounded to one f16 plane + ONE kind::f16 MMA per K-step (default first
 // level, 11 significant bits at the full f16 rate), one TF32 plane (TERMS = 1), or the 3xTF32 split
-// hi*hi + hi*lo + lo*hi on hi/lo planes from pmm_prep.cu (re-query level; also the raw matmul, whose result IS the
-// output and must stay within 1e-5).  f16-stored inputs use kind::f16 on exact planes (products of two f16 values
-// are exact in f32, so only the summation order differs from the reference's upcast path).  f32 accumulation in TMEM.
+// hi*hi + hi*lo + lo*hi on hi/lo planes from pmm_prep.cu (re-query level).  The raw matmul's result IS the output and
+// must stay within 1e-5: it uses the f16 hi/lo split in the order that keeps tcgen05's accumulate truncations small
+// (DESIGN.md 4.5).  f16-stored inputs use kind::f16 on exact planes (products of two f16 values are exact in f32, so
+// only the summation order differs from the reference's upcast path).  f32 accumulation in TMEM.
 //
 // Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (TMEM lane group = warp % 4); the single-plane top-k kernels run a second set of four
-// epilogue warps (6..9), each set owning half of the columns of every tile.  Two accumulator buffers of 256 TMEM
+// warps 2..5 = epilogue (TMEM lane group = warp % 4); the single-plane top-k kernels and the matmul kernels run a
+// second set of four epilogue warps (6..9), each set owning half of the columns of every tile.  Two accumulator buffers of 256 TMEM
 // columns let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Running top-k: per row a threshold (the k-th best packed candidate so far).  Scores that beat it are appended to a

@@ -727,6 +727,48 @@ def test_resident_corpus_handle(native, oracle):
         h.close()
 
 
+@pytest.mark.parametrize("case", ["k10", "k100", "sample_dominates", "host_chunks", "f16"])
+def test_warm_seeds_of_the_first_level(native, oracle, case):
+    """Large calls start the first filter level from thresholds of a sample pre-pass (the r-th best of the first 4096
+    corpus rows): same bits as without, for every metric; a sample that is far better than the rest of the corpus makes
+    the seeds too aggressive - lists do not fill, the losslessness check re-queries those rows - and the result is
+    still the oracle's; zero queries and duplicated top rows ride along."""
+    rng = np.random.default_rng(len(case))
+    if case == "k100":
+        nq, n, d, k = 2304, 210_000, 32, 100
+    else:
+        nq, n, d, k = 2304, 100_000, 48, 10
+    q, c = _randn(rng, nq, d), _randn(rng, n, d)
+    q[5] = 0
+    c[70_000:70_040] = c[3]                       # 41 identical rows: ties inside the top ranks of some queries
+    if case == "sample_dominates":
+        c[:512] *= np.float32(6.0)                # dot / euclidean: all the extreme scores lie inside the sample, whose 8th best
+                                                  # then exceeds the true 10th best: the lists cannot fill
+    if case == "f16":
+        q, c = q.astype(np.float16), c.astype(np.float16)
+    if case == "host_chunks":
+        native.set_option("host_chunk_min_mb", 0)
+    try:
+        for metric in ("dot", "cosine", "euclidean"):
+            outs = []
+            for warm in (1, 0):
+                native.set_option("warm_seed", warm)
+                native.set_option("profile", 1)
+                native.reset_stats()
+                try:
+                    outs.append(native.topk(_hm(q), _hm(c), k, metric))
+                    assert (native.get_stat("tc_topk_warm_launches") >= 1) == bool(warm)
+                    if case == "sample_dominates" and warm and metric == "dot":
+                        assert native.get_stat("requeried_f16_wide") + native.get_stat("requeried_tf32x3") + native.get_stat("fallback_queries") > 100
+                finally:
+                    native.set_option("warm_seed", 1)
+                    native.set_option("profile", 0)
+            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), metric
+            parity.check_topk(outs[0][0], outs[0][1], q.astype(np.float32), c.astype(np.float32), k, metric, oracle, exact=True)
+    finally:
+        native.set_option("host_chunk_min_mb", 64)
+
+
 def test_results_written_straight_into_page_locked_buffers(native, oracle):
     """Host path with page-locked result buffers: the re-scoring kernel (and the scatter of re-queried rows) store into them
     directly, no trailing device->host copy; pageable buffers take the staged copy.  Same bits either way, incl. queries
