@@ -585,7 +585,8 @@ cudaStream_t aux_stream() {
 
 int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t index_base, uint64_t *kept,
               cudaStream_t s, int terms, TcCarry *carry = nullptr, int phase = 3, const float *seed = nullptr,
-              TcPipe *pipe = nullptr, const uint64_t *ceil = nullptr, int k_thr = 0, const char *stat_name = nullptr) {
+              TcPipe *pipe = nullptr, const uint64_t *ceil = nullptr, int k_thr = 0, const char *stat_name = nullptr,
+              int sample_tiles = 0) {
     DevInfo &di = dev_info();
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -610,8 +611,17 @@ int tc_filter(const Prepared &q, const Prepared &c, int kp, int metric, int64_t 
     const int gs = a.cg * a.clm;   // CTAs per scheduling unit
     int units = di.num_sms / gs;
     if (t_opt.tc_max_units > 0 && units > t_opt.tc_max_units) units = t_opt.tc_max_units;
-    const int64_t group_rows = carry ? carry->corpus_rows_total : c.n_rows;
-    a.sched = make_tc_schedule(q.n_rows, c.n_rows, units, tc_group_for(group_rows, q.ld, a.f16 != 0 || a.terms == 1, units, gs), gs,
+    // sample_tiles > 0: the launch covers a strided SAMPLE of the corpus tiles (warm seeds): every stride-th whole tile
+    int64_t sched_rows = c.n_rows;
+    if (sample_tiles > 0) {
+        const int64_t whole = c.n_rows / TC_TILE_N;
+        if (whole < sample_tiles) sample_tiles = (int)whole;
+        if (sample_tiles < 1) return fail(PMM_ERR_INVALID, "tc_filter: corpus smaller than one tile cannot be sampled");
+        a.tile_stride = (int)(whole / sample_tiles);
+        sched_rows = (int64_t)sample_tiles * TC_TILE_N;
+    }
+    const int64_t group_rows = carry ? carry->corpus_rows_total : sched_rows;
+    a.sched = make_tc_schedule(q.n_rows, sched_rows, units, tc_group_for(group_rows, q.ld, a.f16 != 0 || a.terms == 1, units, gs), gs,
                                carry ? carry->layout_rows : 0);
     // the filter runs on f32 copies of the norms (f64 working precision keeps the exact ones for the re-scoring)
     a.q_aux = metric == PMM_METRIC_COSINE ? q.norm_f32() : metric == PMM_METRIC_EUCLIDEAN ? q.sq_f32() : nullptr;
@@ -1015,32 +1025,26 @@ int warm_seed_rank(int64_t c_rows_total, int64_t keff) {
     const int64_t need = (16 * keff * warm_rows_for(c_rows_total) + c_rows_total - 1) / (c_rows_total > 0 ? c_rows_total : 1);
     return need > 32 ? 0 : need < 8 ? 8 : (int)need;
 }
-bool warm_seed_applies(const Prepared &q, int64_t c_rows_total, int64_t c_rows_at_hand, int64_t keff, int kp) {
-    if (!t_opt.warm_seed || !(q.mode == PREP_F16R || q.mode == PREP_F16) || kp > 256) return false;
+bool warm_seed_applies(int q_mode, int64_t q_rows, int64_t c_rows_total, int64_t c_rows_at_hand, int64_t keff, int kp) {
+    if (!t_opt.warm_seed || !(q_mode == PREP_F16R || q_mode == PREP_F16) || kp > 256) return false;
     const int64_t rows = warm_rows_for(c_rows_total);
-    if (q.n_rows < 2048 || c_rows_at_hand < rows) return false;
+    if (q_rows < 2048 || c_rows_at_hand < rows) return false;
     return c_rows_total >= 16 * rows && warm_seed_rank(c_rows_total, keff) > 0;
 }
-// c: prepared planes holding at least warm_rows_for(c_rows_total) rows (the corpus, or its first chunk).  out: [q.rows_pad] floats.
+bool warm_seed_applies(const Prepared &q, int64_t c_rows_total, int64_t c_rows_at_hand, int64_t keff, int kp) {
+    return warm_seed_applies(q.mode, q.n_rows, c_rows_total, c_rows_at_hand, keff, kp);
+}
+// c: prepared planes holding at least warm_rows_for(c_rows_total) rows (the corpus, its first chunk, or a host-side sample).
+// out: [q.rows_pad] floats.
 int warm_seeds(const Prepared &q, const Prepared &c, int64_t c_rows_total, int64_t keff, int metric, int terms, cudaStream_t s, DevBuf *out) {
-    const int64_t WARM_ROWS = warm_rows_for(c_rows_total);
-    Prepared cs;   // view of the first WARM_ROWS rows
-    cs.mode = c.mode;
-    cs.f64 = c.f64;
-    cs.n_rows = WARM_ROWS;
-    cs.dim = c.dim;
-    cs.rows_pad = WARM_ROWS;
-    cs.ld = c.ld;
-    cs.p0.borrow(c.p0.p, (size_t)WARM_ROWS * c.ld * 2, s);
-    const int64_t wsz = c.f64 ? 8 : 4;
-    if (c.norm.p) cs.norm.borrow(c.norm.p, (size_t)WARM_ROWS * wsz, s);
-    if (c.sqnorm.p) cs.sqnorm.borrow(c.sqnorm.p, (size_t)WARM_ROWS * wsz, s);
-    if (c.norm32.p) cs.norm32.borrow(c.norm32.p, (size_t)WARM_ROWS * 4, s);
-    if (c.sqnorm32.p) cs.sqnorm32.borrow(c.sqnorm32.p, (size_t)WARM_ROWS * 4, s);
+    // The sample is STRIDED over the rows at hand (every stride-th whole corpus tile): a corpus sorted by norm, topic or
+    // popularity would otherwise hand every query a sample far better (or worse) than the rest, and seeds that are too
+    // high leave the lists unfilled - correct, but every such row is re-queried.
+    const int sample_tiles = (int)(warm_rows_for(c_rows_total) / TC_TILE_N);
     DevBuf kept_s;
     CUDA_TRY(kept_s.alloc((size_t)q.n_rows * 32 * 8, s));
     const int r = warm_seed_rank(c_rows_total, keff);
-    int rc = tc_filter(q, cs, 32, metric, 0, kept_s.as<uint64_t>(), s, terms, nullptr, 3, nullptr, nullptr, nullptr, r, "tc_topk_warm");
+    int rc = tc_filter(q, c, 32, metric, 0, kept_s.as<uint64_t>(), s, terms, nullptr, 3, nullptr, nullptr, nullptr, r, "tc_topk_warm", sample_tiles);
     if (rc) return rc;
     CUDA_TRY(out->alloc((size_t)q.rows_pad * 4, s));
     CUDA_TRY(launch_counted("seeds", s, [&] { return launch_seeds_from_lists(kept_s.as<uint64_t>(), 32, r, q.n_rows, q.rows_pad, out->as<float>(), s); }));
@@ -1492,8 +1496,8 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
     // included) both streams are drained before a buffer is released: the copy stream may still be writing into the
     // corpus buffer, and the caller's host buffers must not be in use by a DMA after we return.
     Uploaded uq, uc;
-    DevBuf err, kept, c_aux_all, c_aux32_all, d_idx, d_sc, c_max, warm_buf;
-    Prepared q, call;
+    DevBuf err, kept, c_aux_all, c_aux32_all, d_idx, d_sc, c_max, warm_buf, sample_vals;
+    Prepared q, call, sample_prep;
     TcCarry carry;
     struct Drain {
         cudaStream_t s, cs;
@@ -1580,6 +1584,19 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         CUDA_TRY(stage_h2d(uc.row_validity.p, corpus->row_validity, nb, s));
         uc.dm.row_validity = uc.row_validity.as<uint8_t>();
     }
+    // Warm seeds (see warm_seeds) need a sample of the WHOLE corpus, and only its first chunk will be on the device when
+    // the first launch starts: for plain fixed-size rows a strided sample of the host buffer (every (N / sample)-th row,
+    // ~12 MB at C3) goes up FIRST - ahead of the chunk copies in the DMA queue - and its pre-pass runs while the first
+    // chunk is still crossing PCIe.  Other layouts (lists, bitmaps, multi-chunk columns) take a strided sample of the
+    // first chunk instead (in the chunk loop).
+    const bool warm_host_sample = warm_seed_applies(pc.mode, Q, N, N, keff, tc_list_capacity(keff)) && !corpus->offsets && !corpus->validity &&
+                                  !corpus->row_validity && !(corpus->reserved & PMM_MATRIX_CHUNKED);
+    if (warm_host_sample) {
+        const int64_t rows_s = warm_rows_for(N), step = N / rows_s;
+        CUDA_TRY(sample_vals.alloc((size_t)rows_s * D * es, s));
+        CUDA_TRY(stage_h2d_rows(sample_vals.p, corpus->values, (size_t)D * es, (size_t)step * D * es, (size_t)rows_s, s));
+        stat_add("h2d_bytes", (double)rows_s * D * es);
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&drain.ready, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(drain.ready, s));
     CUDA_TRY(cudaStreamWaitEvent(cs, drain.ready, 0));  // the copy stream may touch the buffers once they exist
@@ -1628,6 +1645,17 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         CUDA_TRY(c_aux_all.alloc((size_t)round_up(N, TC_TILE_N) * wsz, s));
         if (pc.f64) CUDA_TRY(c_aux32_all.alloc((size_t)round_up(N, TC_TILE_N) * 4, s));
     }
+    if (warm_host_sample) {   // the strided host sample went up before the chunks (above): its pre-pass runs while chunk 0 is in flight
+        pmm_matrix_t sm;
+        memset(&sm, 0, sizeof(sm));
+        sm.values = sample_vals.p;
+        sm.n_rows = warm_rows_for(N);
+        sm.dim = D;
+        sm.dtype = corpus->dtype;
+        if ((rc = prepare(sm, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &sample_prep))) return rc;
+        if ((rc = warm_seeds(q, sample_prep, N, keff, metric, terms0, s, &warm_buf))) return rc;
+        warm = warm_buf.as<float>();
+    }
     // Plane buffers for the WHOLE corpus; every chunk is prepared into its slice (chunk starts are multiples of the
     // corpus tile), so that after the last chunk the planes of the full corpus are at hand for the re-query levels.
     call.mode = pc.mode;
@@ -1655,7 +1683,7 @@ int host_topk_chunked(const pmm_matrix_t *queries, const pmm_matrix_t *corpus, i
         if (pc.f64 && want_sq) c.sqnorm32.borrow(c_aux32_all.as<float>() + r0, aux_rows * 4, s);
         if ((rc = prepare(dm, pc.mode, pc.f64, TC_TILE_N, want_norm, want_sq, err.as<int>(), s, &c, true, c_max.as<unsigned int>()))) return rc;
         // warm seeds (see warm_seeds) from the first rows of the first chunk; every chunk's launch starts from them
-        if (i == 0 && warm_seed_applies(q, N, rows, keff, kp)) {
+        if (i == 0 && !warm && warm_seed_applies(q, N, rows, keff, kp)) {
             if ((rc = warm_seeds(q, c, N, keff, metric, terms0, s, &warm_buf))) return rc;
             warm = warm_buf.as<float>();
         }

@@ -230,6 +230,8 @@ struct TcArgs {
     const uint64_t *ceil;          // top-k: [q_rows_pad] per-query ceilings (packed candidates) or NULL: only candidates strictly
                                    // below the ceiling are admitted - pass p+1 of a multi-pass top-k collects "the next
                                    // list-full below what pass p kept" (k > 248)
+    int tile_stride;               // top-k: the schedule's corpus tile t is tile t * tile_stride of the planes (0 / 1: contiguous);
+                                   // > 1 = a strided sample of the corpus (warm seeds): sched covers the SAMPLE's tiles, n the planes' rows
     uint64_t *staged;              // top-k: scratch of tc_staged_bytes(grid CTAs) bytes (unsorted candidates per CTA and row)
     // matmul mode
     float *out;                    // [nq x n] row-major

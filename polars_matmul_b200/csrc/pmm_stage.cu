@@ -281,6 +281,30 @@ cudaError_t stage_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStr
     return cudaSuccess;
 }
 
+// `rows` rows of `row_bytes` each, `src_pitch` bytes apart in host memory -> a dense block in device memory.  Through the ring
+// whatever the source (the gather itself needs a page-locked landing area); small: used for a few thousand sampled rows.
+cudaError_t stage_h2d_rows(void *dst_dev, const void *src_host, size_t row_bytes, size_t src_pitch, size_t rows, cudaStream_t stream) {
+    if (rows == 0 || row_bytes == 0) return cudaSuccess;
+    cudaError_t e = t_ring.ensure();
+    if (e != cudaSuccess) {   // no page-locked memory to be had: let the driver do the strided copy
+        cudaGetLastError();
+        return cudaMemcpy2DAsync(dst_dev, row_bytes, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, stream);
+    }
+    const size_t per_slot = t_ring.slot_bytes / row_bytes;
+    if (per_slot == 0) return cudaMemcpy2DAsync(dst_dev, row_bytes, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, stream);
+    for (size_t r0 = 0; r0 < rows; r0 += per_slot) {
+        const size_t n = rows - r0 < per_slot ? rows - r0 : per_slot;
+        Ring::Slot *sl;
+        if ((e = t_ring.acquire(&sl)) != cudaSuccess) return e;
+        for (size_t i = 0; i < n; ++i) memcpy((char *)sl->p + i * row_bytes, (const char *)src_host + (r0 + i) * src_pitch, row_bytes);
+        if ((e = cudaMemcpyAsync((char *)dst_dev + r0 * row_bytes, sl->p, n * row_bytes, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(sl->ev, stream)) != cudaSuccess) return e;
+        sl->busy = true;
+    }
+    g_staged_h2d.fetch_add(rows * row_bytes);
+    return cudaSuccess;
+}
+
 cudaError_t stage_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream) {
     if (bytes == 0) return cudaSuccess;
     if (bytes < kDirectBelow || !g_enabled.load() || host_ptr_is_pinned(dst_host))

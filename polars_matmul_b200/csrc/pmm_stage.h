@@ -35,6 +35,9 @@ bool host_device_view(const void *p, void **dev);
 // buffer is no longer read after return, the device copy completes in stream order).
 cudaError_t stage_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);
 
+// Gather: `rows` rows of `row_bytes`, `src_pitch` bytes apart in host memory, into a dense device block (through the ring).
+cudaError_t stage_h2d_rows(void *dst_dev, const void *src_host, size_t row_bytes, size_t src_pitch, size_t rows, cudaStream_t stream);
+
 // Device -> host copy of `bytes`, complete on return for pageable destinations (DMA into the ring, host threads copy
 // out); page-locked destinations get one cudaMemcpyAsync on `stream` (complete in stream order, like before).
 cudaError_t stage_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream);

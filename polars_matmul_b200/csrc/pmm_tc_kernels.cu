@@ -129,6 +129,7 @@ struct TcKParams {
     float norm_guard;       // cosine: norms at or below this count as zero (1e-6 f32; just under 1e-10 for f64 sources)
     const float *seed_thr;  // per query row (padded like q_aux): initial threshold in filter units, NaN = none; or NULL
     const uint64_t *ceil;   // per query row (padded): only candidates strictly BELOW this packed value are admitted; or NULL
+    int tile_stride;        // corpus tile nt of the schedule is tile nt * tile_stride of the planes (1; > 1: strided sample)
 };
 
 enum { EPI_TOPK = 0, EPI_MATMUL = 1 };
@@ -468,7 +469,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             }
             int j = 0;  // tile counter of this CTA inside the round
             for (int nt = n_start; nt < n_end; nt += n_step, ++j) {
-                const int32_t brow = nt * BN + (int)crank * Cfg::B_ROWS;         // this CTA's part of the corpus tile
+                const int32_t brow = nt * p.tile_stride * BN + (int)crank * Cfg::B_ROWS;   // this CTA's part of the corpus tile
                 if (n_sync && j % p.sync_tiles == 0) {
                     if (issuer) {
                         unsigned int *ctr = sync_base + j / p.sync_tiles;
@@ -725,7 +726,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CU
             }
             if (SPLIT16) rowc = p.q_aux[qrow];   // this row's scale factor (padded to the tile grid)
             for (int nt = n_start; nt < n_end; nt += n_step) {
-                const int64_t col_tile = (int64_t)nt * BN;
+                const int64_t col_tile = (int64_t)nt * p.tile_stride * BN;
                 if (EPI == EPI_TOPK && p.metric != METRIC_DOT) {  // stage this tile's corpus aux values (per warp)
                     __syncwarp();
 #pragma unroll
@@ -965,6 +966,7 @@ cudaError_t launch_t2(const TcArgs &a, cudaStream_t s) {
     p.resume = a.resume;
     p.seed_thr = a.seed_thr;
     p.ceil = a.ceil;
+    p.tile_stride = a.tile_stride > 1 ? a.tile_stride : 1;
     p.norm_guard = a.norm_guard > 0.0f ? a.norm_guard : 1e-6f;
     p.soft_at = a.soft_at > 0 ? a.soft_at : SOFT_AT;
     // merges that fit beside one tile's MMA time: a merge costs about as much as 8 k-blocks of one plane

@@ -727,6 +727,30 @@ def test_resident_corpus_handle(native, oracle):
         h.close()
 
 
+@pytest.mark.parametrize("chunked", [False, True])
+def test_warm_seeds_on_a_sorted_corpus(native, oracle, chunked):
+    """A corpus sorted by norm (dot metric: every query's best rows come first) must not make the seeds too aggressive: the
+    sample is strided over the whole corpus - on the device, or gathered from the host buffer before the first chunk is
+    uploaded - so only a handful of rows need the re-query levels, and the result is the oracle's."""
+    rng = np.random.default_rng(31)
+    nq, n, d, k = 2304, 120_000, 48, 10
+    q, c = _randn(rng, nq, d), _randn(rng, n, d)
+    c *= np.linspace(4.0, 0.25, n, dtype=np.float32)[:, None]
+    if chunked:
+        native.set_option("host_chunk_min_mb", 0)
+    native.set_option("profile", 1)
+    native.reset_stats()
+    try:
+        idx, sc = native.topk(_hm(q), _hm(c), k, "dot")
+        assert native.get_stat("tc_topk_warm_launches") >= 1
+        flagged = native.get_stat("requeried_f16_wide") + native.get_stat("requeried_tf32x3") + native.get_stat("fallback_queries")
+        assert flagged < 0.02 * nq, flagged
+    finally:
+        native.set_option("host_chunk_min_mb", 64)
+        native.set_option("profile", 0)
+    parity.check_topk(idx, sc, q, c, k, "dot", oracle, exact=True)
+
+
 @pytest.mark.parametrize("case", ["k10", "k100", "sample_dominates", "host_chunks", "f16"])
 def test_warm_seeds_of_the_first_level(native, oracle, case):
     """Large calls start the first filter level from thresholds of a sample pre-pass (the r-th best of the first 4096
@@ -742,8 +766,9 @@ def test_warm_seeds_of_the_first_level(native, oracle, case):
     q[5] = 0
     c[70_000:70_040] = c[3]                       # 41 identical rows: ties inside the top ranks of some queries
     if case == "sample_dominates":
-        c[:512] *= np.float32(6.0)                # dot / euclidean: all the extreme scores lie inside the sample, whose 8th best
-                                                  # then exceeds the true 10th best: the lists cannot fill
+        # dot / euclidean: all the extreme scores lie inside the (strided) sample - every 97th corpus tile of 256 rows at this
+        # size - whose 8th best then exceeds the true 10th best: the lists cannot fill
+        c[:256] *= np.float32(6.0)
     if case == "f16":
         q, c = q.astype(np.float16), c.astype(np.float16)
     if case == "host_chunks":
