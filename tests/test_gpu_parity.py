@@ -727,6 +727,46 @@ def test_resident_corpus_handle(native, oracle):
         h.close()
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("PMM_WARM_CASES", "12"))))   # raise for a soak on the GPU box
+def test_warm_seeds_randomised(native, oracle, seed):
+    """Seeded random shapes above the warm-seed thresholds (the hypothesis suite stays below 2048 queries): k, metric,
+    vector length, corpus size and data kind vary - Gaussian, clustered (queries sit on cluster centres, the corpus is
+    ordered cluster by cluster), duplicated rows, zero rows, per-row scales over six decades - alternating between the
+    resident-style and the chunked host path.  Bit-identical to the oracle every time."""
+    rng = np.random.default_rng(1000 + seed)
+    nq = int(rng.integers(2048, 2600))
+    n = int(rng.integers(70_000, 140_000))
+    d = int(rng.choice([16, 24, 40, 64]))
+    k = int(rng.choice([1, 5, 10, 24, 25, 56, 100]))
+    metric = ["dot", "cosine", "euclidean"][seed % 3]
+    kind = ["gauss", "clustered", "dups", "zeros", "scaled", "clustered"][seed % 6]
+    q, c = _randn(rng, nq, d), _randn(rng, n, d)
+    if kind == "clustered":
+        centres = _randn(rng, 40, d) * np.float32(3.0)
+        c = (np.repeat(centres, -(-n // 40), axis=0)[:n] + np.float32(0.3) * c).astype(np.float32)      # cluster by cluster
+        q = (centres[rng.integers(0, 40, size=nq)] + np.float32(0.3) * q).astype(np.float32)
+    elif kind == "dups":
+        src = rng.integers(0, n, size=n // 3)
+        c[rng.integers(0, n, size=n // 3)] = c[src]
+    elif kind == "zeros":
+        c[rng.integers(0, n, size=n // 10)] = 0
+        q[rng.integers(0, nq, size=nq // 10)] = 0
+    elif kind == "scaled":
+        c *= (10.0 ** rng.uniform(-3, 3, size=(n, 1))).astype(np.float32)
+        q *= (10.0 ** rng.uniform(-3, 3, size=(nq, 1))).astype(np.float32)
+    if seed % 2:
+        native.set_option("host_chunk_min_mb", 0)
+    native.set_option("profile", 1)
+    native.reset_stats()
+    try:
+        idx, sc = native.topk(_hm(q), _hm(c), k, metric)
+        assert native.get_stat("tc_topk_warm_launches") >= 1, (n, k)
+    finally:
+        native.set_option("host_chunk_min_mb", 64)
+        native.set_option("profile", 0)
+    parity.check_topk(idx, sc, q, c, k, metric, oracle, exact=True)
+
+
 @pytest.mark.parametrize("chunked", [False, True])
 def test_warm_seeds_on_a_sorted_corpus(native, oracle, chunked):
     """A corpus sorted by norm (dot metric: every query's best rows come first) must not make the seeds too aggressive: the
