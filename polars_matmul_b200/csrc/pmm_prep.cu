@@ -321,11 +321,13 @@ __global__ void __launch_bounds__(256) prep_fast_kernel(PrepArgs a) {
 // scale_out[row] = 2^-e undoes the scaling in the matmul epilogue (two exact multiplications per output).
 // Rows holding inf / NaN, or whose largest element lies outside [2^-60, 2^60] (the two factors of an output must stay
 // representable), are written as zeros and marked for the IEEE fix-up pass like the non-finite rows of the TF32 split.
-template <typename SRC>
+// LANES lanes per row (32, or 16 for short rows: two rows per warp, half as many warps to schedule).
+template <typename SRC, int LANES>
 __global__ void __launch_bounds__(256) prep_split16_kernel(PrepArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= a.rows_out) return;
+    const int lane = threadIdx.x & (LANES - 1);
+    const unsigned gmask = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+    const int64_t row = (int64_t)blockIdx.x * (256 / LANES) + (threadIdx.x / LANES);
+    if (row >= a.rows_out) return;   // (whole lane groups leave together)
     const SRC *values = (const SRC *)a.values;
     int64_t base = 0, len = 0;
     if (row < a.n_rows) {
@@ -351,14 +353,14 @@ __global__ void __launch_bounds__(256) prep_split16_kernel(PrepArgs a) {
     };
     float mx = 0.0f;
     bool bad = false;
-    for (int64_t i = lane; i < len; i += 32) {
+    for (int64_t i = lane; i < len; i += LANES) {
         const float x = fetch(i);
         bad |= (__float_as_uint(x) & 0x7f800000u) == 0x7f800000u;
         mx = fmaxf(mx, fabsf(x));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    bad = __any_sync(0xffffffffu, bad);
+    for (int o = LANES / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, o));
+    bad = (__ballot_sync(gmask, bad) & gmask) != 0u;
     int e = 0;
     if (mx > 0.0f) {
         const int lg = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;   // floor(log2(mx)) for normal mx; -127 for subnormals
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(256) prep_split16_kernel(PrepArgs a) {
     const float down = __uint_as_float((uint32_t)(127 - e) << 23);    // 2^-e
     __half2 *hi = (__half2 *)((__half *)a.out0 + row * a.ld_out);
     __half2 *lo = (__half2 *)((__half *)a.out1 + row * a.ld_out);
-    for (int64_t i = 2 * lane; i < a.ld_out; i += 64) {   // ld_out is a multiple of 64: full 128-byte stores per warp
+    for (int64_t i = 2 * lane; i < a.ld_out; i += 2 * LANES) {   // ld_out is a multiple of 64: 128- / 64-byte stores per lane group
         float x0 = 0.0f, x1 = 0.0f;
         if (!bad) {
             x0 = fetch(i) * up;
@@ -421,10 +423,16 @@ static cudaError_t launch_prep_t(const PrepArgs &a, cudaStream_t s) {
 cudaError_t launch_prep(const PrepArgs &a, int src_dtype, int mode, int work_f64, cudaStream_t s) {
     if (mode == MODE_SPLIT16) {   // raw f32 matmul operands: planes + scale factors, no norms
         if (work_f64 || src_dtype > 1 || !a.out0 || !a.out1 || (a.ld_out & 63)) return cudaErrorInvalidValue;
-        const int64_t blocks = (a.rows_out + 7) / 8;
-        if (blocks <= 0) return cudaSuccess;
-        if (src_dtype == 1) prep_split16_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(a);
-        else prep_split16_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(a);
+        if (a.rows_out <= 0) return cudaSuccess;
+        if (a.ld_out <= 256) {   // short rows: 16 lanes per row
+            const int64_t blocks = (a.rows_out + 15) / 16;
+            if (src_dtype == 1) prep_split16_kernel<float, 16><<<(unsigned)blocks, 256, 0, s>>>(a);
+            else prep_split16_kernel<__half, 16><<<(unsigned)blocks, 256, 0, s>>>(a);
+        } else {
+            const int64_t blocks = (a.rows_out + 7) / 8;
+            if (src_dtype == 1) prep_split16_kernel<float, 32><<<(unsigned)blocks, 256, 0, s>>>(a);
+            else prep_split16_kernel<__half, 32><<<(unsigned)blocks, 256, 0, s>>>(a);
+        }
         return cudaGetLastError();
     }
     if (work_f64 && (mode == MODE_F16R || mode == MODE_TF32)) {
